@@ -1,0 +1,118 @@
+"""Random draws for the oracle (test infrastructure).
+
+Two interchangeable providers:
+
+* ``StreamDraws`` reproduces the RNG topology of ``aesara.tensor.random.utils.
+  RandomStream`` as used by the reference: every ``srng.<dist>()`` *call site*
+  owns a ``numpy.random.default_rng`` seeded with the next ``SeedSequence(seed)
+  .spawn(1)`` child in graph-construction order.  NUTS call sites, in order:
+  momentum normal (reference nuts.py:113 -> metrics.py:66), direction Bernoulli
+  (trajectory.py:516), uniform progressive sampling (proposals.py:99), biased
+  progressive sampling (proposals.py:131).  HMC: momentum (hmc.py:122), accept
+  (hmc.py:194).  ``bernoulli(p)`` is ``Generator.binomial(1, p)``.
+
+* ``InjectedDraws`` is the validation-mode provider shared with the CUDA path:
+  index-addressed arrays of standard normals and uniforms, with the Bernoulli
+  decision rule that ``Generator.binomial(1, p)`` applies to its one uniform
+  (``bernoulli_from_uniform``).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def bernoulli_from_uniform(u: float, p: float) -> bool:
+    """Decision NumPy's ``Generator.binomial(1, p)`` takes given its uniform ``u``.
+
+    p <= 0.5 uses the inversion branch (success iff u > 1-p); p > 0.5 uses the
+    mirrored branch (success iff u <= p).  NaN p never accepts.
+    """
+    if p <= 0.5:
+        return bool(u > 1.0 - p)
+    return bool(u <= p)
+
+
+def uniform_slot(expansion: int, step: int) -> int:
+    """Flat slot of the uniform-sampling draw of sub-tree step ``step`` (>=1) in
+    expansion ``expansion``: expansions before it hold 2**k slots each."""
+    return (1 << expansion) - 1 + (step - 1)
+
+
+class StreamDraws:
+    def __init__(self, seed: int, kind: str = "nuts", first_child: int = 0):
+        children = np.random.SeedSequence(seed).spawn(first_child + 4)[first_child:]
+        gens = [np.random.default_rng(c) for c in children]
+        self.momentum_rng = gens[0]
+        if kind == "nuts":
+            self.direction_rng, self.uniform_rng, self.biased_rng = gens[1:4]
+        elif kind == "hmc":
+            self.accept_rng = gens[1]
+        else:
+            raise ValueError(kind)
+
+    def begin_transition(self):
+        pass
+
+    def normal(self, shape):
+        return self.momentum_rng.normal(0.0, 1.0, size=shape)
+
+    def direction(self, expansion):
+        return bool(self.direction_rng.binomial(1, 0.5))
+
+    def uniform_accept(self, expansion, step, p):
+        return bool(self.uniform_rng.binomial(1, p))
+
+    def biased_accept(self, expansion, p):
+        return bool(self.biased_rng.binomial(1, p))
+
+    def hmc_accept(self, p):
+        return bool(self.accept_rng.binomial(1, p))
+
+
+class InjectedDraws:
+    """Index-addressed draws for ONE chain, ``n_transitions`` transitions.
+
+    z          [T, d]            standard normals for the momentum
+    u_dir      [T, max_exp]      direction uniforms   (go right iff u > 0.5)
+    u_biased   [T, max_exp]      biased-sampling uniforms
+    u_uniform  [T, 2**max_exp-1] uniform-sampling uniforms, slot = uniform_slot(k, s)
+    u_accept   [T]               HMC accept uniforms
+    """
+
+    def __init__(self, z, u_dir=None, u_biased=None, u_uniform=None, u_accept=None):
+        self.z = np.asarray(z, dtype=np.float64)
+        self.u_dir = None if u_dir is None else np.asarray(u_dir, dtype=np.float64)
+        self.u_biased = None if u_biased is None else np.asarray(u_biased, dtype=np.float64)
+        self.u_uniform = None if u_uniform is None else np.asarray(u_uniform, dtype=np.float64)
+        self.u_accept = None if u_accept is None else np.asarray(u_accept, dtype=np.float64)
+        self.t = -1
+
+    @classmethod
+    def random(cls, rng, n_transitions, shape, max_num_expansions=10):
+        d = int(np.prod(shape)) if shape != () else 1
+        return cls(
+            rng.standard_normal((n_transitions, d)),
+            rng.random((n_transitions, max_num_expansions)),
+            rng.random((n_transitions, max_num_expansions)),
+            rng.random((n_transitions, (1 << max_num_expansions) - 1)),
+            rng.random((n_transitions,)),
+        )
+
+    def begin_transition(self):
+        self.t += 1
+
+    def normal(self, shape):
+        z = self.z[self.t]
+        return z[0] if shape == () else z.reshape(shape)
+
+    def direction(self, expansion):
+        return bernoulli_from_uniform(self.u_dir[self.t, expansion], 0.5)
+
+    def uniform_accept(self, expansion, step, p):
+        return bernoulli_from_uniform(self.u_uniform[self.t, uniform_slot(expansion, step)], p)
+
+    def biased_accept(self, expansion, p):
+        return bernoulli_from_uniform(self.u_biased[self.t, expansion], p)
+
+    def hmc_accept(self, p):
+        return bernoulli_from_uniform(self.u_accept[self.t], p)
