@@ -1,0 +1,35 @@
+# Builds libb200hmc.so (sm_100a only) in-tree, plus the CPU-side test tooling.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr
+CSRC      := aehmc_b200/csrc
+LIBDIR    := aehmc_b200/lib
+OBJDIR    := build/obj
+LIB       := $(LIBDIR)/libb200hmc.so
+
+# The engine and the elementwise primitives are compiled WITHOUT fused multiply-add
+# contraction so that the scalar-metric leapfrog rounds exactly like the reference's
+# compiled graph (a*b then +c); the contraction kernels keep FMA.
+OBJS := $(OBJDIR)/capi.o $(OBJDIR)/engine_kernels.o $(OBJDIR)/primitives.o $(OBJDIR)/gemm.o $(OBJDIR)/logreg.o
+HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/b200hmc.h
+
+all: $(LIB)
+
+$(OBJDIR)/engine_kernels.o: $(CSRC)/engine_kernels.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
+$(OBJDIR)/primitives.o: $(CSRC)/primitives.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(OBJS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
+
+clean:
+	rm -rf build $(LIBDIR)/*.so
+
+.PHONY: all clean

@@ -1,0 +1,89 @@
+// Context management, error reporting and the sampler entry points of the C-ABI.
+#include <string.h>
+
+#include "launch.h"
+
+namespace b2h {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what) {
+    g_last_error = std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e);
+    return B2H_ERR_CUDA;
+}
+
+}  // namespace b2h
+
+using namespace b2h;
+
+extern "C" {
+
+const char* b2h_last_error(void) { return g_last_error.c_str(); }
+
+int b2h_version(void) { return 100; }
+
+int b2h_ctx_create(int device, void* stream, b2h_ctx** out) {
+    if (!out) { set_error("null out pointer"); return B2H_ERR_ARG; }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error(std::string("no CUDA device available: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                  " (libb200hmc has no CPU fallback)");
+        return B2H_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { set_error("bad device ordinal"); return B2H_ERR_ARG; }
+    B2H_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    B2H_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("libb200hmc is built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+        return B2H_ERR_UNSUPPORTED;
+    }
+    b2h_ctx* ctx = new b2h_ctx;
+    ctx->device = device;
+    ctx->stream = (cudaStream_t)stream;
+    ctx->sm_count = prop.multiProcessorCount;
+    *out = ctx;
+    return 0;
+}
+
+int b2h_ctx_destroy(b2h_ctx* ctx) {
+    delete ctx;
+    return 0;
+}
+
+int b2h_ctx_sync(b2h_ctx* ctx) {
+    if (!ctx) { set_error("null context"); return B2H_ERR_ARG; }
+    B2H_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b2h_nuts_run(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
+                 const b2h_cfg* cfg, const b2h_adapt* adapt, void* q, void* p, void* U, void* g, double* step_size,
+                 int64_t C, int32_t n_transitions, int64_t max_ticks, int32_t resume, b2h_diag* diag, void* draws,
+                 double* draw_stats, int32_t n_store, int64_t* counters, void* workspace, int64_t workspace_bytes) {
+    return nuts_run_impl(ctx, model, metric, rng, cfg, adapt, q, p, U, g, step_size, C, n_transitions, max_ticks,
+                         resume, diag, draws, draw_stats, n_store, counters, workspace, workspace_bytes, false);
+}
+
+int b2h_hmc_run(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
+                const b2h_cfg* cfg, const b2h_adapt* adapt, void* q, void* p, void* U, void* g, double* step_size,
+                int64_t C, int32_t n_transitions, b2h_diag* diag, void* draws, double* draw_stats, int32_t n_store,
+                int64_t* counters, void* workspace, int64_t workspace_bytes) {
+    return nuts_run_impl(ctx, model, metric, rng, cfg, adapt, q, p, U, g, step_size, C, n_transitions, 0, 0, diag,
+                         draws, draw_stats, n_store, counters, workspace, workspace_bytes, true);
+}
+
+int64_t b2h_nuts_workspace_bytes(const b2h_model* model, const b2h_metric* metric, const b2h_cfg* cfg, int64_t C) {
+    if (!model || !metric || !cfg) return -1;
+    return engine_workspace_bytes(model, metric, cfg, C);
+}
+
+int64_t b2h_hmc_workspace_bytes(const b2h_model* model, const b2h_metric* metric, const b2h_cfg* cfg, int64_t C) {
+    if (!model || !metric || !cfg) return -1;
+    return engine_workspace_bytes(model, metric, cfg, C);
+}
+
+}  // extern "C"

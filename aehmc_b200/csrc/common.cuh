@@ -1,0 +1,167 @@
+// Shared device helpers for the B200 HMC/NUTS engine (sm_100a only).
+//
+// Nothing here is a port: the reference (aesara-devs/aehmc) has no native code.
+// The helpers restate the scalar semantics its graphs rely on
+// (proposals.py:41-52,96-100,130-144; termination.py:207-235) so that the
+// kernels take the same decisions as the reference under injected draws.
+#pragma once
+
+#ifndef B2H_HOST_SIM
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+#include <math.h>
+
+#ifndef B2H_DEVINL
+#define B2H_DEVINL __device__ __forceinline__
+#endif
+
+namespace b2h {
+
+typedef long long i64;
+
+// ---------------------------------------------------------------------------
+// scalar semantics
+// ---------------------------------------------------------------------------
+
+// log(exp(a)+exp(b)) exactly as oracle/tree.py:logaddexp (max + log(sum exp(x-max)),
+// -inf,-inf -> -inf).  Always double: weights are float64 in the reference
+// whatever floatX is (nuts.py:123-124).
+B2H_DEVINL double lae(double a, double b) {
+    if (isnan(a) || isnan(b)) return nan("");
+    double m = a > b ? a : b;
+    if (isinf(m)) {
+        if (m < 0) return m;          // -inf + log(0) = -inf
+        return m;                     // +inf
+    }
+    return m + log(exp(a - m) + exp(b - m));
+}
+
+B2H_DEVINL double expit(double x) {
+    if (isnan(x)) return x;
+    if (x < -709.0) return 0.0;
+    return 1.0 / (1.0 + exp(-x));
+}
+
+// Decision numpy's Generator.binomial(1, p) takes from its single uniform u
+// (oracle/streams.py:bernoulli_from_uniform).  NaN p never accepts.
+B2H_DEVINL bool bern(double u, double p) {
+    if (p <= 0.5) return u > 1.0 - p;
+    return u <= p;
+}
+
+// termination.py:207-235 in closed form: idx_max = popcount(step >> 1),
+// number of sub-trees = trailing one-bits of step.
+B2H_DEVINL void storage_indices(int step, int& idx_min, int& idx_max) {
+    idx_max = __popc((unsigned)step >> 1);
+    int trailing = __ffs(~step) - 1;
+    idx_min = idx_max - trailing + 1;
+}
+
+B2H_DEVINL int uniform_slot(int expansion, int step) { return (1 << expansion) - 1 + (step - 1); }
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 counter RNG (native-RNG mode).  key = seed, counter =
+// (slot, stream kind, transition, global chain id): results do not depend on
+// how chains are sharded over GPUs.
+// ---------------------------------------------------------------------------
+enum DrawKind : uint32_t { DRAW_Z = 0, DRAW_DIR = 1, DRAW_BIASED = 2, DRAW_UNIFORM = 3, DRAW_ACCEPT = 4 };
+
+B2H_DEVINL void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                              uint32_t out[4]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+B2H_DEVINL double u53(uint32_t lo, uint32_t hi) {          // [0, 1)
+    uint64_t x = ((uint64_t)hi << 32) | lo;
+    return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+}
+
+struct PhiloxKey { uint32_t k0, k1; };
+
+B2H_DEVINL double philox_uniform(PhiloxKey key, uint64_t chain, uint32_t transition, uint32_t kind, uint32_t slot) {
+    uint32_t o[4];
+    philox4x32_10(slot, kind, transition, (uint32_t)chain, key.k0 ^ (uint32_t)(chain >> 32), key.k1, o);
+    return u53(o[0], o[1]);
+}
+
+// element j of the standard-normal momentum vector (Box-Muller on one Philox block per pair)
+B2H_DEVINL double philox_normal(PhiloxKey key, uint64_t chain, uint32_t transition, uint32_t j) {
+    uint32_t o[4];
+    philox4x32_10(j >> 1, DRAW_Z, transition, (uint32_t)chain, key.k0 ^ (uint32_t)(chain >> 32), key.k1, o);
+    double u1 = 1.0 - u53(o[0], o[1]);                      // (0, 1]
+    double u2 = u53(o[2], o[3]);
+    double r = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    return (j & 1) ? r * s : r * c;
+}
+
+// ---------------------------------------------------------------------------
+// group-of-G-threads reductions.  G in {1,2,4,8,16,32}: sub-warp groups, shuffles
+// under the group's lane mask (other groups of the warp may be in another branch).
+// G > 32: the group is the whole CTA (one chain per CTA), warp shuffle + smem.
+// ---------------------------------------------------------------------------
+template <int G>
+struct Group {
+    static constexpr bool kBlock = (G > 32);
+    B2H_DEVINL static int lane() { return kBlock ? (int)threadIdx.x : (int)(threadIdx.x & (G - 1)); }
+    B2H_DEVINL static unsigned mask() {
+        if (G >= 32) return 0xffffffffu;
+        unsigned l = threadIdx.x & 31u;
+        return ((1u << G) - 1u) << (l & ~(unsigned)(G - 1));
+    }
+    // all-reduce sum of N doubles across the group
+    template <int N>
+    B2H_DEVINL static void sum(double (&v)[N], double* smem /* >= N*(G/32) doubles when kBlock */) {
+        if (G == 1) return;
+        constexpr int W = G >= 32 ? 32 : G;
+        const unsigned m = mask();
+#pragma unroll
+        for (int off = W / 2; off > 0; off >>= 1) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(m, v[i], off);
+        }
+        if (kBlock) {
+            constexpr int NW = G / 32;
+            int w = threadIdx.x >> 5;
+            __syncthreads();                       // smem reuse guard
+            if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) smem[i * NW + w] = v[i];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < NW; ++k) s += smem[i * NW + k];
+                v[i] = s;
+            }
+        }
+    }
+    B2H_DEVINL static double sum1(double x, double* smem) {
+        double v[1] = {x};
+        sum<1>(v, smem);
+        return v[0];
+    }
+    B2H_DEVINL static void sync() {
+        if (kBlock) __syncthreads();
+        else if (G > 1) __syncwarp(mask());
+    }
+};
+
+template <typename T> struct Num;
+template <> struct Num<float> { static constexpr int dtype = 0; };
+template <> struct Num<double> { static constexpr int dtype = 1; };
+
+}  // namespace b2h

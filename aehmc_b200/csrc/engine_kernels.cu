@@ -1,0 +1,562 @@
+// Kernels and launch logic of the tick engine (see engine.cuh).
+//
+//  fused mode : model gradient is a device function (iid Gaussian, funnel, eight
+//               schools) and the metric is scalar/diagonal -> ONE persistent kernel
+//               runs every chain through all its ticks; nothing returns to the host.
+//  split mode : gradient and/or metric need an all-chain contraction (dense metric,
+//               correlated Gaussian, logistic regression) -> each tick is
+//               pre -> [velocity GEMM -> drift] -> gradient -> [kick -> velocity GEMM] -> post,
+//               all chains in lock-step, chains restarting transitions independently.
+#include <algorithm>
+#include <vector>
+
+#include "engine.cuh"
+#include "launch.h"
+#include "models.cuh"
+
+namespace b2h {
+
+// ---------------------------------------------------------------------------
+// workspace carving
+// ---------------------------------------------------------------------------
+struct Carver {
+    char* base;
+    size_t off;
+    template <typename U>
+    U* take(size_t n) {
+        off = (off + 255) & ~(size_t)255;
+        U* p = base ? (U*)(base + off) : nullptr;
+        off += n * sizeof(U);
+        return p;
+    }
+};
+
+struct EnginePlan {
+    int G;
+    bool dense, split, hmc, per_chain_imm, scalar_imm;
+    size_t model_ws_off, model_ws_bytes;
+};
+
+static int auto_group(int d) {
+    if (d <= 16) return 1;
+    if (d <= 64) return 8;
+    if (d <= 512) return 32;
+    return 256;
+}
+
+static bool model_is_fused(int kind) {
+    return kind == B2H_MODEL_IID_GAUSSIAN || kind == B2H_MODEL_FUNNEL || kind == B2H_MODEL_EIGHT_SCHOOLS;
+}
+
+static int make_plan(const b2h_model* model, const b2h_metric* metric, const b2h_cfg* cfg, EnginePlan& pl) {
+    pl.dense = metric->kind == B2H_IMM_DENSE;
+    pl.per_chain_imm = metric->kind == B2H_IMM_DIAG_PER_CHAIN;
+    pl.scalar_imm = metric->kind == B2H_IMM_SCALAR;
+    pl.split = pl.dense || !model_is_fused(model->kind);
+    int G = cfg->group > 0 ? cfg->group : auto_group(model->dim);
+    if (pl.split && G < 8) G = 8;          // split scratch is row-major: needs the row-major layout
+    if (G != 1 && G != 8 && G != 32 && G != 256) {
+        set_error("group must be one of 0 (auto), 1, 8, 32, 256");
+        return B2H_ERR_ARG;
+    }
+    if ((model->kind == B2H_MODEL_FUNNEL || model->kind == B2H_MODEL_EIGHT_SCHOOLS) && !pl.split && G > 8) G = 8;
+    pl.G = G;
+    return 0;
+}
+
+template <typename T>
+static size_t carve(EngineView<T>& v, char* base, const EnginePlan& pl, const b2h_model* model, int C, int d,
+                    int maxd, bool adapt, size_t model_ws_bytes, size_t* model_ws_off) {
+    Carver cv{base, 0};
+    const size_t n = (size_t)C * d;
+    v.ql = cv.take<T>(n); v.pl = cv.take<T>(n); v.gl = cv.take<T>(n);
+    v.qr = cv.take<T>(n); v.pr = cv.take<T>(n); v.gr = cv.take<T>(n);
+    v.qs = cv.take<T>(n); v.ps = cv.take<T>(n); v.gs = cv.take<T>(n);
+    v.qp = cv.take<T>(n); v.pp = cv.take<T>(n); v.gp = cv.take<T>(n);
+    v.msum = cv.take<T>(n); v.sms = cv.take<T>(n);
+    v.mck = cv.take<T>(n * maxd); v.sckp = cv.take<T>(n * maxd);
+    v.vl = v.vr = v.vck = nullptr;
+    if (pl.dense) { v.vl = cv.take<T>(n); v.vr = cv.take<T>(n); v.vck = cv.take<T>(n * maxd); }
+    v.rec = cv.take<ChainRec>(C);
+    T* imm_own = nullptr;
+    if (pl.per_chain_imm) imm_own = cv.take<T>(n);
+    else if (pl.scalar_imm) imm_own = cv.take<T>(1);
+    v.imm = imm_own;
+    v.adapt.wc_mean = v.adapt.wc_m2 = nullptr;
+    if (adapt) { v.adapt.wc_mean = cv.take<T>(n); v.adapt.wc_m2 = cv.take<T>(n); }
+    v.xa = v.xb = v.Unew = nullptr;
+    v.mom_p = v.mom_v = nullptr; v.mom_count = nullptr; v.mom_list = nullptr;
+    if (pl.split) {
+        v.xa = cv.take<T>(n); v.xb = cv.take<T>(n); v.Unew = cv.take<T>(C);
+    }
+    if (pl.dense) {
+        v.mom_p = cv.take<T>(n); v.mom_v = cv.take<T>(n);
+        v.mom_count = cv.take<int>(4); v.mom_list = cv.take<int>(C);
+    }
+    v.scratch = cv.take<int>(64);
+    if (model_ws_bytes) {
+        cv.off = (cv.off + 255) & ~(size_t)255;
+        if (model_ws_off) *model_ws_off = cv.off;
+        cv.off += model_ws_bytes;
+    }
+    return cv.off + 256;
+}
+
+// ---------------------------------------------------------------------------
+// entry / exit kernels (user row-major arrays <-> engine layout)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void copy_in_kernel(EngineView<T> v, const T* q, const T* g, const T* U, const double* eps,
+                               const T* imm_user, T imm_scalar, int write_scalar, double init_step_size) {
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0 && write_scalar) v.imm[0] = imm_scalar;
+    if (idx >= (i64)v.C * v.d) return;
+    int c = (int)(idx / v.d), j = (int)(idx % v.d);
+    i64 a = (i64)c * v.sc + (i64)j * v.sj;
+    v.qp[a] = q[idx];
+    v.gp[a] = g[idx];
+    if (imm_user) v.imm[a] = imm_user[idx];
+    if (v.adapt.enabled) { ((T*)v.adapt.wc_mean)[a] = 0; ((T*)v.adapt.wc_m2)[a] = 0; }
+    if (j == 0) {
+        ChainRec r;
+        memset(&r, 0, sizeof(r));
+        r.phase = PH_START;
+        r.U_prop = (double)U[c];
+        r.eps = eps[c];
+        if (v.adapt.enabled) {
+            // window_adaptation.init (window_adaptation.py:132-144): mu = initial step size, step size = exp(0)
+            v.adapt.da_step[c] = 1; v.adapt.da_x[c] = 0.0; v.adapt.da_x_avg[c] = 0.0; v.adapt.da_g_avg[c] = 0.0;
+            v.adapt.da_mu[c] = init_step_size;
+            v.adapt.wc_n[c] = 0;
+            r.eps = 1.0;
+        }
+        v.rec[c] = r;
+    }
+}
+
+template <typename T>
+__global__ void copy_out_kernel(EngineView<T> v, T* q, T* p, T* g, T* U, double* eps, T* imm_user) {
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (i64)v.C * v.d) return;
+    int c = (int)(idx / v.d), j = (int)(idx % v.d);
+    i64 a = (i64)c * v.sc + (i64)j * v.sj;
+    q[idx] = v.qp[a];
+    if (p) p[idx] = v.pp[a];
+    g[idx] = v.gp[a];
+    if (imm_user) imm_user[idx] = v.imm[a];
+    if (j == 0) {
+        const ChainRec& r = v.rec[c];
+        U[c] = (T)r.U_prop;
+        eps[c] = r.eps;
+        if (v.out.acceptance_probability) v.out.acceptance_probability[c] = r.accept_prob;
+        if (v.out.num_doublings) v.out.num_doublings[c] = r.last_nd;
+        if (v.out.is_turning) v.out.is_turning[c] = (r.last_flags & 1) ? 1 : 0;
+        if (v.out.is_diverging) v.out.is_diverging[c] = (r.last_flags & 2) ? 1 : 0;
+        if (v.out.n_leapfrog) v.out.n_leapfrog[c] = r.last_nleap;
+        if (v.counters) {
+            atomicAdd((unsigned long long*)&v.counters[0], (unsigned long long)r.total_leap);
+            atomicAdd((unsigned long long*)&v.counters[1], (unsigned long long)(r.t - r.t_base));
+        }
+    }
+}
+
+// resume: refresh only what the caller may have changed between calls (nothing) and clear per-call counters
+template <typename T>
+__global__ void resume_kernel(EngineView<T> v) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= v.C) return;
+    v.rec[c].total_leap = 0;
+    v.rec[c].t_base = v.rec[c].t;
+    if (v.rec[c].phase == PH_DONE) v.rec[c].phase = PH_START;
+}
+
+// ---------------------------------------------------------------------------
+// fused persistent kernel
+// ---------------------------------------------------------------------------
+template <int G>
+struct Geo {
+    static constexpr int kThreads = G > 32 ? G : 128;
+    static constexpr int kChainsPerBlock = G > 32 ? 1 : 128 / G;
+    __device__ static int chain() {
+        return G > 32 ? (int)blockIdx.x : (int)(blockIdx.x * kChainsPerBlock + threadIdx.x / G);
+    }
+    static int grid(int C) { return (C + kChainsPerBlock - 1) / kChainsPerBlock; }
+};
+
+template <typename T, int G, int MODEL, bool HMC>
+__global__ void __launch_bounds__(Geo<G>::kThreads)
+fused_run_kernel(EngineView<T> v, ModelDev m, i64 max_ticks) {
+    __shared__ double red_s[64];
+    const int c = Geo<G>::chain();
+    if (c >= v.C) return;
+    Chain<T, G> ch(v, c, red_s);
+    ch.load();
+    i64 tick = 0;
+    while (max_ticks <= 0 || tick < max_ticks) {
+        if (ch.r.phase == PH_DONE) break;
+        if (ch.r.phase == PH_START) {
+            if (HMC) hmc_begin<T, G, false>(ch);
+            else begin_transition<T, G, false>(ch);
+        }
+        half_kick_drift<T, G, false, false>(ch);
+        Group<G>::sync();
+        T* Q = ch.r.go_right ? v.qr : v.ql;
+        T* Gd = ch.r.go_right ? v.gr : v.gl;
+        T U = model_grad<T, G, MODEL>(m, Q + ch.base, Gd + ch.base, v.sj, ch.lane, ch.red);
+        Group<G>::sync();
+        if (HMC) hmc_post<T, G, false, false>(ch, U);
+        else post_gradient<T, G, false, false>(ch, U);
+        Group<G>::sync();
+        ++tick;
+    }
+    ch.store();
+    if (v.counters && ch.lane == 0) atomicAdd((unsigned long long*)&v.counters[3], (unsigned long long)tick);
+}
+
+// ---------------------------------------------------------------------------
+// split-mode kernels
+// ---------------------------------------------------------------------------
+template <typename T, int G, bool DENSE, bool HMC>
+__global__ void __launch_bounds__(Geo<G>::kThreads) split_pre_kernel(EngineView<T> v) {
+    __shared__ double red_s[64];
+    const int c = Geo<G>::chain();
+    if (c >= v.C) return;
+    Chain<T, G> ch(v, c, red_s);
+    ch.load();
+    if (ch.r.phase == PH_DONE) return;
+    if (ch.r.phase == PH_START) {
+        if (HMC) hmc_begin<T, G, DENSE>(ch);
+        else begin_transition<T, G, DENSE>(ch);
+    }
+    half_kick_drift<T, G, DENSE, true>(ch);
+    ch.store();
+}
+
+// dense metric: q' = q + e * v_half (v_half = xb from the velocity GEMM); xa = q'
+template <typename T, int G>
+__global__ void __launch_bounds__(Geo<G>::kThreads) split_drift_kernel(EngineView<T> v) {
+    const int c = Geo<G>::chain();
+    if (c >= v.C) return;
+    const ChainRec& r = v.rec[c];
+    if (r.phase != PH_RUN) return;
+    T* Q = r.go_right ? v.qr : v.ql;
+    const T e = (T)(r.go_right ? r.eps : -r.eps);
+    const int lane = Group<G>::lane();
+    for (int j = lane; j < v.d; j += G) {
+        i64 a = (i64)c * v.sc + (i64)j * v.sj, x = (i64)c * v.d + j;
+        T qn = Q[a] + e * v.xb[x];
+        Q[a] = qn;
+        v.xa[x] = qn;
+    }
+}
+
+// dense metric: g' = xb; p' = p_half - (0.5 e) g'; xa = p' (input of the second velocity GEMM)
+template <typename T, int G>
+__global__ void __launch_bounds__(Geo<G>::kThreads) split_kick_kernel(EngineView<T> v) {
+    const int c = Geo<G>::chain();
+    if (c >= v.C) return;
+    const ChainRec& r = v.rec[c];
+    if (r.phase != PH_RUN) return;
+    T* P = r.go_right ? v.pr : v.pl;
+    T* Gd = r.go_right ? v.gr : v.gl;
+    const T he = (T)0.5 * (T)(r.go_right ? r.eps : -r.eps);
+    const int lane = Group<G>::lane();
+    for (int j = lane; j < v.d; j += G) {
+        i64 a = (i64)c * v.sc + (i64)j * v.sj, x = (i64)c * v.d + j;
+        T g = v.xb[x];
+        Gd[a] = g;
+        T p = P[a] - he * g;
+        P[a] = p;
+        v.xa[x] = p;
+    }
+}
+
+template <typename T, int G, bool DENSE, bool HMC>
+__global__ void __launch_bounds__(Geo<G>::kThreads) split_post_kernel(EngineView<T> v, int* not_done) {
+    __shared__ double red_s[64];
+    const int c = Geo<G>::chain();
+    if (c >= v.C) return;
+    Chain<T, G> ch(v, c, red_s);
+    ch.load();
+    if (ch.r.phase != PH_RUN) return;
+    const T U = v.Unew[c];
+    if (HMC) hmc_post<T, G, DENSE, true>(ch, U);
+    else post_gradient<T, G, DENSE, true>(ch, U);
+    ch.store();
+    if (ch.lane == 0) {
+        if (ch.r.phase != PH_DONE && not_done) atomicAdd(not_done, 1);
+        if (v.counters) atomicAdd((unsigned long long*)&v.counters[3], 1ull);
+    }
+}
+
+// dense metric momentum: compact the chains that start a transition this tick and emit their normals
+template <typename T>
+__global__ void mom_list_kernel(EngineView<T> v) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= v.C) return;
+    if (v.rec[c].phase == PH_START) {
+        int slot = atomicAdd(v.mom_count, 1);
+        v.mom_list[slot] = c;
+        v.rec[c].mom_slot = slot;
+    }
+}
+
+template <typename T>
+__global__ void mom_fill_kernel(EngineView<T> v) {
+    const int slot = blockIdx.x;
+    if (slot >= *v.mom_count) return;
+    const int c = v.mom_list[slot];
+    const int t = v.rec[c].t;
+    for (int j = threadIdx.x; j < v.d; j += blockDim.x)
+        v.mom_v[(i64)slot * v.d + j] = (T)draw_z(v.rng, c, t, j, v.d);   // z staged in mom_v
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static ModelDev to_dev(const b2h_model* m) {
+    ModelDev d;
+    d.kind = m->kind; d.dim = m->dim; d.n_data = m->n_data;
+    d.a = m->a; d.b = m->b; d.c = m->c; d.s0 = m->s0; d.s1 = m->s1;
+    return d;
+}
+
+template <typename T, int G, bool HMC>
+static int launch_fused(cudaStream_t st, const EngineView<T>& v, const b2h_model* model, i64 max_ticks) {
+    ModelDev m = to_dev(model);
+    const int grid = Geo<G>::grid(v.C), thr = Geo<G>::kThreads;
+    switch (model->kind) {
+        case B2H_MODEL_IID_GAUSSIAN:
+            fused_run_kernel<T, G, MODEL_IID, HMC><<<grid, thr, 0, st>>>(v, m, max_ticks);
+            break;
+        case B2H_MODEL_FUNNEL:
+            if (G > 8) { set_error("funnel: group must be 1 or 8"); return B2H_ERR_ARG; }
+            fused_run_kernel<T, (G > 8 ? 8 : G), MODEL_FUNNEL, HMC><<<Geo<(G > 8 ? 8 : G)>::grid(v.C),
+                                                                       Geo<(G > 8 ? 8 : G)>::kThreads, 0, st>>>(v, m, max_ticks);
+            break;
+        case B2H_MODEL_EIGHT_SCHOOLS:
+            if (G > 8) { set_error("eight schools: group must be 1 or 8"); return B2H_ERR_ARG; }
+            fused_run_kernel<T, (G > 8 ? 8 : G), MODEL_SCHOOLS, HMC><<<Geo<(G > 8 ? 8 : G)>::grid(v.C),
+                                                                        Geo<(G > 8 ? 8 : G)>::kThreads, 0, st>>>(v, m, max_ticks);
+            break;
+        default:
+            set_error("model has no fused gradient");
+            return B2H_ERR_UNSUPPORTED;
+    }
+    B2H_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename T, int G, bool HMC>
+static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const b2h_model* model,
+                     const b2h_metric* metric, const b2h_cfg* cfg, i64 max_ticks, int n_transitions, void* model_ws,
+                     i64 model_ws_bytes, int* not_done_dev) {
+    cudaStream_t st = ctx->stream;
+    const int grid = Geo<G>::grid(v.C), thr = Geo<G>::kThreads;
+    const int C = v.C, d = v.d;
+    const T* imm_dense = (const T*)metric->imm;
+    const T* sqrt_t = (const T*)metric->sqrt_t;
+    i64 bound = max_ticks > 0 ? max_ticks
+                              : (i64)n_transitions * (HMC ? (i64)cfg->num_integration_steps
+                                                          : (((i64)1 << v.maxd) - 1 + v.maxd)) + 1;
+    int* host_flag = nullptr;
+    B2H_CUDA(cudaMallocHost(&host_flag, sizeof(int)));
+    int rc = 0;
+    for (i64 tick = 0; tick < bound; ++tick) {
+        if (pl.dense) {
+            B2H_CUDA(cudaMemsetAsync(v.mom_count, 0, sizeof(int), st));
+            mom_list_kernel<T><<<(C + 255) / 256, 256, 0, st>>>(v);
+            mom_fill_kernel<T><<<C, 128, 0, st>>>(v);
+            // p0 = z . S^T (metrics.py:56-59,67), v0 = p0 . imm (metrics.py:71)
+            launch_dense_apply<T>(st, v.mom_v, sqrt_t, v.mom_p, C, d, d, v.mom_count, nullptr);
+            launch_dense_apply<T>(st, v.mom_p, imm_dense, v.mom_v, C, d, d, v.mom_count, nullptr);
+            split_pre_kernel<T, G, true, HMC><<<grid, thr, 0, st>>>(v);
+            launch_dense_apply<T>(st, v.xa, imm_dense, v.xb, C, d, d, nullptr, nullptr);
+            split_drift_kernel<T, G><<<grid, thr, 0, st>>>(v);
+        } else {
+            split_pre_kernel<T, G, false, HMC><<<grid, thr, 0, st>>>(v);
+        }
+        rc = potential_and_grad_impl<T>(ctx, model, v.xa, v.Unew, v.xb, C, model_ws, model_ws_bytes);
+        if (rc) break;
+        const bool check = (max_ticks <= 0) && ((tick & 3) == 3 || tick + 1 == bound);
+        if (check) B2H_CUDA(cudaMemsetAsync(not_done_dev, 0, sizeof(int), st));
+        if (pl.dense) {
+            split_kick_kernel<T, G><<<grid, thr, 0, st>>>(v);
+            launch_dense_apply<T>(st, v.xa, imm_dense, v.xb, C, d, d, nullptr, nullptr);
+            split_post_kernel<T, G, true, HMC><<<grid, thr, 0, st>>>(v, check ? not_done_dev : nullptr);
+        } else {
+            split_post_kernel<T, G, false, HMC><<<grid, thr, 0, st>>>(v, check ? not_done_dev : nullptr);
+        }
+        if (check) {
+            cudaError_t e = cudaMemcpyAsync(host_flag, not_done_dev, sizeof(int), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "tick poll"); break; }
+            if (*host_flag == 0) break;
+        }
+    }
+    cudaFreeHost(host_flag);
+    if (rc) return rc;
+    B2H_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename T>
+static int run_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
+                     const b2h_cfg* cfg, const b2h_adapt* adapt, void* q, void* p, void* U, void* g,
+                     double* step_size, i64 C64, int n_transitions, i64 max_ticks, int resume, b2h_diag* diag,
+                     void* draws, double* draw_stats, int n_store, int64_t* counters, void* ws, i64 ws_bytes,
+                     bool hmc) {
+    EnginePlan pl;
+    int rc = make_plan(model, metric, cfg, pl);
+    if (rc) return rc;
+    const int C = (int)C64, d = model->dim;
+    const int maxd = hmc ? 1 : cfg->max_num_expansions;
+    if (!hmc && (maxd < 1 || maxd > 24)) { set_error("max_num_expansions must be in [1, 24]"); return B2H_ERR_ARG; }
+    const bool adapting = adapt && adapt->enabled;
+    if (adapting && !pl.per_chain_imm) {
+        set_error("window adaptation needs a DIAG_PER_CHAIN inverse mass matrix (adapted in place)");
+        return B2H_ERR_ARG;
+    }
+    if (pl.dense && (!metric->imm || !metric->sqrt_t)) { set_error("dense metric needs imm and sqrt_t"); return B2H_ERR_ARG; }
+    if (rng->mode == B2H_RNG_INJECTED) {
+        if (!rng->z || rng->n_injected < n_transitions || n_transitions <= 0) {
+            set_error("injected draws need z and n_injected >= n_transitions > 0");
+            return B2H_ERR_ARG;
+        }
+        if (!hmc && (!rng->u_dir || !rng->u_biased || !rng->u_uniform)) { set_error("NUTS needs u_dir/u_biased/u_uniform"); return B2H_ERR_ARG; }
+        if (hmc && !rng->u_accept) { set_error("HMC needs u_accept"); return B2H_ERR_ARG; }
+    }
+
+    EngineView<T> v;
+    memset(&v, 0, sizeof(v));
+    size_t model_ws_bytes = pl.split ? (size_t)potential_workspace_bytes_impl(model, Num<T>::dtype, C) : 0;
+    size_t model_ws_off = 0;
+    size_t need = carve<T>(v, nullptr, pl, model, C, d, maxd, adapting, model_ws_bytes, &model_ws_off);
+    if (!ws || (size_t)ws_bytes < need) {
+        set_error("workspace too small: need " + std::to_string(need) + " bytes");
+        return B2H_ERR_WORKSPACE;
+    }
+    carve<T>(v, (char*)ws, pl, model, C, d, maxd, adapting, model_ws_bytes, &model_ws_off);
+    void* model_ws = model_ws_bytes ? (char*)ws + model_ws_off : nullptr;
+    v.C = C; v.d = d; v.maxd = maxd;
+    if (pl.G == 1) { v.sc = 1; v.sj = C; v.sck = 1; }
+    else { v.sc = d; v.sj = 1; v.sck = (i64)maxd * d; }
+    v.imm_kind = metric->kind;
+    if (pl.scalar_imm) { v.imm_sc = 0; v.imm_sj = 0; }
+    else if (metric->kind == B2H_IMM_DIAG) { v.imm = (T*)metric->imm; v.imm_sc = 0; v.imm_sj = 1; }
+    else if (pl.per_chain_imm) { v.imm_sc = v.sc; v.imm_sj = v.sj; }
+    v.rng.mode = rng->mode;
+    v.rng.key.k0 = (uint32_t)rng->seed; v.rng.key.k1 = (uint32_t)(rng->seed >> 32);
+    v.rng.chain_offset = rng->chain_offset; v.rng.transition_offset = rng->transition_offset;
+    v.rng.n_injected = rng->n_injected;
+    v.rng.z = rng->z; v.rng.u_dir = rng->u_dir; v.rng.u_biased = rng->u_biased; v.rng.u_uniform = rng->u_uniform;
+    v.rng.u_accept = rng->u_accept;
+    v.adapt.enabled = adapting ? 1 : 0;
+    if (adapting) {
+        v.adapt.num_steps = adapt->num_steps; v.adapt.stage = adapt->stage; v.adapt.window_end = adapt->window_end;
+        v.adapt.target = adapt->target_acceptance_rate; v.adapt.gamma = adapt->gamma; v.adapt.t0 = adapt->t0;
+        v.adapt.kappa = adapt->kappa;
+        v.adapt.da_step = (i64*)adapt->da_step; v.adapt.da_x = adapt->da_x; v.adapt.da_x_avg = adapt->da_x_avg;
+        v.adapt.da_g_avg = adapt->da_g_avg; v.adapt.da_mu = adapt->da_mu; v.adapt.wc_n = (i64*)adapt->wc_n;
+    }
+    v.out.draws = draws; v.out.draw_stats = draw_stats; v.out.n_store = n_store;
+    if (diag) {
+        v.out.acceptance_probability = diag->acceptance_probability; v.out.num_doublings = diag->num_doublings;
+        v.out.is_turning = diag->is_turning; v.out.is_diverging = diag->is_diverging;
+        v.out.n_leapfrog = diag->n_leapfrog;
+    }
+    v.div_thr = cfg->divergence_threshold;
+    v.n_transitions = max_ticks > 0 ? 0 : n_transitions;
+    v.hmc_L = cfg->num_integration_steps;
+    v.counters = (i64*)counters;
+    if (hmc && v.hmc_L < 1) { set_error("num_integration_steps must be >= 1"); return B2H_ERR_ARG; }
+    if (max_ticks <= 0 && n_transitions <= 0) { set_error("need n_transitions > 0 or max_ticks > 0"); return B2H_ERR_ARG; }
+
+    cudaStream_t st = ctx->stream;
+    const i64 n = (i64)C * d;
+    const int eb = 256, eg = (int)((n + eb - 1) / eb);
+    if (!resume) {
+        copy_in_kernel<T><<<eg, eb, 0, st>>>(v, (const T*)q, (const T*)g, (const T*)U, step_size,
+                                             pl.per_chain_imm ? (const T*)metric->imm : nullptr,
+                                             (T)metric->scalar, pl.scalar_imm ? 1 : 0,
+                                             adapting ? adapt->initial_step_size : 0.0);
+    } else {
+        resume_kernel<T><<<(C + 255) / 256, 256, 0, st>>>(v);
+    }
+    B2H_LAUNCH_CHECK();
+    int* not_done_dev = v.scratch;
+
+#define B2H_DISPATCH_G(FN, ...)                                          \
+    switch (pl.G) {                                                      \
+        case 1: rc = FN<T, 1, false> __VA_ARGS__; break;                 \
+        case 8: rc = FN<T, 8, false> __VA_ARGS__; break;                 \
+        case 32: rc = FN<T, 32, false> __VA_ARGS__; break;               \
+        default: rc = FN<T, 256, false> __VA_ARGS__; break;              \
+    }
+#define B2H_DISPATCH_G_HMC(FN, ...)                                      \
+    switch (pl.G) {                                                      \
+        case 1: rc = FN<T, 1, true> __VA_ARGS__; break;                  \
+        case 8: rc = FN<T, 8, true> __VA_ARGS__; break;                  \
+        case 32: rc = FN<T, 32, true> __VA_ARGS__; break;                \
+        default: rc = FN<T, 256, true> __VA_ARGS__; break;               \
+    }
+
+    if (!pl.split) {
+        if (hmc) { B2H_DISPATCH_G_HMC(launch_fused, (st, v, model, max_ticks)) }
+        else { B2H_DISPATCH_G(launch_fused, (st, v, model, max_ticks)) }
+    } else {
+        if (pl.G == 1) { set_error("split mode needs group >= 8"); return B2H_ERR_ARG; }
+        if (hmc) {
+            switch (pl.G) {
+                case 8: rc = run_split<T, 8, true>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev); break;
+                case 32: rc = run_split<T, 32, true>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev); break;
+                default: rc = run_split<T, 256, true>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev); break;
+            }
+        } else {
+            switch (pl.G) {
+                case 8: rc = run_split<T, 8, false>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev); break;
+                case 32: rc = run_split<T, 32, false>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev); break;
+                default: rc = run_split<T, 256, false>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev); break;
+            }
+        }
+    }
+    if (rc) return rc;
+    copy_out_kernel<T><<<eg, eb, 0, st>>>(v, (T*)q, (T*)p, (T*)g, (T*)U, step_size,
+                                          pl.per_chain_imm ? (T*)metric->imm : nullptr);
+    B2H_LAUNCH_CHECK();
+    return 0;
+}
+
+int nuts_run_impl(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
+                  const b2h_cfg* cfg, const b2h_adapt* adapt, void* q, void* p, void* U, void* g, double* step_size,
+                  i64 C, int n_transitions, i64 max_ticks, int resume, b2h_diag* diag, void* draws,
+                  double* draw_stats, int n_store, int64_t* counters, void* ws, i64 ws_bytes, bool hmc) {
+    if (!ctx || !model || !metric || !rng || !cfg || !q || !U || !g || !step_size) {
+        set_error("null argument");
+        return B2H_ERR_ARG;
+    }
+    if (C <= 0 || C > (1ll << 30) || model->dim <= 0) { set_error("bad C or dim"); return B2H_ERR_ARG; }
+    if (cfg->dtype == B2H_F64)
+        return run_typed<double>(ctx, model, metric, rng, cfg, adapt, q, p, U, g, step_size, C, n_transitions,
+                                 max_ticks, resume, diag, draws, draw_stats, n_store, counters, ws, ws_bytes, hmc);
+    if (cfg->dtype == B2H_F32)
+        return run_typed<float>(ctx, model, metric, rng, cfg, adapt, q, p, U, g, step_size, C, n_transitions,
+                                max_ticks, resume, diag, draws, draw_stats, n_store, counters, ws, ws_bytes, hmc);
+    set_error("dtype must be B2H_F32 or B2H_F64");
+    return B2H_ERR_ARG;
+}
+
+i64 engine_workspace_bytes(const b2h_model* model, const b2h_metric* metric, const b2h_cfg* cfg, i64 C) {
+    EnginePlan pl;
+    if (make_plan(model, metric, cfg, pl)) return -1;
+    const int maxd = cfg->max_num_expansions > 0 ? cfg->max_num_expansions : 1;
+    size_t mws = pl.split ? (size_t)potential_workspace_bytes_impl(model, cfg->dtype, C) : 0;
+    if (cfg->dtype == B2H_F64) {
+        EngineView<double> v;
+        return (i64)carve<double>(v, nullptr, pl, model, (int)C, model->dim, maxd, true, mws, nullptr);
+    }
+    EngineView<float> v;
+    return (i64)carve<float>(v, nullptr, pl, model, (int)C, model->dim, maxd, true, mws, nullptr);
+}
+
+}  // namespace b2h

@@ -1,0 +1,60 @@
+// Host-side declarations shared by the translation units of libb200hmc.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/b200hmc.h"
+
+struct b2h_ctx {
+    int device;
+    cudaStream_t stream;
+    int sm_count;
+};
+
+namespace b2h {
+
+typedef long long i64;
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define B2H_CUDA(expr)                                        \
+    do {                                                      \
+        cudaError_t _e = (expr);                              \
+        if (_e != cudaSuccess) return ::b2h::cuda_fail(_e, #expr); \
+    } while (0)
+
+#define B2H_LAUNCH_CHECK() B2H_CUDA(cudaGetLastError())
+
+// gemm.cu
+template <typename T>
+void launch_dense_apply(cudaStream_t st, const T* A, const T* B, T* out, int M, int N, int K, const int* m_dev,
+                        const T* sub);
+
+template <typename T>
+void launch_gemm(cudaStream_t st, const T* A, i64 lda, const T* B, i64 ldb, T* out, i64 ldo, int M, int N, int K,
+                 const int* m_dev, const T* sub, int nsplit, i64 split_stride);
+
+// primitives.cu
+template <typename T>
+int potential_and_grad_impl(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U, T* g, i64 C, void* ws, i64 ws_bytes);
+i64 potential_workspace_bytes_impl(const b2h_model* m, int dtype, i64 C);
+
+// logreg.cu
+template <typename T>
+int logistic_potential_and_grad(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U, T* g, i64 C, void* ws,
+                                i64 ws_bytes, int path);
+i64 logistic_workspace_bytes(const b2h_model* m, int dtype, i64 C);
+
+// engine_kernels.cu
+int nuts_run_impl(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
+                  const b2h_cfg* cfg, const b2h_adapt* adapt, void* q, void* p, void* U, void* g, double* step_size,
+                  i64 C, int n_transitions, i64 max_ticks, int resume, b2h_diag* diag, void* draws,
+                  double* draw_stats, int n_store, int64_t* counters, void* ws, i64 ws_bytes, bool hmc);
+i64 engine_workspace_bytes(const b2h_model* model, const b2h_metric* metric, const b2h_cfg* cfg, i64 C);
+
+static inline size_t dtype_size(int dtype) { return dtype == B2H_F64 ? 8 : 4; }
+
+}  // namespace b2h

@@ -1,0 +1,138 @@
+// Bayesian logistic regression, all chains at once (exactness-reference FMA path).
+//
+//   s = X b_c ; U_c = sum_n softplus(s_n) - y_n s_n + 1/2 |b_c|^2 / sigma_b^2
+//   dU/db_c = X^T (sigmoid(s) - y) + b_c / sigma_b^2            (oracle/models.py:LogisticRegression)
+//
+// Batched over chains this is S[C x N] = B[C x D] . X^T[D x N] followed by
+// G[C x D] = R[C x N] . X[N x D], the only dense contraction of the engine.
+// This file is the FP32/FP64 FMA-pipe version built on the tiled GEMM of gemm.cu,
+// chunked over the data dimension so that S never exceeds a bounded scratch,
+// with a deterministic split-K reduction for the tall-skinny second product.
+#include "common.cuh"
+#include "launch.h"
+
+namespace b2h {
+
+static const i64 kChunkBytes = 256ll << 20;     // S-chunk scratch budget
+
+struct LogregPlan {
+    int n_chunk;       // data rows per chunk
+    int nsplit;        // split-K slices of the second product
+    size_t off_S, off_part, off_U, total;
+};
+
+static LogregPlan plan_logreg(const b2h_model* m, int dtype, i64 C) {
+    LogregPlan p;
+    const size_t ts = dtype_size(dtype);
+    i64 nc = kChunkBytes / (i64)(C * ts);
+    nc = std::max<i64>(128, (nc / 128) * 128);
+    if (nc > m->n_data) nc = ((m->n_data + 127) / 128) * 128;
+    p.n_chunk = (int)nc;
+    // enough CTAs to fill 148 SMs: tiles_m * tiles_n * nsplit >= ~2 waves
+    i64 tiles = ((C + 127) / 128) * ((m->dim + 127) / 128);
+    i64 ns = (296 + tiles - 1) / tiles;
+    ns = std::max<i64>(1, std::min<i64>(ns, (p.n_chunk + 255) / 256));
+    p.nsplit = (int)ns;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+    p.off_S = take((size_t)C * p.n_chunk * ts);
+    p.off_part = take((size_t)p.nsplit * C * m->dim * ts);
+    p.off_U = take((size_t)C * sizeof(double));
+    p.total = off + 256;
+    return p;
+}
+
+i64 logistic_workspace_bytes(const b2h_model* m, int dtype, i64 C) { return (i64)plan_logreg(m, dtype, C).total; }
+
+// R = sigmoid(S) - y in place; U_acc[c] += sum_n softplus(s) - y s   (one CTA per chain: deterministic)
+template <typename T>
+__global__ void __launch_bounds__(256)
+logistic_resid_kernel(T* S, const T* y, double* U_acc, int n_valid, i64 ld, int first) {
+    const i64 c = blockIdx.x;
+    T* row = S + c * ld;
+    double acc = 0.0;
+    for (int n = threadIdx.x; n < n_valid; n += 256) {
+        T s = row[n], yy = y[n];
+        T sp = fmax(s, (T)0) + log1p(exp(-fabs(s)));
+        acc += (double)(sp - yy * s);
+        row[n] = (T)1 / ((T)1 + exp(-s)) - yy;
+    }
+    __shared__ double red[8];
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        U_acc[c] = first ? s : U_acc[c] + s;
+    }
+}
+
+// g = (first ? 0 : g) + sum_s partial[s]
+template <typename T>
+__global__ void split_reduce_kernel(const T* part, T* g, i64 n, int nsplit, int first) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T s = first ? (T)0 : g[i];
+    for (int k = 0; k < nsplit; ++k) s += part[(i64)k * n + i];
+    g[i] = s;
+}
+
+// prior: g += b / sigma^2 ; U = U_acc + 1/2 |b|^2 / sigma^2
+template <typename T>
+__global__ void __launch_bounds__(128)
+logistic_prior_kernel(const T* q, T* g, T* U, const double* U_acc, T inv_prior_var, i64 C, int d) {
+    const i64 c = (i64)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (c >= C) return;
+    const int lane = threadIdx.x & 31;
+    T acc = 0;
+    for (int j = lane; j < d; j += 32) {
+        T b = q[c * d + j];
+        g[c * d + j] += inv_prior_var * b;
+        acc += b * b;
+    }
+    double s = Group<32>::sum1((double)acc, nullptr);
+    if (lane == 0) U[c] = (T)U_acc[c] + (T)0.5 * inv_prior_var * (T)s;
+}
+
+template <typename T>
+int logistic_potential_and_grad(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U, T* g, i64 C, void* ws,
+                                i64 ws_bytes, int path) {
+    (void)path;
+    if (!m->a || !m->b || !m->c) { set_error("logistic model needs X (a), y (b) and X^T (c)"); return B2H_ERR_ARG; }
+    LogregPlan p = plan_logreg(m, Num<T>::dtype, C);
+    if (!ws || (size_t)ws_bytes < p.total) {
+        set_error("logistic workspace too small: need " + std::to_string(p.total) + " bytes");
+        return B2H_ERR_WORKSPACE;
+    }
+    cudaStream_t st = ctx->stream;
+    const int d = m->dim;
+    const i64 N = m->n_data;
+    const T* X = (const T*)m->a;      // [N x d]
+    const T* y = (const T*)m->b;      // [N]
+    const T* Xt = (const T*)m->c;     // [d x N]
+    T* S = (T*)((char*)ws + p.off_S);
+    T* part = (T*)((char*)ws + p.off_part);
+    double* U_acc = (double*)((char*)ws + p.off_U);
+    const i64 ng = C * d;
+    for (i64 n0 = 0, it = 0; n0 < N; n0 += p.n_chunk, ++it) {
+        const int nv = (int)std::min<i64>(p.n_chunk, N - n0);
+        // S[C x nv] = B[C x d] . X^T[d x nv]
+        launch_gemm<T>(st, q, (i64)d, Xt + n0, N, S, (i64)p.n_chunk, (int)C, nv, d, nullptr, nullptr, 1, 0);
+        logistic_resid_kernel<T><<<(int)C, 256, 0, st>>>(S, y + n0, U_acc, nv, (i64)p.n_chunk, it == 0);
+        // G[C x d] += R[C x nv] . X[nv x d]   (split-K over the data rows, deterministic reduce)
+        launch_gemm<T>(st, S, (i64)p.n_chunk, X + n0 * d, (i64)d, part, (i64)d, (int)C, d, nv, nullptr, nullptr,
+                       p.nsplit, ng);
+        split_reduce_kernel<T><<<(int)((ng + 255) / 256), 256, 0, st>>>(part, g, ng, p.nsplit, it == 0);
+    }
+    logistic_prior_kernel<T><<<(int)((C + 3) / 4), 128, 0, st>>>(q, g, U, U_acc, (T)m->s0, C, d);
+    B2H_LAUNCH_CHECK();
+    return 0;
+}
+
+template int logistic_potential_and_grad<float>(b2h_ctx*, const b2h_model*, const float*, float*, float*, i64, void*,
+                                                i64, int);
+template int logistic_potential_and_grad<double>(b2h_ctx*, const b2h_model*, const double*, double*, double*, i64,
+                                                 void*, i64, int);
+
+}  // namespace b2h

@@ -1,0 +1,229 @@
+/* b200hmc.h -- C-ABI of libb200hmc.so, the B200-native many-chain HMC/NUTS engine.
+ *
+ * Drop-in boundary for the trajectory hot path of aesara-devs/aehmc.  The
+ * reference is pure Python over Aesara and has no FFI of its own; each entry
+ * point below names the reference closure it replaces (file:line relative to
+ * the reference tree) and is what an Aesara Op's perform() binds through
+ * ctypes.
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error; b2h_last_error() gives a
+ *    thread-local message.
+ *  - the caller owns every data buffer and passes raw DEVICE pointers unless a
+ *    parameter is documented as host.  The library owns only b2h_ctx handles.
+ *  - all work is enqueued on the cudaStream_t given at context creation; no call
+ *    synchronises unless documented.
+ *  - vectors over chains are [C] ; per-chain vectors are row-major [C x d].
+ *  - dtype: B2H_F32 / B2H_F64 is the type of positions, momenta, gradients and
+ *    energies.  Proposal weights and sum_log_p_accept are always float64
+ *    (reference nuts.py:123-124).  Step sizes, draws and diagnostics are float64.
+ */
+#ifndef B200HMC_H
+#define B200HMC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2H_F32 0
+#define B2H_F64 1
+
+#define B2H_OK 0
+#define B2H_ERR_ARG -1
+#define B2H_ERR_CUDA -2
+#define B2H_ERR_UNSUPPORTED -3
+#define B2H_ERR_WORKSPACE -4
+
+typedef struct b2h_ctx b2h_ctx;
+
+/* ---- log-density models (the reference's user logprob_fn; built-in targets) ---- */
+enum {
+    B2H_MODEL_IID_GAUSSIAN = 0,  /* a=mu[d], b=inv_var[d], s0 = additive constant of U            */
+    B2H_MODEL_CORR_GAUSSIAN = 1, /* a=mu[d], b=precision[d x d] (symmetric, row-major)             */
+    B2H_MODEL_FUNNEL = 2,        /* Neal's funnel, q=(v,x_1..x_{d-1})                              */
+    B2H_MODEL_EIGHT_SCHOOLS = 3, /* non-centred; a=y[d-2], b=inv_var[d-2]                          */
+    B2H_MODEL_LOGISTIC = 4       /* a=X[n_data x d] row-major, b=y[n_data], s0 = 1/prior_scale^2   */
+};
+
+typedef struct {
+    int32_t kind;
+    int32_t dim;
+    int64_t n_data;
+    const void* a; /* device, dtype of the call */
+    const void* b; /* device, dtype of the call */
+    const void* c; /* device, model specific (logistic: X^T [d x n_data], optional) */
+    double s0;
+    double s1;
+} b2h_model;
+
+/* ---- gaussian metric (reference metrics.py:10-106) ---- */
+enum {
+    B2H_IMM_SCALAR = 0,         /* 0-d inverse mass matrix, value in .scalar (host)               */
+    B2H_IMM_DIAG = 1,           /* imm[d] shared by all chains                                    */
+    B2H_IMM_DIAG_PER_CHAIN = 2, /* imm[C x d] (per-chain adaptation)                              */
+    B2H_IMM_DENSE = 3           /* imm[d x d] symmetric, shared; sqrt = mass_matrix_sqrt[d x d]   */
+};
+
+typedef struct {
+    int32_t kind;
+    int32_t reserved;
+    double scalar;
+    const void* imm;    /* device; dense: symmetric [d x d] */
+    const void* sqrt_t; /* device, dense only: TRANSPOSE of mass_matrix_sqrt = solve_triangular(chol(imm), I,
+                           lower, trans) (metrics.py:56-58), row-major [d x d]: p_row = z_row . sqrt_t       */
+} b2h_metric;
+
+/* ---- random draws: native Philox4x32-10 or injected (validation mode) ---- */
+enum { B2H_RNG_PHILOX = 0, B2H_RNG_INJECTED = 1 };
+
+typedef struct {
+    int32_t mode;
+    int32_t reserved;
+    uint64_t seed;
+    uint64_t chain_offset;      /* global id of local chain 0 (multi-GPU sharding)               */
+    uint64_t transition_offset; /* global index of the first transition of this call             */
+    /* injected draws, float64, device; T = n_injected transitions per chain                     */
+    int64_t n_injected;
+    const double* z;         /* [C][T][d]                 standard normals (momentum)            */
+    const double* u_dir;     /* [C][T][max_depth]         direction: go right iff u > 0.5        */
+    const double* u_biased;  /* [C][T][max_depth]         biased progressive sampling            */
+    const double* u_uniform; /* [C][T][2^max_depth - 1]   uniform progressive sampling, slot =   */
+                             /*                           2^k - 1 + (s - 1) for sub-tree step s  */
+    const double* u_accept;  /* [C][T]                    HMC accept                             */
+} b2h_rng;
+
+/* ---- per-transition outputs (reference trajectory.py:379-384 Diagnostics) ---- */
+typedef struct {
+    double* acceptance_probability; /* [C] */
+    int32_t* num_doublings;         /* [C] (0 for HMC) */
+    uint8_t* is_turning;            /* [C] */
+    uint8_t* is_diverging;          /* [C] */
+    int32_t* n_leapfrog;            /* [C] integrator steps of the transition (extra) */
+} b2h_diag;
+
+/* ---- window adaptation (reference window_adaptation.py:119-227), per chain ---- */
+typedef struct {
+    int32_t enabled;
+    int32_t num_steps;
+    const uint8_t* stage;       /* device [num_steps] 0 fast / 1 slow (build_schedule)           */
+    const uint8_t* window_end;  /* device [num_steps] is_middle_window_end                       */
+    double target_acceptance_rate;
+    double gamma, t0, kappa;    /* dual averaging (algorithms.py:17-19)                          */
+    double initial_step_size;
+    /* state, device, caller-owned so that warm-up can be resumed                                */
+    int64_t* da_step;           /* [C] */
+    double* da_x;               /* [C] iterates */
+    double* da_x_avg;           /* [C] */
+    double* da_g_avg;           /* [C] */
+    double* da_mu;              /* [C] */
+    void* wc_mean;              /* [C x d] dtype */
+    void* wc_m2;                /* [C x d] dtype */
+    int64_t* wc_n;              /* [C] */
+} b2h_adapt;
+
+/* ---- sampler configuration ---- */
+typedef struct {
+    int32_t dtype;
+    int32_t max_num_expansions;   /* nuts.py:20 default 10 */
+    double divergence_threshold;  /* nuts.py:21 / hmc.py:46 default 1000 */
+    int32_t num_integration_steps;/* HMC only (hmc.py:81) */
+    int32_t group;                /* threads per chain: 0 = auto, else 1,2,4,8,16,32,128,256 */
+    int32_t gradient_path;        /* logistic: 0 auto, 1 FFMA exactness reference, 2 tcgen05 tensor core */
+    int32_t reserved;
+} b2h_cfg;
+
+/* ======================================================================== */
+const char* b2h_last_error(void);
+int b2h_version(void);
+
+/* device: CUDA ordinal; stream: cudaStream_t (NULL = legacy default stream) */
+int b2h_ctx_create(int device, void* stream, b2h_ctx** out);
+int b2h_ctx_destroy(b2h_ctx* ctx);
+int b2h_ctx_sync(b2h_ctx* ctx); /* cudaStreamSynchronize */
+
+/* hmc.new_state (reference hmc.py:16-40): U[C] = -logp(q), g[C x d] = dU/dq */
+int b2h_potential_and_grad(b2h_ctx*, const b2h_model*, int dtype, const void* q, void* U, void* g, int64_t C,
+                           void* workspace, int64_t workspace_bytes);
+int64_t b2h_potential_workspace_bytes(const b2h_model*, int dtype, int64_t C);
+
+/* gaussian_metric(...)[0] momentum_generator (metrics.py:65-68): p[C x d] = M^{1/2} z */
+int b2h_sample_momentum(b2h_ctx*, const b2h_metric*, const b2h_rng*, int dtype, void* p, int64_t C, int64_t d,
+                        int64_t transition, void* workspace, int64_t workspace_bytes /* dense: C*d elements */);
+/* gaussian_metric(...)[1] kinetic_energy (metrics.py:70-73): K[C] = 0.5 p^T imm p */
+int b2h_kinetic_energy(b2h_ctx*, const b2h_metric*, int dtype, const void* p, void* K, int64_t C, int64_t d,
+                       void* workspace, int64_t workspace_bytes /* dense: C*d elements */);
+/* gaussian_metric(...)[2] is_turning (metrics.py:75-104) */
+int b2h_is_turning(b2h_ctx*, const b2h_metric*, int dtype, const void* p_left, const void* p_right,
+                   const void* p_sum, uint8_t* out, int64_t C, int64_t d, void* workspace,
+                   int64_t workspace_bytes /* dense: 2*C*d elements */);
+
+/* integrators.velocity_verlet one_step x n_steps (integrators.py:58-73; trajectory.static_integration
+ * trajectory.py:79-105).  In place on q,p,U,g.  step_size[C] float64; direction[C] int8 (+1/-1) or NULL. */
+int b2h_leapfrog(b2h_ctx*, const b2h_model*, const b2h_metric*, int dtype, void* q, void* p, void* U, void* g,
+                 const double* step_size, const int8_t* direction, int32_t n_steps, int64_t C,
+                 void* workspace, int64_t workspace_bytes);
+
+/* termination.iterative_uturn (termination.py:85-187), batched.  ckpts are [C x max x d]. */
+int b2h_termination_update(b2h_ctx*, int dtype, void* momentum_ckpts, void* momentum_sum_ckpts, int64_t* idx_min,
+                           int64_t* idx_max, const void* momentum_sum, const void* momentum, const int64_t* step,
+                           int64_t C, int64_t d, int32_t max_num_doublings);
+int b2h_is_iterative_turning(b2h_ctx*, const b2h_metric*, int dtype, const void* momentum_ckpts,
+                             const void* momentum_sum_ckpts, const int64_t* idx_min, const int64_t* idx_max,
+                             const void* momentum_sum, const void* momentum, uint8_t* out, int64_t C, int64_t d,
+                             int32_t max_num_doublings /* diag-family metrics */);
+/* termination._find_storage_indices (termination.py:192-235) */
+int b2h_find_storage_indices(b2h_ctx*, const int64_t* step, int64_t* idx_min, int64_t* idx_max, int64_t n);
+
+/* hmc.new_kernel(...)(state, step_size, imm, L) (hmc.py:77-124,157-204): n_transitions HMC transitions per
+ * chain with L = cfg->num_integration_steps.  Arguments as b2h_nuts_run (adapt may be NULL). */
+int b2h_hmc_run(b2h_ctx*, const b2h_model*, const b2h_metric*, const b2h_rng*, const b2h_cfg*,
+                const b2h_adapt* adapt, void* q, void* p, void* U, void* g, double* step_size, int64_t C,
+                int32_t n_transitions, b2h_diag* diag, void* draws, double* draw_stats, int32_t n_store,
+                int64_t* counters, void* workspace, int64_t workspace_bytes);
+
+/* nuts.new_kernel(...)(state, step_size, imm) (nuts.py:56-153 -> trajectory.py:154-374,428-608):
+ * runs the chain state machines until every chain has completed n_transitions transitions
+ * (max_ticks <= 0), or for exactly max_ticks leapfrog ticks (chains keep going; the state machine is
+ * kept in the workspace and continued when resume != 0).  q,U,g in/out [C x d]; p out.
+ * step_size[C] in/out (adapted when adapt.enabled); imm may be DIAG_PER_CHAIN and adapted in place.
+ * diag: values of each chain's LAST completed transition.  draws (optional): [n_store][C][d] positions
+ * after each of the first n_store transitions; draw_stats (optional) [n_store][C][4] float64 rows of
+ * (acceptance_probability, num_doublings, n_leapfrog, flags: bit0 turning, bit1 diverging).
+ * counters (optional, device int64[4]): total leapfrogs, total transitions, ticks run, active chain-ticks. */
+int b2h_nuts_run(b2h_ctx*, const b2h_model*, const b2h_metric*, const b2h_rng*, const b2h_cfg*,
+                 const b2h_adapt* adapt, void* q, void* p, void* U, void* g, double* step_size, int64_t C,
+                 int32_t n_transitions, int64_t max_ticks, int32_t resume, b2h_diag* diag, void* draws,
+                 double* draw_stats, int32_t n_store, int64_t* counters, void* workspace, int64_t workspace_bytes);
+int64_t b2h_nuts_workspace_bytes(const b2h_model*, const b2h_metric*, const b2h_cfg*, int64_t C);
+int64_t b2h_hmc_workspace_bytes(const b2h_model*, const b2h_metric*, const b2h_cfg*, int64_t C);
+
+/* algorithms.dual_averaging update (algorithms.py:79-115) with gradient = target - p_accept
+ * (step_size.py:97); in place on the [C] state arrays. */
+int b2h_dual_averaging_update(b2h_ctx*, const double* p_accept, double target, double gamma, double t0, double kappa,
+                              int64_t* step, double* x, double* x_avg, double* g_avg, const double* mu, int64_t C);
+/* algorithms.welford_covariance update/final (algorithms.py:166-202) and the shrinkage of
+ * mass_matrix.covariance_adaptation.final (mass_matrix.py:81-118).  full != 0: m2/out are [C x d x d]. */
+int b2h_welford_update(b2h_ctx*, int dtype, const void* value, void* mean, void* m2, int64_t* n, int64_t C,
+                       int64_t d, int32_t full);
+int b2h_mass_matrix_final(b2h_ctx*, int dtype, const void* m2, const int64_t* n, void* imm_out, int64_t C, int64_t d,
+                          int32_t full);
+
+/* Native-RNG draws exported in the injected layout (so a Philox run can be replayed by the oracle). */
+int b2h_philox_fill(b2h_ctx*, uint64_t seed, uint64_t chain_offset, uint64_t transition_offset, int64_t C,
+                    int64_t n_transitions, int64_t d, int32_t max_depth, double* z, double* u_dir,
+                    double* u_biased, double* u_uniform, double* u_accept);
+
+/* Dense apply out[C x d] = in[C x d] . M[d x d] (M symmetric): the mass-matrix / precision mat-vec of all chains */
+int b2h_dense_apply(b2h_ctx*, int dtype, const void* in, const void* M, void* out, int64_t C, int64_t d);
+
+/* Convergence statistics of draws [T][C][d] (dtype): per-dimension split-R-hat sufficient statistics.
+ * out [d][4] float64: (sum of chain means, sum of squared chain means, sum of chain variances, n_chains). */
+int b2h_chain_moments(b2h_ctx*, int dtype, const void* draws, int64_t T, int64_t C, int64_t d, double* chain_mean,
+                      double* chain_var);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200HMC_H */

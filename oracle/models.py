@@ -28,17 +28,18 @@ class Normal:
 
 
 class IIDGaussian:
-    """U = 1/2 sum r_i g_i, r = q - mu, g = r * inv_var (inv_var = 1/sigma^2)."""
+    """U = 1/2 sum r_i g_i + const, r = q - mu, g = r * inv_var (inv_var = 1/sigma^2)."""
 
-    def __init__(self, mu, sigma):
+    def __init__(self, mu, sigma, const=0.0):
         self.mu = np.asarray(mu, dtype=np.float64)
         self.sigma = np.asarray(sigma, dtype=np.float64)
         self.inv_var = 1.0 / (self.sigma * self.sigma)
+        self.const = float(const)
 
     def potential_and_grad(self, q):
         r = q - self.mu
         g = r * self.inv_var
-        return 0.5 * np.sum(r * g), g
+        return 0.5 * np.sum(r * g) + self.const, g
 
 
 class CorrelatedGaussian:

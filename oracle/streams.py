@@ -116,3 +116,65 @@ class InjectedDraws:
 
     def hmc_accept(self, p):
         return bernoulli_from_uniform(self.u_accept[self.t], p)
+
+
+class RecordingStreamDraws(StreamDraws):
+    """``StreamDraws`` that also writes every draw it consumes into injected-layout
+    arrays (one transition per ``begin_transition``), so that a transition driven by
+    the reference's RNG topology can be replayed index-addressed by the CUDA path.
+    Each Bernoulli takes its uniform with ``Generator.random()`` -- the same double
+    ``binomial(1, p)`` would consume -- and applies ``bernoulli_from_uniform``;
+    p == 0 consumes nothing, like NumPy."""
+
+    def __init__(self, seed, kind="nuts", first_child=0, max_num_expansions=10):
+        super().__init__(seed, kind, first_child)
+        self.max_num_expansions = max_num_expansions
+        self.rows = []
+
+    def begin_transition(self):
+        m = self.max_num_expansions
+        self.rows.append({
+            "z": None, "u_dir": np.full(m, 0.25), "u_biased": np.full(m, 0.25),
+            "u_uniform": np.full((1 << m) - 1, 0.25), "u_accept": 0.25,
+        })
+
+    def _bern(self, rng, p):
+        if p == 0.0:
+            return 0.25, False
+        u = rng.random()
+        return u, bernoulli_from_uniform(u, p)
+
+    def normal(self, shape):
+        z = super().normal(shape)
+        self.rows[-1]["z"] = np.atleast_1d(np.asarray(z, dtype=np.float64)).ravel()
+        return z
+
+    def direction(self, expansion):
+        u, ok = self._bern(self.direction_rng, 0.5)
+        self.rows[-1]["u_dir"][expansion] = u
+        return ok
+
+    def uniform_accept(self, expansion, step, p):
+        u, ok = self._bern(self.uniform_rng, p)
+        self.rows[-1]["u_uniform"][uniform_slot(expansion, step)] = u
+        return ok
+
+    def biased_accept(self, expansion, p):
+        u, ok = self._bern(self.biased_rng, p)
+        self.rows[-1]["u_biased"][expansion] = u
+        return ok
+
+    def hmc_accept(self, p):
+        u, ok = self._bern(self.accept_rng, p)
+        self.rows[-1]["u_accept"] = u
+        return ok
+
+    def injected(self):
+        """Arrays [T, ...] in the InjectedDraws / b2h_rng layout."""
+        return {
+            "z": np.stack([r["z"] for r in self.rows]),
+            "u_dir": np.stack([r["u_dir"] for r in self.rows]),
+            "u_biased": np.stack([r["u_biased"] for r in self.rows]),
+            "u_uniform": np.stack([r["u_uniform"] for r in self.rows]),
+            "u_accept": np.array([r["u_accept"] for r in self.rows]),
+        }

@@ -1,0 +1,126 @@
+"""engine.cuh / models.cuh (the CUDA chain state machine and model gradients) compiled with
+g++ through tests/host_sim and compared with the oracle under injected draws.  This checks the
+device code's LOGIC where there is no GPU; the same comparisons run against the real kernels
+in tests/test_gpu_*.py."""
+import shutil
+import sys
+import os
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "host_sim"))
+import hostsim  # noqa: E402
+import parity  # noqa: E402
+from oracle import adaptation, kernels, models, streams  # noqa: E402
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+
+
+def test_readme_golden_bit_exact_through_engine_code():
+    rec = streams.RecordingStreamDraws(0, "nuts")
+    model = models.IIDGaussian([0.0], [1.0], const=models._LOG_SQRT_2PI)
+    kernel = kernels.nuts_new_kernel(rec, model)
+    info, extras = kernel(kernels.new_state(np.zeros(1), model), 1e-2, np.float64(1.0))
+    assert float(info.state.position[0]) == 1.1034719409361107
+    inj = {k: v[None] for k, v in rec.injected().items()}
+    out = hostsim.run(0, [0.0], [1.0], models._LOG_SQRT_2PI, 1.0, np.zeros((1, 1)), 1e-2, inj, 1)
+    assert float(out["q"][0, 0]) == 1.1034719409361107           # reference README.md:54
+    assert out["num_doublings"][0] == 8 and out["n_leapfrog"][0] == 136
+    assert out["acceptance_probability"][0] == pytest.approx(info.acceptance_probability, rel=1e-14)
+
+
+@pytest.mark.parametrize("d, imm_kind, eps", [(1, "scalar", 0.3), (5, "diag", 0.4), (5, "diag", 1.7),
+                                             (3, "per_chain", 0.2), (7, "scalar", 1e-3), (2, "diag", 30.0)])
+def test_nuts_iid_gaussian(d, imm_kind, eps):
+    rng = np.random.default_rng(100 + d)
+    C, T = 12, 3
+    mu, sigma = rng.standard_normal(d), np.exp(0.5 * rng.standard_normal(d))
+    imm = {"scalar": np.float64(0.7), "diag": sigma ** 2 * np.exp(0.2 * rng.standard_normal(d)),
+           "per_chain": np.exp(0.3 * rng.standard_normal((C, d)))}[imm_kind]
+    q0 = mu + sigma * rng.standard_normal((C, d))
+    eps_c = eps * np.exp(0.3 * rng.standard_normal(C))
+    maxd = 6 if eps < 0.01 else 10
+    draws = parity.random_draws(rng, C, T, d, maxd)
+    model = models.IIDGaussian(mu, sigma, const=0.25)
+    ref = parity.oracle_nuts(model, q0, eps_c, imm, draws, T, maxd=maxd, per_chain_imm=imm_kind == "per_chain")
+    got = hostsim.run(0, mu, model.inv_var, 0.25, imm, q0, eps_c, draws, T, maxd=maxd, n_store=T)
+    parity.assert_nuts_parity(got, ref, rtol=1e-11, what=f"iid d={d}")
+    np.testing.assert_allclose(got["draws"], ref["draws"], rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize("eps", [0.05, 0.5, 3.0])
+def test_nuts_funnel(eps):
+    rng = np.random.default_rng(7)
+    C, T, d = 16, 3, 10
+    q0 = rng.standard_normal((C, d))
+    draws = parity.random_draws(rng, C, T, d)
+    model = models.NealFunnel(d)
+    ref = parity.oracle_nuts(model, q0, eps, np.ones(d), draws, T)
+    got = hostsim.run(2, None, None, 0.0, np.ones(d), q0, eps, draws, T, n_store=T)
+    parity.assert_nuts_parity(got, ref, rtol=1e-10, what="funnel")
+    assert ref["is_diverging"].any() or eps < 1.0
+
+
+def test_nuts_eight_schools():
+    rng = np.random.default_rng(8)
+    C, T, d = 16, 4, 10
+    q0 = 0.5 * rng.standard_normal((C, d))
+    draws = parity.random_draws(rng, C, T, d)
+    model = models.EightSchools()
+    ref = parity.oracle_nuts(model, q0, 0.3, np.ones(d), draws, T)
+    got = hostsim.run(3, model.y, model.inv_var, 0.0, np.ones(d), q0, 0.3, draws, T, n_store=T)
+    parity.assert_nuts_parity(got, ref, rtol=1e-10, what="eight schools")
+    assert len(set(ref["num_doublings"].tolist())) > 1          # heterogeneous tree depths
+
+
+def test_window_adaptation_gaussian():
+    """window_adaptation.run (reference window_adaptation.py:17-116) per chain: dual averaging +
+    Welford + two slow-window ends + final averaged step size, 200 warm-up steps then 2 draws.
+    (A linear target: rounding differences do not amplify chaotically over 200 transitions.)"""
+    rng = np.random.default_rng(9)
+    C, W, extra, d = 4, 200, 2, 5
+    mu, sigma = rng.standard_normal(d), np.exp(rng.standard_normal(d))
+    q0 = mu + sigma * rng.standard_normal((C, d))
+    draws = parity.random_draws(rng, C, W + extra, d)
+    model = models.IIDGaussian(mu, sigma)
+    sched = adaptation.build_schedule(W)
+    assert sum(e for _, e in sched) == 2
+    ref = parity.oracle_nuts(model, q0, 1.0, np.ones(d), draws, W + extra, schedule_steps=W)
+    got = hostsim.run(0, mu, model.inv_var, 0.0, np.ones((C, d)), q0, 1.0, draws, W + extra, schedule=sched)
+    parity.assert_nuts_parity(got, ref, rtol=1e-8, what="adapt")
+    np.testing.assert_allclose(got["eps"], ref["eps"], rtol=1e-9)
+    np.testing.assert_allclose(got["imm"], ref["imm"], rtol=1e-9)
+    assert np.all(np.abs(ref["imm"] / sigma ** 2 - 1) < 0.9)      # adapted towards the target variances
+
+
+def test_window_adaptation_funnel_short():
+    """Same on a chaotic target, kept short (25 steps, one slow-window end at step 21)."""
+    rng = np.random.default_rng(9)
+    C, W, d = 6, 25, 10
+    q0 = rng.standard_normal((C, d))
+    draws = parity.random_draws(rng, C, W, d)
+    model = models.NealFunnel(d)
+    sched = adaptation.build_schedule(W)
+    ref = parity.oracle_nuts(model, q0, 1.0, np.ones(d), draws, W, schedule_steps=W)
+    got = hostsim.run(2, None, None, 0.0, np.ones((C, d)), q0, 1.0, draws, W, schedule=sched)
+    parity.assert_nuts_parity(got, ref, rtol=1e-6, what="adapt funnel")
+    np.testing.assert_allclose(got["eps"], ref["eps"], rtol=1e-7)
+    np.testing.assert_allclose(got["imm"], ref["imm"], rtol=1e-7)
+
+
+def test_hmc_iid_gaussian():
+    rng = np.random.default_rng(10)
+    C, T, d, L = 10, 4, 6, 10
+    mu, sigma = rng.standard_normal(d), np.exp(0.5 * rng.standard_normal(d))
+    q0 = mu + sigma * rng.standard_normal((C, d))
+    draws = parity.random_draws(rng, C, T, d)
+    model = models.IIDGaussian(mu, sigma)
+    imm = sigma ** 2
+    for eps in (0.25, 1.2):
+        ref = parity.oracle_hmc(model, q0, eps, imm, draws, T, L)
+        got = hostsim.run(0, mu, model.inv_var, 0.0, imm, q0, eps, draws, T, hmc_L=L, n_store=T)
+        for k in ("q", "p", "g", "U", "acceptance_probability"):
+            np.testing.assert_allclose(got[k], ref[k], rtol=1e-11, atol=1e-13, err_msg=k)
+        np.testing.assert_array_equal(got["is_diverging"].astype(bool), ref["is_diverging"])
+        np.testing.assert_allclose(got["draws"], ref["draws"], rtol=1e-11, atol=1e-13)
