@@ -1,0 +1,94 @@
+"""ctypes binding of libb200hmc.so (include/b200hmc.h).
+
+There is no CPU fallback: importing a sampler entry point without the built CUDA
+library, or creating a context without a B200, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200hmc.so")
+
+F32, F64 = 0, 1
+MODEL_IID_GAUSSIAN, MODEL_CORR_GAUSSIAN, MODEL_FUNNEL, MODEL_EIGHT_SCHOOLS, MODEL_LOGISTIC = range(5)
+IMM_SCALAR, IMM_DIAG, IMM_DIAG_PER_CHAIN, IMM_DENSE = range(4)
+RNG_PHILOX, RNG_INJECTED = 0, 1
+
+
+class Model(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("dim", C.c_int32), ("n_data", C.c_int64), ("a", C.c_void_p),
+                ("b", C.c_void_p), ("c", C.c_void_p), ("s0", C.c_double), ("s1", C.c_double)]
+
+
+class Metric(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("scalar", C.c_double), ("imm", C.c_void_p),
+                ("sqrt_t", C.c_void_p)]
+
+
+class Rng(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_uint64),
+                ("chain_offset", C.c_uint64), ("transition_offset", C.c_uint64), ("n_injected", C.c_int64),
+                ("z", C.c_void_p), ("u_dir", C.c_void_p), ("u_biased", C.c_void_p), ("u_uniform", C.c_void_p),
+                ("u_accept", C.c_void_p)]
+
+
+class Diag(C.Structure):
+    _fields_ = [("acceptance_probability", C.c_void_p), ("num_doublings", C.c_void_p),
+                ("is_turning", C.c_void_p), ("is_diverging", C.c_void_p), ("n_leapfrog", C.c_void_p)]
+
+
+class Adapt(C.Structure):
+    _fields_ = [("enabled", C.c_int32), ("num_steps", C.c_int32), ("stage", C.c_void_p),
+                ("window_end", C.c_void_p), ("target_acceptance_rate", C.c_double), ("gamma", C.c_double),
+                ("t0", C.c_double), ("kappa", C.c_double), ("initial_step_size", C.c_double),
+                ("da_step", C.c_void_p), ("da_x", C.c_void_p), ("da_x_avg", C.c_void_p),
+                ("da_g_avg", C.c_void_p), ("da_mu", C.c_void_p), ("wc_mean", C.c_void_p),
+                ("wc_m2", C.c_void_p), ("wc_n", C.c_void_p)]
+
+
+class Cfg(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("max_num_expansions", C.c_int32), ("divergence_threshold", C.c_double),
+                ("num_integration_steps", C.c_int32), ("group", C.c_int32), ("gradient_path", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+# every symbol include/b200hmc.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "b2h_last_error", "b2h_version", "b2h_ctx_create", "b2h_ctx_destroy", "b2h_ctx_sync",
+    "b2h_potential_and_grad", "b2h_potential_workspace_bytes", "b2h_sample_momentum", "b2h_kinetic_energy",
+    "b2h_is_turning", "b2h_leapfrog", "b2h_termination_update", "b2h_is_iterative_turning",
+    "b2h_find_storage_indices", "b2h_hmc_run", "b2h_nuts_run", "b2h_nuts_workspace_bytes",
+    "b2h_hmc_workspace_bytes", "b2h_dual_averaging_update", "b2h_welford_update", "b2h_mass_matrix_final",
+    "b2h_philox_fill", "b2h_dense_apply", "b2h_chain_moments",
+]
+
+_lib = None
+
+
+class B200HMCError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it was not built: the package never
+    falls back to another implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200HMCError(
+            f"{LIB_PATH} not found: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "aehmc_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.b2h_last_error.restype = C.c_char_p
+    for name in ("b2h_potential_workspace_bytes", "b2h_nuts_workspace_bytes", "b2h_hmc_workspace_bytes"):
+        getattr(lib, name).restype = C.c_int64
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise B200HMCError(f"libb200hmc error {rc}: {load().b2h_last_error().decode()}")

@@ -118,7 +118,7 @@ struct Group {
     B2H_DEVINL static unsigned mask() {
         if (G >= 32) return 0xffffffffu;
         unsigned l = threadIdx.x & 31u;
-        return ((1u << G) - 1u) << (l & ~(unsigned)(G - 1));
+        return ((1u << (G & 31)) - 1u) << (l & ~(unsigned)((G & 31) - 1));
     }
     // all-reduce sum of N doubles across the group
     template <int N>

@@ -1,0 +1,124 @@
+"""Built-in log-density models: the ``logprob_fn`` argument of hmc/nuts.new_kernel.
+
+The reference takes an arbitrary Python ``logprob_fn`` and differentiates it with
+aesara.grad (reference hmc.py:33-34).  The CUDA engine needs the gradient as device
+code, so ``logprob_fn`` is a model descriptor here; calling it returns the log-density
+like the reference's function would.  Definitions match oracle/models.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, backend
+
+EIGHT_SCHOOLS_Y = (28.0, 8.0, -3.0, 7.0, -1.0, 1.0, 18.0, 12.0)
+EIGHT_SCHOOLS_SIGMA = (15.0, 10.0, 16.0, 11.0, 9.0, 11.0, 10.0, 18.0)
+
+
+class Model:
+    kind = -1
+    dim = 0
+
+    def __init__(self, dtype=torch.float64, device=None):
+        self.dtype = backend.torch_dtype(dtype)
+        self.device = backend.device(device)
+        self._ws = backend.Workspace()
+
+    # -- C-ABI view ---------------------------------------------------------------------------
+    def struct(self):
+        raise NotImplementedError
+
+    # -- hmc.new_state (reference hmc.py:16-40) ----------------------------------------------------
+    def potential_and_grad(self, q):
+        """U[C], dU/dq[C,d] for positions q[C,d]."""
+        q = backend.as_device(q, self.dtype, self.device)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"position must be [chains, {self.dim}], got {tuple(q.shape)}")
+        lib = _lib.load()
+        Cn = q.shape[0]
+        U = torch.empty(Cn, dtype=self.dtype, device=self.device)
+        g = torch.empty_like(q)
+        m = self.struct()
+        nbytes = lib.b2h_potential_workspace_bytes(C.byref(m), backend.code(self.dtype), C.c_int64(Cn))
+        ws = self._ws.get(nbytes, self.device)
+        _lib.check(lib.b2h_potential_and_grad(backend.context(self.device), C.byref(m), backend.code(self.dtype),
+                                              backend.ptr(q), backend.ptr(U), backend.ptr(g), C.c_int64(Cn),
+                                              backend.ptr(ws), C.c_int64(ws.numel())))
+        return U, g
+
+    def __call__(self, q):
+        """log-density, like the reference's ``logprob_fn(q)``."""
+        return -self.potential_and_grad(q)[0]
+
+
+class IIDGaussian(Model):
+    kind = _lib.MODEL_IID_GAUSSIAN
+
+    def __init__(self, mu, sigma, const=0.0, dtype=torch.float64, device=None):
+        super().__init__(dtype, device)
+        sigma = np.asarray(sigma, dtype=np.float64)
+        self.mu = backend.as_device(np.asarray(mu, dtype=np.float64), self.dtype, self.device)
+        self.inv_var = backend.as_device(1.0 / (sigma * sigma), self.dtype, self.device)
+        self.const = float(const)
+        self.dim = int(self.mu.numel())
+
+    def struct(self):
+        return _lib.Model(self.kind, self.dim, 0, self.mu.data_ptr(), self.inv_var.data_ptr(), None, self.const, 0.0)
+
+
+class CorrelatedGaussian(Model):
+    kind = _lib.MODEL_CORR_GAUSSIAN
+
+    def __init__(self, mu, precision, dtype=torch.float64, device=None):
+        super().__init__(dtype, device)
+        self.mu = backend.as_device(np.asarray(mu, dtype=np.float64), self.dtype, self.device)
+        prec = np.asarray(precision.cpu() if isinstance(precision, torch.Tensor) else precision, dtype=np.float64)
+        self.precision = backend.as_device(0.5 * (prec + prec.T), self.dtype, self.device)
+        self.dim = int(self.mu.numel())
+
+    def struct(self):
+        return _lib.Model(self.kind, self.dim, 0, self.mu.data_ptr(), self.precision.data_ptr(), None, 0.0, 0.0)
+
+
+class NealFunnel(Model):
+    kind = _lib.MODEL_FUNNEL
+
+    def __init__(self, dim=10, dtype=torch.float64, device=None):
+        super().__init__(dtype, device)
+        self.dim = int(dim)
+
+    def struct(self):
+        return _lib.Model(self.kind, self.dim, 0, None, None, None, 0.0, 0.0)
+
+
+class EightSchools(Model):
+    kind = _lib.MODEL_EIGHT_SCHOOLS
+
+    def __init__(self, y=EIGHT_SCHOOLS_Y, sigma=EIGHT_SCHOOLS_SIGMA, dtype=torch.float64, device=None):
+        super().__init__(dtype, device)
+        sigma = np.asarray(sigma, dtype=np.float64)
+        self.y = backend.as_device(np.asarray(y, dtype=np.float64), self.dtype, self.device)
+        self.inv_var = backend.as_device(1.0 / (sigma * sigma), self.dtype, self.device)
+        self.dim = 2 + int(self.y.numel())
+
+    def struct(self):
+        return _lib.Model(self.kind, self.dim, 0, self.y.data_ptr(), self.inv_var.data_ptr(), None, 0.0, 0.0)
+
+
+class LogisticRegression(Model):
+    kind = _lib.MODEL_LOGISTIC
+
+    def __init__(self, X, y, prior_scale=1.0, dtype=torch.float64, device=None):
+        super().__init__(dtype, device)
+        self.X = backend.as_device(X, self.dtype, self.device)
+        self.Xt = self.X.t().contiguous()
+        self.y = backend.as_device(y, self.dtype, self.device)
+        self.inv_prior_var = 1.0 / float(prior_scale) ** 2
+        self.n_data, self.dim = int(self.X.shape[0]), int(self.X.shape[1])
+
+    def struct(self):
+        return _lib.Model(self.kind, self.dim, self.n_data, self.X.data_ptr(), self.y.data_ptr(),
+                          self.Xt.data_ptr(), self.inv_prior_var, 0.0)
