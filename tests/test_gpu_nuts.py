@@ -34,7 +34,7 @@ def gpu_nuts(ab, model, imm, q0, eps, draws, T, maxd=10, group=0, schedule=None,
     adapt = None
     if schedule is not None:
         adapt = _engine.AdaptState(Cn, schedule, model.device)
-    info, extras = _engine.run("nuts", model, imm, srng, state, torch.as_tensor(eps), n_transitions=T,
+    info, extras = _engine.run("nuts", model, imm, srng, state, torch.as_tensor(eps, dtype=torch.float64), n_transitions=T,
                                max_num_expansions=maxd, divergence_threshold=div_thr, store_draws=T, group=group,
                                adapt=adapt)
     out = dict(q=_np(info.state.position), p=_np(info.state.momentum), U=_np(info.state.potential_energy),
@@ -229,7 +229,7 @@ def test_window_adaptation_composed_matches_fused(ab):
 def gpu_hmc(ab, model, imm, q0, eps, draws, T, L, group=0):
     from aehmc_b200 import _engine
     srng = ab.InjectedDraws(z=draws["z"], u_accept=draws["u_accept"])
-    info, extras = _engine.run("hmc", model, imm, srng, ab.hmc.new_state(q0, model), torch.as_tensor(eps),
+    info, extras = _engine.run("hmc", model, imm, srng, ab.hmc.new_state(q0, model), torch.as_tensor(eps, dtype=torch.float64),
                                n_transitions=T, num_integration_steps=L, store_draws=T, group=group)
     return dict(q=_np(info.state.position), p=_np(info.state.momentum), U=_np(info.state.potential_energy),
                 g=_np(info.state.potential_energy_grad), acceptance_probability=_np(info.acceptance_probability),
