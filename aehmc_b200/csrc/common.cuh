@@ -154,6 +154,17 @@ struct Group {
         sum<1>(v, smem);
         return v[0];
     }
+    // value held by the group's lane 0, broadcast to the whole group
+    B2H_DEVINL static int bcast(int x, double* smem) {
+        if (G == 1) return x;
+        if (!kBlock) return __shfl_sync(mask(), x, (threadIdx.x & 31u) & ~(unsigned)((G & 31) - 1));
+        __syncthreads();
+        if (threadIdx.x == 0) reinterpret_cast<int*>(smem)[0] = x;
+        __syncthreads();
+        int r = reinterpret_cast<int*>(smem)[0];
+        __syncthreads();
+        return r;
+    }
     B2H_DEVINL static void sync() {
         if (kBlock) __syncthreads();
         else if (G > 1) __syncwarp(mask());

@@ -86,9 +86,13 @@ struct EngineView {
     i64 imm_sc, imm_sj;
     // split-mode scratch (row-major [C][d]) and dense-momentum compaction
     T *xa, *xb, *Unew;
-    T *mom_p, *mom_v;                    // compact rows [count][d]
-    int* mom_count;
-    int* mom_list;
+    // dense-metric momentum, one transition of lookahead: mom_p/mom_v [C][d] hold p0 = sqrt z and v0 = imm p0 of
+    // each chain's NEXT transition; a chain that starts a transition consumes them and queues a request
+    // (list/count of parity mom_parity, normals in mom_z) that rides along the following dense applies.
+    T *mom_p, *mom_v, *mom_z;            // mom_z: [2][C][d] compact request rows
+    int* mom_count;                      // [2]
+    int* mom_list;                       // [2][C]
+    int mom_parity;
     int* scratch;                        // [0] chains not yet done (split-mode poll)
     RngView rng;
     AdaptView adapt;
@@ -168,7 +172,7 @@ B2H_DEVINL void begin_transition(Chain<T, G>& ch) {
         i64 a = ch.at(j);
         T p0, vel;
         if (DENSE) {
-            i64 m = (i64)ch.r.mom_slot * v.d + j;
+            i64 m = (i64)ch.c * v.d + j;
             p0 = v.mom_p[m];
             vel = v.mom_v[m];
             v.vl[a] = vel;
@@ -197,6 +201,19 @@ B2H_DEVINL void begin_transition(Chain<T, G>& ch) {
     ch.r.k = 0;
     ch.r.nleap = 0;
     ch.r.phase = PH_RUN;
+    if (DENSE) {
+        // queue the momentum of the NEXT transition (consumed at the earliest two ticks from now)
+        int slot = 0;
+        if (ch.lane == 0) {
+            slot = atomicAdd(v.mom_count + v.mom_parity, 1);
+            v.mom_list[(i64)v.mom_parity * v.C + slot] = ch.c;
+        }
+        slot = Group<G>::bcast(slot, ch.red);
+        const int tn = ch.r.t + 1;
+        const bool have = (v.rng.mode == 0) || (tn < v.rng.n_injected);
+        T* zrow = v.mom_z + ((i64)v.mom_parity * v.C + slot) * v.d;
+        for (int j = ch.lane; j < v.d; j += G) zrow[j] = have ? (T)draw_z(v.rng, ch.c, tn, j, v.d) : (T)0;
+    }
     if (NUTS) begin_subtree(ch);
 }
 
@@ -337,24 +354,90 @@ B2H_DEVINL void post_gradient(Chain<T, G>& ch, T U_new) {
     const T e = (T)(r.go_right ? r.eps : -r.eps);
     const T he = (T)0.5 * e;
 
-    // ---- p' = p_half - (0.5 e) g'  (integrators.py:66) and K(p') (metrics.py:70-73)
-    T kacc = 0;
+    // ---- one pass over the chain's vectors, one group reduction --------------------------------
+    //  p' = p_half - (0.5 e) g' (integrators.py:66), K(p') (metrics.py:70-73), sub-tree momentum sum
+    //  (trajectory.py:243,278), checkpoint write on even steps at the step's storage index
+    //  (termination.py:109-124; stale index at step 0, Q2/Q3) and the U-turn dot products of the first LV
+    //  checkpoint levels (termination.py:164-187 with metrics.py:95-102).  Which levels are read depends
+    //  only on the step number, so nothing here waits for the energy.
+    const int s = r.s, k = r.k;
+    int imin, imax;
+    if (s == 0) { imin = r.imin; imax = r.imax; }
+    else storage_indices(s, imin, imax);
+    r.imin = imin; r.imax = imax;
+    const bool even = (s & 1) == 0;
+    const int nlev = (s >= 1 && imax >= imin) ? (imax - imin + 1) : 0;
+    constexpr int LV = 4;
+    T kacc = 0, dl[LV], dr[LV];
+#pragma unroll
+    for (int l = 0; l < LV; ++l) { dl[l] = 0; dr[l] = 0; }
     for (int j = ch.lane; j < d; j += G) {
         i64 a = ch.at(j);
+        T p, vel, im = 0;
         if (DENSE) {
-            T vel = v.xb[(i64)ch.c * d + j];
+            vel = v.xb[(i64)ch.c * d + j];
             V[a] = vel;
-            kacc += vel * P[a];
+            p = P[a];
         } else {
             T g;
             if (SPLIT) { g = v.xb[(i64)ch.c * d + j]; Gd[a] = g; }
             else g = Gd[a];
-            T p = P[a] - he * g;
+            p = P[a] - he * g;
             P[a] = p;
-            kacc += (ch.imm(j) * p) * p;
+            im = ch.imm(j);
+            vel = im * p;
+        }
+        kacc += vel * p;
+        T sm = (s == 0) ? p : v.sms[a] + p;
+        v.sms[a] = sm;
+        if (even) {
+            i64 b = ch.ck(imax, j);
+            v.mck[b] = p;
+            v.sckp[b] = sm;
+            if (DENSE) v.vck[b] = vel;
+        }
+#pragma unroll
+        for (int l = 0; l < LV; ++l) {
+            if (l < nlev) {
+                i64 b = ch.ck(imax - l, j);
+                T m = v.mck[b], sc = v.sckp[b];
+                T subsum = sm - sc + m;
+                T rho = subsum - (p + m) / (T)2;
+                T vleft = DENSE ? v.vck[b] : im * m;
+                dl[l] += vleft * rho;
+                dr[l] += vel * rho;
+            }
         }
     }
-    const T K = (T)0.5 * (T)Group<G>::sum1((double)kacc, ch.red);
+    double red[1 + 2 * LV];
+    red[0] = (double)kacc;
+#pragma unroll
+    for (int l = 0; l < LV; ++l) { red[1 + 2 * l] = (double)dl[l]; red[2 + 2 * l] = (double)dr[l]; }
+    Group<G>::template sum<1 + 2 * LV>(red, ch.red);
+    const T K = (T)0.5 * (T)red[0];
+    bool term = false;
+#pragma unroll
+    for (int l = 0; l < LV; ++l)
+        if (l < nlev && ((T)red[1 + 2 * l] <= (T)0 || (T)red[2 + 2 * l] <= (T)0)) term = true;
+    if (!term && nlev > LV) {                       // deeper levels (a step with >= 5 trailing one-bits): rare
+        for (int i = imax - LV; i >= imin; --i) {
+            T xl = 0, xr = 0;
+            for (int j = ch.lane; j < d; j += G) {
+                i64 a = ch.at(j), b = ch.ck(i, j);
+                T m = v.mck[b], sc = v.sckp[b], p = P[a], sm = v.sms[a];
+                T subsum = sm - sc + m;
+                T rho = subsum - (p + m) / (T)2;
+                T vleft, vright;
+                if (DENSE) { vleft = v.vck[b]; vright = V[a]; }
+                else { T im = ch.imm(j); vleft = im * m; vright = im * p; }
+                xl += vleft * rho;
+                xr += vright * rho;
+            }
+            double r2[2] = {(double)xl, (double)xr};
+            Group<G>::template sum<2>(r2, ch.red);
+            if ((T)r2[0] <= (T)0 || (T)r2[1] <= (T)0) { term = true; break; }
+        }
+    }
 
     // ---- proposal for the new state (proposals.py:41-52, Q10)
     const T E = U_new + K;
@@ -365,7 +448,6 @@ B2H_DEVINL void post_gradient(Chain<T, G>& ch, T U_new) {
     const double lpa = delta > 0 ? 0.0 : delta;
 
     // ---- progressive uniform sampling inside the sub-tree (proposals.py:96-100, Q7)
-    const int s = r.s, k = r.k;
     bool take;
     if (s == 0) {
         take = true;                                   // trajectory.py:276-277: proposal = first state
@@ -378,47 +460,11 @@ B2H_DEVINL void post_gradient(Chain<T, G>& ch, T U_new) {
         r.w_sub = lae(r.w_sub, w_new);                 // proposals.py:141-144
         r.slpa_sub = lae(r.slpa_sub, lpa);
     }
-    if (take) { r.E_sub = (double)E; r.U_sub = (double)U_new; }
-
-    // ---- termination.update (termination.py:109-124): stale indices at step 0 (Q2), write on even steps (Q3)
-    int imin, imax;
-    if (s == 0) { imin = r.imin; imax = r.imax; }
-    else storage_indices(s, imin, imax);
-    r.imin = imin; r.imax = imax;
-    const bool even = (s & 1) == 0;
-    for (int j = ch.lane; j < d; j += G) {
-        i64 a = ch.at(j);
-        T p = P[a];
-        if (take) { v.qs[a] = Q[a]; v.ps[a] = p; v.gs[a] = Gd[a]; }
-        T sm = (s == 0) ? p : v.sms[a] + p;            // trajectory.py:243,278
-        v.sms[a] = sm;
-        if (even) {
-            i64 b = ch.ck(imax, j);
-            v.mck[b] = p;
-            v.sckp[b] = sm;
-            if (DENSE) v.vck[b] = V[a];
-        }
-    }
-
-    // ---- is_iterative_turning (termination.py:164-187, Q5) with is_turning (metrics.py:95-102, Q6)
-    bool term = false;
-    if (s >= 1 && imax >= imin) {
-        for (int i = imax; i >= imin; --i) {
-            T dl = 0, dr = 0;
-            for (int j = ch.lane; j < d; j += G) {
-                i64 a = ch.at(j), b = ch.ck(i, j);
-                T m = v.mck[b], sc = v.sckp[b], p = P[a], sm = v.sms[a];
-                T subsum = sm - sc + m;
-                T rho = subsum - (p + m) / (T)2;
-                T vleft, vright;
-                if (DENSE) { vleft = v.vck[b]; vright = V[a]; }
-                else { T im = ch.imm(j); vleft = im * m; vright = im * p; }
-                dl += vleft * rho;
-                dr += vright * rho;
-            }
-            double red[2] = {(double)dl, (double)dr};
-            Group<G>::template sum<2>(red, ch.red);
-            if ((T)red[0] <= (T)0 || (T)red[1] <= (T)0) { term = true; break; }
+    if (take) {
+        r.E_sub = (double)E; r.U_sub = (double)U_new;
+        for (int j = ch.lane; j < d; j += G) {
+            i64 a = ch.at(j);
+            v.qs[a] = Q[a]; v.ps[a] = P[a]; v.gs[a] = Gd[a];
         }
     }
     r.sub_len = (s == 0) ? 1 : r.sub_len + 1;
@@ -430,7 +476,7 @@ B2H_DEVINL void post_gradient(Chain<T, G>& ch, T U_new) {
 
     // ================= end of the sub-tree: expand_once (trajectory.py:537-608) =================
     // edges are already in place; msum += sub-tree sum; top-level U-turn on (left, right, msum)
-    T dl = 0, dr = 0;
+    T tl = 0, tr = 0;
     for (int j = ch.lane; j < d; j += G) {
         i64 a = ch.at(j);
         T ms = v.msum[a] + v.sms[a];
@@ -440,10 +486,10 @@ B2H_DEVINL void post_gradient(Chain<T, G>& ch, T U_new) {
         T vleft, vright;
         if (DENSE) { vleft = v.vl[a]; vright = v.vr[a]; }
         else { T im = ch.imm(j); vleft = im * plv; vright = im * prv; }
-        dl += vleft * rho;
-        dr += vright * rho;
+        tl += vleft * rho;
+        tr += vright * rho;
     }
-    double red2[2] = {(double)dl, (double)dr};
+    double red2[2] = {(double)tl, (double)tr};
     Group<G>::template sum<2>(red2, ch.red);
     const bool top_turn = ((T)red2[0] <= (T)0) || ((T)red2[1] <= (T)0);
 

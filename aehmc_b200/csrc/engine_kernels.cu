@@ -85,13 +85,13 @@ static size_t carve(EngineView<T>& v, char* base, const EnginePlan& pl, const b2
     v.adapt.wc_mean = v.adapt.wc_m2 = nullptr;
     if (adapt) { v.adapt.wc_mean = cv.take<T>(n); v.adapt.wc_m2 = cv.take<T>(n); }
     v.xa = v.xb = v.Unew = nullptr;
-    v.mom_p = v.mom_v = nullptr; v.mom_count = nullptr; v.mom_list = nullptr;
+    v.mom_p = v.mom_v = v.mom_z = nullptr; v.mom_count = nullptr; v.mom_list = nullptr;
     if (pl.split) {
         v.xa = cv.take<T>(n); v.xb = cv.take<T>(n); v.Unew = cv.take<T>(C);
     }
     if (pl.dense) {
-        v.mom_p = cv.take<T>(n); v.mom_v = cv.take<T>(n);
-        v.mom_count = cv.take<int>(4); v.mom_list = cv.take<int>(C);
+        v.mom_p = cv.take<T>(n); v.mom_v = cv.take<T>(n); v.mom_z = cv.take<T>(2 * n);
+        v.mom_count = cv.take<int>(4); v.mom_list = cv.take<int>(2 * (size_t)C);
     }
     v.scratch = cv.take<int>(64);
     if (model_ws_bytes) {
@@ -186,7 +186,7 @@ struct Geo {
 template <typename T, int G, int MODEL, bool HMC>
 __global__ void __launch_bounds__(Geo<G>::kThreads)
 fused_run_kernel(EngineView<T> v, ModelDev m, i64 max_ticks) {
-    __shared__ double red_s[64];
+    __shared__ double red_s[128];
     const int c = Geo<G>::chain();
     if (c >= v.C) return;
     Chain<T, G> ch(v, c, red_s);
@@ -218,7 +218,7 @@ fused_run_kernel(EngineView<T> v, ModelDev m, i64 max_ticks) {
 // ---------------------------------------------------------------------------
 template <typename T, int G, bool DENSE, bool HMC>
 __global__ void __launch_bounds__(Geo<G>::kThreads) split_pre_kernel(EngineView<T> v) {
-    __shared__ double red_s[64];
+    __shared__ double red_s[128];
     const int c = Geo<G>::chain();
     if (c >= v.C) return;
     Chain<T, G> ch(v, c, red_s);
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(Geo<G>::kThreads) split_kick_kernel(EngineView
 
 template <typename T, int G, bool DENSE, bool HMC>
 __global__ void __launch_bounds__(Geo<G>::kThreads) split_post_kernel(EngineView<T> v, int* not_done) {
-    __shared__ double red_s[64];
+    __shared__ double red_s[128];
     const int c = Geo<G>::chain();
     if (c >= v.C) return;
     Chain<T, G> ch(v, c, red_s);
@@ -289,26 +289,12 @@ __global__ void __launch_bounds__(Geo<G>::kThreads) split_post_kernel(EngineView
     }
 }
 
-// dense metric momentum: compact the chains that start a transition this tick and emit their normals
+// dense metric momentum at the start of a run: normals of every chain's first transition (row c of mom_z)
 template <typename T>
-__global__ void mom_list_kernel(EngineView<T> v) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= v.C) return;
-    if (v.rec[c].phase == PH_START) {
-        int slot = atomicAdd(v.mom_count, 1);
-        v.mom_list[slot] = c;
-        v.rec[c].mom_slot = slot;
-    }
-}
-
-template <typename T>
-__global__ void mom_fill_kernel(EngineView<T> v) {
-    const int slot = blockIdx.x;
-    if (slot >= *v.mom_count) return;
-    const int c = v.mom_list[slot];
+__global__ void mom_init_kernel(EngineView<T> v) {
+    const int c = blockIdx.x;
     const int t = v.rec[c].t;
-    for (int j = threadIdx.x; j < v.d; j += blockDim.x)
-        v.mom_v[(i64)slot * v.d + j] = (T)draw_z(v.rng, c, t, j, v.d);   // z staged in mom_v
+    for (int j = threadIdx.x; j < v.d; j += blockDim.x) v.mom_z[(i64)c * v.d + j] = (T)draw_z(v.rng, c, t, j, v.d);
 }
 
 // ---------------------------------------------------------------------------
@@ -350,7 +336,7 @@ static int launch_fused(cudaStream_t st, const EngineView<T>& v, const b2h_model
 template <typename T, int G, bool HMC>
 static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const b2h_model* model,
                      const b2h_metric* metric, const b2h_cfg* cfg, i64 max_ticks, int n_transitions, void* model_ws,
-                     i64 model_ws_bytes, int* not_done_dev) {
+                     i64 model_ws_bytes, int* not_done_dev, int resume) {
     cudaStream_t st = ctx->stream;
     const int grid = Geo<G>::grid(v.C), thr = Geo<G>::kThreads;
     const int C = v.C, d = v.d;
@@ -362,16 +348,29 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
     int* host_flag = nullptr;
     B2H_CUDA(cudaMallocHost(&host_flag, sizeof(int)));
     int rc = 0;
+    GemmGroup<T> none{nullptr, 0, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr};
+    int last_parity = 0;
+    if (pl.dense) {
+        B2H_CUDA(cudaMemsetAsync(v.mom_count, 0, 4 * sizeof(int), st));
+        if (!resume) {
+            // p0 = z . S^T (metrics.py:56-59,67), v0 = p0 . imm (metrics.py:71) for every chain's first transition
+            mom_init_kernel<T><<<C, 128, 0, st>>>(v);
+            launch_dense_apply<T>(st, v.mom_z, sqrt_t, v.mom_p, C, d, d, nullptr, nullptr);
+            launch_dense_apply<T>(st, v.mom_p, imm_dense, v.mom_v, C, d, d, nullptr, nullptr);
+        }
+    }
     for (i64 tick = 0; tick < bound; ++tick) {
         if (pl.dense) {
-            B2H_CUDA(cudaMemsetAsync(v.mom_count, 0, sizeof(int), st));
-            mom_list_kernel<T><<<(C + 255) / 256, 256, 0, st>>>(v);
-            mom_fill_kernel<T><<<C, 128, 0, st>>>(v);
-            // p0 = z . S^T (metrics.py:56-59,67), v0 = p0 . imm (metrics.py:71)
-            launch_dense_apply<T>(st, v.mom_v, sqrt_t, v.mom_p, C, d, d, v.mom_count, nullptr);
-            launch_dense_apply<T>(st, v.mom_p, imm_dense, v.mom_v, C, d, d, v.mom_count, nullptr);
+            const int b = (int)(tick & 1);
+            last_parity = b;
+            v.mom_parity = b;
+            B2H_CUDA(cudaMemsetAsync(v.mom_count + b, 0, sizeof(int), st));
             split_pre_kernel<T, G, true, HMC><<<grid, thr, 0, st>>>(v);
-            launch_dense_apply<T>(st, v.xa, imm_dense, v.xb, C, d, d, nullptr, nullptr);
+            // half-step velocities of all chains + v0 of the transitions queued one tick ago
+            GemmGroup<T> g0{v.xa, (i64)d, imm_dense, (i64)d, v.xb, (i64)d, C, nullptr, nullptr, nullptr, nullptr};
+            GemmGroup<T> g1{v.mom_p, (i64)d, imm_dense, (i64)d, v.mom_v, (i64)d, C, v.mom_count + (b ^ 1), nullptr,
+                            v.mom_list + (size_t)(b ^ 1) * C, v.mom_list + (size_t)(b ^ 1) * C};
+            launch_gemm_grouped<T>(st, g0, g1, d, d, 1, 0);
             split_drift_kernel<T, G><<<grid, thr, 0, st>>>(v);
         } else {
             split_pre_kernel<T, G, false, HMC><<<grid, thr, 0, st>>>(v);
@@ -381,8 +380,13 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
         const bool check = (max_ticks <= 0) && ((tick & 3) == 3 || tick + 1 == bound);
         if (check) B2H_CUDA(cudaMemsetAsync(not_done_dev, 0, sizeof(int), st));
         if (pl.dense) {
+            const int b = (int)(tick & 1);
             split_kick_kernel<T, G><<<grid, thr, 0, st>>>(v);
-            launch_dense_apply<T>(st, v.xa, imm_dense, v.xb, C, d, d, nullptr, nullptr);
+            // full-step velocities + p0 of the transitions queued this tick
+            GemmGroup<T> g0{v.xa, (i64)d, imm_dense, (i64)d, v.xb, (i64)d, C, nullptr, nullptr, nullptr, nullptr};
+            GemmGroup<T> g1{v.mom_z + (size_t)b * C * d, (i64)d, sqrt_t, (i64)d, v.mom_p, (i64)d, C, v.mom_count + b,
+                            nullptr, nullptr, v.mom_list + (size_t)b * C};
+            launch_gemm_grouped<T>(st, g0, g1, d, d, 1, 0);
             split_post_kernel<T, G, true, HMC><<<grid, thr, 0, st>>>(v, check ? not_done_dev : nullptr);
         } else {
             split_post_kernel<T, G, false, HMC><<<grid, thr, 0, st>>>(v, check ? not_done_dev : nullptr);
@@ -393,6 +397,12 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
             if (e != cudaSuccess) { rc = cuda_fail(e, "tick poll"); break; }
             if (*host_flag == 0) break;
         }
+    }
+    if (pl.dense && rc == 0) {
+        // flush: v0 of the transitions queued in the last tick, so that a resumed run starts with no request pending
+        GemmGroup<T> g0{v.mom_p, (i64)d, imm_dense, (i64)d, v.mom_v, (i64)d, C, v.mom_count + last_parity, nullptr,
+                        v.mom_list + (size_t)last_parity * C, v.mom_list + (size_t)last_parity * C};
+        launch_gemm_grouped<T>(st, g0, none, d, d, 1, 0);
     }
     cudaFreeHost(host_flag);
     if (rc) return rc;
@@ -508,15 +518,15 @@ static int run_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* met
         if (pl.G == 1) { set_error("split mode needs group >= 8"); return B2H_ERR_ARG; }
         if (hmc) {
             switch (pl.G) {
-                case 8: rc = run_split<T, 8, true>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev); break;
-                case 32: rc = run_split<T, 32, true>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev); break;
-                default: rc = run_split<T, 256, true>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev); break;
+                case 8: rc = run_split<T, 8, true>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev, resume); break;
+                case 32: rc = run_split<T, 32, true>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev, resume); break;
+                default: rc = run_split<T, 256, true>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev, resume); break;
             }
         } else {
             switch (pl.G) {
-                case 8: rc = run_split<T, 8, false>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev); break;
-                case 32: rc = run_split<T, 32, false>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev); break;
-                default: rc = run_split<T, 256, false>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev); break;
+                case 8: rc = run_split<T, 8, false>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev, resume); break;
+                case 32: rc = run_split<T, 32, false>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev, resume); break;
+                default: rc = run_split<T, 256, false>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev, resume); break;
             }
         }
     }

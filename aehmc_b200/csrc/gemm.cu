@@ -5,42 +5,67 @@
 // B is shared by all chains, so the per-chain mat-vecs of the reference become
 // one [C x d].[d x d] product: FP64/FP32 FMA-pipe bound, not HBM bound
 // (SURVEY.md section 8d).  FP64 has no tcgen05 path on sm_100a, so this is a
-// register-tiled SIMT kernel: 128x128x8 CTA tile, 256 threads, 8x8 outputs per
+// register-tiled SIMT kernel: 128x128x16 CTA tile, 256 threads, 8x8 outputs per
 // thread laid out as 4x4 chunks of 2 so that every shared-memory read is a
-// conflict-free 128-bit load, global->shared software-pipelined through
-// registers.  Rows may be limited by a DEVICE-side count (compacted momentum
-// rows), so no host synchronisation is needed to size the problem.
+// conflict-free 128-bit load; global->shared is software-pipelined through
+// registers and the shared->register fragments are double-buffered.
+//
+// One launch can carry TWO problems ("groups") that share N and K: the engine
+// uses the second group for the few momentum rows of chains that start a new
+// transition (p0 = z . sqrt^T, v0 = p0 . imm), whose row count is only known on
+// the device and which would otherwise cost a full launch latency each.  Rows
+// can be gathered (in_rows) and scattered (out_rows) through index lists.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "launch.h"
 
 namespace b2h {
 
-constexpr int BM = 128, BN = 128, BK = 8, GT = 256;
+constexpr int BM = 128, BN = 128, BK = 16, GT = 256;
 
 template <typename T>
 __global__ void __launch_bounds__(GT, 1)
-dense_apply_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ out, int M, int N, int K,
-                   i64 lda, i64 ldb, i64 ldo, const int* __restrict__ m_dev, const T* __restrict__ sub,
-                   int tiles_n, int k_chunk, i64 split_stride) {
-    if (m_dev) M = min(M, *m_dev);
-    const int tile_m = blockIdx.x / tiles_n, tile_n = blockIdx.x % tiles_n;
+dense_apply_kernel(GemmGroup<T> g0, GemmGroup<T> g1, int N, int K, int tiles_n, int tiles_m0, int k_chunk,
+                   i64 split_stride) {
+    int tile_m = blockIdx.x / tiles_n;
+    const int tile_n = blockIdx.x % tiles_n;
+    const bool second = tile_m >= tiles_m0;
+    const GemmGroup<T>& g = second ? g1 : g0;
+    if (second) tile_m -= tiles_m0;
+    int M = g.M;
+    if (g.m_dev) M = min(M, *g.m_dev);
     const int m0 = tile_m * BM, n0 = tile_n * BN;
     if (m0 >= M) return;
+    const T* __restrict__ A = g.A;
+    const T* __restrict__ B = g.B;
+    const T* __restrict__ sub = g.sub;
+    const i64 lda = g.lda, ldb = g.ldb, ldo = g.ldo;
     // split-K: slice blockIdx.y handles k in [k_begin, k_end) and writes its own partial plane
     const int k_begin = blockIdx.y * k_chunk;
     const int k_end = min(K, k_begin + k_chunk);
-    out += (i64)blockIdx.y * split_stride;
+    T* __restrict__ out = g.out + (i64)blockIdx.y * split_stride;
 
-    __shared__ __align__(16) T As[2][BK][BM];   // transposed: [k][m]
-    __shared__ __align__(16) T Bs[2][BK][BN];   // [k][n]
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef T (*TileA)[BK][BM];
+    typedef T (*TileB)[BK][BN];
+    TileA As = reinterpret_cast<TileA>(smem_raw);                                  // [2][k][m] (transposed)
+    TileB Bs = reinterpret_cast<TileB>(smem_raw + 2 * BK * BM * sizeof(T));        // [2][k][n]
 
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
 
-    // global->smem assignment: A tile 128 rows x 8 k : thread loads 4 consecutive k of one row
-    const int a_row = tid >> 1, a_k = (tid & 1) * 4;
-    // B tile 8 k x 128 n : thread loads 4 consecutive n of one k row
-    const int b_k = tid >> 5, b_n = (tid & 31) * 4;
+    // global->smem assignment.  A tile 128 rows x 16 k: a warp takes 32 consecutive rows, each thread 8
+    // consecutive k of its row (two full 32-byte sectors); the transposed smem stores are conflict-free.
+    const int a_row = tid & 127, a_k = (tid >> 7) * 8;
+    // B tile 16 k x 128 n: a warp reads 512 contiguous bytes of one k row (2 n per thread), 4 k rows per thread.
+    const int b_k = tid >> 6, b_n = (tid & 63) * 2;
+
+    i64 a_src = -1;
+    {
+        const int gr = m0 + a_row;
+        if (gr < M) a_src = (i64)(g.in_rows ? g.in_rows[gr] : gr) * lda;
+    }
 
     T acc[8][8];
 #pragma unroll
@@ -48,55 +73,62 @@ dense_apply_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restri
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = (T)0;
 
-    T ra[4], rb[4];
+    T ra[8], rb[8];
     auto load_tile = [&](int k0) {
-        const int gr = m0 + a_row;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 8; ++i) {
             int gk = k0 + a_k + i;
             T x = (T)0;
-            if (gr < M && gk < k_end) {
-                x = A[(i64)gr * lda + gk];
+            if (a_src >= 0 && gk < k_end) {
+                x = A[a_src + gk];
                 if (sub) x -= sub[gk];
             }
             ra[i] = x;
         }
-        const int gk = k0 + b_k;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            int gn = n0 + b_n + i;
-            rb[i] = (gk < k_end && gn < N) ? B[(i64)gk * ldb + gn] : (T)0;
+            const int gk = k0 + b_k + 4 * i, gn = n0 + b_n;
+            rb[2 * i] = (gk < k_end && gn < N) ? B[(i64)gk * ldb + gn] : (T)0;
+            rb[2 * i + 1] = (gk < k_end && gn + 1 < N) ? B[(i64)gk * ldb + gn + 1] : (T)0;
         }
     };
     auto store_tile = [&](int buf) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) As[buf][a_k + i][a_row] = ra[i];
+        for (int i = 0; i < 8; ++i) As[buf][a_k + i][a_row] = ra[i];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) Bs[buf][b_k][b_n + i] = rb[i];
+        for (int i = 0; i < 4; ++i) {
+            Bs[buf][b_k + 4 * i][b_n] = rb[2 * i];
+            Bs[buf][b_k + 4 * i][b_n + 1] = rb[2 * i + 1];
+        }
+    };
+    auto load_frag = [&](int buf, int kk, T (&a)[8], T (&b)[8]) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            // rows ty*2 + 32*c + {0,1}, cols tx*2 + 32*c + {0,1}
+            a[2 * c] = As[buf][kk][ty * 2 + 32 * c];
+            a[2 * c + 1] = As[buf][kk][ty * 2 + 32 * c + 1];
+            b[2 * c] = Bs[buf][kk][tx * 2 + 32 * c];
+            b[2 * c + 1] = Bs[buf][kk][tx * 2 + 32 * c + 1];
+        }
     };
 
     const int nk = (k_end - k_begin + BK - 1) / BK;
     load_tile(k_begin);
     store_tile(0);
     __syncthreads();
+    T fa[2][8], fb[2][8];
     for (int kt = 0; kt < nk; ++kt) {
         const int buf = kt & 1;
         if (kt + 1 < nk) load_tile(k_begin + (kt + 1) * BK);
+        load_frag(buf, 0, fa[0], fb[0]);
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
-            T a[8], b[8];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                // rows ty*2 + 32*c + {0,1}, cols tx*2 + 32*c + {0,1}
-                a[2 * c] = As[buf][kk][ty * 2 + 32 * c];
-                a[2 * c + 1] = As[buf][kk][ty * 2 + 32 * c + 1];
-                b[2 * c] = Bs[buf][kk][tx * 2 + 32 * c];
-                b[2 * c + 1] = Bs[buf][kk][tx * 2 + 32 * c + 1];
-            }
+            const int cur = kk & 1;
+            if (kk + 1 < BK) load_frag(buf, kk + 1, fa[cur ^ 1], fb[cur ^ 1]);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 8; ++j) acc[i][j] = fma(fa[cur][i], fb[cur][j], acc[i][j]);
         }
         if (kt + 1 < nk) {
             store_tile(buf ^ 1);
@@ -108,12 +140,432 @@ dense_apply_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restri
     for (int i = 0; i < 8; ++i) {
         const int gr = m0 + ty * 2 + 32 * (i >> 1) + (i & 1);
         if (gr >= M) continue;
+        const i64 orow = (i64)(g.out_rows ? g.out_rows[gr] : gr) * ldo;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int gn = n0 + tx * 2 + 32 * (j >> 1) + (j & 1);
-            if (gn < N) out[(i64)gr * ldo + gn] = acc[i][j];
+        for (int j = 0; j < 8; j += 2) {
+            const int gn = n0 + tx * 2 + 32 * (j >> 1);
+            if (gn + 1 < N) {
+                out[orow + gn] = acc[i][j];
+                out[orow + gn + 1] = acc[i][j + 1];
+            } else if (gn < N) {
+                out[orow + gn] = acc[i][j];
+            }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64: same CTA tile, but the inner product runs on the FP64 tensor path (mma.sync m8n8k4, SASS DMMA --
+// the only tensor-core path FP64 has on sm_100a; tcgen05 has no f64 kind).  8 warps as 4 (M) x 2 (N),
+// warp tile 32 x 64 = 4 x 8 DMMA tiles, 64 accumulators per thread.  Versus the FMA-pipe version this
+// needs 8x fewer issue slots and ~5x fewer shared-memory loads per FMA.  Shared rows are padded to 136
+// doubles so that the 4 k-rows x 8 columns a warp reads per fragment land in 2 wavefronts (the minimum).
+// ---------------------------------------------------------------------------------------------
+constexpr int DPAD = 8, DLD = BM + DPAD;
+
+// D(16x8) += A(16xKI) . B(KIx8), FP64.  Fragment ownership (lane = 4*g + t): a[2i] = A[g][t+4i],
+// a[2i+1] = A[g+8][t+4i]; b[i] = B[t+4i][g]; c0,c1 = C[g][2t..2t+1], c2,c3 = C[g+8][2t..2t+1].
+template <int KI> struct Dmma;
+template <> struct Dmma<4> {
+    __device__ __forceinline__ static void run(double (&c)[4], const double* a, const double* b) {
+        asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                     : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3]) : "d"(a[0]), "d"(a[1]), "d"(b[0]));
+    }
+};
+template <> struct Dmma<8> {
+    __device__ __forceinline__ static void run(double (&c)[4], const double* a, const double* b) {
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+                     : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
+    }
+};
+template <> struct Dmma<16> {
+    __device__ __forceinline__ static void run(double (&c)[4], const double* a, const double* b) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+                     "{%12,%13,%14,%15}, {%0,%1,%2,%3};"
+                     : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+                     : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]),
+                       "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]));
+    }
+};
+
+template <int KI>
+__global__ void __launch_bounds__(GT, 1)
+dense_apply_dmma_kernel(GemmGroup<double> g0, GemmGroup<double> g1, int N, int K, int tiles_n, int tiles_m0,
+                        int k_chunk, i64 split_stride) {
+    typedef double T;
+    int tile_m = blockIdx.x / tiles_n;
+    const int tile_n = blockIdx.x % tiles_n;
+    const bool second = tile_m >= tiles_m0;
+    const GemmGroup<T>& g = second ? g1 : g0;
+    if (second) tile_m -= tiles_m0;
+    int M = g.M;
+    if (g.m_dev) M = min(M, *g.m_dev);
+    const int m0 = tile_m * BM, n0 = tile_n * BN;
+    if (m0 >= M) return;
+    const T* __restrict__ A = g.A;
+    const T* __restrict__ B = g.B;
+    const T* __restrict__ sub = g.sub;
+    const i64 lda = g.lda, ldb = g.ldb, ldo = g.ldo;
+    const int k_begin = blockIdx.y * k_chunk;
+    const int k_end = min(K, k_begin + k_chunk);
+    T* __restrict__ out = g.out + (i64)blockIdx.y * split_stride;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* As = reinterpret_cast<T*>(smem_raw);                       // [2][BK][DLD]  (k-major: A transposed)
+    T* Bs = As + 2 * BK * DLD;                                    // [2][BK][DLD]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp & 3) * 32, wn = (warp >> 2) * 64;        // warp tile origin inside the CTA tile
+    const int gq = lane >> 2, tq = lane & 3;                      // MMA fragment coordinates
+
+    const int a_row = tid & 127, a_k = (tid >> 7) * 8;
+    const int b_k = tid >> 6, b_n = (tid & 63) * 2;
+    i64 a_src = -1;
+    {
+        const int gr = m0 + a_row;
+        if (gr < M) a_src = (i64)(g.in_rows ? g.in_rows[gr] : gr) * lda;
+    }
+
+    T acc[2][8][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.0;
+
+    T ra[8], rb[8];
+    auto load_tile = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int gk = k0 + a_k + i;
+            T x = 0.0;
+            if (a_src >= 0 && gk < k_end) {
+                x = A[a_src + gk];
+                if (sub) x -= sub[gk];
+            }
+            ra[i] = x;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int gk = k0 + b_k + 4 * i, gn = n0 + b_n;
+            rb[2 * i] = (gk < k_end && gn < N) ? B[(i64)gk * ldb + gn] : 0.0;
+            rb[2 * i + 1] = (gk < k_end && gn + 1 < N) ? B[(i64)gk * ldb + gn + 1] : 0.0;
+        }
+    };
+    auto store_tile = [&](int buf) {
+        T* as = As + buf * BK * DLD;
+        T* bs = Bs + buf * BK * DLD;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) as[(a_k + i) * DLD + a_row] = ra[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            bs[(b_k + 4 * i) * DLD + b_n] = rb[2 * i];
+            bs[(b_k + 4 * i) * DLD + b_n + 1] = rb[2 * i + 1];
+        }
+    };
+
+    const int nk = (k_end - k_begin + BK - 1) / BK;
+    load_tile(k_begin);
+    store_tile(0);
+    __syncthreads();
+    constexpr int NI = KI / 4;                                    // k-quads per instruction
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) load_tile(k_begin + (kt + 1) * BK);
+        const T* as = As + buf * BK * DLD + wm + gq;
+        const T* bs = Bs + buf * BK * DLD + wn + gq;
+#pragma unroll
+        for (int k0 = 0; k0 < BK; k0 += KI) {
+            T fa[2][2 * NI], fb[8][NI];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int q = 0; q < NI; ++q) {
+                    fa[i][2 * q] = as[(k0 + tq + 4 * q) * DLD + i * 16];
+                    fa[i][2 * q + 1] = as[(k0 + tq + 4 * q) * DLD + i * 16 + 8];
+                }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int q = 0; q < NI; ++q) fb[j][q] = bs[(k0 + tq + 4 * q) * DLD + j * 8];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) Dmma<KI>::run(acc[i][j], fa[i], fb[j]);
+        }
+        if (kt + 1 < nk) {
+            store_tile(buf ^ 1);
+            __syncthreads();
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int gr = m0 + wm + i * 16 + h * 8 + gq;
+            if (gr >= M) continue;
+            const i64 orow = (i64)(g.out_rows ? g.out_rows[gr] : gr) * ldo;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int gn = n0 + wn + j * 8 + tq * 2;
+                if (gn + 1 < N) {
+                    out[orow + gn] = acc[i][j][2 * h];
+                    out[orow + gn + 1] = acc[i][j][2 * h + 1];
+                } else if (gn < N) {
+                    out[orow + gn] = acc[i][j][2 * h];
+                }
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 main path: the same DMMA warp tiling fed by a 3-stage cp.async (LDGSTS) pipeline -- no register
+// staging, one barrier per k-tile -- and a CTA tile width chosen per problem (BN = 128 / 112 / 96) so
+// that the tile count fills whole waves of 148 SMs (d = 1000: 32 x 9 tiles of 128 x 112 = 288 of 296
+// slots).  A stays row-major [m][k] in shared memory (rows padded to 20 doubles: the 8 rows x 4 k a warp
+// reads per fragment are 32 distinct 8-byte words = 2 wavefronts); B is [k][n] with rows padded by 8.
+// Requires 16-byte aligned rows (even K, N, leading dimensions); otherwise the register-staged kernel runs.
+// ---------------------------------------------------------------------------------------------
+constexpr int STAGES = 3, ALD = BK + 4;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N_)); }
+
+template <int BN_>
+__global__ void __launch_bounds__(GT, 1)
+dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, int N, int K, int tiles_n, int tiles_m0) {
+    typedef double T;
+    constexpr int NJ = BN_ / 16;               // 8-wide MMA tiles per warp along N (warp tile 32 x BN_/2)
+    constexpr int BLD = BN_ + 8;
+    constexpr int A_STAGE = BM * ALD, B_STAGE = BK * BLD;
+    int tile_m = blockIdx.x / tiles_n;
+    const int tile_n = blockIdx.x % tiles_n;
+    const bool second = tile_m >= tiles_m0;
+    const GemmGroup<T>& g = second ? g1 : g0;
+    if (second) tile_m -= tiles_m0;
+    int M = g.M;
+    if (g.m_dev) M = min(M, *g.m_dev);
+    const int m0 = tile_m * BM, n0 = tile_n * BN_;
+    if (m0 >= M) return;
+    const T* __restrict__ A = g.A;
+    const T* __restrict__ B = g.B;
+    const T* __restrict__ sub = g.sub;
+    const i64 lda = g.lda, ldb = g.ldb, ldo = g.ldo;
+    T* __restrict__ out = g.out;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* As = reinterpret_cast<T*>(smem_raw);                       // [STAGES][BM][ALD]
+    T* Bs = As + STAGES * A_STAGE;                                // [STAGES][BK][BLD]
+    T* Ss = Bs + STAGES * B_STAGE;                                // [STAGES][BK]   (sub vector slices)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp & 3) * 32, wn = (warp >> 2) * (BN_ / 2);
+    const int gq = lane >> 2, tq = lane & 3;
+
+    // copy assignment: A tile = 128 rows x 8 chunks (16 B = 2 k); 8 consecutive threads take one row
+    i64 a_src[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = (tid + GT * i) >> 3, gr = m0 + row;
+        a_src[i] = gr < M ? (i64)(g.in_rows ? g.in_rows[gr] : gr) * lda : -1;
+    }
+    constexpr int B_CHUNKS = BK * (BN_ / 2);
+    constexpr int B_ITERS = (B_CHUNKS + GT - 1) / GT;
+
+    auto issue = [&](int kt, int stage) {
+        const int k0 = kt * BK;
+        T* as = As + stage * A_STAGE;
+        T* bs = Bs + stage * B_STAGE;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = tid + GT * i, row = c >> 3, kc = (c & 7) * 2;
+            const int gk = k0 + kc;
+            const bool ok = a_src[i] >= 0 && gk < K;
+            cp_async16(as + row * ALD + kc, ok ? (const void*)(A + a_src[i] + gk) : (const void*)A, ok ? 16 : 0);
+        }
+#pragma unroll
+        for (int i = 0; i < B_ITERS; ++i) {
+            const int c = tid + GT * i;
+            if (c < B_CHUNKS) {
+                const int kr = c / (BN_ / 2), nc = (c % (BN_ / 2)) * 2;
+                const int gk = k0 + kr, gn = n0 + nc;
+                const bool ok = gk < K && gn < N;
+                cp_async16(bs + kr * BLD + nc, ok ? (const void*)(B + (i64)gk * ldb + gn) : (const void*)B, ok ? 16 : 0);
+            }
+        }
+        if (sub && tid < BK / 2) {
+            const int gk = k0 + tid * 2;
+            cp_async16(Ss + stage * BK + tid * 2, gk < K ? (const void*)(sub + gk) : (const void*)sub, gk < K ? 16 : 0);
+        }
+    };
+
+    T acc[2][NJ][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.0;
+
+    const int nk = (K + BK - 1) / BK;
+#pragma unroll
+    for (int st = 0; st < STAGES - 1; ++st) {
+        if (st < nk) issue(st, st);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();                                          // tile kt landed; buffer (kt-1)%STAGES is free
+        {
+            const int nx = kt + STAGES - 1;
+            if (nx < nk) issue(nx, nx % STAGES);
+            cp_async_commit();
+        }
+        const int stage = kt % STAGES;
+        const T* as = As + stage * A_STAGE + (wm + gq) * ALD;
+        const T* bs = Bs + stage * B_STAGE + wn + gq;
+        const T* ss = Ss + stage * BK;
+#pragma unroll
+        for (int k0 = 0; k0 < BK; k0 += 8) {
+            T fa[2][4], fb[NJ][2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int kk = k0 + tq + 4 * q;
+                const T sv = sub ? ss[kk] : 0.0;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    fa[i][2 * q] = as[(i * 16) * ALD + kk] - sv;
+                    fa[i][2 * q + 1] = as[(i * 16 + 8) * ALD + kk] - sv;
+                }
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) fb[j][q] = bs[kk * BLD + j * 8];
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) Dmma<8>::run(acc[i][j], fa[i], fb[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int gr = m0 + wm + i * 16 + h * 8 + gq;
+            if (gr >= M) continue;
+            const i64 orow = (i64)(g.out_rows ? g.out_rows[gr] : gr) * ldo;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int gn = n0 + wn + j * 8 + tq * 2;
+                if (gn < N) *reinterpret_cast<double2*>(out + orow + gn) = make_double2(acc[i][j][2 * h], acc[i][j][2 * h + 1]);
+            }
+        }
+}
+
+template <int BN_>
+static void launch_async(cudaStream_t st, const GemmGroup<double>& g0, const GemmGroup<double>& g1, int N, int K) {
+    constexpr int smem = (STAGES * (BM * ALD + BK * (BN_ + 8)) + STAGES * BK) * (int)sizeof(double);
+    int tiles_m0 = (g0.M + BM - 1) / BM, tiles_m1 = (g1.M + BM - 1) / BM, tiles_n = (N + BN_ - 1) / BN_;
+    cudaFuncSetAttribute(dense_apply_dmma_async_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    dense_apply_dmma_async_kernel<BN_><<<(tiles_m0 + tiles_m1) * tiles_n, GT, smem, st>>>(g0, g1, N, K, tiles_n, tiles_m0);
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+static bool group_async_ok(const GemmGroup<double>& g) {
+    if (g.M <= 0) return true;
+    return aligned16(g.A) && aligned16(g.B) && aligned16(g.out) && (g.lda % 2 == 0) && (g.ldb % 2 == 0) &&
+           (g.ldo % 2 == 0) && (!g.sub || aligned16(g.sub));
+}
+
+// pick the tile width whose tile count wastes the least of the last wave of 148 SMs
+static int pick_bn(int M0, int N) {
+    const int cand[3] = {128, 112, 96};
+    int best = 128;
+    double best_cost = 1e300;
+    for (int c = 0; c < 3; ++c) {
+        const int bn = cand[c];
+        const long tiles = (long)((M0 + BM - 1) / BM) * ((N + bn - 1) / bn);
+        const long waves = (tiles + 147) / 148;
+        const double cost = (double)waves * bn;        // time ~ waves x tile work
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+
+template <typename T>
+static void launch_tile_kernel(dim3 grid, cudaStream_t st, const GemmGroup<T>& g0, const GemmGroup<T>& g1, int N,
+                               int K, int tiles_n, int tiles_m0, int k_chunk, i64 split_stride);
+
+template <>
+void launch_tile_kernel<double>(dim3 grid, cudaStream_t st, const GemmGroup<double>& g0, const GemmGroup<double>& g1,
+                                int N, int K, int tiles_n, int tiles_m0, int k_chunk, i64 split_stride) {
+    static int use_async = -1;
+    if (use_async < 0) {
+        const char* e = getenv("B2H_GEMM_ASYNC");
+        use_async = e ? atoi(e) : 1;
+    }
+    if (use_async && grid.y == 1 && N % 2 == 0 && K % 2 == 0 && group_async_ok(g0) && group_async_ok(g1)) {
+        static int force_bn = -1;
+        if (force_bn < 0) { const char* e = getenv("B2H_GEMM_BN"); force_bn = e ? atoi(e) : 0; }
+        // the second group's row count lives on the device: budget an eighth of the first group's rows for it
+        const int bn = force_bn ? force_bn : pick_bn(g0.M + (g1.M > 0 ? (g0.M / 8 < g1.M ? g0.M / 8 : g1.M) : 0), N);
+        if (bn == 112) launch_async<112>(st, g0, g1, N, K);
+        else if (bn == 96) launch_async<96>(st, g0, g1, N, K);
+        else launch_async<128>(st, g0, g1, N, K);
+        return;
+    }
+    constexpr int smem = 2 * 2 * BK * DLD * (int)sizeof(double);
+    static int ki = 0;
+    if (ki == 0) {
+        const char* e = getenv("B2H_DMMA_K");
+        ki = e ? atoi(e) : 8;
+    }
+#define B2H_DMMA_LAUNCH(KI)                                                                                    \
+    cudaFuncSetAttribute(dense_apply_dmma_kernel<KI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);        \
+    dense_apply_dmma_kernel<KI><<<grid, GT, smem, st>>>(g0, g1, N, K, tiles_n, tiles_m0, k_chunk, split_stride);
+    if (ki == 4) { B2H_DMMA_LAUNCH(4) }
+    else if (ki == 16) { B2H_DMMA_LAUNCH(16) }
+    else { B2H_DMMA_LAUNCH(8) }
+#undef B2H_DMMA_LAUNCH
+}
+
+template <>
+void launch_tile_kernel<float>(dim3 grid, cudaStream_t st, const GemmGroup<float>& g0, const GemmGroup<float>& g1,
+                               int N, int K, int tiles_n, int tiles_m0, int k_chunk, i64 split_stride) {
+    constexpr int smem = 2 * BK * (BM + BN) * (int)sizeof(float);
+    cudaFuncSetAttribute(dense_apply_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    dense_apply_kernel<float><<<grid, GT, smem, st>>>(g0, g1, N, K, tiles_n, tiles_m0, k_chunk, split_stride);
+}
+
+// Two problems in one launch (second may be empty: g1.M == 0).
+template <typename T>
+void launch_gemm_grouped(cudaStream_t st, const GemmGroup<T>& g0, const GemmGroup<T>& g1, int N, int K, int nsplit,
+                         i64 split_stride) {
+    int tiles_m0 = (g0.M + BM - 1) / BM, tiles_m1 = (g1.M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    if (tiles_m0 + tiles_m1 <= 0 || N <= 0) return;
+    if (nsplit < 1) nsplit = 1;
+    int k_chunk = (K + nsplit - 1) / nsplit;
+    k_chunk = ((k_chunk + BK - 1) / BK) * BK;
+    dim3 grid((tiles_m0 + tiles_m1) * tiles_n, nsplit);
+    launch_tile_kernel<T>(grid, st, g0, g1, N, K, tiles_n, tiles_m0, k_chunk, split_stride);
+}
+
+// General strided form with split-K: slice s of nsplit writes out + s*split_stride (a partial plane).
+template <typename T>
+void launch_gemm(cudaStream_t st, const T* A, i64 lda, const T* B, i64 ldb, T* out, i64 ldo, int M, int N, int K,
+                 const int* m_dev, const T* sub, int nsplit, i64 split_stride) {
+    if (M <= 0 || N <= 0) return;
+    GemmGroup<T> g0{A, lda, B, ldb, out, ldo, M, m_dev, sub, nullptr, nullptr};
+    GemmGroup<T> g1{nullptr, 0, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr};
+    launch_gemm_grouped<T>(st, g0, g1, N, K, nsplit, split_stride);
 }
 
 // out = (A - sub) . B ; sub (optional, [K]) is subtracted from every row of A on load (q - mu).
@@ -123,28 +575,12 @@ void launch_dense_apply(cudaStream_t st, const T* A, const T* B, T* out, int M, 
     launch_gemm<T>(st, A, (i64)K, B, (i64)N, out, (i64)N, M, N, K, m_dev, sub, 1, 0);
 }
 
-// General strided form with split-K: slice s of nsplit writes out + s*split_stride (a partial plane).
-template <typename T>
-void launch_gemm(cudaStream_t st, const T* A, i64 lda, const T* B, i64 ldb, T* out, i64 ldo, int M, int N, int K,
-                 const int* m_dev, const T* sub, int nsplit, i64 split_stride) {
-    if (M <= 0 || N <= 0) return;
-    int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
-    if (nsplit < 1) nsplit = 1;
-    int k_chunk = (K + nsplit - 1) / nsplit;
-    k_chunk = ((k_chunk + BK - 1) / BK) * BK;
-    dim3 grid(tiles_m * tiles_n, nsplit);
-    dense_apply_kernel<T><<<grid, GT, 0, st>>>(A, B, out, M, N, K, lda, ldb, ldo, m_dev, sub, tiles_n, k_chunk,
-                                               split_stride);
-}
-
-template void launch_gemm<float>(cudaStream_t, const float*, i64, const float*, i64, float*, i64, int, int, int,
-                                 const int*, const float*, int, i64);
-template void launch_gemm<double>(cudaStream_t, const double*, i64, const double*, i64, double*, i64, int, int, int,
-                                  const int*, const double*, int, i64);
-
-template void launch_dense_apply<float>(cudaStream_t, const float*, const float*, float*, int, int, int, const int*,
-                                        const float*);
-template void launch_dense_apply<double>(cudaStream_t, const double*, const double*, double*, int, int, int,
-                                         const int*, const double*);
+#define B2H_INST(T)                                                                                                  \
+    template void launch_gemm_grouped<T>(cudaStream_t, const GemmGroup<T>&, const GemmGroup<T>&, int, int, int, i64); \
+    template void launch_gemm<T>(cudaStream_t, const T*, i64, const T*, i64, T*, i64, int, int, int, const int*,     \
+                                 const T*, int, i64);                                                                \
+    template void launch_dense_apply<T>(cudaStream_t, const T*, const T*, T*, int, int, int, const int*, const T*);
+B2H_INST(float)
+B2H_INST(double)
 
 }  // namespace b2h

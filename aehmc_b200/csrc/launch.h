@@ -30,6 +30,21 @@ int cuda_fail(cudaError_t e, const char* what);
 
 // gemm.cu
 template <typename T>
+struct GemmGroup {
+    const T* A; i64 lda;
+    const T* B; i64 ldb;
+    T* out; i64 ldo;
+    int M;                 // rows (upper bound when m_dev is given)
+    const int* m_dev;      // optional device-side row count
+    const T* sub;          // optional [K] vector subtracted from every A row on load
+    const int* in_rows;    // optional gather list: A row of logical row r is in_rows[r]
+    const int* out_rows;   // optional scatter list for the output rows
+};
+template <typename T>
+void launch_gemm_grouped(cudaStream_t st, const GemmGroup<T>& g0, const GemmGroup<T>& g1, int N, int K, int nsplit,
+                         i64 split_stride);
+
+template <typename T>
 void launch_dense_apply(cudaStream_t st, const T* A, const T* B, T* out, int M, int N, int K, const int* m_dev,
                         const T* sub);
 

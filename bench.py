@@ -282,6 +282,15 @@ def run_gpu_arm(args):
         best = min(best, p0.elapsed_time(p1))
     fp64_peak = 2.0 * n ** 3 / (best * 1e-3) / 1e12
     del x, y
+    # cuBLAS on the kernel's own shape, for context
+    mm = metric.imm
+    torch.matmul(a, mm)
+    best = 1e9
+    for _ in range(5):
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(); torch.matmul(a, mm); p1.record(); torch.cuda.synchronize(dev)
+        best = min(best, p0.elapsed_time(p1))
+    cublas_same_shape = flops / (best * 1e-3) / 1e12
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -317,7 +326,8 @@ def run_gpu_arm(args):
                          "flops_per_launch": flops, "avg_launch_ms": gemm_ms,
                          "peak_source": f"measured in this run: torch.matmul fp64 {n}^3 (cuBLAS), best of 5 "
                                         "(MEASURED_PEAKS.json has no FP64 figure; SURVEY.md 8d names FP64 FMA as the bound)",
-                         "share_of_step": ticks * 3.0 * gemm_ms / step_ms},
+                         "share_of_step": ticks * 3.0 * gemm_ms / step_ms,
+                         "cublas_same_shape_tflops": cublas_same_shape},
             "roofline_elementwise": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                                      "frac": hbm_achieved / hbm_peak, "traffic": None,
                                      "how": "derived: 11*d*8 algorithmic bytes per chain-tick over (step time - 3 dense applies per tick)"},

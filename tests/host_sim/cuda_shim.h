@@ -24,5 +24,7 @@ static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline void sincospi(double x, double* s, double* c) { *s = sin(M_PI * x); *c = cos(M_PI * x); }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
 static inline void __syncthreads() {}
 static inline void __syncwarp(unsigned = 0) {}
