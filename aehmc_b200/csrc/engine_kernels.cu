@@ -177,6 +177,8 @@ template <int G>
 struct Geo {
     static constexpr int kThreads = G > 32 ? G : 128;
     static constexpr int kChainsPerBlock = G > 32 ? 1 : 128 / G;
+    // the per-tick (split) kernels are latency-bound streams: cap registers at 64 for 50% occupancy
+    static constexpr int kMinBlocksSplit = G > 32 ? 4 : 8;
     __device__ static int chain() {
         return G > 32 ? (int)blockIdx.x : (int)(blockIdx.x * kChainsPerBlock + threadIdx.x / G);
     }
@@ -217,7 +219,7 @@ fused_run_kernel(EngineView<T> v, ModelDev m, i64 max_ticks) {
 // split-mode kernels
 // ---------------------------------------------------------------------------
 template <typename T, int G, bool DENSE, bool HMC>
-__global__ void __launch_bounds__(Geo<G>::kThreads) split_pre_kernel(EngineView<T> v) {
+__global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksSplit) split_pre_kernel(EngineView<T> v) {
     __shared__ double red_s[128];
     const int c = Geo<G>::chain();
     if (c >= v.C) return;
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(Geo<G>::kThreads) split_kick_kernel(EngineView
 }
 
 template <typename T, int G, bool DENSE, bool HMC>
-__global__ void __launch_bounds__(Geo<G>::kThreads) split_post_kernel(EngineView<T> v, int* not_done) {
+__global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksSplit) split_post_kernel(EngineView<T> v, int* not_done) {
     __shared__ double red_s[128];
     const int c = Geo<G>::chain();
     if (c >= v.C) return;

@@ -477,6 +477,35 @@ __global__ void chain_moments_kernel(const T* draws, i64 T_, i64 C, int d, doubl
     var[idx] = T_ > 1 ? m2 / (double)(T_ - 1) : 0.0;
 }
 
+// per-chain mean and biased autocovariance (divided by T, as Stan / arviz do) up to max_lag, by direct summation:
+// one thread per (chain, dim, lag) -- diagnostics, not the hot path
+template <typename T>
+__global__ void chain_autocov_kernel(const T* draws, i64 T_, i64 C, int d, int max_lag, double* mean, double* acov) {
+    const i64 cd = (i64)blockIdx.x;                  // chain * d + dim
+    if (cd >= C * d) return;
+    __shared__ double m_s;
+    double part = 0.0;
+    for (i64 t = threadIdx.x; t < T_; t += blockDim.x) part += (double)draws[t * C * d + cd];
+    __shared__ double red[32];
+    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+        m_s = s / (double)T_;
+        mean[cd] = m_s;
+    }
+    __syncthreads();
+    const double m = m_s;
+    for (int lag = threadIdx.x; lag <= max_lag; lag += blockDim.x) {
+        double acc = 0.0;
+        for (i64 t = 0; t + lag < T_; ++t)
+            acc += ((double)draws[t * C * d + cd] - m) * ((double)draws[(t + lag) * C * d + cd] - m);
+        acov[cd * (max_lag + 1) + lag] = acc / (double)T_;
+    }
+}
+
 }  // namespace b2h
 
 // ===========================================================================
@@ -685,6 +714,18 @@ int b2h_chain_moments(b2h_ctx* ctx, int dtype, const void* draws, int64_t T_, in
     B2H_TYPED(dtype,
               (chain_moments_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float*)draws, T_, C, (int)d, mean, var)),
               (chain_moments_kernel<double><<<grid, 256, 0, ctx->stream>>>((const double*)draws, T_, C, (int)d, mean, var)));
+    B2H_LAUNCH_CHECK();
+    return 0;
+}
+
+int b2h_chain_autocov(b2h_ctx* ctx, int dtype, const void* draws, int64_t T_, int64_t C, int64_t d, int32_t max_lag,
+                      double* mean, double* acov) {
+    B2H_CHECK_CTX();
+    if (!draws || !mean || !acov || T_ < 2 || max_lag < 0 || max_lag >= T_) { set_error("bad argument"); return B2H_ERR_ARG; }
+    int grid = (int)(C * d);
+    B2H_TYPED(dtype,
+              (chain_autocov_kernel<float><<<grid, 128, 0, ctx->stream>>>((const float*)draws, T_, C, (int)d, max_lag, mean, acov)),
+              (chain_autocov_kernel<double><<<grid, 128, 0, ctx->stream>>>((const double*)draws, T_, C, (int)d, max_lag, mean, acov)));
     B2H_LAUNCH_CHECK();
     return 0;
 }

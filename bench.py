@@ -303,8 +303,28 @@ def run_gpu_arm(args):
     b_nuts = 11.0 * d * 8.0       # algorithmic bytes of one NUTS inner step incl. U-turn bookkeeping
     hbm_achieved = b_nuts * Cn * ticks / (elementwise_ms * 1e-3) / 1e9
 
+    # ---- second metric of BASELINE.json: NUTS ESS/s (min over the monitored dims, all chains, all ranks) ----
+    ess_per_s = None
+    if not args.no_ess:
+        n_tr = args.ess_transitions
+        st0 = ab.nuts.new_state(q_host.to(dev), model)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        info, ex = _engine.run("nuts", model, metric, ab.RandomStream(seed=7, chain_offset=chain_offset), st0, EPS,
+                               n_transitions=n_tr, store_draws=n_tr, workspace_key=("ess", rank))
+        s1.record()
+        barrier()
+        t_ess = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_ess, op=dist.ReduceOp.MAX)
+        burn = n_tr // 4
+        ess = ab.diagnostics.ess(ex["draws"][burn:], dims=list(range(min(8, d))))
+        ess_per_s = float(np.nanmin(ess)) / (t_ess.item() * 1e-3)
+        del ex
+
     if rank == 0:
-        kernels_per_tick = 13
+        kernels_per_tick = 11
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
@@ -320,6 +340,11 @@ def run_gpu_arm(args):
                     "what": "pinned host positions -> device, new_state, TICKS ticks, position + acceptance back to pinned host"},
             "gpu_launches": int(args.steps * (ticks * kernels_per_tick + 3)),
             "clocks": clocks,
+            "nuts_ess_per_sec": ess_per_s,
+            "ess_how": None if ess_per_s is None else
+            f"{args.ess_transitions} NUTS transitions per chain from the initial positions, first quarter discarded, "
+            "multi-chain ESS (Stan/arviz estimator, no rank normalisation) of the first 8 coordinates, minimum, "
+            "divided by the wall time of all transitions incl. the discarded ones",
             "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak, "traffic": None,
                          "kernel": "dense_apply_kernel<double> (out[C x d] = in[C x d] . M[d x d]); 3 launches per tick",
@@ -352,6 +377,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ess", action="store_true", help="skip the ESS/s leg")
+    ap.add_argument("--ess-transitions", type=int, default=40)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

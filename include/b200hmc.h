@@ -218,10 +218,14 @@ int b2h_philox_fill(b2h_ctx*, uint64_t seed, uint64_t chain_offset, uint64_t tra
 /* Dense apply out[C x d] = in[C x d] . M[d x d] (M symmetric): the mass-matrix / precision mat-vec of all chains */
 int b2h_dense_apply(b2h_ctx*, int dtype, const void* in, const void* M, void* out, int64_t C, int64_t d);
 
-/* Convergence statistics of draws [T][C][d] (dtype): per-dimension split-R-hat sufficient statistics.
- * out [d][4] float64: (sum of chain means, sum of squared chain means, sum of chain variances, n_chains). */
+/* Per-chain mean and unbiased variance (float64 [C x d] each) of draws [T][C][d]: the per-GPU part of R-hat. */
 int b2h_chain_moments(b2h_ctx*, int dtype, const void* draws, int64_t T, int64_t C, int64_t d, double* chain_mean,
                       double* chain_var);
+
+/* Per-chain mean[C x d] and biased autocovariance acov[C x d x (max_lag+1)] (divided by T, the convention of the
+ * arviz.ess the reference's tests use, tests/test_hmc.py:158-167) of draws [T][C][d]; building blocks of ESS. */
+int b2h_chain_autocov(b2h_ctx*, int dtype, const void* draws, int64_t T, int64_t C, int64_t d, int32_t max_lag,
+                      double* mean, double* acov);
 
 #ifdef __cplusplus
 }

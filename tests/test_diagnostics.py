@@ -1,0 +1,95 @@
+"""ESS / R-hat arithmetic (host part) and the N>1 reduction path on the gloo backend."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+
+def _load():
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import aehmc_b200.diagnostics as d
+    return d
+
+
+def _ar1(rng, phi, T, C):
+    x = np.zeros((T, C, 1))
+    e = rng.standard_normal((T, C, 1)) * np.sqrt(1 - phi ** 2)
+    x[0] = rng.standard_normal((C, 1))
+    for t in range(1, T):
+        x[t] = phi * x[t - 1] + e[t]
+    return x
+
+
+@pytest.mark.parametrize("phi", [0.0, 0.5, 0.9, -0.5])
+def test_ess_matches_ar1_theory(phi):
+    diag = _load()
+    rng = np.random.default_rng(0)
+    T, C = 2000, 16
+    x = _ar1(rng, phi, T, C)
+    stats = diag.sufficient_statistics_numpy(x, 300)
+    ess = diag.ess_from_statistics(stats)[0]
+    theory = T * C * (1 - phi) / (1 + phi)
+    assert ess == pytest.approx(theory, rel=0.15)
+    assert diag.rhat_from_statistics(stats)[0] == pytest.approx(1.0, abs=0.01)
+
+
+def test_rhat_detects_disagreeing_chains():
+    diag = _load()
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((500, 8, 2))
+    x[:, :4, 1] += 3.0
+    r = diag.rhat_from_statistics(diag.sufficient_statistics_numpy(x, 1))
+    assert r[0] < 1.02 and r[1] > 1.5
+
+
+def test_bulk_ess_single_chain_iid():
+    diag = _load()
+    x = np.random.default_rng(2).standard_normal(4000)
+    assert diag.ess_bulk_single_chain(x) == pytest.approx(4000, rel=0.15)
+
+
+def test_shard_chains_covers_everything():
+    diag = _load()
+    for n, w in ((10, 3), (4096, 8), (7, 8), (1 << 20, 8)):
+        blocks = [diag.shard_chains(n, r, w) for r in range(w)]
+        assert blocks[0][0] == 0 and sum(c for _, c in blocks) == n
+        for (o1, c1), (o2, _) in zip(blocks, blocks[1:]):
+            assert o1 + c1 == o2
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import aehmc_b200.diagnostics as diag
+    rng = np.random.default_rng(5)
+    x = _ar1(rng, 0.6, 800, 12)                    # the same global draws on every rank
+    off, cnt = diag.shard_chains(12)
+    local = diag.sufficient_statistics_numpy(x[:, off:off + cnt], 150)
+    merged = diag.all_reduce_statistics(local)
+    q.put((rank, float(diag.ess_from_statistics(merged)[0]), float(diag.rhat_from_statistics(merged)[0]), off, cnt))
+    dist.destroy_process_group()
+
+
+def test_sharded_statistics_reduce_to_the_global_answer_gloo():
+    """world_size = 2 on gloo: each rank holds a shard of the chains; the all-reduced sufficient statistics
+    give the same ESS / R-hat as the single-process computation over all chains."""
+    import torch.multiprocessing as mp
+    diag = _load()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    x = _ar1(np.random.default_rng(5), 0.6, 800, 12)
+    full = diag.sufficient_statistics_numpy(x, 150)
+    ess, rhat = diag.ess_from_statistics(full)[0], diag.rhat_from_statistics(full)[0]
+    assert [r[3:] for r in res] == [(0, 6), (6, 6)]
+    for r in res:
+        assert r[1] == pytest.approx(ess, rel=1e-12) and r[2] == pytest.approx(rhat, rel=1e-12)

@@ -317,3 +317,21 @@ def test_philox_fill_statistics_and_determinism(ab):
     from scipy import stats
     assert stats.kstest(_np(z).ravel()[:20000], "norm").pvalue > 1e-3
     assert stats.kstest(_np(uu).ravel()[:20000], "uniform").pvalue > 1e-3
+
+
+def test_device_autocov_and_ess_match_host(ab):
+    rng = np.random.default_rng(8)
+    T, Cn, d = 300, 20, 3
+    x = np.zeros((T, Cn, d))
+    for t in range(1, T):
+        x[t] = 0.7 * x[t - 1] + rng.standard_normal((Cn, d))
+    for dt, tol in ((torch.float64, 1e-10), (torch.float32, 1e-4)):
+        dev_stats = ab.diagnostics.sufficient_statistics(torch.tensor(x, dtype=dt, device="cuda"), 60)
+        host_stats = ab.diagnostics.sufficient_statistics_numpy(x, 60)
+        for k in ("sum_mean", "sum_mean_sq", "sum_acov"):
+            np.testing.assert_allclose(dev_stats[k], host_stats[k], rtol=tol, atol=tol)
+    e_dev = ab.diagnostics.ess(torch.tensor(x, device="cuda"), 60)
+    e_host = ab.diagnostics.ess_from_statistics(host_stats)
+    np.testing.assert_allclose(e_dev, e_host, rtol=1e-8)
+    r = ab.diagnostics.rhat(torch.tensor(x, device="cuda"))
+    assert np.all(np.abs(r - 1) < 0.1)
