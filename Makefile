@@ -10,7 +10,7 @@ LIB       := $(LIBDIR)/libb200hmc.so
 # The engine and the elementwise primitives are compiled WITHOUT fused multiply-add
 # contraction so that the scalar-metric leapfrog rounds exactly like the reference's
 # compiled graph (a*b then +c); the contraction kernels keep FMA.
-OBJS := $(OBJDIR)/capi.o $(OBJDIR)/engine_kernels.o $(OBJDIR)/primitives.o $(OBJDIR)/gemm.o $(OBJDIR)/logreg.o
+OBJS := $(OBJDIR)/capi.o $(OBJDIR)/engine_kernels.o $(OBJDIR)/primitives.o $(OBJDIR)/gemm.o $(OBJDIR)/logreg.o $(OBJDIR)/tc_gemm.o
 HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/b200hmc.h
 
 all: $(LIB)

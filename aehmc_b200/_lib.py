@@ -19,7 +19,8 @@ RNG_PHILOX, RNG_INJECTED = 0, 1
 
 class Model(C.Structure):
     _fields_ = [("kind", C.c_int32), ("dim", C.c_int32), ("n_data", C.c_int64), ("a", C.c_void_p),
-                ("b", C.c_void_p), ("c", C.c_void_p), ("s0", C.c_double), ("s1", C.c_double)]
+                ("b", C.c_void_p), ("c", C.c_void_p), ("s0", C.c_double), ("s1", C.c_double),
+                ("x_bf16", C.c_void_p), ("xt_bf16", C.c_void_p)]
 
 
 class Metric(C.Structure):
@@ -61,7 +62,7 @@ EXPORTS = [
     "b2h_is_turning", "b2h_leapfrog", "b2h_termination_update", "b2h_is_iterative_turning",
     "b2h_find_storage_indices", "b2h_hmc_run", "b2h_nuts_run", "b2h_nuts_workspace_bytes",
     "b2h_hmc_workspace_bytes", "b2h_dual_averaging_update", "b2h_welford_update", "b2h_mass_matrix_final",
-    "b2h_philox_fill", "b2h_dense_apply", "b2h_chain_moments", "b2h_chain_autocov",
+    "b2h_philox_fill", "b2h_dense_apply", "b2h_chain_moments", "b2h_chain_autocov", "b2h_tc_gemm_bf16",
 ]
 
 _lib = None

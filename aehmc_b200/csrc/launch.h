@@ -63,6 +63,10 @@ int logistic_potential_and_grad(b2h_ctx* ctx, const b2h_model* m, const T* q, T*
                                 i64 ws_bytes, int path);
 i64 logistic_workspace_bytes(const b2h_model* m, int dtype, i64 C);
 
+// tc_gemm.cu (tcgen05 / TMA); returns the number of split-K planes written, or < 0
+int tc_gemm(cudaStream_t st, const void* A, long long lda, const void* B, long long ldb, float* out, int M, int N, int K,
+            int pieces, int piece_rows, int ldo, int nsplit, long long split_stride);
+
 // engine_kernels.cu
 int nuts_run_impl(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
                   const b2h_cfg* cfg, const b2h_adapt* adapt, void* q, void* p, void* U, void* g, double* step_size,

@@ -8,6 +8,8 @@
 // This file is the FP32/FP64 FMA-pipe version built on the tiled GEMM of gemm.cu,
 // chunked over the data dimension so that S never exceeds a bounded scratch,
 // with a deterministic split-K reduction for the tall-skinny second product.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "launch.h"
 
@@ -42,7 +44,7 @@ static LogregPlan plan_logreg(const b2h_model* m, int dtype, i64 C) {
     return p;
 }
 
-i64 logistic_workspace_bytes(const b2h_model* m, int dtype, i64 C) { return (i64)plan_logreg(m, dtype, C).total; }
+
 
 // R = sigmoid(S) - y in place; U_acc[c] += sum_n softplus(s) - y s   (one CTA per chain: deterministic)
 template <typename T>
@@ -95,10 +97,141 @@ logistic_prior_kernel(const T* q, T* g, T* U, const double* U_acc, T inv_prior_v
     if (lane == 0) U[c] = (T)U_acc[c] + (T)0.5 * inv_prior_var * (T)s;
 }
 
+// =============================================================================================================
+// tensor-core path (tcgen05 / TMA, tc_gemm.cu): bf16 operands, fp32 accumulation in TMEM
+// =============================================================================================================
+struct LogregTcPlan {
+    int n_chunk, nsplit;
+    size_t off_bp, off_S, off_R, off_part, off_U, total;
+};
+
+static LogregTcPlan plan_logreg_tc(const b2h_model* m, i64 C) {
+    LogregTcPlan p;
+    i64 nc = kChunkBytes / (i64)(C * 4);
+    nc = std::max<i64>(128, (nc / 128) * 128);
+    if (nc > m->n_data) nc = ((m->n_data + 127) / 128) * 128;
+    p.n_chunk = (int)nc;
+    i64 tiles = ((C + 127) / 128) * ((m->dim + 127) / 128);
+    i64 ns = (296 + tiles - 1) / tiles;
+    ns = std::max<i64>(1, std::min<i64>(ns, (p.n_chunk + 511) / 512));
+    p.nsplit = (int)ns;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 1023) & ~(size_t)1023; return o; };
+    p.off_bp = take((size_t)3 * C * m->dim * 2);
+    p.off_S = take((size_t)C * p.n_chunk * 4);
+    p.off_R = take((size_t)3 * C * p.n_chunk * 2);
+    p.off_part = take((size_t)p.nsplit * C * m->dim * 4);
+    p.off_U = take((size_t)C * sizeof(double));
+    p.total = off + 1024;
+    return p;
+}
+
+__device__ __forceinline__ void split3(double x, __nv_bfloat16& a, __nv_bfloat16& b, __nv_bfloat16& c) {
+    a = __double2bfloat16(x);
+    double r = x - (double)__bfloat162float(a);
+    b = __double2bfloat16(r);
+    r -= (double)__bfloat162float(b);
+    c = __double2bfloat16(r);
+}
+
+// beta[C x d] (T) -> three stacked bf16 pieces [3*C x d] whose sum carries 24 significant bits
+template <typename T>
+__global__ void beta_split_kernel(const T* q, __nv_bfloat16* bp, i64 n) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    __nv_bfloat16 a, b, c;
+    split3((double)q[i], a, b, c);
+    bp[i] = a; bp[n + i] = b; bp[2 * n + i] = c;
+}
+
+// S (fp32) -> residual pieces R_p = split3(sigmoid(s) - y) as bf16 [3*C x ld]; U_acc[c] += sum softplus(s) - y s
+template <typename T>
+__global__ void __launch_bounds__(256)
+logistic_resid_tc_kernel(const float* S, const T* y, __nv_bfloat16* R, double* U_acc, int n_valid, i64 ld, i64 C, int first) {
+    const i64 c = blockIdx.x;
+    const float* row = S + c * ld;
+    __nv_bfloat16* r0 = R + c * ld;
+    __nv_bfloat16* r1 = R + (C + c) * ld;
+    __nv_bfloat16* r2 = R + (2 * C + c) * ld;
+    double acc = 0.0;
+    for (int n = threadIdx.x; n < n_valid; n += 256) {
+        float s = row[n], yy = (float)y[n];
+        float sp = fmaxf(s, 0.f) + log1pf(expf(-fabsf(s)));
+        acc += (double)(sp - yy * s);
+        float r = 1.f / (1.f + expf(-s)) - yy;
+        __nv_bfloat16 a, b, cc;
+        split3((double)r, a, b, cc);
+        r0[n] = a; r1[n] = b; r2[n] = cc;
+    }
+    __shared__ double red[8];
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        U_acc[c] = first ? s : U_acc[c] + s;
+    }
+}
+
+// g (T) = (first ? 0 : g) + sum_s partial[s] (fp32 planes)
+template <typename T>
+__global__ void split_reduce_f32_kernel(const float* part, T* g, i64 n, int nsplit, int first) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = first ? 0.0 : (double)g[i];
+    for (int k = 0; k < nsplit; ++k) s += (double)part[(i64)k * n + i];
+    g[i] = (T)s;
+}
+
+template <typename T>
+static int logistic_tc(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U, T* g, i64 C, void* ws, i64 ws_bytes) {
+    if (!m->x_bf16 || !m->xt_bf16) { set_error("logistic tensor-core path needs x_bf16 and xt_bf16"); return B2H_ERR_ARG; }
+    if (m->dim % 8 || m->n_data % 8) { set_error("logistic tensor-core path needs dim and n_data multiples of 8"); return B2H_ERR_ARG; }
+    LogregTcPlan p = plan_logreg_tc(m, C);
+    if (!ws || (size_t)ws_bytes < p.total) {
+        set_error("logistic workspace too small: need " + std::to_string(p.total) + " bytes");
+        return B2H_ERR_WORKSPACE;
+    }
+    cudaStream_t st = ctx->stream;
+    const int d = m->dim;
+    const i64 N = m->n_data;
+    char* base = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+    __nv_bfloat16* bp = (__nv_bfloat16*)(base + p.off_bp);
+    float* S = (float*)(base + p.off_S);
+    __nv_bfloat16* R = (__nv_bfloat16*)(base + p.off_R);
+    float* part = (float*)(base + p.off_part);
+    double* U_acc = (double*)(base + p.off_U);
+    const __nv_bfloat16* Xb = (const __nv_bfloat16*)m->x_bf16;      // [N x d]
+    const __nv_bfloat16* Xtb = (const __nv_bfloat16*)m->xt_bf16;    // [d x N]
+    const T* y = (const T*)m->b;
+    const i64 ng = C * d;
+    beta_split_kernel<T><<<(int)((ng + 255) / 256), 256, 0, st>>>(q, bp, ng);
+    for (i64 n0 = 0, it = 0; n0 < N; n0 += p.n_chunk, ++it) {
+        const int nv = (int)std::min<i64>(p.n_chunk, N - n0);
+        // S[C x nv] = sum_p Beta_p[C x d] . X[n0.., d]^T
+        int rc = tc_gemm(st, bp, d, Xb + n0 * d, d, S, (int)C, nv, d, 3, (int)C, p.n_chunk, 1, 0);
+        if (rc < 0) return rc;
+        logistic_resid_tc_kernel<T><<<(int)C, 256, 0, st>>>(S, y + n0, R, U_acc, nv, (i64)p.n_chunk, C, it == 0);
+        // G[C x d] += sum_p R_p[C x nv] . Xt[d, n0..]^T   (split-K over the data rows)
+        rc = tc_gemm(st, R, p.n_chunk, Xtb + n0, N, part, (int)C, d, nv, 3, (int)C, d, p.nsplit, ng);
+        if (rc < 0) return rc;
+        split_reduce_f32_kernel<T><<<(int)((ng + 255) / 256), 256, 0, st>>>(part, g, ng, rc, it == 0);
+    }
+    logistic_prior_kernel<T><<<(int)((C + 3) / 4), 128, 0, st>>>(q, g, U, U_acc, (T)m->s0, C, d);
+    B2H_LAUNCH_CHECK();
+    return 0;
+}
+
+i64 logistic_workspace_bytes(const b2h_model* m, int dtype, i64 C) {
+    if ((int)m->s1 == 2) return (i64)plan_logreg_tc(m, C).total + 1024;
+    return (i64)plan_logreg(m, dtype, C).total;
+}
+
 template <typename T>
 int logistic_potential_and_grad(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U, T* g, i64 C, void* ws,
                                 i64 ws_bytes, int path) {
-    (void)path;
+    if (path == 2 || (path == 0 && (int)m->s1 == 2)) return logistic_tc<T>(ctx, m, q, U, g, C, ws, ws_bytes);
     if (!m->a || !m->b || !m->c) { set_error("logistic model needs X (a), y (b) and X^T (c)"); return B2H_ERR_ARG; }
     LogregPlan p = plan_logreg(m, Num<T>::dtype, C);
     if (!ws || (size_t)ws_bytes < p.total) {

@@ -66,7 +66,8 @@ class IIDGaussian(Model):
         self.dim = int(self.mu.numel())
 
     def struct(self):
-        return _lib.Model(self.kind, self.dim, 0, self.mu.data_ptr(), self.inv_var.data_ptr(), None, self.const, 0.0)
+        return _lib.Model(self.kind, self.dim, 0, self.mu.data_ptr(), self.inv_var.data_ptr(), None, self.const, 0.0,
+                          None, None)
 
 
 class CorrelatedGaussian(Model):
@@ -80,7 +81,8 @@ class CorrelatedGaussian(Model):
         self.dim = int(self.mu.numel())
 
     def struct(self):
-        return _lib.Model(self.kind, self.dim, 0, self.mu.data_ptr(), self.precision.data_ptr(), None, 0.0, 0.0)
+        return _lib.Model(self.kind, self.dim, 0, self.mu.data_ptr(), self.precision.data_ptr(), None, 0.0, 0.0,
+                          None, None)
 
 
 class NealFunnel(Model):
@@ -91,7 +93,7 @@ class NealFunnel(Model):
         self.dim = int(dim)
 
     def struct(self):
-        return _lib.Model(self.kind, self.dim, 0, None, None, None, 0.0, 0.0)
+        return _lib.Model(self.kind, self.dim, 0, None, None, None, 0.0, 0.0, None, None)
 
 
 class EightSchools(Model):
@@ -105,20 +107,36 @@ class EightSchools(Model):
         self.dim = 2 + int(self.y.numel())
 
     def struct(self):
-        return _lib.Model(self.kind, self.dim, 0, self.y.data_ptr(), self.inv_var.data_ptr(), None, 0.0, 0.0)
+        return _lib.Model(self.kind, self.dim, 0, self.y.data_ptr(), self.inv_var.data_ptr(), None, 0.0, 0.0,
+                          None, None)
 
 
 class LogisticRegression(Model):
+    """``tensor_core=True`` evaluates the batched gradient X.B / X^T.R on tcgen05 tensor cores (bf16 operands,
+    beta and the residuals split into three bf16 pieces, fp32 accumulation in TMEM): fp32-class accuracy.  It
+    needs X to be bf16-representable.  The default is the FP64/FP32 FMA-DMMA path (exactness reference)."""
     kind = _lib.MODEL_LOGISTIC
 
-    def __init__(self, X, y, prior_scale=1.0, dtype=torch.float64, device=None):
+    def __init__(self, X, y, prior_scale=1.0, dtype=torch.float64, device=None, tensor_core=False):
         super().__init__(dtype, device)
         self.X = backend.as_device(X, self.dtype, self.device)
         self.Xt = self.X.t().contiguous()
         self.y = backend.as_device(y, self.dtype, self.device)
         self.inv_prior_var = 1.0 / float(prior_scale) ** 2
         self.n_data, self.dim = int(self.X.shape[0]), int(self.X.shape[1])
+        self.tensor_core = bool(tensor_core)
+        self.X_bf16 = self.Xt_bf16 = None
+        if self.tensor_core:
+            xb = self.X.to(torch.bfloat16)
+            if not torch.equal(xb.to(self.dtype), self.X):
+                raise ValueError("tensor_core=True needs a bf16-representable design matrix X")
+            if self.n_data % 8 or self.dim % 8:
+                raise ValueError("tensor_core=True needs n_data and dim to be multiples of 8 (16-byte TMA pitches)")
+            self.X_bf16 = xb.contiguous()
+            self.Xt_bf16 = xb.t().contiguous()
 
     def struct(self):
+        p = lambda t: None if t is None else t.data_ptr()
         return _lib.Model(self.kind, self.dim, self.n_data, self.X.data_ptr(), self.y.data_ptr(),
-                          self.Xt.data_ptr(), self.inv_prior_var, 0.0)
+                          self.Xt.data_ptr(), self.inv_prior_var, 2.0 if self.tensor_core else 0.0,
+                          p(self.X_bf16), p(self.Xt_bf16))

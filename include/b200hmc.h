@@ -44,7 +44,9 @@ enum {
     B2H_MODEL_CORR_GAUSSIAN = 1, /* a=mu[d], b=precision[d x d] (symmetric, row-major)             */
     B2H_MODEL_FUNNEL = 2,        /* Neal's funnel, q=(v,x_1..x_{d-1})                              */
     B2H_MODEL_EIGHT_SCHOOLS = 3, /* non-centred; a=y[d-2], b=inv_var[d-2]                          */
-    B2H_MODEL_LOGISTIC = 4       /* a=X[n_data x d] row-major, b=y[n_data], s0 = 1/prior_scale^2   */
+    B2H_MODEL_LOGISTIC = 4       /* a=X[n_data x d] row-major, b=y[n_data], c=X^T[d x n_data], s0 = 1/prior_scale^2;
+                                    s1 = gradient path: 0 FMA/DMMA exactness reference, 2 tcgen05 tensor core
+                                    (needs x_bf16 = X and xt_bf16 = X^T as bf16, X bf16-representable)         */
 };
 
 typedef struct {
@@ -53,9 +55,11 @@ typedef struct {
     int64_t n_data;
     const void* a; /* device, dtype of the call */
     const void* b; /* device, dtype of the call */
-    const void* c; /* device, model specific (logistic: X^T [d x n_data], optional) */
+    const void* c; /* device, model specific (logistic: X^T [d x n_data]) */
     double s0;
     double s1;
+    const void* x_bf16;  /* device, logistic tensor-core path: X   [n_data x d] as bf16 */
+    const void* xt_bf16; /* device, logistic tensor-core path: X^T [d x n_data] as bf16 */
 } b2h_model;
 
 /* ---- gaussian metric (reference metrics.py:10-106) ---- */
@@ -221,6 +225,12 @@ int b2h_dense_apply(b2h_ctx*, int dtype, const void* in, const void* M, void* ou
 /* Per-chain mean and unbiased variance (float64 [C x d] each) of draws [T][C][d]: the per-GPU part of R-hat. */
 int b2h_chain_moments(b2h_ctx*, int dtype, const void* draws, int64_t T, int64_t C, int64_t d, double* chain_mean,
                       double* chain_var);
+
+/* tcgen05/TMA contraction used by the logistic tensor-core path, exposed for testing:
+ * out[z][M x N] (fp32, row pitch ldo, plane stride split_stride) = sum_{p<pieces} A[p*piece_rows + m][k] * B[n][k]
+ * with A [pieces*piece_rows x K] and B [N x K] bf16, K contiguous, 16-byte aligned pitches; split-K over z. */
+int b2h_tc_gemm_bf16(b2h_ctx*, const void* A, int64_t lda, const void* B, int64_t ldb, float* out, int64_t M, int64_t N,
+                     int64_t K, int32_t pieces, int64_t piece_rows, int64_t ldo, int32_t nsplit, int64_t split_stride);
 
 /* Per-chain mean[C x d] and biased autocovariance acov[C x d x (max_lag+1)] (divided by T, the convention of the
  * arviz.ess the reference's tests use, tests/test_hmc.py:158-167) of draws [T][C][d]; building blocks of ESS. */
