@@ -67,6 +67,11 @@ i64 logistic_workspace_bytes(const b2h_model* m, int dtype, i64 C);
 int tc_gemm(cudaStream_t st, const void* A, long long lda, const void* B, long long ldb, float* out, int M, int N, int K,
             int pieces, int piece_rows, int ldo, int nsplit, long long split_stride);
 
+int tc_gemm_logistic(cudaStream_t st, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                     int pieces, int piece_rows, const float* y, void* R, long long r_piece_stride, double* upart);
+int tc_gemm_blocked_a(cudaStream_t st, const void* R, long long r_piece_stride, const void* B, long long ldb, float* out,
+                      int M, int N, int K, int pieces, int ldo, int nsplit, long long split_stride);
+
 // engine_kernels.cu
 int nuts_run_impl(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
                   const b2h_cfg* cfg, const b2h_adapt* adapt, void* q, void* p, void* U, void* g, double* step_size,

@@ -102,12 +102,12 @@ logistic_prior_kernel(const T* q, T* g, T* U, const double* U_acc, T inv_prior_v
 // =============================================================================================================
 struct LogregTcPlan {
     int n_chunk, nsplit;
-    size_t off_bp, off_S, off_R, off_part, off_U, total;
+    size_t off_bp, off_y, off_R, off_part, off_U, off_upart, total;
 };
 
 static LogregTcPlan plan_logreg_tc(const b2h_model* m, i64 C) {
     LogregTcPlan p;
-    i64 nc = kChunkBytes / (i64)(C * 4);
+    i64 nc = (2 * kChunkBytes) / (i64)(C * 6);              // residual pieces: 3 x bf16 per (chain, data row)
     nc = std::max<i64>(128, (nc / 128) * 128);
     if (nc > m->n_data) nc = ((m->n_data + 127) / 128) * 128;
     p.n_chunk = (int)nc;
@@ -118,10 +118,11 @@ static LogregTcPlan plan_logreg_tc(const b2h_model* m, i64 C) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 1023) & ~(size_t)1023; return o; };
     p.off_bp = take((size_t)3 * C * m->dim * 2);
-    p.off_S = take((size_t)C * p.n_chunk * 4);
-    p.off_R = take((size_t)3 * C * p.n_chunk * 2);
+    p.off_y = take((size_t)m->n_data * 4);
+    p.off_R = take((size_t)3 * ((C + 127) / 128) * 128 * p.n_chunk * 2);     // tile-blocked, rows padded to 128
     p.off_part = take((size_t)p.nsplit * C * m->dim * 4);
     p.off_U = take((size_t)C * sizeof(double));
+    p.off_upart = take((size_t)4 * (p.n_chunk / 128) * C * sizeof(double));
     p.total = off + 1024;
     return p;
 }
@@ -144,34 +145,26 @@ __global__ void beta_split_kernel(const T* q, __nv_bfloat16* bp, i64 n) {
     bp[i] = a; bp[n + i] = b; bp[2 * n + i] = c;
 }
 
-// S (fp32) -> residual pieces R_p = split3(sigmoid(s) - y) as bf16 [3*C x ld]; U_acc[c] += sum softplus(s) - y s
 template <typename T>
-__global__ void __launch_bounds__(256)
-logistic_resid_tc_kernel(const float* S, const T* y, __nv_bfloat16* R, double* U_acc, int n_valid, i64 ld, i64 C, int first) {
-    const i64 c = blockIdx.x;
-    const float* row = S + c * ld;
-    __nv_bfloat16* r0 = R + c * ld;
-    __nv_bfloat16* r1 = R + (C + c) * ld;
-    __nv_bfloat16* r2 = R + (2 * C + c) * ld;
-    double acc = 0.0;
-    for (int n = threadIdx.x; n < n_valid; n += 256) {
-        float s = row[n], yy = (float)y[n];
-        float sp = fmaxf(s, 0.f) + log1pf(expf(-fabsf(s)));
-        acc += (double)(sp - yy * s);
-        float r = 1.f / (1.f + expf(-s)) - yy;
-        __nv_bfloat16 a, b, cc;
-        split3((double)r, a, b, cc);
-        r0[n] = a; r1[n] = b; r2[n] = cc;
+__global__ void to_float_kernel(const T* x, float* y, i64 n) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = (float)x[i];
+}
+
+// U_acc[c] (+)= sum over the tile partials written by the contraction's epilogue (fixed order: deterministic)
+__global__ void upart_reduce_kernel(const double* upart, double* U_acc, i64 C, int n_part, int first) {
+    i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s0 = first ? 0.0 : U_acc[c], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int t = 0;
+    for (; t + 3 < n_part; t += 4) {              // four independent loads in flight per thread
+        s0 += upart[(i64)t * C + c];
+        s1 += upart[(i64)(t + 1) * C + c];
+        s2 += upart[(i64)(t + 2) * C + c];
+        s3 += upart[(i64)(t + 3) * C + c];
     }
-    __shared__ double red[8];
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int i = 0; i < 8; ++i) s += red[i];
-        U_acc[c] = first ? s : U_acc[c] + s;
-    }
+    for (; t < n_part; ++t) s0 += upart[(i64)t * C + c];
+    U_acc[c] = (s0 + s1) + (s2 + s3);
 }
 
 // g (T) = (first ? 0 : g) + sum_s partial[s] (fp32 planes)
@@ -198,7 +191,8 @@ static int logistic_tc(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U, T* g,
     const i64 N = m->n_data;
     char* base = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
     __nv_bfloat16* bp = (__nv_bfloat16*)(base + p.off_bp);
-    float* S = (float*)(base + p.off_S);
+    float* yf = (float*)(base + p.off_y);
+    double* upart = (double*)(base + p.off_upart);
     __nv_bfloat16* R = (__nv_bfloat16*)(base + p.off_R);
     float* part = (float*)(base + p.off_part);
     double* U_acc = (double*)(base + p.off_U);
@@ -207,14 +201,16 @@ static int logistic_tc(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U, T* g,
     const T* y = (const T*)m->b;
     const i64 ng = C * d;
     beta_split_kernel<T><<<(int)((ng + 255) / 256), 256, 0, st>>>(q, bp, ng);
+    to_float_kernel<T><<<(int)((N + 255) / 256), 256, 0, st>>>(y, yf, N);
     for (i64 n0 = 0, it = 0; n0 < N; n0 += p.n_chunk, ++it) {
         const int nv = (int)std::min<i64>(p.n_chunk, N - n0);
-        // S[C x nv] = sum_p Beta_p[C x d] . X[n0.., d]^T
-        int rc = tc_gemm(st, bp, d, Xb + n0 * d, d, S, (int)C, nv, d, 3, (int)C, p.n_chunk, 1, 0);
+        // S[C x nv] = sum_p Beta_p[C x d] . X[n0.., d]^T stays in TMEM; the epilogue emits the residual pieces
+        const i64 r_piece = (i64)((C + 127) / 128) * 128 * p.n_chunk;
+        int rc = tc_gemm_logistic(st, bp, d, Xb + n0 * d, d, (int)C, nv, d, 3, (int)C, yf + n0, R, r_piece, upart);
         if (rc < 0) return rc;
-        logistic_resid_tc_kernel<T><<<(int)C, 256, 0, st>>>(S, y + n0, R, U_acc, nv, (i64)p.n_chunk, C, it == 0);
+        upart_reduce_kernel<<<(int)((C + 63) / 64), 64, 0, st>>>(upart, U_acc, C, 4 * ((nv + 127) / 128), it == 0);
         // G[C x d] += sum_p R_p[C x nv] . Xt[d, n0..]^T   (split-K over the data rows)
-        rc = tc_gemm(st, R, p.n_chunk, Xtb + n0, N, part, (int)C, d, nv, 3, (int)C, d, p.nsplit, ng);
+        rc = tc_gemm_blocked_a(st, R, r_piece, Xtb + n0, N, part, (int)C, d, nv, 3, d, p.nsplit, ng);
         if (rc < 0) return rc;
         split_reduce_f32_kernel<T><<<(int)((ng + 255) / 256), 256, 0, st>>>(part, g, ng, rc, it == 0);
     }

@@ -9,14 +9,20 @@
 // has fp32-class accuracy, which is what the float32 parity bar (1e-4) needs; the FMA path stays the exactness
 // reference.
 //
-// Kernel anatomy (one 128 x 128 output tile per CTA, optional split-K over blockIdx.z):
+// Kernel anatomy (persistent: one CTA per SM loops over 128 x 128 output tiles, optional split-K planes; the
+// accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the loads and MMAs of tile i+1):
 //   warp 0 : TMA producer  -- cp.async.bulk.tensor 2D loads of 128 x 64 bf16 boxes (SWIZZLE_128B) into a 6-stage ring
 //   warp 1 : MMA issuer    -- one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 N128 K16) from smem
 //                             descriptors, tcgen05.commit releases the smem stage / signals the epilogue
 //   warp 2 : TMEM allocator (128 columns)
-//   warps 4-7 : epilogue   -- tcgen05.ld 32x32b.x32 (TMEM lane quadrant = warp % 4), fp32 -> global
+//   warps 4-19: epilogue   -- tcgen05.ld 32x32b.x32 (TMEM lane quadrant = warp % 4, four warps per quadrant take
+//                             32 of the 128 columns each: the epilogue is latency-bound, so it needs the warps); either fp32 -> global, or (logistic mode) the residual
+//                             r = sigmoid(s) - y split into three bf16 pieces plus the potential's partial sums,
+//                             so S is never written to memory
 #include <cuda.h>
 #include <cuda_bf16.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 #include "launch.h"
@@ -29,9 +35,24 @@ constexpr int BM = 128, BN = 128, BK = 64;          // BK bf16 = one 128-byte sw
 constexpr int STAGES = 6;
 constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int THREADS = 256;
-constexpr int TMEM_COLS = 128;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int THREADS = 640;                        // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-19: epilogue
+constexpr int EPI_WARPS = 16, EPI_PARTS = EPI_WARPS / 4;   // 4 warps per TMEM lane quadrant, 32 columns each
+constexpr int TMEM_COLS = 256;                      // two 128-column fp32 accumulators
+constexpr size_t smem_bytes(int stages) { return (size_t)stages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
+
+struct Epilogue {                 // mode 0: fp32 store.  mode 1: logistic residual pieces
+    int mode;
+    const float* y;               // [N] responses of this chunk
+    __nv_bfloat16* r;             // residual pieces, TILE-BLOCKED: [3][column tile][row tile][128][128] bf16, so that
+                                  // every 128 x 128 tile is one contiguous 32 KB block (DRAM-friendly writes)
+    long long piece_stride;       // elements between pieces
+    int tiles_m;                  // row tiles per column tile
+    double* upart;                // [2 * gridDim.x][M] partial sums of softplus(s) - y s
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 lo, __nv_bfloat16 hi) {
+    return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -86,31 +107,255 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 // instruction descriptor: D = F32, A = B = BF16, both K-major, N = 128, M = 128
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
+// Epilogue of one 128 x 128 accumulator for one warp: TMEM lane quadrant q, 32-column part `part`.
+__device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int buf, int q, int part, int lane, int m0, int n0,
+                                              int z, int M, int N, float* out, int ldo, long long split_stride,
+                                              const Epilogue& ep, uint64_t* tmem_empty_bar) {
+    const int row = m0 + q * 32 + lane;
+    const int c0 = part * 32;
+    uint32_t r[32];
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    // the accumulator is in registers: hand the TMEM buffer back to the MMA warp before doing the math
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tmem_empty_bar)) : "memory");
+    if (row >= M) return;
+    if (ep.mode == 0) {
+        float* orow = out + (long long)z * split_stride + (long long)row * ldo + n0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const int col = n0 + c0 + j;
+            if (col + 3 < N) {
+                *reinterpret_cast<float4*>(orow + c0 + j) =
+                    make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                __uint_as_float(r[j + 3]));
+            } else {
+                for (int e = 0; e < 4; ++e)
+                    if (col + e < N) orow[c0 + j + e] = __uint_as_float(r[j + e]);
+            }
+        }
+        return;
+    }
+    // logistic residual: r = sigmoid(s) - y as three bf16 pieces (exact split), potential partial sums
+    float uacc = 0.f;
+    uint32_t p0[16], p1[16], p2[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const int col = n0 + c0 + j;
+        // y is warp-uniform per column: one 128-bit load serves four columns
+        float4 y4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col + 3 < N) y4 = __ldg(reinterpret_cast<const float4*>(ep.y + col));
+        else {
+            if (col < N) y4.x = __ldg(ep.y + col);
+            if (col + 1 < N) y4.y = __ldg(ep.y + col + 1);
+            if (col + 2 < N) y4.z = __ldg(ep.y + col + 2);
+        }
+        const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+        float rr[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            // hardware exp2/log2/rcp approximations (abs error ~1e-7 here)
+            const float sv = __uint_as_float(r[j + e]);
+            const float ex = __expf(-fabsf(sv));
+            const float inv = __fdividef(1.f, 1.f + ex);
+            const bool ok = col + e < N;
+            uacc += ok ? fmaxf(sv, 0.f) + __logf(1.f + ex) - yv[e] * sv : 0.f;
+            rr[e] = ok ? (sv >= 0.f ? inv : ex * inv) - yv[e] : 0.f;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            // exact three-way split, two columns per packed conversion
+            const __nv_bfloat162 a = __floats2bfloat162_rn(rr[2 * h], rr[2 * h + 1]);
+            const float2 af = __bfloat1622float2(a);
+            const float r1x = rr[2 * h] - af.x, r1y = rr[2 * h + 1] - af.y;
+            const __nv_bfloat162 b = __floats2bfloat162_rn(r1x, r1y);
+            const float2 bf = __bfloat1622float2(b);
+            const __nv_bfloat162 c = __floats2bfloat162_rn(r1x - bf.x, r1y - bf.y);
+            p0[(j >> 1) + h] = *reinterpret_cast<const uint32_t*>(&a);
+            p1[(j >> 1) + h] = *reinterpret_cast<const uint32_t*>(&b);
+            p2[(j >> 1) + h] = *reinterpret_cast<const uint32_t*>(&c);
+        }
+    }
+    __nv_bfloat16* dst = ep.r + (((long long)(n0 / BN) * ep.tiles_m + m0 / BM) * BM + (row - m0)) * BN + c0;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        *reinterpret_cast<uint4*>(dst + 8 * v) = make_uint4(p0[4 * v], p0[4 * v + 1], p0[4 * v + 2], p0[4 * v + 3]);
+        *reinterpret_cast<uint4*>(dst + ep.piece_stride + 8 * v) =
+            make_uint4(p1[4 * v], p1[4 * v + 1], p1[4 * v + 2], p1[4 * v + 3]);
+        *reinterpret_cast<uint4*>(dst + 2 * ep.piece_stride + 8 * v) =
+            make_uint4(p2[4 * v], p2[4 * v + 1], p2[4 * v + 2], p2[4 * v + 3]);
+    }
+    ep.upart[((long long)(n0 / BN) * EPI_PARTS + part) * M + row] = (double)uacc;
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, float* out,
-               int M, int N, int K, int pieces, int piece_rows, int ldo, int k_blocks_per_split, long long split_stride) {
+               int M, int N, int K, int pieces, int piece_rows, int ldo, int k_blocks_per_split, long long split_stride,
+               int stages, int tiles_m, int tiles_n, int nsplit, int a_blocked, Epilogue ep) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = (uint64_t*)(tiles + (size_t)STAGES * STAGE_BYTES);
+    uint64_t* full_bar = (uint64_t*)(tiles + (size_t)stages * STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full = empty_bar + STAGES;
-    uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+    uint64_t* tmem_full = empty_bar + STAGES;              // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                  // [2]
+    uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int kb_total = (K + BK - 1) / BK;
-    const int kb_begin = blockIdx.z * k_blocks_per_split;
-    const int kb_end = min(kb_total, kb_begin + k_blocks_per_split);
-    const int n_kb = max(kb_end - kb_begin, 0);
-    const int iters = n_kb * pieces;                       // (piece, k-block) pairs accumulated into one tile
+    const int total_tiles = tiles_m * tiles_n * nsplit;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile -> (split plane z, m tile, n tile), n fastest
+    auto decode = [&](int tile, int& z, int& m0, int& n0, int& kb_begin, int& n_kb) {
+        z = tile / (tiles_m * tiles_n);
+        const int rem = tile - z * tiles_m * tiles_n;
+        m0 = (rem / tiles_n) * BM;
+        n0 = (rem % tiles_n) * BN;
+        kb_begin = z * k_blocks_per_split;
+        n_kb = max(min(kb_total, kb_begin + k_blocks_per_split) - kb_begin, 0);
+    };
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int g = 0;                                     // ring position, continues across tiles
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int z, m0, n0, kb_begin, n_kb;
+                decode(tile, z, m0, n0, kb_begin, n_kb);
+                const int iters = n_kb * pieces;
+                for (int it = 0; it < iters; ++it, ++g) {
+                    const int s = g % stages, round = g / stages;
+                    mbar_wait(&empty_bar[s], (round & 1) ^ 1);
+                    const int p = it / n_kb, kb = kb_begin + it % n_kb;
+                    uint8_t* a_dst = tiles + (size_t)s * STAGE_BYTES;
+                    uint8_t* b_dst = a_dst + A_BYTES;
+                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                    if (a_blocked)   // A is tile-blocked [piece][k tile of 128][row tile][128][128]: box = half a tile row
+                        tma_load_2d(a_dst, &map_a, &full_bar[s], (kb & 1) * BK,
+                                    p * piece_rows + ((kb >> 1) * tiles_m) * BM + m0);
+                    else
+                        tma_load_2d(a_dst, &map_a, &full_bar[s], kb * BK, p * piece_rows + m0);
+                    tma_load_2d(b_dst, &map_b, &full_bar[s], kb * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int g = 0, local = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+                int z, m0, n0, kb_begin, n_kb;
+                decode(tile, z, m0, n0, kb_begin, n_kb);
+                const int iters = n_kb * pieces;
+                const int buf = local & 1;
+                mbar_wait(&tmem_empty[buf], ((local >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+                for (int it = 0; it < iters; ++it, ++g) {
+                    const int s = g % stages, round = g / stages;
+                    mbar_wait(&full_bar[s], round & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t ad = make_desc(a_addr + k * UMMA_K * 2);
+                        const uint64_t bd = make_desc(b_addr + k * UMMA_K * 2);
+                        umma_bf16(tmem_d, ad, bd, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+                    }
+                    tcgen05_commit(&empty_bar[s]);         // frees the smem stage when these MMAs retire
+                }
+                tcgen05_commit(&tmem_full[buf]);           // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> global =====
+        const int q = warp & 3;                            // TMEM lane quadrant this warp may access
+        const int half = (warp - 4) >> 2;                  // which 32 of the 128 accumulator columns
+        int local = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+            int z, m0, n0, kb_begin, n_kb;
+            decode(tile, z, m0, n0, kb_begin, n_kb);
+            const int buf = local & 1;
+            mbar_wait(&tmem_full[buf], (local >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            epilogue_tile(tmem_base, buf, q, half, lane, m0, n0, z, M, N, out, ldo, split_stride, ep, &tmem_empty[buf]);
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// A-resident variant for short reductions (the S product: K = dim <= 128, so pieces * K/64 <= 6 blocks).
+// All (piece, k-block) tiles of A for the CTA's current 128 rows stay in shared memory; the CTA walks a contiguous
+// range of column tiles and streams each B tile (full K) exactly once through a 3-slot ring.  Operand traffic per
+// output tile drops from pieces * 2 * K/64 * 16 KB to K/64 * 16 KB.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int RES_A_BLOCKS = 6, RES_B_SLOTS = 3, RES_KB = 2;
+constexpr size_t RES_SMEM = (size_t)RES_A_BLOCKS * A_BYTES + (size_t)RES_B_SLOTS * RES_KB * B_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(THREADS, 1)
+tc_gemm_resident_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, float* out,
+                        int M, int N, int K, int pieces, int piece_rows, int ldo, int tiles_m, int tiles_n,
+                        int tiles_per_cta, Epilogue ep) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* a_res = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* b_ring = a_res + (size_t)RES_A_BLOCKS * A_BYTES;
+    uint64_t* bars = (uint64_t*)(b_ring + (size_t)RES_B_SLOTS * RES_KB * B_BYTES);
+    uint64_t* b_full = bars;                   // [3]
+    uint64_t* b_empty = bars + 3;              // [3]
+    uint64_t* a_full = bars + 6;               // [1]
+    uint64_t* a_free = bars + 7;               // [1]
+    uint64_t* tmem_full = bars + 8;            // [2]
+    uint64_t* tmem_empty = bars + 10;          // [2]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kb_total = (K + BK - 1) / BK;                    // <= RES_KB
+    const int total_tiles = tiles_m * tiles_n;
+    const int t_begin = blockIdx.x * tiles_per_cta;
+    const int t_end = min(total_tiles, t_begin + tiles_per_cta);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < 3; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        mbar_init(a_full, 1); mbar_init(a_free, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -124,77 +369,70 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== TMA producer =====
         if (lane == 0) {
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % STAGES, round = it / STAGES;
-                mbar_wait(&empty_bar[s], (round & 1) ^ 1);
-                const int p = it / n_kb, kb = kb_begin + it % n_kb;
-                uint8_t* a_dst = tiles + (size_t)s * STAGE_BYTES;
-                uint8_t* b_dst = a_dst + A_BYTES;
-                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                tma_load_2d(a_dst, &map_a, &full_bar[s], kb * BK, p * piece_rows + m0);
-                tma_load_2d(b_dst, &map_b, &full_bar[s], kb * BK, n0);
+            int a_loads = 0, cur_m = -1;
+            for (int tile = t_begin, local = 0; tile < t_end; ++tile, ++local) {
+                const int m_tile = tile / tiles_n, n0 = (tile % tiles_n) * BN;
+                if (m_tile != cur_m) {
+                    // the previous rows' MMAs must have retired before A is overwritten
+                    mbar_wait(a_free, (a_loads & 1) ^ 1);
+                    mbar_expect_tx(a_full, (uint32_t)(pieces * kb_total * A_BYTES));
+                    for (int p = 0; p < pieces; ++p)
+                        for (int kb = 0; kb < kb_total; ++kb)
+                            tma_load_2d(a_res + (size_t)(p * kb_total + kb) * A_BYTES, &map_a, a_full, kb * BK,
+                                        p * piece_rows + m_tile * BM);
+                    ++a_loads;
+                    cur_m = m_tile;
+                }
+                const int slot = local % RES_B_SLOTS, round = local / RES_B_SLOTS;
+                mbar_wait(&b_empty[slot], (round & 1) ^ 1);
+                mbar_expect_tx(&b_full[slot], (uint32_t)(kb_total * B_BYTES));
+                for (int kb = 0; kb < kb_total; ++kb)
+                    tma_load_2d(b_ring + (size_t)(slot * RES_KB + kb) * B_BYTES, &map_b, &b_full[slot], kb * BK, n0);
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
         if (lane == 0) {
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % STAGES, round = it / STAGES;
-                mbar_wait(&full_bar[s], round & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES);
-                const uint32_t b_addr = a_addr + A_BYTES;
-#pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    const uint64_t ad = make_desc(a_addr + k * UMMA_K * 2);
-                    const uint64_t bd = make_desc(b_addr + k * UMMA_K * 2);
-                    umma_bf16(tmem_base, ad, bd, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+            int a_loads = 0, cur_m = -1;
+            for (int tile = t_begin, local = 0; tile < t_end; ++tile, ++local) {
+                const int m_tile = tile / tiles_n;
+                if (m_tile != cur_m) {
+                    mbar_wait(a_full, a_loads & 1);
+                    ++a_loads;
+                    cur_m = m_tile;
                 }
-                tcgen05_commit(&empty_bar[s]);             // frees the smem stage when these MMAs retire
+                const int buf = local & 1;
+                mbar_wait(&tmem_empty[buf], ((local >> 1) & 1) ^ 1);
+                const int slot = local % RES_B_SLOTS, round = local / RES_B_SLOTS;
+                mbar_wait(&b_full[slot], round & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+                bool first = true;
+                for (int p = 0; p < pieces; ++p)
+                    for (int kb = 0; kb < kb_total; ++kb) {
+                        const uint32_t a_addr = smem_u32(a_res + (size_t)(p * kb_total + kb) * A_BYTES);
+                        const uint32_t b_addr = smem_u32(b_ring + (size_t)(slot * RES_KB + kb) * B_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            umma_bf16(tmem_d, make_desc(a_addr + k * UMMA_K * 2), make_desc(b_addr + k * UMMA_K * 2), IDESC,
+                                      first ? 0u : 1u);
+                            first = false;
+                        }
+                    }
+                tcgen05_commit(&b_empty[slot]);
+                tcgen05_commit(&tmem_full[buf]);
+                const bool last_of_rows = (tile + 1 >= t_end) || ((tile + 1) / tiles_n != m_tile);
+                if (last_of_rows) tcgen05_commit(a_free);
             }
-            tcgen05_commit(tmem_full);                     // accumulator complete
         }
     } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> registers -> global =====
-        const int q = warp & 3;                            // TMEM lane quadrant this warp may access
-        mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = m0 + q * 32 + lane;
-        float* orow = out + (long long)blockIdx.z * split_stride + (long long)row * ldo + n0;
-#pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < M) {
-                if (iters == 0) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = 0u;
-                }
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int col = n0 + c0 + j;
-                    if (col + 3 < N) {
-                        *reinterpret_cast<float4*>(orow + c0 + j) =
-                            make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                        __uint_as_float(r[j + 3]));
-                    } else {
-                        for (int e = 0; e < 4; ++e)
-                            if (col + e < N) orow[c0 + j + e] = __uint_as_float(r[j + e]);
-                    }
-                }
-            }
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        for (int tile = t_begin, local = 0; tile < t_end; ++tile, ++local) {
+            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            const int buf = local & 1;
+            mbar_wait(&tmem_full[buf], (local >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            epilogue_tile(tmem_base, buf, q, half, lane, m0, n0, 0, M, N, out, ldo, 0, ep, &tmem_empty[buf]);
         }
     }
 
@@ -242,15 +480,18 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
 
 // out[z][M x N] (fp32, row pitch ldo, plane stride split_stride) = sum_p A[p*piece_rows + m][k] * B[n][k]
 // over the k-blocks of split z.  A: [pieces*piece_rows x K] bf16 (pitch lda), B: [N x K] bf16 (pitch ldb).
-int tc_gemm(cudaStream_t st, const void* A, long long lda, const void* B, long long ldb, float* out, int M, int N, int K,
-            int pieces, int piece_rows, int ldo, int nsplit, long long split_stride) {
+static int tc_launch(cudaStream_t st, const void* A, long long lda, const void* B, long long ldb, float* out, int M, int N,
+                     int K, int pieces, int piece_rows, int ldo, int nsplit, long long split_stride, tc::Epilogue ep,
+                     int a_blocked = 0) {
     using namespace tc;
     if ((lda * 2) % 16 || (ldb * 2) % 16 || ((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)out & 15) || ldo % 4) {
         set_error("tc_gemm: operands must be 16-byte aligned with 16-byte row pitches");
         return B2H_ERR_ARG;
     }
     CUtensorMap ma, mb;
-    int rc = make_map(&ma, A, (long long)pieces * piece_rows, K, lda);
+    // blocked A: a 2D view [pieces * piece_rows][128] with a 128-element pitch (piece_rows counts blocked rows)
+    int rc = a_blocked ? make_map(&ma, A, (long long)pieces * piece_rows, BN, BN)
+                       : make_map(&ma, A, (long long)pieces * piece_rows, K, lda);
     if (rc) return rc;
     rc = make_map(&mb, B, N, K, ldb);
     if (rc) return rc;
@@ -259,11 +500,59 @@ int tc_gemm(cudaStream_t st, const void* A, long long lda, const void* B, long l
     if (nsplit > kb_total) nsplit = kb_total;
     const int kb_per = (kb_total + nsplit - 1) / nsplit;
     nsplit = (kb_total + kb_per - 1) / kb_per;
-    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, nsplit);
-    B2H_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    tc_gemm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, out, M, N, K, pieces, piece_rows, ldo, kb_per, split_stride);
+    const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BM - 1) / BM;
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (sm_count <= 0) sm_count = 148;
+    }
+    const long long total = (long long)tiles_n * tiles_m * nsplit;
+    if (!a_blocked && nsplit == 1 && pieces * kb_total <= RES_A_BLOCKS && kb_total <= RES_KB && total >= 2 * sm_count) {
+        // short reduction, many column tiles: keep A resident, stream B once per tile
+        const int per = (int)((total + sm_count - 1) / sm_count);
+        const int grid_r = (int)((total + per - 1) / per);
+        B2H_CUDA(cudaFuncSetAttribute(tc_gemm_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM));
+        tc_gemm_resident_kernel<<<grid_r, THREADS, RES_SMEM, st>>>(ma, mb, out, M, N, K, pieces, piece_rows, ldo, tiles_m,
+                                                                   tiles_n, per, ep);
+        B2H_LAUNCH_CHECK();
+        return 1;
+    }
+    const int grid = (int)std::min<long long>(total, sm_count);
+    // short reductions (the S product: K = dim) take a shallow ring so that three CTAs share an SM and one CTA's
+    // epilogue overlaps the others' loads and MMAs; long reductions take the full 6-stage ring
+    const int iters = kb_per * pieces;
+    const int stages = STAGES;
+    (void)iters;
+    B2H_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(STAGES)));
+    tc_gemm_kernel<<<grid, THREADS, smem_bytes(stages), st>>>(ma, mb, out, M, N, K, pieces, piece_rows, ldo, kb_per,
+                                                             split_stride, stages, tiles_m, tiles_n, nsplit, a_blocked, ep);
     B2H_LAUNCH_CHECK();
     return nsplit;
+}
+
+int tc_gemm(cudaStream_t st, const void* A, long long lda, const void* B, long long ldb, float* out, int M, int N, int K,
+            int pieces, int piece_rows, int ldo, int nsplit, long long split_stride) {
+    tc::Epilogue ep{0, nullptr, nullptr, 0, 0, nullptr};
+    return tc_launch(st, A, lda, B, ldb, out, M, N, K, pieces, piece_rows, ldo, nsplit, split_stride, ep, 0);
+}
+
+// S = sum_p A_p . B^T never leaves the SM: the epilogue writes the residual pieces (bf16, tile-blocked:
+// [3][ceil(N/128)][ceil(M/128)][128][128]) and the per-tile partial sums of the potential, upart[4 * ceil(N/128)][M].
+int tc_gemm_logistic(cudaStream_t st, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                     int pieces, int piece_rows, const float* y, void* R, long long r_piece_stride, double* upart) {
+    if (((uintptr_t)R & 1023)) { set_error("tc_gemm_logistic: residual buffer must be 1024-byte aligned"); return B2H_ERR_ARG; }
+    tc::Epilogue ep{1, y, (__nv_bfloat16*)R, r_piece_stride, (M + tc::BM - 1) / tc::BM, upart};
+    return tc_launch(st, A, lda, B, ldb, nullptr, M, N, K, pieces, piece_rows, 4, 1, 0, ep);
+}
+
+// out[z] = sum_p R_p . B^T with R in the tile-blocked layout written by tc_gemm_logistic (K = data rows).
+int tc_gemm_blocked_a(cudaStream_t st, const void* R, long long r_piece_stride, const void* B, long long ldb, float* out,
+                      int M, int N, int K, int pieces, int ldo, int nsplit, long long split_stride) {
+    tc::Epilogue ep{0, nullptr, nullptr, 0, 0, nullptr};
+    const int piece_rows = (int)(r_piece_stride / tc::BN);
+    return tc_launch(st, R, tc::BN, B, ldb, out, M, N, K, pieces, piece_rows, ldo, nsplit, split_stride, ep, 1);
 }
 
 }  // namespace b2h

@@ -34,6 +34,7 @@ def _tc_gemm(A, B, M, N, K, pieces, piece_rows, nsplit):
 @pytest.mark.parametrize("M, N, K, pieces, nsplit", [
     (128, 128, 64, 1, 1), (128, 128, 256, 1, 1), (256, 384, 128, 1, 1), (300, 200, 136, 3, 1),
     (128, 128, 2048, 1, 4), (4096, 128, 1024, 3, 3), (192, 1000, 128, 3, 1),
+    (256, 20000, 128, 3, 1), (300, 19000, 64, 1, 1),      # A-resident variant (short K, many column tiles)
 ])
 def test_tc_gemm_matches_exact_reference(ab, M, N, K, pieces, nsplit):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
