@@ -68,7 +68,8 @@ int tc_gemm(cudaStream_t st, const void* A, long long lda, const void* B, long l
             int pieces, int piece_rows, int ldo, int nsplit, long long split_stride);
 
 int tc_gemm_logistic(cudaStream_t st, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
-                     int pieces, int piece_rows, const float* y, void* R, long long r_piece_stride, double* upart);
+                     int pieces, int piece_rows, const float* y, void* R, long long r_piece_stride, double* upart,
+                     int* tiles_per_cta);
 int tc_gemm_blocked_a(cudaStream_t st, const void* R, long long r_piece_stride, const void* B, long long ldb, float* out,
                       int M, int N, int K, int pieces, int ldo, int nsplit, long long split_stride);
 

@@ -122,7 +122,7 @@ static LogregTcPlan plan_logreg_tc(const b2h_model* m, i64 C) {
     p.off_R = take((size_t)3 * ((C + 127) / 128) * 128 * p.n_chunk * 2);     // tile-blocked, rows padded to 128
     p.off_part = take((size_t)p.nsplit * C * m->dim * 4);
     p.off_U = take((size_t)C * sizeof(double));
-    p.off_upart = take((size_t)4 * (p.n_chunk / 128) * C * sizeof(double));
+    p.off_upart = take((size_t)4 * std::max<i64>(p.n_chunk / 128, 160) * C * sizeof(double));
     p.total = off + 1024;
     return p;
 }
@@ -151,20 +151,21 @@ __global__ void to_float_kernel(const T* x, float* y, i64 n) {
     if (i < n) y[i] = (float)x[i];
 }
 
-// U_acc[c] (+)= sum over the tile partials written by the contraction's epilogue (fixed order: deterministic)
-__global__ void upart_reduce_kernel(const double* upart, double* U_acc, i64 C, int n_part, int first) {
+// U_acc[c] (+)= sum over the partials written by the contraction's epilogue (fixed order: deterministic).
+// per_cta == 0: planes [column tile][4]; per_cta > 0: planes [CTA][4] where CTA b covered tiles [b*per, (b+1)*per)
+// of the (row tile, column tile) grid, column tile fastest -- only the CTAs that touched chain c's row tile count.
+__global__ void upart_reduce_kernel(const double* upart, double* U_acc, i64 C, int tiles_n, int per_cta, int first) {
     i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    double s0 = first ? 0.0 : U_acc[c], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int t = 0;
-    for (; t + 3 < n_part; t += 4) {              // four independent loads in flight per thread
-        s0 += upart[(i64)t * C + c];
-        s1 += upart[(i64)(t + 1) * C + c];
-        s2 += upart[(i64)(t + 2) * C + c];
-        s3 += upart[(i64)(t + 3) * C + c];
+    int p_begin = 0, p_end = 4 * tiles_n;
+    if (per_cta > 0) {
+        const i64 mt = c / 128;
+        p_begin = (int)((mt * tiles_n) / per_cta) * 4;
+        p_end = (int)(((mt + 1) * tiles_n - 1) / per_cta + 1) * 4;
     }
-    for (; t < n_part; ++t) s0 += upart[(i64)t * C + c];
-    U_acc[c] = (s0 + s1) + (s2 + s3);
+    double s = first ? 0.0 : U_acc[c];
+    for (int t = p_begin; t < p_end; ++t) s += upart[(i64)t * C + c];
+    U_acc[c] = s;
 }
 
 // g (T) = (first ? 0 : g) + sum_s partial[s] (fp32 planes)
@@ -206,9 +207,10 @@ static int logistic_tc(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U, T* g,
         const int nv = (int)std::min<i64>(p.n_chunk, N - n0);
         // S[C x nv] = sum_p Beta_p[C x d] . X[n0.., d]^T stays in TMEM; the epilogue emits the residual pieces
         const i64 r_piece = (i64)((C + 127) / 128) * 128 * p.n_chunk;
-        int rc = tc_gemm_logistic(st, bp, d, Xb + n0 * d, d, (int)C, nv, d, 3, (int)C, yf + n0, R, r_piece, upart);
+        int per_cta = 0;
+        int rc = tc_gemm_logistic(st, bp, d, Xb + n0 * d, d, (int)C, nv, d, 3, (int)C, yf + n0, R, r_piece, upart, &per_cta);
         if (rc < 0) return rc;
-        upart_reduce_kernel<<<(int)((C + 63) / 64), 64, 0, st>>>(upart, U_acc, C, 4 * ((nv + 127) / 128), it == 0);
+        upart_reduce_kernel<<<(int)((C + 63) / 64), 64, 0, st>>>(upart, U_acc, C, (nv + 127) / 128, per_cta, it == 0);
         // G[C x d] += sum_p R_p[C x nv] . Xt[d, n0..]^T   (split-K over the data rows)
         rc = tc_gemm_blocked_a(st, R, r_piece, Xtb + n0, N, part, (int)C, d, nv, 3, d, p.nsplit, ng);
         if (rc < 0) return rc;

@@ -108,7 +108,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 // Epilogue of one 128 x 128 accumulator for one warp: TMEM lane quadrant q, 32-column part `part`.
-__device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int buf, int q, int part, int lane, int m0, int n0,
+__device__ __forceinline__ float epilogue_tile(uint32_t tmem_base, int buf, int q, int part, int lane, int m0, int n0,
                                               int z, int M, int N, float* out, int ldo, long long split_stride,
                                               const Epilogue& ep, uint64_t* tmem_empty_bar) {
     const int row = m0 + q * 32 + lane;
@@ -128,7 +128,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int buf, int q
     // the accumulator is in registers: hand the TMEM buffer back to the MMA warp before doing the math
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tmem_empty_bar)) : "memory");
-    if (row >= M) return;
+    if (row >= M) return 0.f;
     if (ep.mode == 0) {
         float* orow = out + (long long)z * split_stride + (long long)row * ldo + n0;
 #pragma unroll
@@ -143,7 +143,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int buf, int q
                     if (col + e < N) orow[c0 + j + e] = __uint_as_float(r[j + e]);
             }
         }
-        return;
+        return 0.f;
     }
     // logistic residual: r = sigmoid(s) - y as three bf16 pieces (exact split), potential partial sums
     float uacc = 0.f;
@@ -194,7 +194,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int buf, int q
         *reinterpret_cast<uint4*>(dst + 2 * ep.piece_stride + 8 * v) =
             make_uint4(p2[4 * v], p2[4 * v + 1], p2[4 * v + 2], p2[4 * v + 3]);
     }
-    ep.upart[((long long)(n0 / BN) * EPI_PARTS + part) * M + row] = (double)uacc;
+    return uacc;
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -306,7 +306,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int buf = local & 1;
             mbar_wait(&tmem_full[buf], (local >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            epilogue_tile(tmem_base, buf, q, half, lane, m0, n0, z, M, N, out, ldo, split_stride, ep, &tmem_empty[buf]);
+            const float u = epilogue_tile(tmem_base, buf, q, half, lane, m0, n0, z, M, N, out, ldo, split_stride, ep,
+                                          &tmem_empty[buf]);
+            const int row = m0 + q * 32 + lane;
+            if (ep.mode == 1 && row < M) ep.upart[((long long)(n0 / BN) * EPI_PARTS + half) * M + row] = (double)u;
         }
     }
 
@@ -427,12 +430,19 @@ tc_gemm_resident_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         }
     } else if (warp >= 4) {
         const int q = warp & 3, half = (warp - 4) >> 2;
+        float urun = 0.f;                      // potential partial sum of this thread's row over the CTA's tiles
         for (int tile = t_begin, local = 0; tile < t_end; ++tile, ++local) {
             const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
             const int buf = local & 1;
             mbar_wait(&tmem_full[buf], (local >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            epilogue_tile(tmem_base, buf, q, half, lane, m0, n0, 0, M, N, out, ldo, 0, ep, &tmem_empty[buf]);
+            urun += epilogue_tile(tmem_base, buf, q, half, lane, m0, n0, 0, M, N, out, ldo, 0, ep, &tmem_empty[buf]);
+            const bool last_of_rows = (tile + 1 >= t_end) || ((tile + 1) / tiles_n != tile / tiles_n);
+            if (last_of_rows) {
+                const int row = m0 + q * 32 + lane;
+                if (ep.mode == 1 && row < M) ep.upart[((long long)blockIdx.x * EPI_PARTS + half) * M + row] = (double)urun;
+                urun = 0.f;
+            }
         }
     }
 
@@ -482,7 +492,7 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
 // over the k-blocks of split z.  A: [pieces*piece_rows x K] bf16 (pitch lda), B: [N x K] bf16 (pitch ldb).
 static int tc_launch(cudaStream_t st, const void* A, long long lda, const void* B, long long ldb, float* out, int M, int N,
                      int K, int pieces, int piece_rows, int ldo, int nsplit, long long split_stride, tc::Epilogue ep,
-                     int a_blocked = 0) {
+                     int a_blocked = 0, int* resident_tiles_per_cta = nullptr) {
     using namespace tc;
     if ((lda * 2) % 16 || (ldb * 2) % 16 || ((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)out & 15) || ldo % 4) {
         set_error("tc_gemm: operands must be 16-byte aligned with 16-byte row pitches");
@@ -517,8 +527,10 @@ static int tc_launch(cudaStream_t st, const void* A, long long lda, const void* 
         tc_gemm_resident_kernel<<<grid_r, THREADS, RES_SMEM, st>>>(ma, mb, out, M, N, K, pieces, piece_rows, ldo, tiles_m,
                                                                    tiles_n, per, ep);
         B2H_LAUNCH_CHECK();
+        if (resident_tiles_per_cta) *resident_tiles_per_cta = per;
         return 1;
     }
+    if (resident_tiles_per_cta) *resident_tiles_per_cta = 0;
     const int grid = (int)std::min<long long>(total, sm_count);
     // short reductions (the S product: K = dim) take a shallow ring so that three CTAs share an SM and one CTA's
     // epilogue overlaps the others' loads and MMAs; long reductions take the full 6-stage ring
@@ -540,11 +552,14 @@ int tc_gemm(cudaStream_t st, const void* A, long long lda, const void* B, long l
 
 // S = sum_p A_p . B^T never leaves the SM: the epilogue writes the residual pieces (bf16, tile-blocked:
 // [3][ceil(N/128)][ceil(M/128)][128][128]) and the per-tile partial sums of the potential, upart[4 * ceil(N/128)][M].
+// *tiles_per_cta > 0: upart is [CTA][4][M] (each CTA covers tiles_per_cta consecutive tiles, column tile fastest);
+// otherwise upart is [column tile][4][M].
 int tc_gemm_logistic(cudaStream_t st, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
-                     int pieces, int piece_rows, const float* y, void* R, long long r_piece_stride, double* upart) {
+                     int pieces, int piece_rows, const float* y, void* R, long long r_piece_stride, double* upart,
+                     int* tiles_per_cta) {
     if (((uintptr_t)R & 1023)) { set_error("tc_gemm_logistic: residual buffer must be 1024-byte aligned"); return B2H_ERR_ARG; }
     tc::Epilogue ep{1, y, (__nv_bfloat16*)R, r_piece_stride, (M + tc::BM - 1) / tc::BM, upart};
-    return tc_launch(st, A, lda, B, ldb, nullptr, M, N, K, pieces, piece_rows, 4, 1, 0, ep);
+    return tc_launch(st, A, lda, B, ldb, nullptr, M, N, K, pieces, piece_rows, 4, 1, 0, ep, 0, tiles_per_cta);
 }
 
 // out[z] = sum_p R_p . B^T with R in the tile-blocked layout written by tc_gemm_logistic (K = data rows).
