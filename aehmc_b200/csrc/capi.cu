@@ -45,11 +45,24 @@ int b2h_ctx_create(int device, void* stream, b2h_ctx** out) {
     ctx->device = device;
     ctx->stream = (cudaStream_t)stream;
     ctx->sm_count = prop.multiProcessorCount;
+    // highest priority: the few momentum tiles must be picked up as soon as SMs free up, not after the main
+    // stream's full-size launches (the next tick waits for them)
+    int prio_least = 0, prio_greatest = 0;
+    B2H_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    B2H_CUDA(cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_greatest));
+    for (int i = 0; i < 2; ++i) {
+        B2H_CUDA(cudaEventCreateWithFlags(&ctx->ev_pre[i], cudaEventDisableTiming));
+        B2H_CUDA(cudaEventCreateWithFlags(&ctx->ev_side[i], cudaEventDisableTiming));
+    }
     *out = ctx;
     return 0;
 }
 
 int b2h_ctx_destroy(b2h_ctx* ctx) {
+    if (ctx) {
+        cudaStreamDestroy(ctx->side);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_pre[i]); cudaEventDestroy(ctx->ev_side[i]); }
+    }
     delete ctx;
     return 0;
 }

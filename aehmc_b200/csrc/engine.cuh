@@ -78,14 +78,16 @@ struct EngineView {
     T *qp, *pp, *gp;                     // transition proposal == chain position between transitions
     T *msum, *sms;                       // momentum sums: whole trajectory / current sub-tree
     T *mck, *sckp;                       // U-turn checkpoints [C][maxd][d]
-    T *vl, *vr, *vck;                    // dense metric only: velocities of pl, pr, checkpoints
+    T *vl, *vr, *vck;                    // dense metric only: velocities imm.p of pl, pr, checkpoints
+    T *wl, *wr, *ws, *wp;                // dense metric only: imm.g of the edges / sub-tree proposal / proposal, so that
+                                         // the half-step velocity is a recurrence: imm.(p - h g) = v - h w (no contraction)
     ChainRec* rec;
     // metric (diag family): imm(c, j) = imm[c*imm_sc + j*imm_sj]
     int imm_kind;
     T* imm;
     i64 imm_sc, imm_sj;
     // split-mode scratch (row-major [C][d]) and dense-momentum compaction
-    T *xa, *xb, *Unew;
+    T *xa, *xb, *xc, *Unew;              // xa = q' (gradient input), xb = g' (gradient output), xc = imm.g' (dense)
     // dense-metric momentum, one transition of lookahead: mom_p/mom_v [C][d] hold p0 = sqrt z and v0 = imm p0 of
     // each chain's NEXT transition; a chain that starts a transition consumes them and queues a request
     // (list/count of parity mom_parity, normals in mom_z) that rides along the following dense applies.
@@ -177,6 +179,9 @@ B2H_DEVINL void begin_transition(Chain<T, G>& ch) {
             vel = v.mom_v[m];
             v.vl[a] = vel;
             v.vr[a] = vel;
+            T w0 = v.wp[a];
+            v.wl[a] = w0;
+            v.wr[a] = w0;
         } else {
             T im = ch.imm(j);
             T z = (T)draw_z(v.rng, ch.c, ch.r.t, j, v.d);
@@ -219,8 +224,8 @@ B2H_DEVINL void begin_transition(Chain<T, G>& ch) {
 
 // ---------------------------------------------------------------------------
 // first half of velocity Verlet (integrators.py:59-62) in place on the edge:
-//   p_half = p - (0.5*e) g ;  q' = q + e * (imm p_half)        (diag family)
-// Dense: only p_half is formed (and copied to xa for the velocity GEMM).
+//   p_half = p - (0.5*e) g ;  q' = q + e * (imm p_half)
+// Dense metric: imm p_half = v - (0.5*e) w with v = imm p and w = imm g carried along with the state.
 // ---------------------------------------------------------------------------
 template <typename T, int G, bool DENSE, bool SPLIT>
 B2H_DEVINL void half_kick_drift(Chain<T, G>& ch) {
@@ -228,19 +233,24 @@ B2H_DEVINL void half_kick_drift(Chain<T, G>& ch) {
     T* Q = ch.r.go_right ? v.qr : v.ql;
     T* P = ch.r.go_right ? v.pr : v.pl;
     T* Gd = ch.r.go_right ? v.gr : v.gl;
+    T* V = ch.r.go_right ? v.vr : v.vl;     // dense only
+    T* W = ch.r.go_right ? v.wr : v.wl;     // dense only
     T e = (T)(ch.r.go_right ? ch.r.eps : -ch.r.eps);
     T he = (T)0.5 * e;
     for (int j = ch.lane; j < v.d; j += G) {
         i64 a = ch.at(j);
         T ph = P[a] - he * Gd[a];
         P[a] = ph;
+        T vh;
         if (DENSE) {
-            v.xa[(i64)ch.c * v.d + j] = ph;
+            vh = V[a] - he * W[a];           // imm.(p - h g) by linearity
+            V[a] = vh;
         } else {
-            T qn = Q[a] + e * (ch.imm(j) * ph);
-            Q[a] = qn;
-            if (SPLIT) v.xa[(i64)ch.c * v.d + j] = qn;
+            vh = ch.imm(j) * ph;
         }
+        T qn = Q[a] + e * vh;
+        Q[a] = qn;
+        if (SPLIT) v.xa[(i64)ch.c * v.d + j] = qn;
     }
 }
 
@@ -340,7 +350,8 @@ B2H_DEVINL void end_transition(Chain<T, G>& ch, int num_doublings, bool is_turni
 // second half of the leapfrog + everything the reference does per integration
 // step.  Inputs: the edge holds (q', p_half), the new gradient is in the edge's g
 // (fused) or in xb (split), the new potential is U_new.
-// DENSE: xb holds v' = imm p' (velocity GEMM) and the edge already holds p'.
+// DENSE: xb holds g' and xc = imm g' (the one metric contraction of the tick); the edge holds p_half and
+// V = imm p_half.
 // ---------------------------------------------------------------------------
 template <typename T, int G, bool DENSE, bool SPLIT>
 B2H_DEVINL void post_gradient(Chain<T, G>& ch, T U_new) {
@@ -351,6 +362,7 @@ B2H_DEVINL void post_gradient(Chain<T, G>& ch, T U_new) {
     T* P = r.go_right ? v.pr : v.pl;
     T* Gd = r.go_right ? v.gr : v.gl;
     T* V = r.go_right ? v.vr : v.vl;     // dense only
+    T* W = r.go_right ? v.wr : v.wl;     // dense only
     const T e = (T)(r.go_right ? r.eps : -r.eps);
     const T he = (T)0.5 * e;
 
@@ -375,9 +387,13 @@ B2H_DEVINL void post_gradient(Chain<T, G>& ch, T U_new) {
         i64 a = ch.at(j);
         T p, vel, im = 0;
         if (DENSE) {
-            vel = v.xb[(i64)ch.c * d + j];
+            T g = v.xb[(i64)ch.c * d + j], wv = v.xc[(i64)ch.c * d + j];
+            Gd[a] = g;
+            W[a] = wv;
+            p = P[a] - he * g;
+            P[a] = p;
+            vel = V[a] - he * wv;            // imm p' = imm p_half - (0.5 e) imm g'
             V[a] = vel;
-            p = P[a];
         } else {
             T g;
             if (SPLIT) { g = v.xb[(i64)ch.c * d + j]; Gd[a] = g; }
@@ -465,6 +481,7 @@ B2H_DEVINL void post_gradient(Chain<T, G>& ch, T U_new) {
         for (int j = ch.lane; j < d; j += G) {
             i64 a = ch.at(j);
             v.qs[a] = Q[a]; v.ps[a] = P[a]; v.gs[a] = Gd[a];
+            if (DENSE) v.ws[a] = W[a];
         }
     }
     r.sub_len = (s == 0) ? 1 : r.sub_len + 1;
@@ -507,6 +524,7 @@ B2H_DEVINL void post_gradient(Chain<T, G>& ch, T U_new) {
             for (int j = ch.lane; j < d; j += G) {
                 i64 a = ch.at(j);
                 v.qp[a] = v.qs[a]; v.pp[a] = v.ps[a]; v.gp[a] = v.gs[a];
+                if (DENSE) v.wp[a] = v.ws[a];
             }
             r.E_prop = r.E_sub; r.U_prop = r.U_sub;
         }
@@ -543,9 +561,14 @@ B2H_DEVINL void hmc_post(Chain<T, G>& ch, T U_new) {
     for (int j = ch.lane; j < d; j += G) {
         i64 a = ch.at(j);
         if (DENSE) {
-            T vel = v.xb[(i64)ch.c * d + j];
+            T g = v.xb[(i64)ch.c * d + j], wv = v.xc[(i64)ch.c * d + j];
+            v.gr[a] = g;
+            v.wr[a] = wv;
+            T p = v.pr[a] - he * g;
+            v.pr[a] = p;
+            T vel = v.vr[a] - he * wv;
             v.vr[a] = vel;
-            kacc += vel * v.pr[a];
+            kacc += vel * p;
         } else {
             T g;
             if (SPLIT) { g = v.xb[(i64)ch.c * d + j]; v.gr[a] = g; }
@@ -569,7 +592,10 @@ B2H_DEVINL void hmc_post(Chain<T, G>& ch, T U_new) {
     bool acc = bern(u, p_accept);
     for (int j = ch.lane; j < d; j += G) {
         i64 a = ch.at(j);
-        if (acc) { v.qp[a] = v.qr[a]; v.pp[a] = -v.pr[a]; v.gp[a] = v.gr[a]; }
+        if (acc) {
+            v.qp[a] = v.qr[a]; v.pp[a] = -v.pr[a]; v.gp[a] = v.gr[a];
+            if (DENSE) v.wp[a] = v.wr[a];
+        }
         // on reject the state keeps (q, fresh momentum, g): pp already holds p0 (hmc.py:122,195)
     }
     if (acc) r.U_prop = (double)U_new;

@@ -5,7 +5,7 @@
 //               runs every chain through all its ticks; nothing returns to the host.
 //  split mode : gradient and/or metric need an all-chain contraction (dense metric,
 //               correlated Gaussian, logistic regression) -> each tick is
-//               pre -> [velocity GEMM -> drift] -> gradient -> [kick -> velocity GEMM] -> post,
+//               pre (half kick + drift) -> gradient -> [dense metric: w' = imm.g', one contraction] -> post,
 //               all chains in lock-step, chains restarting transitions independently.
 #include <algorithm>
 #include <vector>
@@ -79,7 +79,11 @@ static size_t carve(EngineView<T>& v, char* base, const EnginePlan& pl, const b2
     v.msum = cv.take<T>(n); v.sms = cv.take<T>(n);
     v.mck = cv.take<T>(n * maxd); v.sckp = cv.take<T>(n * maxd);
     v.vl = v.vr = v.vck = nullptr;
-    if (pl.dense) { v.vl = cv.take<T>(n); v.vr = cv.take<T>(n); v.vck = cv.take<T>(n * maxd); }
+    v.wl = v.wr = v.ws = v.wp = nullptr;
+    if (pl.dense) {
+        v.vl = cv.take<T>(n); v.vr = cv.take<T>(n); v.vck = cv.take<T>(n * maxd);
+        v.wl = cv.take<T>(n); v.wr = cv.take<T>(n); v.ws = cv.take<T>(n); v.wp = cv.take<T>(n);
+    }
     v.rec = cv.take<ChainRec>(C);
     T* imm_own = nullptr;
     if (pl.per_chain_imm) imm_own = cv.take<T>(n);
@@ -87,12 +91,13 @@ static size_t carve(EngineView<T>& v, char* base, const EnginePlan& pl, const b2
     v.imm = imm_own;
     v.adapt.wc_mean = v.adapt.wc_m2 = nullptr;
     if (adapt) { v.adapt.wc_mean = cv.take<T>(n); v.adapt.wc_m2 = cv.take<T>(n); }
-    v.xa = v.xb = v.Unew = nullptr;
+    v.xa = v.xb = v.xc = v.Unew = nullptr;
     v.mom_p = v.mom_v = v.mom_z = nullptr; v.mom_count = nullptr; v.mom_list = nullptr;
     if (pl.split) {
         v.xa = cv.take<T>(n); v.xb = cv.take<T>(n); v.Unew = cv.take<T>(C);
     }
     if (pl.dense) {
+        v.xc = cv.take<T>(n);
         v.mom_p = cv.take<T>(n); v.mom_v = cv.take<T>(n); v.mom_z = cv.take<T>(2 * n);
         v.mom_count = cv.take<int>(4); v.mom_list = cv.take<int>(2 * (size_t)C);
     }
@@ -237,45 +242,6 @@ __global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksSplit) spl
     ch.store();
 }
 
-// dense metric: q' = q + e * v_half (v_half = xb from the velocity GEMM); xa = q'
-template <typename T, int G>
-__global__ void __launch_bounds__(Geo<G>::kThreads) split_drift_kernel(EngineView<T> v) {
-    const int c = Geo<G>::chain();
-    if (c >= v.C) return;
-    const ChainRec& r = v.rec[c];
-    if (r.phase != PH_RUN) return;
-    T* Q = r.go_right ? v.qr : v.ql;
-    const T e = (T)(r.go_right ? r.eps : -r.eps);
-    const int lane = Group<G>::lane();
-    for (int j = lane; j < v.d; j += G) {
-        i64 a = (i64)c * v.sc + (i64)j * v.sj, x = (i64)c * v.d + j;
-        T qn = Q[a] + e * v.xb[x];
-        Q[a] = qn;
-        v.xa[x] = qn;
-    }
-}
-
-// dense metric: g' = xb; p' = p_half - (0.5 e) g'; xa = p' (input of the second velocity GEMM)
-template <typename T, int G>
-__global__ void __launch_bounds__(Geo<G>::kThreads) split_kick_kernel(EngineView<T> v) {
-    const int c = Geo<G>::chain();
-    if (c >= v.C) return;
-    const ChainRec& r = v.rec[c];
-    if (r.phase != PH_RUN) return;
-    T* P = r.go_right ? v.pr : v.pl;
-    T* Gd = r.go_right ? v.gr : v.gl;
-    const T he = (T)0.5 * (T)(r.go_right ? r.eps : -r.eps);
-    const int lane = Group<G>::lane();
-    for (int j = lane; j < v.d; j += G) {
-        i64 a = (i64)c * v.sc + (i64)j * v.sj, x = (i64)c * v.d + j;
-        T g = v.xb[x];
-        Gd[a] = g;
-        T p = P[a] - he * g;
-        P[a] = p;
-        v.xa[x] = p;
-    }
-}
-
 template <typename T, int G, bool DENSE, bool HMC>
 __global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksSplit) split_post_kernel(EngineView<T> v, int* not_done) {
     __shared__ double red_s[128];
@@ -358,25 +324,38 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
     if (pl.dense) {
         B2H_CUDA(cudaMemsetAsync(v.mom_count, 0, 4 * sizeof(int), st));
         if (!resume) {
-            // p0 = z . S^T (metrics.py:56-59,67), v0 = p0 . imm (metrics.py:71) for every chain's first transition
+            // p0 = z . S^T (metrics.py:56-59,67), v0 = p0 . imm (metrics.py:71) for every chain's first transition,
+            // and w = imm . g of the starting positions
             mom_init_kernel<T><<<C, 128, 0, st>>>(v);
             launch_dense_apply<T>(st, v.mom_z, sqrt_t, v.mom_p, C, d, d, nullptr, nullptr);
             launch_dense_apply<T>(st, v.mom_p, imm_dense, v.mom_v, C, d, d, nullptr, nullptr);
+            launch_dense_apply<T>(st, v.gp, imm_dense, v.wp, C, d, d, nullptr, nullptr);
         }
     }
+    bool side_pending[2] = {false, false};
     for (i64 tick = 0; tick < bound; ++tick) {
+        const int b = (int)(tick & 1);
         if (pl.dense) {
-            const int b = (int)(tick & 1);
             last_parity = b;
             v.mom_parity = b;
+            // all momentum contractions launched so far must have landed: a chain that started a transition two
+            // ticks ago may start the next one now (its v0 came from the previous tick's side launch), and this
+            // parity's request list is about to be reused
+            for (int k = 0; k < 2; ++k)
+                if (side_pending[k]) { B2H_CUDA(cudaStreamWaitEvent(st, ctx->ev_side[k], 0)); side_pending[k] = false; }
             B2H_CUDA(cudaMemsetAsync(v.mom_count + b, 0, sizeof(int), st));
-            split_pre_kernel<T, G, true, HMC><<<grid, thr, 0, st>>>(v);
-            // half-step velocities of all chains + v0 of the transitions queued one tick ago
-            GemmGroup<T> g0{v.xa, (i64)d, imm_dense, (i64)d, v.xb, (i64)d, C, nullptr, nullptr, nullptr, nullptr};
-            GemmGroup<T> g1{v.mom_p, (i64)d, imm_dense, (i64)d, v.mom_v, (i64)d, C, v.mom_count + (b ^ 1), nullptr,
+            split_pre_kernel<T, G, true, HMC><<<grid, thr, 0, st>>>(v);      // half kick + drift by the v/w recurrence
+            // side stream: p0 = z . S^T of the transitions queued by this pre kernel, and v0 = imm . p0 of the
+            // transitions queued one tick ago (their p0 was produced by the previous side launch)
+            B2H_CUDA(cudaEventRecord(ctx->ev_pre[b], st));
+            B2H_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_pre[b], 0));
+            GemmGroup<T> g1{v.mom_z + (size_t)b * C * d, (i64)d, sqrt_t, (i64)d, v.mom_p, (i64)d, C, v.mom_count + b,
+                            nullptr, nullptr, v.mom_list + (size_t)b * C};
+            GemmGroup<T> g2{v.mom_p, (i64)d, imm_dense, (i64)d, v.mom_v, (i64)d, C, v.mom_count + (b ^ 1), nullptr,
                             v.mom_list + (size_t)(b ^ 1) * C, v.mom_list + (size_t)(b ^ 1) * C};
-            launch_gemm_grouped<T>(st, g0, g1, d, d, 1, 0);
-            split_drift_kernel<T, G><<<grid, thr, 0, st>>>(v);
+            launch_gemm_grouped<T>(ctx->side, g1, g2, none, d, d, 1, 0, 0);
+            B2H_CUDA(cudaEventRecord(ctx->ev_side[b], ctx->side));
+            side_pending[b] = true;
         } else {
             split_pre_kernel<T, G, false, HMC><<<grid, thr, 0, st>>>(v);
         }
@@ -385,13 +364,8 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
         const bool check = (max_ticks <= 0) && ((tick & 3) == 3 || tick + 1 == bound);
         if (check) B2H_CUDA(cudaMemsetAsync(not_done_dev, 0, sizeof(int), st));
         if (pl.dense) {
-            const int b = (int)(tick & 1);
-            split_kick_kernel<T, G><<<grid, thr, 0, st>>>(v);
-            // full-step velocities + p0 of the transitions queued this tick
-            GemmGroup<T> g0{v.xa, (i64)d, imm_dense, (i64)d, v.xb, (i64)d, C, nullptr, nullptr, nullptr, nullptr};
-            GemmGroup<T> g1{v.mom_z + (size_t)b * C * d, (i64)d, sqrt_t, (i64)d, v.mom_p, (i64)d, C, v.mom_count + b,
-                            nullptr, nullptr, v.mom_list + (size_t)b * C};
-            launch_gemm_grouped<T>(st, g0, g1, d, d, 1, 0);
+            // the tick's only metric contraction on the main stream: w' = imm . g'
+            launch_dense_apply<T>(st, v.xb, imm_dense, v.xc, C, d, d, nullptr, nullptr);
             split_post_kernel<T, G, true, HMC><<<grid, thr, 0, st>>>(v, check ? not_done_dev : nullptr);
         } else {
             split_post_kernel<T, G, false, HMC><<<grid, thr, 0, st>>>(v, check ? not_done_dev : nullptr);
@@ -404,10 +378,13 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
         }
     }
     if (pl.dense && rc == 0) {
-        // flush: v0 of the transitions queued in the last tick, so that a resumed run starts with no request pending
+        // join the side stream, then flush: v0 of the transitions queued in the last tick, so that a resumed run
+        // starts with no request pending
+        for (int b = 0; b < 2; ++b)
+            if (side_pending[b]) B2H_CUDA(cudaStreamWaitEvent(st, ctx->ev_side[b], 0));
         GemmGroup<T> g0{v.mom_p, (i64)d, imm_dense, (i64)d, v.mom_v, (i64)d, C, v.mom_count + last_parity, nullptr,
                         v.mom_list + (size_t)last_parity * C, v.mom_list + (size_t)last_parity * C};
-        launch_gemm_grouped<T>(st, g0, none, d, d, 1, 0);
+        launch_gemm_grouped<T>(st, g0, none, none, d, d, 1, 0, 0);
     }
     cudaFreeHost(host_flag);
     if (rc) return rc;

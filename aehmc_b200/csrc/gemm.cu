@@ -26,13 +26,13 @@ constexpr int BM = 128, BN = 128, BK = 16, GT = 256;
 
 template <typename T>
 __global__ void __launch_bounds__(GT, 1)
-dense_apply_kernel(GemmGroup<T> g0, GemmGroup<T> g1, int N, int K, int tiles_n, int tiles_m0, int k_chunk,
-                   i64 split_stride) {
+dense_apply_kernel(GemmGroup<T> g0, GemmGroup<T> g1, GemmGroup<T> g2, int N, int K, int tiles_n, int tiles_m0,
+                   int tiles_m1, int k_chunk, i64 split_stride) {
     int tile_m = blockIdx.x / tiles_n;
     const int tile_n = blockIdx.x % tiles_n;
-    const bool second = tile_m >= tiles_m0;
-    const GemmGroup<T>& g = second ? g1 : g0;
-    if (second) tile_m -= tiles_m0;
+    const int which = tile_m < tiles_m0 ? 0 : (tile_m < tiles_m0 + tiles_m1 ? 1 : 2);
+    const GemmGroup<T>& g = which == 0 ? g0 : (which == 1 ? g1 : g2);
+    tile_m -= which == 0 ? 0 : (which == 1 ? tiles_m0 : tiles_m0 + tiles_m1);
     int M = g.M;
     if (g.m_dev) M = min(M, *g.m_dev);
     const int m0 = tile_m * BM, n0 = tile_n * BN;
@@ -191,14 +191,14 @@ template <> struct Dmma<16> {
 
 template <int KI>
 __global__ void __launch_bounds__(GT, 1)
-dense_apply_dmma_kernel(GemmGroup<double> g0, GemmGroup<double> g1, int N, int K, int tiles_n, int tiles_m0,
-                        int k_chunk, i64 split_stride) {
+dense_apply_dmma_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGroup<double> g2, int N, int K, int tiles_n,
+                        int tiles_m0, int tiles_m1, int k_chunk, i64 split_stride) {
     typedef double T;
     int tile_m = blockIdx.x / tiles_n;
     const int tile_n = blockIdx.x % tiles_n;
-    const bool second = tile_m >= tiles_m0;
-    const GemmGroup<T>& g = second ? g1 : g0;
-    if (second) tile_m -= tiles_m0;
+    const int which = tile_m < tiles_m0 ? 0 : (tile_m < tiles_m0 + tiles_m1 ? 1 : 2);
+    const GemmGroup<T>& g = which == 0 ? g0 : (which == 1 ? g1 : g2);
+    tile_m -= which == 0 ? 0 : (which == 1 ? tiles_m0 : tiles_m0 + tiles_m1);
     int M = g.M;
     if (g.m_dev) M = min(M, *g.m_dev);
     const int m0 = tile_m * BM, n0 = tile_n * BN;
@@ -340,16 +340,17 @@ template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile
 
 template <int BN_>
 __global__ void __launch_bounds__(GT, 1)
-dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, int N, int K, int tiles_n, int tiles_m0) {
+dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGroup<double> g2, int N, int K, int tiles_n,
+                              int tiles_m0, int tiles_m1) {
     typedef double T;
     constexpr int NJ = BN_ / 16;               // 8-wide MMA tiles per warp along N (warp tile 32 x BN_/2)
     constexpr int BLD = BN_ + 8;
     constexpr int A_STAGE = BM * ALD, B_STAGE = BK * BLD;
     int tile_m = blockIdx.x / tiles_n;
     const int tile_n = blockIdx.x % tiles_n;
-    const bool second = tile_m >= tiles_m0;
-    const GemmGroup<T>& g = second ? g1 : g0;
-    if (second) tile_m -= tiles_m0;
+    const int which = tile_m < tiles_m0 ? 0 : (tile_m < tiles_m0 + tiles_m1 ? 1 : 2);
+    const GemmGroup<T>& g = which == 0 ? g0 : (which == 1 ? g1 : g2);
+    tile_m -= which == 0 ? 0 : (which == 1 ? tiles_m0 : tiles_m0 + tiles_m1);
     int M = g.M;
     if (g.m_dev) M = min(M, *g.m_dev);
     const int m0 = tile_m * BM, n0 = tile_n * BN_;
@@ -471,11 +472,14 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, int N,
 }
 
 template <int BN_>
-static void launch_async(cudaStream_t st, const GemmGroup<double>& g0, const GemmGroup<double>& g1, int N, int K) {
+static void launch_async(cudaStream_t st, const GemmGroup<double>& g0, const GemmGroup<double>& g1,
+                         const GemmGroup<double>& g2, int N, int K) {
     constexpr int smem = (STAGES * (BM * ALD + BK * (BN_ + 8)) + STAGES * BK) * (int)sizeof(double);
-    int tiles_m0 = (g0.M + BM - 1) / BM, tiles_m1 = (g1.M + BM - 1) / BM, tiles_n = (N + BN_ - 1) / BN_;
+    int tiles_m0 = (g0.M + BM - 1) / BM, tiles_m1 = (g1.M + BM - 1) / BM, tiles_m2 = (g2.M + BM - 1) / BM;
+    int tiles_n = (N + BN_ - 1) / BN_;
     cudaFuncSetAttribute(dense_apply_dmma_async_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    dense_apply_dmma_async_kernel<BN_><<<(tiles_m0 + tiles_m1) * tiles_n, GT, smem, st>>>(g0, g1, N, K, tiles_n, tiles_m0);
+    dense_apply_dmma_async_kernel<BN_><<<(tiles_m0 + tiles_m1 + tiles_m2) * tiles_n, GT, smem, st>>>(g0, g1, g2, N, K, tiles_n,
+                                                                                                tiles_m0, tiles_m1);
 }
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -486,13 +490,13 @@ static bool group_async_ok(const GemmGroup<double>& g) {
 }
 
 // pick the tile width whose tile count wastes the least of the last wave of 148 SMs
-static int pick_bn(int M0, int N) {
+static int pick_bn(int M0, int rider_tile_rows, int N) {
     const int cand[3] = {128, 112, 96};
     int best = 128;
     double best_cost = 1e300;
     for (int c = 0; c < 3; ++c) {
         const int bn = cand[c];
-        const long tiles = (long)((M0 + BM - 1) / BM) * ((N + bn - 1) / bn);
+        const long tiles = (long)((M0 + BM - 1) / BM + rider_tile_rows) * ((N + bn - 1) / bn);
         const long waves = (tiles + 147) / 148;
         const double cost = (double)waves * bn;        // time ~ waves x tile work
         if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
@@ -501,25 +505,28 @@ static int pick_bn(int M0, int N) {
 }
 
 template <typename T>
-static void launch_tile_kernel(dim3 grid, cudaStream_t st, const GemmGroup<T>& g0, const GemmGroup<T>& g1, int N,
-                               int K, int tiles_n, int tiles_m0, int k_chunk, i64 split_stride);
+static void launch_tile_kernel(dim3 grid, cudaStream_t st, const GemmGroup<T>& g0, const GemmGroup<T>& g1,
+                               const GemmGroup<T>& g2, int N, int K, int tiles_n, int tiles_m0, int tiles_m1, int k_chunk,
+                               i64 split_stride, int extra_rows_hint);
 
 template <>
 void launch_tile_kernel<double>(dim3 grid, cudaStream_t st, const GemmGroup<double>& g0, const GemmGroup<double>& g1,
-                                int N, int K, int tiles_n, int tiles_m0, int k_chunk, i64 split_stride) {
+                                const GemmGroup<double>& g2, int N, int K, int tiles_n, int tiles_m0, int tiles_m1,
+                                int k_chunk, i64 split_stride, int extra_rows_hint) {
     static int use_async = -1;
     if (use_async < 0) {
         const char* e = getenv("B2H_GEMM_ASYNC");
         use_async = e ? atoi(e) : 1;
     }
-    if (use_async && grid.y == 1 && N % 2 == 0 && K % 2 == 0 && group_async_ok(g0) && group_async_ok(g1)) {
+    if (use_async && grid.y == 1 && N % 2 == 0 && K % 2 == 0 && group_async_ok(g0) && group_async_ok(g1) &&
+        group_async_ok(g2)) {
         static int force_bn = -1;
         if (force_bn < 0) { const char* e = getenv("B2H_GEMM_BN"); force_bn = e ? atoi(e) : 0; }
-        // the second group's row count lives on the device: budget an eighth of the first group's rows for it
-        const int bn = force_bn ? force_bn : pick_bn(g0.M + (g1.M > 0 ? (g0.M / 8 < g1.M ? g0.M / 8 : g1.M) : 0), N);
-        if (bn == 112) launch_async<112>(st, g0, g1, N, K);
-        else if (bn == 96) launch_async<96>(st, g0, g1, N, K);
-        else launch_async<128>(st, g0, g1, N, K);
+        // the rider groups' row counts live on the device: the caller passes the expected number of rider TILE ROWS
+        const int bn = force_bn ? force_bn : pick_bn(g0.M, extra_rows_hint, N);
+        if (bn == 112) launch_async<112>(st, g0, g1, g2, N, K);
+        else if (bn == 96) launch_async<96>(st, g0, g1, g2, N, K);
+        else launch_async<128>(st, g0, g1, g2, N, K);
         return;
     }
     constexpr int smem = 2 * 2 * BK * DLD * (int)sizeof(double);
@@ -530,7 +537,7 @@ void launch_tile_kernel<double>(dim3 grid, cudaStream_t st, const GemmGroup<doub
     }
 #define B2H_DMMA_LAUNCH(KI)                                                                                    \
     cudaFuncSetAttribute(dense_apply_dmma_kernel<KI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);        \
-    dense_apply_dmma_kernel<KI><<<grid, GT, smem, st>>>(g0, g1, N, K, tiles_n, tiles_m0, k_chunk, split_stride);
+    dense_apply_dmma_kernel<KI><<<grid, GT, smem, st>>>(g0, g1, g2, N, K, tiles_n, tiles_m0, tiles_m1, k_chunk, split_stride);
     if (ki == 4) { B2H_DMMA_LAUNCH(4) }
     else if (ki == 16) { B2H_DMMA_LAUNCH(16) }
     else { B2H_DMMA_LAUNCH(8) }
@@ -539,23 +546,27 @@ void launch_tile_kernel<double>(dim3 grid, cudaStream_t st, const GemmGroup<doub
 
 template <>
 void launch_tile_kernel<float>(dim3 grid, cudaStream_t st, const GemmGroup<float>& g0, const GemmGroup<float>& g1,
-                               int N, int K, int tiles_n, int tiles_m0, int k_chunk, i64 split_stride) {
+                               const GemmGroup<float>& g2, int N, int K, int tiles_n, int tiles_m0, int tiles_m1,
+                               int k_chunk, i64 split_stride, int extra_rows_hint) {
+    (void)extra_rows_hint;
     constexpr int smem = 2 * BK * (BM + BN) * (int)sizeof(float);
     cudaFuncSetAttribute(dense_apply_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    dense_apply_kernel<float><<<grid, GT, smem, st>>>(g0, g1, N, K, tiles_n, tiles_m0, k_chunk, split_stride);
+    dense_apply_kernel<float><<<grid, GT, smem, st>>>(g0, g1, g2, N, K, tiles_n, tiles_m0, tiles_m1, k_chunk, split_stride);
 }
 
-// Two problems in one launch (second may be empty: g1.M == 0).
+// Up to three problems in one launch (riders may be empty: M == 0).  rider_tile_rows: expected number of 128-row
+// tiles the riders will really occupy (their row counts live on the device), used to pick the tile width.
 template <typename T>
-void launch_gemm_grouped(cudaStream_t st, const GemmGroup<T>& g0, const GemmGroup<T>& g1, int N, int K, int nsplit,
-                         i64 split_stride) {
-    int tiles_m0 = (g0.M + BM - 1) / BM, tiles_m1 = (g1.M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
-    if (tiles_m0 + tiles_m1 <= 0 || N <= 0) return;
+void launch_gemm_grouped(cudaStream_t st, const GemmGroup<T>& g0, const GemmGroup<T>& g1, const GemmGroup<T>& g2, int N,
+                         int K, int nsplit, i64 split_stride, int rider_tile_rows) {
+    int tiles_m0 = (g0.M + BM - 1) / BM, tiles_m1 = (g1.M + BM - 1) / BM, tiles_m2 = (g2.M + BM - 1) / BM;
+    int tiles_n = (N + BN - 1) / BN;
+    if (tiles_m0 + tiles_m1 + tiles_m2 <= 0 || N <= 0) return;
     if (nsplit < 1) nsplit = 1;
     int k_chunk = (K + nsplit - 1) / nsplit;
     k_chunk = ((k_chunk + BK - 1) / BK) * BK;
-    dim3 grid((tiles_m0 + tiles_m1) * tiles_n, nsplit);
-    launch_tile_kernel<T>(grid, st, g0, g1, N, K, tiles_n, tiles_m0, k_chunk, split_stride);
+    dim3 grid((tiles_m0 + tiles_m1 + tiles_m2) * tiles_n, nsplit);
+    launch_tile_kernel<T>(grid, st, g0, g1, g2, N, K, tiles_n, tiles_m0, tiles_m1, k_chunk, split_stride, rider_tile_rows);
 }
 
 // General strided form with split-K: slice s of nsplit writes out + s*split_stride (a partial plane).
@@ -565,7 +576,7 @@ void launch_gemm(cudaStream_t st, const T* A, i64 lda, const T* B, i64 ldb, T* o
     if (M <= 0 || N <= 0) return;
     GemmGroup<T> g0{A, lda, B, ldb, out, ldo, M, m_dev, sub, nullptr, nullptr};
     GemmGroup<T> g1{nullptr, 0, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr};
-    launch_gemm_grouped<T>(st, g0, g1, N, K, nsplit, split_stride);
+    launch_gemm_grouped<T>(st, g0, g1, g1, N, K, nsplit, split_stride, 0);
 }
 
 // out = (A - sub) . B ; sub (optional, [K]) is subtracted from every row of A on load (q - mu).
@@ -576,7 +587,8 @@ void launch_dense_apply(cudaStream_t st, const T* A, const T* B, T* out, int M, 
 }
 
 #define B2H_INST(T)                                                                                                  \
-    template void launch_gemm_grouped<T>(cudaStream_t, const GemmGroup<T>&, const GemmGroup<T>&, int, int, int, i64); \
+    template void launch_gemm_grouped<T>(cudaStream_t, const GemmGroup<T>&, const GemmGroup<T>&, const GemmGroup<T>&,  \
+                                         int, int, int, i64, int);                                                    \
     template void launch_gemm<T>(cudaStream_t, const T*, i64, const T*, i64, T*, i64, int, int, int, const int*,     \
                                  const T*, int, i64);                                                                \
     template void launch_dense_apply<T>(cudaStream_t, const T*, const T*, T*, int, int, int, const int*, const T*);

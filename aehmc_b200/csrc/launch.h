@@ -11,6 +11,10 @@ struct b2h_ctx {
     int device;
     cudaStream_t stream;
     int sm_count;
+    // side stream for the dense-metric momentum contractions (a few row tiles per tick): run beside the main
+    // stream's kernels they share SMs fluidly instead of adding a mostly empty wave to a full launch
+    cudaStream_t side;
+    cudaEvent_t ev_pre[2], ev_side[2];
 };
 
 namespace b2h {
@@ -41,8 +45,8 @@ struct GemmGroup {
     const int* out_rows;   // optional scatter list for the output rows
 };
 template <typename T>
-void launch_gemm_grouped(cudaStream_t st, const GemmGroup<T>& g0, const GemmGroup<T>& g1, int N, int K, int nsplit,
-                         i64 split_stride);
+void launch_gemm_grouped(cudaStream_t st, const GemmGroup<T>& g0, const GemmGroup<T>& g1, const GemmGroup<T>& g2, int N,
+                         int K, int nsplit, i64 split_stride, int rider_tile_rows);
 
 template <typename T>
 void launch_dense_apply(cudaStream_t st, const T* A, const T* B, T* out, int M, int N, int K, const int* m_dev,

@@ -117,6 +117,33 @@ def c4(small):
     return out
 
 
+def wide(small):
+    """Fused persistent NUTS kernel on an elementwise target (iid Gaussian, diagonal imm): the streaming
+    formulation's 11*d*s algorithmic bytes per leapfrog against the HBM peak."""
+    out = []
+    for d, Cn, dt, G in ((128, 131072, torch.float64, 0), (128, 131072, torch.float32, 0), (1000, 16384, torch.float64, 0),
+                         (32, 262144, torch.float64, 0)):
+        if small:
+            Cn //= 8
+        rng = np.random.default_rng(0)
+        sigma = np.exp(0.3 * rng.standard_normal(d))
+        model = ab.models.IIDGaussian(np.zeros(d), sigma, dtype=dt)
+        q0 = rng.standard_normal((Cn, d)) * sigma
+        state = ab.nuts.new_state(q0, model)
+        eps = 1.2 / d ** 0.25
+        run = lambda: _engine.run("nuts", model, sigma ** 2, ab.RandomStream(seed=5), state, eps, n_transitions=20,
+                                  return_counters=True, group=G)
+        run()
+        (info, ex), ms = timed(run)
+        leap = int(ex["counters"][0].item())
+        s_ = 8 if dt == torch.float64 else 4
+        out.append({"workload": f"fused NUTS iid Gaussian d={d} {str(dt)[6:]}", "chains": Cn, "transitions": 20,
+                    "ms": ms, "grad_evals_per_sec": leap / (ms * 1e-3), "mean_leapfrogs": leap / (Cn * 20),
+                    "hbm_frac_11ds": leap * 11 * d * s_ / (ms * 1e-3) / 1e9 / PEAK_HBM,
+                    "mean_accept": float(info.acceptance_probability.mean())})
+    return out
+
+
 def c3(small):
     """config 2: NUTS Bayesian logistic regression, N = 100k, D = 128, 4096 chains (FP64/FP32 FMA-path gradient)."""
     out = []
@@ -149,7 +176,7 @@ def c3(small):
 
 if __name__ == "__main__":
     small = "--small" in sys.argv
-    names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["leapfrog", "c1", "c4", "c3"]
+    names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["leapfrog", "c1", "wide", "c4", "c3"]
     for n in names:
-        for line in {"c1": c1, "c3": c3, "c4": c4, "leapfrog": leapfrog}[n](small):
+        for line in {"c1": c1, "c3": c3, "c4": c4, "leapfrog": leapfrog, "wide": wide}[n](small):
             print(json.dumps(line), flush=True)
