@@ -54,6 +54,7 @@ int b2h_ctx_create(int device, void* stream, b2h_ctx** out) {
         B2H_CUDA(cudaEventCreateWithFlags(&ctx->ev_pre[i], cudaEventDisableTiming));
         B2H_CUDA(cudaEventCreateWithFlags(&ctx->ev_side[i], cudaEventDisableTiming));
     }
+    B2H_CUDA(cudaMallocHost(&ctx->host_flag, sizeof(int)));
     *out = ctx;
     return 0;
 }
@@ -61,6 +62,7 @@ int b2h_ctx_create(int device, void* stream, b2h_ctx** out) {
 int b2h_ctx_destroy(b2h_ctx* ctx) {
     if (ctx) {
         cudaStreamDestroy(ctx->side);
+        cudaFreeHost(ctx->host_flag);
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_pre[i]); cudaEventDestroy(ctx->ev_side[i]); }
     }
     delete ctx;

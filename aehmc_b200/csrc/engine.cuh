@@ -92,6 +92,7 @@ struct EngineView {
     // each chain's NEXT transition; a chain that starts a transition consumes them and queues a request
     // (list/count of parity mom_parity, normals in mom_z) that rides along the following dense applies.
     T *mom_p, *mom_v, *mom_z;            // mom_z: [2][C][d] compact request rows
+    T *mom_part;                         // split-K partial planes of the two momentum contractions
     int* mom_count;                      // [2]
     int* mom_list;                       // [2][C]
     int mom_parity;

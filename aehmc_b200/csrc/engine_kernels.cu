@@ -7,6 +7,8 @@
 //               correlated Gaussian, logistic regression) -> each tick is
 //               pre (half kick + drift) -> gradient -> [dense metric: w' = imm.g', one contraction] -> post,
 //               all chains in lock-step, chains restarting transitions independently.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -30,6 +32,8 @@ struct Carver {
         return p;
     }
 };
+
+constexpr int kRiderSplit = 5;      // split-K slices of the momentum contractions (few rows, full K)
 
 struct EnginePlan {
     int G;
@@ -100,6 +104,7 @@ static size_t carve(EngineView<T>& v, char* base, const EnginePlan& pl, const b2
         v.xc = cv.take<T>(n);
         v.mom_p = cv.take<T>(n); v.mom_v = cv.take<T>(n); v.mom_z = cv.take<T>(2 * n);
         v.mom_count = cv.take<int>(4); v.mom_list = cv.take<int>(2 * (size_t)C);
+        v.mom_part = cv.take<T>(2 * (size_t)kRiderSplit * n);
     }
     v.scratch = cv.take<int>(64);
     if (model_ws_bytes) {
@@ -260,6 +265,25 @@ __global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksSplit) spl
     }
 }
 
+// sum the split-K planes of a rider contraction and scatter the rows to their chains:
+// out[list[r]][:] = sum_s part[s][r][:] for r < *count   (two riders per launch: blockIdx.y)
+template <typename T>
+__global__ void rider_reduce_kernel(const T* part0, const int* count0, const int* list0, T* out0, const T* part1,
+                                    const int* count1, const int* list1, T* out1, int nsplit, i64 plane, int d) {
+    const T* part = blockIdx.y ? part1 : part0;
+    const int* count = blockIdx.y ? count1 : count0;
+    const int* list = blockIdx.y ? list1 : list0;
+    T* out = blockIdx.y ? out1 : out0;
+    const int r = blockIdx.x;
+    if (r >= *count) return;
+    const i64 dst = (i64)list[r] * d;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        T s = 0;
+        for (int k = 0; k < nsplit; ++k) s += part[(i64)k * plane + (i64)r * d + j];
+        out[dst + j] = s;
+    }
+}
+
 // dense metric momentum at the start of a run: normals of every chain's first transition (row c of mom_z)
 template <typename T>
 __global__ void mom_init_kernel(EngineView<T> v) {
@@ -316,8 +340,7 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
     i64 bound = max_ticks > 0 ? max_ticks
                               : (i64)n_transitions * (HMC ? (i64)cfg->num_integration_steps
                                                           : (((i64)1 << v.maxd) - 1 + v.maxd)) + 1;
-    int* host_flag = nullptr;
-    B2H_CUDA(cudaMallocHost(&host_flag, sizeof(int)));
+    int* host_flag = ctx->host_flag;
     int rc = 0;
     GemmGroup<T> none{nullptr, 0, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr};
     int last_parity = 0;
@@ -333,6 +356,9 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
         }
     }
     bool side_pending[2] = {false, false};
+    static int use_side = -1;
+    if (use_side < 0) { const char* e = getenv("B2H_SIDE_STREAM"); use_side = e ? atoi(e) : 1; }
+    cudaStream_t rider_stream = use_side ? ctx->side : st;
     for (i64 tick = 0; tick < bound; ++tick) {
         const int b = (int)(tick & 1);
         if (pl.dense) {
@@ -347,15 +373,26 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
             split_pre_kernel<T, G, true, HMC><<<grid, thr, 0, st>>>(v);      // half kick + drift by the v/w recurrence
             // side stream: p0 = z . S^T of the transitions queued by this pre kernel, and v0 = imm . p0 of the
             // transitions queued one tick ago (their p0 was produced by the previous side launch)
-            B2H_CUDA(cudaEventRecord(ctx->ev_pre[b], st));
-            B2H_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_pre[b], 0));
-            GemmGroup<T> g1{v.mom_z + (size_t)b * C * d, (i64)d, sqrt_t, (i64)d, v.mom_p, (i64)d, C, v.mom_count + b,
-                            nullptr, nullptr, v.mom_list + (size_t)b * C};
-            GemmGroup<T> g2{v.mom_p, (i64)d, imm_dense, (i64)d, v.mom_v, (i64)d, C, v.mom_count + (b ^ 1), nullptr,
-                            v.mom_list + (size_t)(b ^ 1) * C, v.mom_list + (size_t)(b ^ 1) * C};
-            launch_gemm_grouped<T>(ctx->side, g1, g2, none, d, d, 1, 0, 0);
-            B2H_CUDA(cudaEventRecord(ctx->ev_side[b], ctx->side));
-            side_pending[b] = true;
+            if (use_side) {
+                B2H_CUDA(cudaEventRecord(ctx->ev_pre[b], st));
+                B2H_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_pre[b], 0));
+            }
+            // few rows, full reduction length: split K so that the tiles spread over all SMs, then reduce + scatter
+            const i64 plane = (i64)C * d;
+            T* part1 = v.mom_part;
+            T* part2 = v.mom_part + (size_t)kRiderSplit * plane;
+            GemmGroup<T> g1{v.mom_z + (size_t)b * C * d, (i64)d, sqrt_t, (i64)d, part1, (i64)d, C, v.mom_count + b,
+                            nullptr, nullptr, nullptr};
+            GemmGroup<T> g2{v.mom_p, (i64)d, imm_dense, (i64)d, part2, (i64)d, C, v.mom_count + (b ^ 1), nullptr,
+                            v.mom_list + (size_t)(b ^ 1) * C, nullptr};
+            launch_gemm_grouped<T>(rider_stream, g1, g2, none, d, d, kRiderSplit, plane, 0);
+            rider_reduce_kernel<T><<<dim3(C, 2), 128, 0, rider_stream>>>(
+                part1, v.mom_count + b, v.mom_list + (size_t)b * C, v.mom_p, part2, v.mom_count + (b ^ 1),
+                v.mom_list + (size_t)(b ^ 1) * C, v.mom_v, kRiderSplit, plane, d);
+            if (use_side) {
+                B2H_CUDA(cudaEventRecord(ctx->ev_side[b], ctx->side));
+                side_pending[b] = true;
+            }
         } else {
             split_pre_kernel<T, G, false, HMC><<<grid, thr, 0, st>>>(v);
         }
@@ -386,7 +423,6 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
                         v.mom_list + (size_t)last_parity * C, v.mom_list + (size_t)last_parity * C};
         launch_gemm_grouped<T>(st, g0, none, none, d, d, 1, 0, 0);
     }
-    cudaFreeHost(host_flag);
     if (rc) return rc;
     B2H_LAUNCH_CHECK();
     return 0;

@@ -341,7 +341,7 @@ template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile
 template <int BN_>
 __global__ void __launch_bounds__(GT, 1)
 dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGroup<double> g2, int N, int K, int tiles_n,
-                              int tiles_m0, int tiles_m1) {
+                              int tiles_m0, int tiles_m1, int k_chunk, i64 split_stride) {
     typedef double T;
     constexpr int NJ = BN_ / 16;               // 8-wide MMA tiles per warp along N (warp tile 32 x BN_/2)
     constexpr int BLD = BN_ + 8;
@@ -359,7 +359,11 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
     const T* __restrict__ B = g.B;
     const T* __restrict__ sub = g.sub;
     const i64 lda = g.lda, ldb = g.ldb, ldo = g.ldo;
-    T* __restrict__ out = g.out;
+    // split-K: slice blockIdx.y reduces k in [k_begin, k_end) into its own partial plane (rows not scattered)
+    const int k_begin = blockIdx.y * k_chunk;
+    const int k_end = min(K, k_begin + k_chunk);
+    const bool split = gridDim.y > 1;
+    T* __restrict__ out = g.out + (i64)blockIdx.y * split_stride;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* As = reinterpret_cast<T*>(smem_raw);                       // [STAGES][BM][ALD]
@@ -381,14 +385,14 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
     constexpr int B_ITERS = (B_CHUNKS + GT - 1) / GT;
 
     auto issue = [&](int kt, int stage) {
-        const int k0 = kt * BK;
+        const int k0 = k_begin + kt * BK;
         T* as = As + stage * A_STAGE;
         T* bs = Bs + stage * B_STAGE;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int c = tid + GT * i, row = c >> 3, kc = (c & 7) * 2;
             const int gk = k0 + kc;
-            const bool ok = a_src[i] >= 0 && gk < K;
+            const bool ok = a_src[i] >= 0 && gk < k_end;
             cp_async16(as + row * ALD + kc, ok ? (const void*)(A + a_src[i] + gk) : (const void*)A, ok ? 16 : 0);
         }
 #pragma unroll
@@ -397,13 +401,13 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
             if (c < B_CHUNKS) {
                 const int kr = c / (BN_ / 2), nc = (c % (BN_ / 2)) * 2;
                 const int gk = k0 + kr, gn = n0 + nc;
-                const bool ok = gk < K && gn < N;
+                const bool ok = gk < k_end && gn < N;
                 cp_async16(bs + kr * BLD + nc, ok ? (const void*)(B + (i64)gk * ldb + gn) : (const void*)B, ok ? 16 : 0);
             }
         }
         if (sub && tid < BK / 2) {
             const int gk = k0 + tid * 2;
-            cp_async16(Ss + stage * BK + tid * 2, gk < K ? (const void*)(sub + gk) : (const void*)sub, gk < K ? 16 : 0);
+            cp_async16(Ss + stage * BK + tid * 2, gk < k_end ? (const void*)(sub + gk) : (const void*)sub, gk < k_end ? 16 : 0);
         }
     };
 
@@ -415,7 +419,7 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.0;
 
-    const int nk = (K + BK - 1) / BK;
+    const int nk = max((k_end - k_begin + BK - 1) / BK, 0);
 #pragma unroll
     for (int st = 0; st < STAGES - 1; ++st) {
         if (st < nk) issue(st, st);
@@ -462,7 +466,7 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
         for (int h = 0; h < 2; ++h) {
             const int gr = m0 + wm + i * 16 + h * 8 + gq;
             if (gr >= M) continue;
-            const i64 orow = (i64)(g.out_rows ? g.out_rows[gr] : gr) * ldo;
+            const i64 orow = (i64)((g.out_rows && !split) ? g.out_rows[gr] : gr) * ldo;
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 const int gn = n0 + wn + j * 8 + tq * 2;
@@ -473,13 +477,14 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
 
 template <int BN_>
 static void launch_async(cudaStream_t st, const GemmGroup<double>& g0, const GemmGroup<double>& g1,
-                         const GemmGroup<double>& g2, int N, int K) {
+                         const GemmGroup<double>& g2, int N, int K, int nsplit, int k_chunk, i64 split_stride) {
     constexpr int smem = (STAGES * (BM * ALD + BK * (BN_ + 8)) + STAGES * BK) * (int)sizeof(double);
     int tiles_m0 = (g0.M + BM - 1) / BM, tiles_m1 = (g1.M + BM - 1) / BM, tiles_m2 = (g2.M + BM - 1) / BM;
     int tiles_n = (N + BN_ - 1) / BN_;
     cudaFuncSetAttribute(dense_apply_dmma_async_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    dense_apply_dmma_async_kernel<BN_><<<(tiles_m0 + tiles_m1 + tiles_m2) * tiles_n, GT, smem, st>>>(g0, g1, g2, N, K, tiles_n,
-                                                                                                tiles_m0, tiles_m1);
+    dim3 grid((tiles_m0 + tiles_m1 + tiles_m2) * tiles_n, nsplit);
+    dense_apply_dmma_async_kernel<BN_><<<grid, GT, smem, st>>>(g0, g1, g2, N, K, tiles_n, tiles_m0, tiles_m1, k_chunk,
+                                                               split_stride);
 }
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -518,15 +523,15 @@ void launch_tile_kernel<double>(dim3 grid, cudaStream_t st, const GemmGroup<doub
         const char* e = getenv("B2H_GEMM_ASYNC");
         use_async = e ? atoi(e) : 1;
     }
-    if (use_async && grid.y == 1 && N % 2 == 0 && K % 2 == 0 && group_async_ok(g0) && group_async_ok(g1) &&
-        group_async_ok(g2)) {
+    if (use_async && N % 2 == 0 && K % 2 == 0 && k_chunk % 2 == 0 && split_stride % 2 == 0 && group_async_ok(g0) &&
+        group_async_ok(g1) && group_async_ok(g2)) {
         static int force_bn = -1;
         if (force_bn < 0) { const char* e = getenv("B2H_GEMM_BN"); force_bn = e ? atoi(e) : 0; }
         // the rider groups' row counts live on the device: the caller passes the expected number of rider TILE ROWS
         const int bn = force_bn ? force_bn : pick_bn(g0.M, extra_rows_hint, N);
-        if (bn == 112) launch_async<112>(st, g0, g1, g2, N, K);
-        else if (bn == 96) launch_async<96>(st, g0, g1, g2, N, K);
-        else launch_async<128>(st, g0, g1, g2, N, K);
+        if (bn == 112) launch_async<112>(st, g0, g1, g2, N, K, grid.y, k_chunk, split_stride);
+        else if (bn == 96) launch_async<96>(st, g0, g1, g2, N, K, grid.y, k_chunk, split_stride);
+        else launch_async<128>(st, g0, g1, g2, N, K, grid.y, k_chunk, split_stride);
         return;
     }
     constexpr int smem = 2 * 2 * BK * DLD * (int)sizeof(double);

@@ -15,6 +15,7 @@ struct b2h_ctx {
     // stream's kernels they share SMs fluidly instead of adding a mostly empty wave to a full launch
     cudaStream_t side;
     cudaEvent_t ev_pre[2], ev_side[2];
+    int* host_flag;   // pinned, for the split engine's completion poll
 };
 
 namespace b2h {

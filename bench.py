@@ -120,35 +120,59 @@ def run_reference_arm(args):
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region, through NVML in a background thread (a looping
+    `nvidia-smi -lms` process perturbs kernel launches enough to halve the measured throughput)."""
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period=0.1):
+        self.index, self.period, self.rows, self.stop_flag, self.thread, self.ok = index, period, [], False, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a list of ordinals
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except Exception:
+                    phys = index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append((sm, mx, int(reasons)))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        if self.ok:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted({n for _, _, r in self.rows for n, bit in names.items() if r & bit})
+        sm = [r[0] for r in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(r[1] for r in self.rows) if sm else None,
                 "reasons": reasons, "samples": len(sm)}
 
 
@@ -281,6 +305,14 @@ def run_gpu_arm(args):
         p0.record(); torch.matmul(x, y); p1.record(); torch.cuda.synchronize(dev)
         best = min(best, p0.elapsed_time(p1))
     fp64_peak = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    # the same product back to back for ~1.5 s: what the FP64 tensor path sustains under the power cap
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps_s = max(10, int(1500.0 / best))
+    p0.record()
+    for _ in range(reps_s):
+        torch.matmul(x, y)
+    p1.record(); torch.cuda.synchronize(dev)
+    fp64_sustained = 2.0 * n ** 3 * reps_s / (p0.elapsed_time(p1) * 1e-3) / 1e12
     del x, y
     # cuBLAS on the kernel's own shape, for context
     mm = metric.imm
@@ -299,7 +331,7 @@ def run_gpu_arm(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     gemms_per_tick = 4.0          # 3 whole-batch applies + the (small) momentum applies, upper bound on their share
     step_ms = ms_total / args.steps
-    elementwise_ms = max(step_ms - ticks * 3.0 * gemm_ms, 1e-9)
+    elementwise_ms = max(step_ms - ticks * 2.0 * gemm_ms, 1e-9)
     b_nuts = 11.0 * d * 8.0       # algorithmic bytes of one NUTS inner step incl. U-turn bookkeeping
     hbm_achieved = b_nuts * Cn * ticks / (elementwise_ms * 1e-3) / 1e9
 
@@ -324,7 +356,7 @@ def run_gpu_arm(args):
         del ex
 
     if rank == 0:
-        kernels_per_tick = 11
+        kernels_per_tick = 6          # pre, gradient apply, potential, imm.g apply, post + the momentum side launch
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
@@ -347,15 +379,16 @@ def run_gpu_arm(args):
             "divided by the wall time of all transitions incl. the discarded ones",
             "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak, "traffic": None,
-                         "kernel": "dense_apply_kernel<double> (out[C x d] = in[C x d] . M[d x d]); 3 launches per tick",
+                         "kernel": "dense_apply_dmma_async_kernel<BN> (out[C x d] = in[C x d] . M[d x d], FP64 DMMA + cp.async): gradient and imm.g, 2 launches per tick",
                          "flops_per_launch": flops, "avg_launch_ms": gemm_ms,
                          "peak_source": f"measured in this run: torch.matmul fp64 {n}^3 (cuBLAS), best of 5 "
                                         "(MEASURED_PEAKS.json has no FP64 figure; SURVEY.md 8d names FP64 FMA as the bound)",
-                         "share_of_step": ticks * 3.0 * gemm_ms / step_ms,
+                         "peak_sustained": fp64_sustained, "frac_of_sustained": achieved / fp64_sustained,
+                         "launches_per_tick": 2, "share_of_step": ticks * 2.0 * gemm_ms / step_ms,
                          "cublas_same_shape_tflops": cublas_same_shape},
             "roofline_elementwise": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                                      "frac": hbm_achieved / hbm_peak, "traffic": None,
-                                     "how": "derived: 11*d*8 algorithmic bytes per chain-tick over (step time - 3 dense applies per tick)"},
+                                     "how": "derived: 11*d*8 algorithmic bytes per chain-tick over (step time - 2 dense applies per tick); pre + post + potential kernels"},
         }
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
@@ -372,7 +405,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
