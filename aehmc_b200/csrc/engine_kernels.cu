@@ -192,6 +192,8 @@ struct Geo {
     static constexpr int kChainsPerBlock = G > 32 ? 1 : 128 / G;
     // the per-tick (split) kernels are latency-bound streams: cap registers at 64 for 50% occupancy
     static constexpr int kMinBlocksSplit = G > 32 ? 4 : 8;
+    // the persistent fused kernel is latency / instruction-fetch bound: favour resident warps over registers
+    static constexpr int kMinBlocksFused = G > 32 ? 3 : 5;
     __device__ static int chain() {
         return G > 32 ? (int)blockIdx.x : (int)(blockIdx.x * kChainsPerBlock + threadIdx.x / G);
     }
@@ -199,7 +201,7 @@ struct Geo {
 };
 
 template <typename T, int G, int MODEL, bool HMC>
-__global__ void __launch_bounds__(Geo<G>::kThreads)
+__global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksFused)
 fused_run_kernel(EngineView<T> v, ModelDev m, i64 max_ticks) {
     __shared__ double red_s[128];
     const int c = Geo<G>::chain();
