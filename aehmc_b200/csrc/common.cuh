@@ -154,6 +154,12 @@ struct Group {
         sum<1>(v, smem);
         return v[0];
     }
+    // value held by lane `src` of the group (sub-warp / warp groups only), broadcast to the whole group
+    template <typename V>
+    B2H_DEVINL static V shfl(V x, int src) {
+        if (G == 1) return x;
+        return __shfl_sync(mask(), x, (int)((threadIdx.x & 31u) & ~(unsigned)((G & 31) - 1)) + src);
+    }
     // value held by the group's lane 0, broadcast to the whole group
     B2H_DEVINL static int bcast(int x, double* smem) {
         if (G == 1) return x;

@@ -152,6 +152,69 @@ struct Chain {
 };
 
 // ---------------------------------------------------------------------------
+// The integration front (q, p, dU/dq of the edge being extended).  MemFront reads and writes the edge arrays
+// every tick (split engine, dense metric, large rows).  RegFront keeps the front in registers of the chain's
+// group for the whole sub-tree and writes it back only at sub-tree ends, which removes 8 of the ~15 row
+// accesses per leapfrog of the persistent fused kernel.  Element e of lane l is coordinate j = l + e*G.
+// ---------------------------------------------------------------------------
+template <typename T>
+struct MemFront {
+    static constexpr int kE = 1 << 30;
+    static constexpr bool kRegs = false;
+    T *Q, *P, *Gd;
+    template <int G> B2H_DEVINL void bind(const Chain<T, G>& ch) {
+        Q = ch.r.go_right ? ch.v.qr : ch.v.ql;
+        P = ch.r.go_right ? ch.v.pr : ch.v.pl;
+        Gd = ch.r.go_right ? ch.v.gr : ch.v.gl;
+    }
+    template <int G> B2H_DEVINL void flush(const Chain<T, G>&) {}
+    B2H_DEVINL T q(int, i64 a) const { return Q[a]; }
+    B2H_DEVINL T p(int, i64 a) const { return P[a]; }
+    B2H_DEVINL T g(int, i64 a) const { return Gd[a]; }
+    B2H_DEVINL void set_q(int, i64 a, T x) { Q[a] = x; }
+    B2H_DEVINL void set_p(int, i64 a, T x) { P[a] = x; }
+    B2H_DEVINL void set_g(int, i64 a, T x) { Gd[a] = x; }
+};
+
+template <typename T, int E>
+struct RegFront {
+    static constexpr int kE = E;
+    static constexpr bool kRegs = true;
+    T fq[E], fp[E], fg[E];
+    template <int G> B2H_DEVINL void bind(const Chain<T, G>& ch) {
+        const T* Q = ch.r.go_right ? ch.v.qr : ch.v.ql;
+        const T* P = ch.r.go_right ? ch.v.pr : ch.v.pl;
+        const T* Gd = ch.r.go_right ? ch.v.gr : ch.v.gl;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int j = ch.lane + e * G;
+            if (j < ch.v.d) { i64 a = ch.at(j); fq[e] = Q[a]; fp[e] = P[a]; fg[e] = Gd[a]; }
+            else { fq[e] = 0; fp[e] = 0; fg[e] = 0; }
+        }
+    }
+    template <int G> B2H_DEVINL void flush(const Chain<T, G>& ch) {
+        T* Q = ch.r.go_right ? ch.v.qr : ch.v.ql;
+        T* P = ch.r.go_right ? ch.v.pr : ch.v.pl;
+        T* Gd = ch.r.go_right ? ch.v.gr : ch.v.gl;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int j = ch.lane + e * G;
+            if (j < ch.v.d) { i64 a = ch.at(j); Q[a] = fq[e]; P[a] = fp[e]; Gd[a] = fg[e]; }
+        }
+    }
+    B2H_DEVINL T q(int e, i64) const { return fq[e]; }
+    B2H_DEVINL T p(int e, i64) const { return fp[e]; }
+    B2H_DEVINL T g(int e, i64) const { return fg[e]; }
+    B2H_DEVINL void set_q(int e, i64, T x) { fq[e] = x; }
+    B2H_DEVINL void set_p(int e, i64, T x) { fp[e] = x; }
+    B2H_DEVINL void set_g(int e, i64, T x) { fg[e] = x; }
+};
+
+// loop over this lane's coordinates: fully unrolled for a register front, a plain strided loop otherwise
+#define B2H_ELEMS(Front, e, j, lane, d, G) \
+    _Pragma("unroll") for (int e = 0, j = (lane); e < Front::kE && j < (d); ++e, j += (G))
+
+// ---------------------------------------------------------------------------
 // sub-tree start: direction draw (trajectory.py:516-518)
 // ---------------------------------------------------------------------------
 template <typename T, int G>
@@ -228,20 +291,17 @@ B2H_DEVINL void begin_transition(Chain<T, G>& ch) {
 //   p_half = p - (0.5*e) g ;  q' = q + e * (imm p_half)
 // Dense metric: imm p_half = v - (0.5*e) w with v = imm p and w = imm g carried along with the state.
 // ---------------------------------------------------------------------------
-template <typename T, int G, bool DENSE, bool SPLIT>
-B2H_DEVINL void half_kick_drift(Chain<T, G>& ch) {
+template <typename T, int G, bool DENSE, bool SPLIT, class Front>
+B2H_DEVINL void half_kick_drift(Chain<T, G>& ch, Front& f) {
     const EngineView<T>& v = ch.v;
-    T* Q = ch.r.go_right ? v.qr : v.ql;
-    T* P = ch.r.go_right ? v.pr : v.pl;
-    T* Gd = ch.r.go_right ? v.gr : v.gl;
     T* V = ch.r.go_right ? v.vr : v.vl;     // dense only
     T* W = ch.r.go_right ? v.wr : v.wl;     // dense only
     T e = (T)(ch.r.go_right ? ch.r.eps : -ch.r.eps);
     T he = (T)0.5 * e;
-    for (int j = ch.lane; j < v.d; j += G) {
+    B2H_ELEMS(Front, ee, j, ch.lane, v.d, G) {
         i64 a = ch.at(j);
-        T ph = P[a] - he * Gd[a];
-        P[a] = ph;
+        T ph = f.p(ee, a) - he * f.g(ee, a);
+        f.set_p(ee, a, ph);
         T vh;
         if (DENSE) {
             vh = V[a] - he * W[a];           // imm.(p - h g) by linearity
@@ -249,8 +309,8 @@ B2H_DEVINL void half_kick_drift(Chain<T, G>& ch) {
         } else {
             vh = ch.imm(j) * ph;
         }
-        T qn = Q[a] + e * vh;
-        Q[a] = qn;
+        T qn = f.q(ee, a) + e * vh;
+        f.set_q(ee, a, qn);
         if (SPLIT) v.xa[(i64)ch.c * v.d + j] = qn;
     }
 }
@@ -354,14 +414,12 @@ B2H_DEVINL void end_transition(Chain<T, G>& ch, int num_doublings, bool is_turni
 // DENSE: xb holds g' and xc = imm g' (the one metric contraction of the tick); the edge holds p_half and
 // V = imm p_half.
 // ---------------------------------------------------------------------------
-template <typename T, int G, bool DENSE, bool SPLIT>
-B2H_DEVINL void post_gradient(Chain<T, G>& ch, T U_new) {
+// Returns true when the tick ended a sub-tree (the front was written back and must be re-bound).
+template <typename T, int G, bool DENSE, bool SPLIT, class Front>
+B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
     const EngineView<T>& v = ch.v;
     ChainRec& r = ch.r;
     const int d = v.d;
-    T* Q = r.go_right ? v.qr : v.ql;
-    T* P = r.go_right ? v.pr : v.pl;
-    T* Gd = r.go_right ? v.gr : v.gl;
     T* V = r.go_right ? v.vr : v.vl;     // dense only
     T* W = r.go_right ? v.wr : v.wl;     // dense only
     const T e = (T)(r.go_right ? r.eps : -r.eps);
@@ -384,23 +442,23 @@ B2H_DEVINL void post_gradient(Chain<T, G>& ch, T U_new) {
     T kacc = 0, dl[LV], dr[LV];
 #pragma unroll
     for (int l = 0; l < LV; ++l) { dl[l] = 0; dr[l] = 0; }
-    for (int j = ch.lane; j < d; j += G) {
+    B2H_ELEMS(Front, ee, j, ch.lane, d, G) {
         i64 a = ch.at(j);
         T p, vel, im = 0;
         if (DENSE) {
             T g = v.xb[(i64)ch.c * d + j], wv = v.xc[(i64)ch.c * d + j];
-            Gd[a] = g;
+            f.set_g(ee, a, g);
             W[a] = wv;
-            p = P[a] - he * g;
-            P[a] = p;
+            p = f.p(ee, a) - he * g;
+            f.set_p(ee, a, p);
             vel = V[a] - he * wv;            // imm p' = imm p_half - (0.5 e) imm g'
             V[a] = vel;
         } else {
             T g;
-            if (SPLIT) { g = v.xb[(i64)ch.c * d + j]; Gd[a] = g; }
-            else g = Gd[a];
-            p = P[a] - he * g;
-            P[a] = p;
+            if (SPLIT) { g = v.xb[(i64)ch.c * d + j]; f.set_g(ee, a, g); }
+            else g = f.g(ee, a);
+            p = f.p(ee, a) - he * g;
+            f.set_p(ee, a, p);
             im = ch.imm(j);
             vel = im * p;
         }
@@ -439,9 +497,9 @@ B2H_DEVINL void post_gradient(Chain<T, G>& ch, T U_new) {
     if (!term && nlev > LV) {                       // deeper levels (a step with >= 5 trailing one-bits): rare
         for (int i = imax - LV; i >= imin; --i) {
             T xl = 0, xr = 0;
-            for (int j = ch.lane; j < d; j += G) {
+            B2H_ELEMS(Front, ee, j, ch.lane, d, G) {
                 i64 a = ch.at(j), b = ch.ck(i, j);
-                T m = v.mck[b], sc = v.sckp[b], p = P[a], sm = v.sms[a];
+                T m = v.mck[b], sc = v.sckp[b], p = f.p(ee, a), sm = v.sms[a];
                 T subsum = sm - sc + m;
                 T rho = subsum - (p + m) / (T)2;
                 T vleft, vright;
@@ -479,9 +537,9 @@ B2H_DEVINL void post_gradient(Chain<T, G>& ch, T U_new) {
     }
     if (take) {
         r.E_sub = (double)E; r.U_sub = (double)U_new;
-        for (int j = ch.lane; j < d; j += G) {
+        B2H_ELEMS(Front, ee, j, ch.lane, d, G) {
             i64 a = ch.at(j);
-            v.qs[a] = Q[a]; v.ps[a] = P[a]; v.gs[a] = Gd[a];
+            v.qs[a] = f.q(ee, a); v.ps[a] = f.p(ee, a); v.gs[a] = f.g(ee, a);
             if (DENSE) v.ws[a] = W[a];
         }
     }
@@ -490,7 +548,9 @@ B2H_DEVINL void post_gradient(Chain<T, G>& ch, T U_new) {
     r.total_leap += 1;
 
     const bool end_sub = div || term || (s == (1 << k));       // Q1: 2**k more steps after step 0
-    if (!end_sub) { r.s = s + 1; return; }
+    if (!end_sub) { r.s = s + 1; return false; }
+    f.flush(ch);                                                // the edge arrays must be current from here on
+    Group<G>::sync();
 
     // ================= end of the sub-tree: expand_once (trajectory.py:537-608) =================
     // edges are already in place; msum += sub-tree sum; top-level U-turn on (left, right, msum)
@@ -539,6 +599,7 @@ B2H_DEVINL void post_gradient(Chain<T, G>& ch, T U_new) {
         r.k = nd;
         begin_subtree(ch);
     }
+    return true;
 }
 
 // ---------------------------------------------------------------------------
@@ -552,37 +613,37 @@ B2H_DEVINL void hmc_begin(Chain<T, G>& ch) {
     ch.r.hmc_step = 0;
 }
 
-template <typename T, int G, bool DENSE, bool SPLIT>
-B2H_DEVINL void hmc_post(Chain<T, G>& ch, T U_new) {
+template <typename T, int G, bool DENSE, bool SPLIT, class Front>
+B2H_DEVINL bool hmc_post(Chain<T, G>& ch, T U_new, Front& f) {
     const EngineView<T>& v = ch.v;
     ChainRec& r = ch.r;
     const int d = v.d;
     const T he = (T)0.5 * (T)r.eps;
     T kacc = 0;
-    for (int j = ch.lane; j < d; j += G) {
+    B2H_ELEMS(Front, ee, j, ch.lane, d, G) {
         i64 a = ch.at(j);
         if (DENSE) {
             T g = v.xb[(i64)ch.c * d + j], wv = v.xc[(i64)ch.c * d + j];
-            v.gr[a] = g;
+            f.set_g(ee, a, g);
             v.wr[a] = wv;
-            T p = v.pr[a] - he * g;
-            v.pr[a] = p;
+            T p = f.p(ee, a) - he * g;
+            f.set_p(ee, a, p);
             T vel = v.vr[a] - he * wv;
             v.vr[a] = vel;
             kacc += vel * p;
         } else {
             T g;
-            if (SPLIT) { g = v.xb[(i64)ch.c * d + j]; v.gr[a] = g; }
-            else g = v.gr[a];
-            T p = v.pr[a] - he * g;
-            v.pr[a] = p;
+            if (SPLIT) { g = v.xb[(i64)ch.c * d + j]; f.set_g(ee, a, g); }
+            else g = f.g(ee, a);
+            T p = f.p(ee, a) - he * g;
+            f.set_p(ee, a, p);
             kacc += (ch.imm(j) * p) * p;
         }
     }
     r.hmc_step += 1;
     r.nleap += 1;
     r.total_leap += 1;
-    if (r.hmc_step < v.hmc_L) return;           // uniform across the group: no reduction skipped unevenly
+    if (r.hmc_step < v.hmc_L) return false;     // uniform across the group: no reduction skipped unevenly
     const T K = (T)0.5 * (T)Group<G>::sum1((double)kacc, ch.red);   // K(-p) == K(p)
     const T E = U_new + K;
     double delta = (double)((T)r.E0 - E);
@@ -591,10 +652,10 @@ B2H_DEVINL void hmc_post(Chain<T, G>& ch, T U_new) {
     double p_accept = fmin(fmax(exp(delta), 0.0), 1.0);
     double u = draw_u(v.rng, DRAW_ACCEPT, ch.c, r.t, 0, v.maxd);
     bool acc = bern(u, p_accept);
-    for (int j = ch.lane; j < d; j += G) {
+    B2H_ELEMS(Front, ee, j, ch.lane, d, G) {
         i64 a = ch.at(j);
         if (acc) {
-            v.qp[a] = v.qr[a]; v.pp[a] = -v.pr[a]; v.gp[a] = v.gr[a];
+            v.qp[a] = f.q(ee, a); v.pp[a] = -f.p(ee, a); v.gp[a] = f.g(ee, a);
             if (DENSE) v.wp[a] = v.wr[a];
         }
         // on reject the state keeps (q, fresh momentum, g): pp already holds p0 (hmc.py:122,195)
@@ -602,6 +663,7 @@ B2H_DEVINL void hmc_post(Chain<T, G>& ch, T U_new) {
     if (acc) r.U_prop = (double)U_new;
     r.accept_prob = p_accept;
     end_transition(ch, 0, false, div);
+    return true;
 }
 
 }  // namespace b2h

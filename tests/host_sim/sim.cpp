@@ -9,27 +9,47 @@
 
 using namespace b2h;
 
-template <int MODEL, bool HMC>
-static void run_chain(EngineView<double>& v, const ModelDev& m, int c, long long max_ticks) {
+static int g_reg_front = 0;      // 0: memory front; 16: register front with 16 elements per (single) lane
+
+template <int MODEL, bool HMC, class Front>
+static void run_chain_f(EngineView<double>& v, const ModelDev& m, int c, long long max_ticks) {
     Chain<double, 1> ch(v, c, nullptr);
     ch.load();
+    Front f;
+    bool bound = false;
     long long tick = 0;
     while (max_ticks <= 0 || tick < max_ticks) {
         if (ch.r.phase == PH_DONE) break;
         if (ch.r.phase == PH_START) {
             if (HMC) hmc_begin<double, 1, false>(ch);
             else begin_transition<double, 1, false>(ch);
+            bound = false;
         }
-        half_kick_drift<double, 1, false, false>(ch);
-        double* Q = ch.r.go_right ? v.qr : v.ql;
-        double* Gd = ch.r.go_right ? v.gr : v.gl;
-        double U = model_grad<double, 1, MODEL>(m, Q + ch.base, Gd + ch.base, v.sj, 0, nullptr);
-        if (HMC) hmc_post<double, 1, false, false>(ch, U);
-        else post_gradient<double, 1, false, false>(ch, U);
+        if (!bound) { f.bind(ch); bound = Front::kRegs; }
+        half_kick_drift<double, 1, false, false>(ch, f);
+        double U;
+        if constexpr (Front::kRegs) {
+            U = model_grad_front<double, 1, MODEL>(m, f, 0, nullptr);
+        } else {
+            U = model_grad<double, 1, MODEL>(m, f.Q + ch.base, f.Gd + ch.base, v.sj, 0, nullptr);
+        }
+        bool ended;
+        if (HMC) ended = hmc_post<double, 1, false, false>(ch, U, f);
+        else ended = post_gradient<double, 1, false, false>(ch, U, f);
+        if (ended) bound = false;
         ++tick;
     }
+    if (bound) f.flush(ch);
     ch.store();
 }
+
+template <int MODEL, bool HMC>
+static void run_chain(EngineView<double>& v, const ModelDev& m, int c, long long max_ticks) {
+    if (g_reg_front) run_chain_f<MODEL, HMC, RegFront<double, 16>>(v, m, c, max_ticks);
+    else run_chain_f<MODEL, HMC, MemFront<double>>(v, m, c, max_ticks);
+}
+
+extern "C" void sim_set_reg_front(int on) { g_reg_front = on; }
 
 extern "C" int sim_run(int model_kind, int hmc, int C, int d, int maxd, const double* a, const double* b, double s0,
                        int imm_kind, const double* imm, double imm_scalar, double* q, double* p, double* U, double* g,

@@ -144,3 +144,57 @@ def test_hmc_iid_gaussian():
             np.testing.assert_allclose(got[k], ref[k], rtol=1e-11, atol=1e-13, err_msg=k)
         np.testing.assert_array_equal(got["is_diverging"].astype(bool), ref["is_diverging"])
         np.testing.assert_allclose(got["draws"], ref["draws"], rtol=1e-11, atol=1e-13)
+
+
+# ---- the same state machine with the integration front held in "registers" (engine.cuh RegFront) -------------
+@pytest.mark.parametrize("case", ["iid", "funnel", "schools", "adapt", "hmc"])
+def test_register_front_matches_oracle(case):
+    rng = np.random.default_rng(123)
+    if case == "iid":
+        C, T, d = 10, 3, 7
+        mu, sigma = rng.standard_normal(d), np.exp(0.5 * rng.standard_normal(d))
+        q0 = mu + sigma * rng.standard_normal((C, d))
+        eps = 0.5 * np.exp(0.3 * rng.standard_normal(C))
+        draws = parity.random_draws(rng, C, T, d)
+        model = models.IIDGaussian(mu, sigma, const=0.1)
+        ref = parity.oracle_nuts(model, q0, eps, sigma ** 2, draws, T)
+        got = hostsim.run(0, mu, model.inv_var, 0.1, sigma ** 2, q0, eps, draws, T, n_store=T, reg_front=True)
+        parity.assert_nuts_parity(got, ref, rtol=1e-11, what="iid regs")
+        np.testing.assert_allclose(got["draws"], ref["draws"], rtol=1e-11, atol=1e-13)
+    elif case == "funnel":
+        C, T, d = 16, 3, 10
+        q0 = rng.standard_normal((C, d))
+        draws = parity.random_draws(rng, C, T, d)
+        for eps in (0.1, 3.0):
+            ref = parity.oracle_nuts(models.NealFunnel(d), q0, eps, np.ones(d), draws, T)
+            got = hostsim.run(2, None, None, 0.0, np.ones(d), q0, eps, draws, T, reg_front=True)
+            parity.assert_nuts_parity(got, ref, rtol=1e-10, what="funnel regs")
+    elif case == "schools":
+        C, T, d = 16, 3, 10
+        q0 = 0.5 * rng.standard_normal((C, d))
+        draws = parity.random_draws(rng, C, T, d)
+        model = models.EightSchools()
+        ref = parity.oracle_nuts(model, q0, 0.3, np.ones(d), draws, T)
+        got = hostsim.run(3, model.y, model.inv_var, 0.0, np.ones(d), q0, 0.3, draws, T, reg_front=True)
+        parity.assert_nuts_parity(got, ref, rtol=1e-10, what="schools regs")
+    elif case == "adapt":
+        C, W, d = 4, 22, 5
+        mu, sigma = rng.standard_normal(d), np.exp(rng.standard_normal(d))
+        q0 = mu + sigma * rng.standard_normal((C, d))
+        draws = parity.random_draws(rng, C, W, d)
+        model = models.IIDGaussian(mu, sigma)
+        sched = adaptation.build_schedule(W)
+        ref = parity.oracle_nuts(model, q0, 1.0, np.ones(d), draws, W, schedule_steps=W)
+        got = hostsim.run(0, mu, model.inv_var, 0.0, np.ones((C, d)), q0, 1.0, draws, W, schedule=sched, reg_front=True)
+        parity.assert_nuts_parity(got, ref, rtol=1e-7, what="adapt regs")
+        np.testing.assert_allclose(got["eps"], ref["eps"], rtol=1e-8)
+    else:
+        C, T, d, L = 8, 3, 6, 10
+        mu, sigma = rng.standard_normal(d), np.exp(0.5 * rng.standard_normal(d))
+        q0 = mu + sigma * rng.standard_normal((C, d))
+        draws = parity.random_draws(rng, C, T, d)
+        model = models.IIDGaussian(mu, sigma)
+        ref = parity.oracle_hmc(model, q0, 0.4, sigma ** 2, draws, T, L)
+        got = hostsim.run(0, mu, model.inv_var, 0.0, sigma ** 2, q0, 0.4, draws, T, hmc_L=L, n_store=T, reg_front=True)
+        for k in ("q", "p", "g", "U", "acceptance_probability"):
+            np.testing.assert_allclose(got[k], ref[k], rtol=1e-11, atol=1e-13, err_msg=k)
