@@ -49,6 +49,26 @@ class Adapt(C.Structure):
                 ("wc_m2", C.c_void_p), ("wc_n", C.c_void_p)]
 
 
+class State(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("p", C.c_void_p), ("g", C.c_void_p), ("U", C.c_void_p)]
+
+
+class Tree(C.Structure):
+    _fields_ = [("proposal", State), ("proposal_energy", C.c_void_p), ("proposal_weight", C.c_void_p),
+                ("proposal_slpa", C.c_void_p), ("left", State), ("right", State), ("momentum_sum", C.c_void_p),
+                ("momentum_ckpts", C.c_void_p), ("momentum_sum_ckpts", C.c_void_p), ("idx_min", C.c_void_p),
+                ("idx_max", C.c_void_p), ("initial_energy", C.c_void_p)]
+
+
+class Subtree(C.Structure):
+    _fields_ = [("state", State), ("direction", C.c_void_p), ("proposal", State), ("proposal_energy", C.c_void_p),
+                ("proposal_weight", C.c_void_p), ("proposal_slpa", C.c_void_p), ("momentum_sum", C.c_void_p),
+                ("momentum_ckpts", C.c_void_p), ("momentum_sum_ckpts", C.c_void_p), ("idx_min", C.c_void_p),
+                ("idx_max", C.c_void_p), ("initial_energy", C.c_void_p), ("max_num_steps", C.c_int32),
+                ("expansion", C.c_int32), ("trajectory_length", C.c_void_p), ("is_diverging", C.c_void_p),
+                ("has_terminated", C.c_void_p)]
+
+
 class Cfg(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("max_num_expansions", C.c_int32), ("divergence_threshold", C.c_double),
                 ("num_integration_steps", C.c_int32), ("group", C.c_int32), ("gradient_path", C.c_int32),
@@ -62,7 +82,8 @@ EXPORTS = [
     "b2h_is_turning", "b2h_leapfrog", "b2h_termination_update", "b2h_is_iterative_turning",
     "b2h_find_storage_indices", "b2h_hmc_run", "b2h_nuts_run", "b2h_nuts_workspace_bytes",
     "b2h_hmc_workspace_bytes", "b2h_dual_averaging_update", "b2h_welford_update", "b2h_mass_matrix_final",
-    "b2h_philox_fill", "b2h_dense_apply", "b2h_chain_moments", "b2h_chain_autocov", "b2h_tc_gemm_bf16",
+    "b2h_philox_fill", "b2h_dense_apply", "b2h_chain_moments", "b2h_chain_autocov", "b2h_tc_gemm_bf16", "b2h_nuts_expand", "b2h_nuts_subtree", "b2h_proposal_update",
+    "b2h_progressive_sampling", "b2h_select_rows",
 ]
 
 _lib = None

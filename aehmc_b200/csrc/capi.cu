@@ -91,6 +91,18 @@ int b2h_hmc_run(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, 
                          draws, draw_stats, n_store, counters, workspace, workspace_bytes, true);
 }
 
+int b2h_nuts_expand(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
+                    const b2h_cfg* cfg, b2h_tree* tree, const double* step_size, int64_t C, b2h_diag* diag,
+                    void* workspace, int64_t workspace_bytes) {
+    return nuts_expand_impl(ctx, model, metric, rng, cfg, tree, step_size, C, diag, workspace, workspace_bytes);
+}
+
+int b2h_nuts_subtree(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
+                     const b2h_cfg* cfg, b2h_subtree* sub, const double* step_size, int64_t C, void* workspace,
+                     int64_t workspace_bytes) {
+    return nuts_subtree_impl(ctx, model, metric, rng, cfg, sub, step_size, C, workspace, workspace_bytes);
+}
+
 int64_t b2h_nuts_workspace_bytes(const b2h_model* model, const b2h_metric* metric, const b2h_cfg* cfg, int64_t C) {
     if (!model || !metric || !cfg) return -1;
     return engine_workspace_bytes(model, metric, cfg, C);

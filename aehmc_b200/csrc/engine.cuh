@@ -35,8 +35,9 @@ struct __align__(16) ChainRec {
     int nleap;                                   // integrator steps of the running transition
     int last_nd, last_flags, last_nleap, hmc_step;
     i64 total_leap;
-    int t_base, pad_i;                           // t at the start of the current call (resume)
-    double pad[11];
+    int t_base, sub_term;                        // t at the start of the current call (resume); sub-tree U-turn flag
+    double U_left, U_right, U_front;             // potential energy at the edges / at the front (explicit-state API)
+    double pad[8];
 };
 static_assert(sizeof(ChainRec) == 256, "ChainRec must be one 256-byte record");
 
@@ -103,6 +104,8 @@ struct EngineView {
     double div_thr;
     int n_transitions;                   // per chain; <=0 : free running
     int hmc_L;
+    int sub_max_steps;                   // > 0: stand-alone dynamic_integration: scan length of the one sub-tree
+    int stop_at_subtree_end;             // stand-alone dynamic_integration: stop instead of running expand_once
     i64* counters;                       // [0] leapfrogs [1] transitions [2] ticks [3] active chain-ticks
 };
 
@@ -263,6 +266,7 @@ B2H_DEVINL void begin_transition(Chain<T, G>& ch) {
     T K0 = (T)0.5 * (T)Group<G>::sum1((double)kacc, ch.red);
     T E0 = (T)ch.r.U_prop + K0;                       // nuts.py:117-119
     ch.r.E0 = (double)E0;
+    ch.r.U_left = ch.r.U_prop; ch.r.U_right = ch.r.U_prop;
     ch.r.E_prop = (double)E0;
     ch.r.w_prop = 0.0;                                // nuts.py:123
     ch.r.slpa_prop = -INFINITY;                       // nuts.py:124
@@ -389,7 +393,7 @@ B2H_DEVINL void end_transition(Chain<T, G>& ch, int num_doublings, bool is_turni
     const int t = ch.r.t;
     const int tl = t - ch.r.t_base;              // index within this call
     ch.r.last_nd = num_doublings;
-    ch.r.last_flags = (is_turning ? 1 : 0) | (is_diverging ? 2 : 0);
+    ch.r.last_flags = (is_turning ? 1 : 0) | (is_diverging ? 2 : 0) | (ch.r.sub_term ? 4 : 0);
     ch.r.last_nleap = ch.r.nleap;
     if (tl < v.out.n_store) {
         if (v.out.draws) {
@@ -546,11 +550,21 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
     r.sub_len = (s == 0) ? 1 : r.sub_len + 1;
     r.nleap += 1;
     r.total_leap += 1;
+    r.U_front = (double)U_new;
 
-    const bool end_sub = div || term || (s == (1 << k));       // Q1: 2**k more steps after step 0
+    const int sub_limit = v.sub_max_steps > 0 ? v.sub_max_steps : (1 << k);
+    const bool end_sub = div || term || (s == sub_limit);      // Q1: 2**k more steps after step 0
     if (!end_sub) { r.s = s + 1; return false; }
     f.flush(ch);                                                // the edge arrays must be current from here on
     Group<G>::sync();
+    if (r.go_right) r.U_right = r.U_front; else r.U_left = r.U_front;
+    r.sub_term = term ? 1 : 0;
+    if (v.stop_at_subtree_end) {                                // trajectory.dynamic_integration.integrate on its own
+        r.last_flags = (div ? 2 : 0) | (term ? 4 : 0);
+        r.last_nleap = r.sub_len;
+        r.phase = PH_DONE;
+        return true;
+    }
 
     // ================= end of the sub-tree: expand_once (trajectory.py:537-608) =================
     // edges are already in place; msum += sub-tree sum; top-level U-turn on (left, right, msum)

@@ -598,6 +598,244 @@ static int run_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* met
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// stand-alone trajectory builders (caller-supplied tree state): the same state machine, entered after
+// begin_transition (expand) or for exactly one sub-tree (integrate)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void tree_in_kernel(EngineView<T> v, b2h_tree t, const double* eps) {
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0 && v.imm_kind == B2H_IMM_SCALAR) {}
+    if (idx >= (i64)v.C * v.d) return;
+    int c = (int)(idx / v.d), j = (int)(idx % v.d);
+    i64 a = (i64)c * v.sc + (i64)j * v.sj;
+    v.qp[a] = ((const T*)t.proposal.q)[idx]; v.pp[a] = ((const T*)t.proposal.p)[idx]; v.gp[a] = ((const T*)t.proposal.g)[idx];
+    v.ql[a] = ((const T*)t.left.q)[idx]; v.pl[a] = ((const T*)t.left.p)[idx]; v.gl[a] = ((const T*)t.left.g)[idx];
+    v.qr[a] = ((const T*)t.right.q)[idx]; v.pr[a] = ((const T*)t.right.p)[idx]; v.gr[a] = ((const T*)t.right.g)[idx];
+    v.msum[a] = ((const T*)t.momentum_sum)[idx];
+    for (int l = 0; l < v.maxd; ++l) {
+        i64 b = (i64)c * v.sck + ((i64)l * v.d + j) * v.sj;
+        v.mck[b] = ((const T*)t.momentum_ckpts)[((i64)c * v.maxd + l) * v.d + j];
+        v.sckp[b] = ((const T*)t.momentum_sum_ckpts)[((i64)c * v.maxd + l) * v.d + j];
+    }
+    if (j == 0) {
+        ChainRec r;
+        memset(&r, 0, sizeof(r));
+        r.phase = PH_RUN;
+        r.eps = eps[c];
+        r.E0 = (double)((const T*)t.initial_energy)[c];
+        r.U_prop = (double)((const T*)t.proposal.U)[c];
+        r.E_prop = (double)((const T*)t.proposal_energy)[c];
+        r.w_prop = t.proposal_weight[c];
+        r.slpa_prop = t.proposal_slpa[c];
+        r.U_left = (double)((const T*)t.left.U)[c];
+        r.U_right = (double)((const T*)t.right.U)[c];
+        r.imin = (int)t.idx_min[c]; r.imax = (int)t.idx_max[c];
+        r.k = 0; r.s = 0;
+        double u = draw_u(v.rng, DRAW_DIR, c, 0, 0, v.maxd);          // trajectory.py:516 for expansion 0
+        r.go_right = bern(u, 0.5) ? 1 : 0;
+        v.rec[c] = r;
+    }
+}
+
+template <typename T>
+__global__ void tree_out_kernel(EngineView<T> v, b2h_tree t) {
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (i64)v.C * v.d) return;
+    int c = (int)(idx / v.d), j = (int)(idx % v.d);
+    i64 a = (i64)c * v.sc + (i64)j * v.sj;
+    ((T*)t.proposal.q)[idx] = v.qp[a]; ((T*)t.proposal.p)[idx] = v.pp[a]; ((T*)t.proposal.g)[idx] = v.gp[a];
+    ((T*)t.left.q)[idx] = v.ql[a]; ((T*)t.left.p)[idx] = v.pl[a]; ((T*)t.left.g)[idx] = v.gl[a];
+    ((T*)t.right.q)[idx] = v.qr[a]; ((T*)t.right.p)[idx] = v.pr[a]; ((T*)t.right.g)[idx] = v.gr[a];
+    ((T*)t.momentum_sum)[idx] = v.msum[a];
+    for (int l = 0; l < v.maxd; ++l) {
+        i64 b = (i64)c * v.sck + ((i64)l * v.d + j) * v.sj;
+        ((T*)t.momentum_ckpts)[((i64)c * v.maxd + l) * v.d + j] = v.mck[b];
+        ((T*)t.momentum_sum_ckpts)[((i64)c * v.maxd + l) * v.d + j] = v.sckp[b];
+    }
+    if (j == 0) {
+        const ChainRec& r = v.rec[c];
+        ((T*)t.proposal.U)[c] = (T)r.U_prop;
+        ((T*)t.proposal_energy)[c] = (T)r.E_prop;
+        t.proposal_weight[c] = r.w_prop;
+        t.proposal_slpa[c] = r.slpa_prop;
+        ((T*)t.left.U)[c] = (T)r.U_left;
+        ((T*)t.right.U)[c] = (T)r.U_right;
+        t.idx_min[c] = r.imin; t.idx_max[c] = r.imax;
+        if (v.out.acceptance_probability) v.out.acceptance_probability[c] = r.accept_prob;
+        if (v.out.num_doublings) v.out.num_doublings[c] = r.last_nd;
+        if (v.out.is_turning) v.out.is_turning[c] = (r.last_flags & 1) ? 1 : 0;
+        if (v.out.is_diverging) v.out.is_diverging[c] = (r.last_flags & 2) ? 1 : 0;
+        if (v.out.n_leapfrog) v.out.n_leapfrog[c] = r.last_nleap;
+    }
+}
+
+template <typename T>
+__global__ void subtree_in_kernel(EngineView<T> v, b2h_subtree t, const double* eps) {
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (i64)v.C * v.d) return;
+    int c = (int)(idx / v.d), j = (int)(idx % v.d);
+    i64 a = (i64)c * v.sc + (i64)j * v.sj;
+    T q = ((const T*)t.state.q)[idx], p = ((const T*)t.state.p)[idx], g = ((const T*)t.state.g)[idx];
+    v.ql[a] = q; v.pl[a] = p; v.gl[a] = g;
+    v.qr[a] = q; v.pr[a] = p; v.gr[a] = g;
+    for (int l = 0; l < v.maxd; ++l) {
+        i64 b = (i64)c * v.sck + ((i64)l * v.d + j) * v.sj;
+        v.mck[b] = ((const T*)t.momentum_ckpts)[((i64)c * v.maxd + l) * v.d + j];
+        v.sckp[b] = ((const T*)t.momentum_sum_ckpts)[((i64)c * v.maxd + l) * v.d + j];
+    }
+    if (j == 0) {
+        ChainRec r;
+        memset(&r, 0, sizeof(r));
+        r.phase = PH_RUN;
+        r.eps = eps[c];
+        r.E0 = (double)((const T*)t.initial_energy)[c];
+        r.imin = (int)t.idx_min[c]; r.imax = (int)t.idx_max[c];
+        r.k = t.expansion; r.s = 0;
+        r.go_right = t.direction[c] > 0 ? 1 : 0;
+        v.rec[c] = r;
+    }
+}
+
+template <typename T>
+__global__ void subtree_out_kernel(EngineView<T> v, b2h_subtree t) {
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (i64)v.C * v.d) return;
+    int c = (int)(idx / v.d), j = (int)(idx % v.d);
+    i64 a = (i64)c * v.sc + (i64)j * v.sj;
+    const ChainRec& r = v.rec[c];
+    const T* Q = r.go_right ? v.qr : v.ql; const T* P = r.go_right ? v.pr : v.pl; const T* Gd = r.go_right ? v.gr : v.gl;
+    ((T*)t.state.q)[idx] = Q[a]; ((T*)t.state.p)[idx] = P[a]; ((T*)t.state.g)[idx] = Gd[a];
+    ((T*)t.proposal.q)[idx] = v.qs[a]; ((T*)t.proposal.p)[idx] = v.ps[a]; ((T*)t.proposal.g)[idx] = v.gs[a];
+    ((T*)t.momentum_sum)[idx] = v.sms[a];
+    for (int l = 0; l < v.maxd; ++l) {
+        i64 b = (i64)c * v.sck + ((i64)l * v.d + j) * v.sj;
+        ((T*)t.momentum_ckpts)[((i64)c * v.maxd + l) * v.d + j] = v.mck[b];
+        ((T*)t.momentum_sum_ckpts)[((i64)c * v.maxd + l) * v.d + j] = v.sckp[b];
+    }
+    if (j == 0) {
+        ((T*)t.state.U)[c] = (T)r.U_front;
+        ((T*)t.proposal.U)[c] = (T)r.U_sub;
+        ((T*)t.proposal_energy)[c] = (T)r.E_sub;
+        t.proposal_weight[c] = r.w_sub;
+        t.proposal_slpa[c] = r.slpa_sub;
+        t.idx_min[c] = r.imin; t.idx_max[c] = r.imax;
+        t.trajectory_length[c] = r.sub_len;
+        t.is_diverging[c] = (r.last_flags & 2) ? 1 : 0;
+        t.has_terminated[c] = (r.last_flags & 4) ? 1 : 0;
+    }
+}
+
+// shared set-up of the two entry points: fused models, diagonal-family metrics
+template <typename T>
+static int tree_setup(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng, const b2h_cfg* cfg,
+                      i64 C64, void* ws, i64 ws_bytes, EngineView<T>& v, EnginePlan& pl) {
+    int rc = make_plan(model, metric, cfg, pl, C64);
+    if (rc) return rc;
+    if (pl.split) { set_error("stand-alone trajectory builders support the fused models with scalar/diagonal metrics"); return B2H_ERR_UNSUPPORTED; }
+    const int C = (int)C64, d = model->dim, maxd = cfg->max_num_expansions;
+    if (maxd < 1 || maxd > 24) { set_error("max_num_expansions must be in [1, 24]"); return B2H_ERR_ARG; }
+    memset(&v, 0, sizeof(v));
+    size_t need = carve<T>(v, nullptr, pl, model, C, d, maxd, false, 0, nullptr);
+    if (!ws || (size_t)ws_bytes < need) { set_error("workspace too small: need " + std::to_string(need) + " bytes"); return B2H_ERR_WORKSPACE; }
+    carve<T>(v, (char*)ws, pl, model, C, d, maxd, false, 0, nullptr);
+    v.C = C; v.d = d; v.maxd = maxd;
+    if (pl.G == 1) { v.sc = 1; v.sj = C; v.sck = 1; }
+    else { v.sc = d; v.sj = 1; v.sck = (i64)maxd * d; }
+    v.imm_kind = metric->kind;
+    if (pl.scalar_imm) {
+        v.imm_sc = 0; v.imm_sj = 0;
+        T val = (T)metric->scalar;
+        B2H_CUDA(cudaMemcpyAsync(v.imm, &val, sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        B2H_CUDA(cudaStreamSynchronize(ctx->stream));
+    } else if (metric->kind == B2H_IMM_DIAG) { v.imm = (T*)metric->imm; v.imm_sc = 0; v.imm_sj = 1; }
+    else { set_error("per-chain metrics are not supported here"); return B2H_ERR_UNSUPPORTED; }
+    v.rng.mode = rng->mode;
+    v.rng.key.k0 = (uint32_t)rng->seed; v.rng.key.k1 = (uint32_t)(rng->seed >> 32);
+    v.rng.chain_offset = rng->chain_offset; v.rng.transition_offset = rng->transition_offset;
+    v.rng.n_injected = rng->n_injected;
+    v.rng.z = rng->z; v.rng.u_dir = rng->u_dir; v.rng.u_biased = rng->u_biased; v.rng.u_uniform = rng->u_uniform;
+    v.rng.u_accept = rng->u_accept;
+    v.div_thr = cfg->divergence_threshold;
+    v.n_transitions = 1;
+    return 0;
+}
+
+template <typename T>
+static int expand_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
+                        const b2h_cfg* cfg, b2h_tree* tree, const double* eps, i64 C, b2h_diag* diag, void* ws, i64 ws_bytes) {
+    EngineView<T> v;
+    EnginePlan pl;
+    int rc = tree_setup<T>(ctx, model, metric, rng, cfg, C, ws, ws_bytes, v, pl);
+    if (rc) return rc;
+    if (diag) {
+        v.out.acceptance_probability = diag->acceptance_probability; v.out.num_doublings = diag->num_doublings;
+        v.out.is_turning = diag->is_turning; v.out.is_diverging = diag->is_diverging; v.out.n_leapfrog = diag->n_leapfrog;
+    }
+    cudaStream_t st = ctx->stream;
+    const i64 n = C * model->dim;
+    const int eb = 256, eg = (int)((n + eb - 1) / eb);
+    tree_in_kernel<T><<<eg, eb, 0, st>>>(v, *tree, eps);
+    switch (pl.G) {
+        case 1: rc = launch_fused<T, 1, false>(st, v, model, 0); break;
+        case 8: rc = launch_fused<T, 8, false>(st, v, model, 0); break;
+        case 32: rc = launch_fused<T, 32, false>(st, v, model, 0); break;
+        default: rc = launch_fused<T, 256, false>(st, v, model, 0); break;
+    }
+    if (rc) return rc;
+    tree_out_kernel<T><<<eg, eb, 0, st>>>(v, *tree);
+    B2H_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename T>
+static int subtree_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
+                         const b2h_cfg* cfg, b2h_subtree* sub, const double* eps, i64 C, void* ws, i64 ws_bytes) {
+    EngineView<T> v;
+    EnginePlan pl;
+    int rc = tree_setup<T>(ctx, model, metric, rng, cfg, C, ws, ws_bytes, v, pl);
+    if (rc) return rc;
+    if (sub->max_num_steps < 1 || sub->expansion < 0 ||
+        ((i64)1 << sub->expansion) - 1 + sub->max_num_steps > ((i64)1 << cfg->max_num_expansions) - 1) {
+        set_error("sub-tree: the uniform-draw slots 2**expansion - 1 + step must fit 2**max_num_expansions - 1");
+        return B2H_ERR_ARG;
+    }
+    v.sub_max_steps = sub->max_num_steps;
+    v.stop_at_subtree_end = 1;
+    cudaStream_t st = ctx->stream;
+    const i64 n = C * model->dim;
+    const int eb = 256, eg = (int)((n + eb - 1) / eb);
+    subtree_in_kernel<T><<<eg, eb, 0, st>>>(v, *sub, eps);
+    switch (pl.G) {
+        case 1: rc = launch_fused<T, 1, false>(st, v, model, 0); break;
+        case 8: rc = launch_fused<T, 8, false>(st, v, model, 0); break;
+        case 32: rc = launch_fused<T, 32, false>(st, v, model, 0); break;
+        default: rc = launch_fused<T, 256, false>(st, v, model, 0); break;
+    }
+    if (rc) return rc;
+    subtree_out_kernel<T><<<eg, eb, 0, st>>>(v, *sub);
+    B2H_LAUNCH_CHECK();
+    return 0;
+}
+
+int nuts_expand_impl(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
+                     const b2h_cfg* cfg, b2h_tree* tree, const double* eps, i64 C, b2h_diag* diag, void* ws, i64 ws_bytes) {
+    if (!ctx || !model || !metric || !rng || !cfg || !tree || !eps) { set_error("null argument"); return B2H_ERR_ARG; }
+    if (cfg->dtype == B2H_F64) return expand_typed<double>(ctx, model, metric, rng, cfg, tree, eps, C, diag, ws, ws_bytes);
+    if (cfg->dtype == B2H_F32) return expand_typed<float>(ctx, model, metric, rng, cfg, tree, eps, C, diag, ws, ws_bytes);
+    set_error("bad dtype");
+    return B2H_ERR_ARG;
+}
+
+int nuts_subtree_impl(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
+                      const b2h_cfg* cfg, b2h_subtree* sub, const double* eps, i64 C, void* ws, i64 ws_bytes) {
+    if (!ctx || !model || !metric || !rng || !cfg || !sub || !eps) { set_error("null argument"); return B2H_ERR_ARG; }
+    if (cfg->dtype == B2H_F64) return subtree_typed<double>(ctx, model, metric, rng, cfg, sub, eps, C, ws, ws_bytes);
+    if (cfg->dtype == B2H_F32) return subtree_typed<float>(ctx, model, metric, rng, cfg, sub, eps, C, ws, ws_bytes);
+    set_error("bad dtype");
+    return B2H_ERR_ARG;
+}
+
 int nuts_run_impl(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
                   const b2h_cfg* cfg, const b2h_adapt* adapt, void* q, void* p, void* U, void* g, double* step_size,
                   i64 C, int n_transitions, i64 max_ticks, int resume, b2h_diag* diag, void* draws,

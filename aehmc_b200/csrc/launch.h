@@ -83,6 +83,10 @@ int nuts_run_impl(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric
                   const b2h_cfg* cfg, const b2h_adapt* adapt, void* q, void* p, void* U, void* g, double* step_size,
                   i64 C, int n_transitions, i64 max_ticks, int resume, b2h_diag* diag, void* draws,
                   double* draw_stats, int n_store, int64_t* counters, void* ws, i64 ws_bytes, bool hmc);
+int nuts_expand_impl(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
+                     const b2h_cfg* cfg, b2h_tree* tree, const double* eps, i64 C, b2h_diag* diag, void* ws, i64 ws_bytes);
+int nuts_subtree_impl(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
+                      const b2h_cfg* cfg, b2h_subtree* sub, const double* eps, i64 C, void* ws, i64 ws_bytes);
 i64 engine_workspace_bytes(const b2h_model* model, const b2h_metric* metric, const b2h_cfg* cfg, i64 C);
 
 static inline size_t dtype_size(int dtype) { return dtype == B2H_F64 ? 8 : 4; }

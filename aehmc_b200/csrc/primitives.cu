@@ -443,6 +443,43 @@ __global__ void mass_matrix_final_kernel(const T* m2, const int64_t* n, T* out, 
 }
 
 // ---------------------------------------------------------------------------
+// proposal scalars (proposals.py:41-52, 96-100, 130-174)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void proposal_update_kernel(const T* E0, const T* U, const T* K, double thr, T* energy, double* weight,
+                                       double* lpa, uint8_t* div, i64 C) {
+    i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    T e = U[c] + K[c];
+    double delta = (double)(E0[c] - e);
+    if (isnan(delta)) delta = -INFINITY;
+    energy[c] = e;
+    weight[c] = delta;
+    lpa[c] = delta > 0 ? 0.0 : delta;
+    div[c] = fabs(delta) > thr ? 1 : 0;
+}
+
+__global__ void progressive_sampling_kernel(int biased, const double* w_old, const double* w_new, const double* s_old,
+                                            const double* s_new, const double* u, uint8_t* acc, double* w_out,
+                                            double* s_out, i64 C) {
+    i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double p;
+    if (biased) p = fmin(fmax(exp(w_new[c] - w_old[c]), 0.0), 1.0);
+    else { p = expit(w_new[c] - w_old[c]); if (isnan(p)) p = 0.0; }
+    acc[c] = bern(u[c], p) ? 1 : 0;
+    w_out[c] = lae(w_old[c], w_new[c]);
+    s_out[c] = lae(s_old[c], s_new[c]);
+}
+
+template <typename T>
+__global__ void select_rows_kernel(const uint8_t* mask, const T* a, const T* b, T* out, i64 C, int d) {
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= C * d) return;
+    out[idx] = mask[idx / d] ? a[idx] : b[idx];
+}
+
+// ---------------------------------------------------------------------------
 // native draws exported in the injected layout
 // ---------------------------------------------------------------------------
 __global__ void philox_fill_kernel(RngView rng, i64 C, i64 T_, int d, int maxd, double* z, double* u_dir,
@@ -714,6 +751,36 @@ int b2h_chain_moments(b2h_ctx* ctx, int dtype, const void* draws, int64_t T_, in
     B2H_TYPED(dtype,
               (chain_moments_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float*)draws, T_, C, (int)d, mean, var)),
               (chain_moments_kernel<double><<<grid, 256, 0, ctx->stream>>>((const double*)draws, T_, C, (int)d, mean, var)));
+    B2H_LAUNCH_CHECK();
+    return 0;
+}
+
+int b2h_proposal_update(b2h_ctx* ctx, int dtype, const void* E0, const void* U, const void* K, double thr, void* energy,
+                        double* weight, double* lpa, uint8_t* div, int64_t C) {
+    B2H_CHECK_CTX();
+    int grid = (int)((C + 255) / 256);
+    B2H_TYPED(dtype,
+              (proposal_update_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float*)E0, (const float*)U, (const float*)K, thr, (float*)energy, weight, lpa, div, C)),
+              (proposal_update_kernel<double><<<grid, 256, 0, ctx->stream>>>((const double*)E0, (const double*)U, (const double*)K, thr, (double*)energy, weight, lpa, div, C)));
+    B2H_LAUNCH_CHECK();
+    return 0;
+}
+
+int b2h_progressive_sampling(b2h_ctx* ctx, int biased, const double* w_old, const double* w_new, const double* s_old,
+                             const double* s_new, const double* u, uint8_t* acc, double* w_out, double* s_out, int64_t C) {
+    B2H_CHECK_CTX();
+    progressive_sampling_kernel<<<(int)((C + 255) / 256), 256, 0, ctx->stream>>>(biased, w_old, w_new, s_old, s_new, u, acc, w_out, s_out, C);
+    B2H_LAUNCH_CHECK();
+    return 0;
+}
+
+int b2h_select_rows(b2h_ctx* ctx, int dtype, const uint8_t* mask, const void* a, const void* b, void* out, int64_t C,
+                    int64_t d) {
+    B2H_CHECK_CTX();
+    int grid = (int)((C * d + 255) / 256);
+    B2H_TYPED(dtype,
+              (select_rows_kernel<float><<<grid, 256, 0, ctx->stream>>>(mask, (const float*)a, (const float*)b, (float*)out, C, (int)d)),
+              (select_rows_kernel<double><<<grid, 256, 0, ctx->stream>>>(mask, (const double*)a, (const double*)b, (double*)out, C, (int)d)));
     B2H_LAUNCH_CHECK();
     return 0;
 }

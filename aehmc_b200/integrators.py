@@ -51,6 +51,8 @@ def velocity_verlet(potential_fn, kinetic_energy_fn):
                                     C.c_int64(w.numel())))
         return IntegratorState(q, p, U, g)
 
+    one_step.model = model
+    one_step.metric = metric
     return one_step
 
 

@@ -27,6 +27,18 @@ class RandomStream:
     def advance(self, n):
         self.transition += int(n)
 
+    def uniform(self, n, device):
+        """[n] float64 uniforms for the stand-alone proposal samplers (the accept slot of one Philox transition)."""
+        import ctypes as C
+        lib = _lib.load()
+        dev = backend.device(device)
+        out = torch.empty(n, dtype=torch.float64, device=dev)
+        _lib.check(lib.b2h_philox_fill(backend.context(dev), C.c_uint64(self.seed), C.c_uint64(self.chain_offset),
+                                       C.c_uint64(self.transition), C.c_int64(n), C.c_int64(1), C.c_int64(1),
+                                       C.c_int32(1), None, None, None, None, backend.ptr(out)))
+        self.advance(1)
+        return out
+
 
 class InjectedDraws:
     """z [C,T,d], u_dir [C,T,max], u_biased [C,T,max], u_uniform [C,T,2**max-1], u_accept [C,T] (float64)."""
@@ -36,8 +48,10 @@ class InjectedDraws:
         up = lambda a: None if a is None else backend.as_device(a, torch.float64, dev)
         self.z, self.u_dir, self.u_biased = up(z), up(u_dir), up(u_biased)
         self.u_uniform, self.u_accept = up(u_uniform), up(u_accept)
-        self.n_injected = int(self.z.shape[1])
+        first = next(a for a in (self.z, self.u_dir, self.u_biased, self.u_uniform, self.u_accept) if a is not None)
+        self.n_injected = int(first.shape[1])
         self.transition = 0
+        self._cursor = 0
 
     def struct(self, n_transitions=1):
         if self.transition != 0:
@@ -49,3 +63,11 @@ class InjectedDraws:
 
     def advance(self, n):
         self.transition += int(n)
+
+    def uniform(self, n, device):
+        """stand-alone proposal samplers: the k-th call consumes u_accept[:, k]."""
+        if self.u_accept is None or self._cursor >= self.u_accept.shape[1]:
+            raise ValueError("injected draws: u_accept exhausted")
+        out = self.u_accept[:, self._cursor].contiguous()
+        self._cursor += 1
+        return out

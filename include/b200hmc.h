@@ -194,7 +194,8 @@ int b2h_hmc_run(b2h_ctx*, const b2h_model*, const b2h_metric*, const b2h_rng*, c
  * step_size[C] in/out (adapted when adapt.enabled); imm may be DIAG_PER_CHAIN and adapted in place.
  * diag: values of each chain's LAST completed transition.  draws (optional): [n_store][C][d] positions
  * after each of the first n_store transitions; draw_stats (optional) [n_store][C][4] float64 rows of
- * (acceptance_probability, num_doublings, n_leapfrog, flags: bit0 turning, bit1 diverging).
+ * (acceptance_probability, num_doublings, n_leapfrog, flags: bit0 turning, bit1 diverging, bit2 last sub-tree
+ * stopped on the iterative U-turn criterion).
  * counters (optional, device int64[4]): total leapfrogs, total transitions, ticks run, active chain-ticks. */
 int b2h_nuts_run(b2h_ctx*, const b2h_model*, const b2h_metric*, const b2h_rng*, const b2h_cfg*,
                  const b2h_adapt* adapt, void* q, void* p, void* U, void* g, double* step_size, int64_t C,
@@ -202,6 +203,66 @@ int b2h_nuts_run(b2h_ctx*, const b2h_model*, const b2h_metric*, const b2h_rng*, 
                  double* draw_stats, int32_t n_store, int64_t* counters, void* workspace, int64_t workspace_bytes);
 int64_t b2h_nuts_workspace_bytes(const b2h_model*, const b2h_metric*, const b2h_cfg*, int64_t C);
 int64_t b2h_hmc_workspace_bytes(const b2h_model*, const b2h_metric*, const b2h_cfg*, int64_t C);
+
+/* ---- stand-alone trajectory builders with caller-supplied tree state (fused models, diagonal-family metrics) ---- */
+typedef struct {
+    void *q, *p, *g; /* [C x d] */
+    void* U;         /* [C]     */
+} b2h_state;
+
+/* trajectory.multiplicative_expansion(...).expand(proposal, left_state, right_state, momentum_sum,
+ * termination_state, initial_energy, step_size) (trajectory.py:428-712): all members in/out. */
+typedef struct {
+    b2h_state proposal;          /* ProposalState.state                                   */
+    void* proposal_energy;       /* [C] dtype                                             */
+    double* proposal_weight;     /* [C] float64                                           */
+    double* proposal_slpa;       /* [C] float64 sum_log_p_accept                          */
+    b2h_state left, right;       /* trajectory edges                                      */
+    void* momentum_sum;          /* [C x d]                                               */
+    void* momentum_ckpts;        /* [C x max_num_expansions x d] TerminationState         */
+    void* momentum_sum_ckpts;    /* [C x max_num_expansions x d]                          */
+    int64_t *idx_min, *idx_max;  /* [C]                                                   */
+    const void* initial_energy;  /* [C] dtype                                             */
+} b2h_tree;
+int b2h_nuts_expand(b2h_ctx*, const b2h_model*, const b2h_metric*, const b2h_rng*, const b2h_cfg*, b2h_tree* tree,
+                    const double* step_size, int64_t C, b2h_diag* diag, void* workspace, int64_t workspace_bytes);
+
+/* trajectory.dynamic_integration(...).integrate(previous_last_state, direction, termination_state, max_num_steps,
+ * step_size, initial_energy) (trajectory.py:154-374): one sub-tree of 1 + max_num_steps leapfrogs at most. */
+typedef struct {
+    b2h_state state;             /* in: previous_last_state; out: last state of the sub-tree */
+    const int8_t* direction;     /* [C] +1 / -1                                              */
+    b2h_state proposal;          /* out: sub-tree proposal                                   */
+    void* proposal_energy;       /* out [C] dtype                                            */
+    double* proposal_weight;     /* out [C]                                                  */
+    double* proposal_slpa;       /* out [C]                                                  */
+    void* momentum_sum;          /* out [C x d] sum of the sub-tree's momenta                */
+    void* momentum_ckpts;        /* in/out [C x max_num_expansions x d]                      */
+    void* momentum_sum_ckpts;    /* in/out                                                   */
+    int64_t *idx_min, *idx_max;  /* in/out [C]                                               */
+    const void* initial_energy;  /* [C] dtype                                                */
+    int32_t max_num_steps;       /* scan length after the first step (2**k in NUTS)          */
+    int32_t expansion;           /* k: selects the uniform-draw slots 2**k - 1 + (s - 1)     */
+    int32_t* trajectory_length;  /* out [C]                                                  */
+    uint8_t* is_diverging;       /* out [C]                                                  */
+    uint8_t* has_terminated;     /* out [C]                                                  */
+} b2h_subtree;
+int b2h_nuts_subtree(b2h_ctx*, const b2h_model*, const b2h_metric*, const b2h_rng*, const b2h_cfg*, b2h_subtree* sub,
+                     const double* step_size, int64_t C, void* workspace, int64_t workspace_bytes);
+
+/* proposals.proposal_generator(...).update scalars (proposals.py:41-52): energy = U + K, delta = E0 - energy
+ * (NaN -> -inf), weight = delta, log_p_accept = min(delta, 0), diverging = |delta| > threshold. */
+int b2h_proposal_update(b2h_ctx*, int dtype, const void* initial_energy, const void* U, const void* K, double threshold,
+                        void* energy, double* weight, double* log_p_accept, uint8_t* is_diverging, int64_t C);
+/* proposals.progressive_{uniform,biased}_sampling + maybe_update_proposal scalars (proposals.py:72-174):
+ * biased == 0: p = expit(w_new - w_old) (NaN -> 0); biased != 0: p = clip(exp(w_new - w_old), 0, 1).
+ * do_accept from the uniform u[C]; weight / sum_log_p_accept merged with logaddexp. */
+int b2h_progressive_sampling(b2h_ctx*, int biased, const double* w_old, const double* w_new, const double* slpa_old,
+                             const double* slpa_new, const double* u, uint8_t* do_accept, double* w_out,
+                             double* slpa_out, int64_t C);
+/* row-wise select (maybe_update_proposal / where_proposal): out[c] = mask[c] ? a[c] : b[c], rows of d elements */
+int b2h_select_rows(b2h_ctx*, int dtype, const uint8_t* mask, const void* a, const void* b, void* out, int64_t C,
+                    int64_t d);
 
 /* algorithms.dual_averaging update (algorithms.py:79-115) with gradient = target - p_accept
  * (step_size.py:97); in place on the [C] state arrays. */
