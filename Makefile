@@ -10,12 +10,13 @@ LIB       := $(LIBDIR)/libb200hmc.so
 # The engine and the elementwise primitives are compiled WITHOUT fused multiply-add
 # contraction so that the scalar-metric leapfrog rounds exactly like the reference's
 # compiled graph (a*b then +c); the contraction kernels keep FMA.
-OBJS := $(OBJDIR)/capi.o $(OBJDIR)/engine_kernels.o $(OBJDIR)/primitives.o $(OBJDIR)/gemm.o $(OBJDIR)/logreg.o $(OBJDIR)/tc_gemm.o
-HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/b200hmc.h
+OBJS := $(OBJDIR)/capi.o $(OBJDIR)/engine_kernels.o $(OBJDIR)/engine_fused_f32.o $(OBJDIR)/engine_fused_f64.o \
+        $(OBJDIR)/engine_split_f32.o $(OBJDIR)/engine_split_f64.o $(OBJDIR)/primitives.o $(OBJDIR)/gemm.o $(OBJDIR)/logreg.o $(OBJDIR)/tc_gemm.o
+HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.inl) include/b200hmc.h
 
 all: $(LIB)
 
-$(OBJDIR)/engine_kernels.o: $(CSRC)/engine_kernels.cu $(HDRS)
+$(OBJDIR)/engine_%.o: $(CSRC)/engine_%.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
 $(OBJDIR)/primitives.o: $(CSRC)/primitives.cu $(HDRS)

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200hmc.so")
+# B2H_LIB: development aid for A/B-ing alternative builds of the same library (still no other implementation)
+LIB_PATH = os.environ.get("B2H_LIB") or os.path.join(_HERE, "lib", "libb200hmc.so")
 
 F32, F64 = 0, 1
 MODEL_IID_GAUSSIAN, MODEL_CORR_GAUSSIAN, MODEL_FUNNEL, MODEL_EIGHT_SCHOOLS, MODEL_LOGISTIC = range(5)

@@ -23,6 +23,9 @@ namespace b2h {
 
 enum Phase : int { PH_START = 0, PH_RUN = 1, PH_DONE = 2 };
 
+// elements per lane whose loads are issued together before the first store of the batch
+constexpr int kBatch = 4;
+
 // Per-chain scalar record (one 256-byte line per chain).
 struct __align__(16) ChainRec {
     double w_sub, slpa_sub, w_prop, slpa_prop;  // Q13: always float64
@@ -164,19 +167,25 @@ template <typename T>
 struct MemFront {
     static constexpr int kE = 1 << 30;
     static constexpr bool kRegs = false;
-    T *Q, *P, *Gd;
+    T *Q, *P, *Gd, *V, *W;              // V = imm p, W = imm g: dense metric only
     template <int G> B2H_DEVINL void bind(const Chain<T, G>& ch) {
         Q = ch.r.go_right ? ch.v.qr : ch.v.ql;
         P = ch.r.go_right ? ch.v.pr : ch.v.pl;
         Gd = ch.r.go_right ? ch.v.gr : ch.v.gl;
+        V = ch.r.go_right ? ch.v.vr : ch.v.vl;
+        W = ch.r.go_right ? ch.v.wr : ch.v.wl;
     }
     template <int G> B2H_DEVINL void flush(const Chain<T, G>&) {}
     B2H_DEVINL T q(int, i64 a) const { return Q[a]; }
     B2H_DEVINL T p(int, i64 a) const { return P[a]; }
     B2H_DEVINL T g(int, i64 a) const { return Gd[a]; }
+    B2H_DEVINL T vel(int, i64 a) const { return V[a]; }
+    B2H_DEVINL T w(int, i64 a) const { return W[a]; }
     B2H_DEVINL void set_q(int, i64 a, T x) { Q[a] = x; }
     B2H_DEVINL void set_p(int, i64 a, T x) { P[a] = x; }
     B2H_DEVINL void set_g(int, i64 a, T x) { Gd[a] = x; }
+    B2H_DEVINL void set_vel(int, i64 a, T x) { V[a] = x; }
+    B2H_DEVINL void set_w(int, i64 a, T x) { W[a] = x; }
 };
 
 template <typename T, int E>
@@ -208,9 +217,75 @@ struct RegFront {
     B2H_DEVINL T q(int e, i64) const { return fq[e]; }
     B2H_DEVINL T p(int e, i64) const { return fp[e]; }
     B2H_DEVINL T g(int e, i64) const { return fg[e]; }
+    B2H_DEVINL T vel(int, i64) const { return 0; }      // diagonal-family metrics carry no V / W
+    B2H_DEVINL T w(int, i64) const { return 0; }
     B2H_DEVINL void set_q(int e, i64, T x) { fq[e] = x; }
     B2H_DEVINL void set_p(int e, i64, T x) { fp[e] = x; }
     B2H_DEVINL void set_g(int e, i64, T x) { fg[e] = x; }
+    B2H_DEVINL void set_vel(int, i64, T) {}
+    B2H_DEVINL void set_w(int, i64, T) {}
+};
+
+// Split engine (one launch per tick part): the front of the tick lives in registers between the second half
+// kick of one leapfrog (post) and the first half kick + drift of the next (pre), so each of q, p, g (and V, W
+// for a dense metric) is read once and written once per tick.  bind_post loads what the post part needs (g and
+// W arrive from the gradient / metric contractions); bind loads the whole front after a sub-tree or transition
+// switch.  DENSE selects whether V / W exist.
+template <typename T, int E, bool DENSE>
+struct TickFront {
+    static constexpr int kE = E;
+    static constexpr bool kRegs = true;
+    T fq[E], fp[E], fg[E], fv[DENSE ? E : 1], fw[DENSE ? E : 1];
+    template <int G> B2H_DEVINL void load(const Chain<T, G>& ch, bool all) {
+        const bool rt = ch.r.go_right != 0;
+        const T* Q = rt ? ch.v.qr : ch.v.ql;
+        const T* P = rt ? ch.v.pr : ch.v.pl;
+        const T* Gd = rt ? ch.v.gr : ch.v.gl;
+        const T* V = rt ? ch.v.vr : ch.v.vl;
+        const T* W = rt ? ch.v.wr : ch.v.wl;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int j = ch.lane + e * G;
+            const bool in = j < ch.v.d;
+            const i64 a = in ? ch.at(j) : ch.at(0);
+            fq[e] = in ? Q[a] : (T)0;
+            fp[e] = in ? P[a] : (T)0;
+            if (DENSE) fv[e] = in ? V[a] : (T)0;
+            fg[e] = (all && in) ? Gd[a] : (T)0;
+            if (DENSE) fw[e] = (all && in) ? W[a] : (T)0;
+        }
+    }
+    template <int G> B2H_DEVINL void bind(const Chain<T, G>& ch) { load(ch, true); }
+    template <int G> B2H_DEVINL void bind_post(const Chain<T, G>& ch) { load(ch, false); }
+    template <int G> B2H_DEVINL void store(const Chain<T, G>& ch, bool all) {
+        const bool rt = ch.r.go_right != 0;
+        T* Q = rt ? ch.v.qr : ch.v.ql;
+        T* P = rt ? ch.v.pr : ch.v.pl;
+        T* Gd = rt ? ch.v.gr : ch.v.gl;
+        T* V = rt ? ch.v.vr : ch.v.vl;
+        T* W = rt ? ch.v.wr : ch.v.wl;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int j = ch.lane + e * G;
+            if (j < ch.v.d) {
+                const i64 a = ch.at(j);
+                Q[a] = fq[e]; P[a] = fp[e];
+                if (DENSE) V[a] = fv[e];
+                if (all) { Gd[a] = fg[e]; if (DENSE) W[a] = fw[e]; }
+            }
+        }
+    }
+    template <int G> B2H_DEVINL void flush(const Chain<T, G>& ch) { store(ch, true); }
+    B2H_DEVINL T q(int e, i64) const { return fq[e]; }
+    B2H_DEVINL T p(int e, i64) const { return fp[e]; }
+    B2H_DEVINL T g(int e, i64) const { return fg[e]; }
+    B2H_DEVINL T vel(int e, i64) const { return fv[DENSE ? e : 0]; }
+    B2H_DEVINL T w(int e, i64) const { return fw[DENSE ? e : 0]; }
+    B2H_DEVINL void set_q(int e, i64, T x) { fq[e] = x; }
+    B2H_DEVINL void set_p(int e, i64, T x) { fp[e] = x; }
+    B2H_DEVINL void set_g(int e, i64, T x) { fg[e] = x; }
+    B2H_DEVINL void set_vel(int e, i64, T x) { fv[DENSE ? e : 0] = x; }
+    B2H_DEVINL void set_w(int e, i64, T x) { fw[DENSE ? e : 0] = x; }
 };
 
 // loop over this lane's coordinates: fully unrolled for a register front, a plain strided loop otherwise
@@ -236,32 +311,47 @@ B2H_DEVINL void begin_subtree(Chain<T, G>& ch) {
 template <typename T, int G, bool DENSE, bool NUTS = true>
 B2H_DEVINL void begin_transition(Chain<T, G>& ch) {
     const EngineView<T>& v = ch.v;
+    constexpr int CH = DENSE ? kBatch : 1;             // dense metric == split engine
     T kacc = 0;
-    for (int j = ch.lane; j < v.d; j += G) {
-        i64 a = ch.at(j);
-        T p0, vel;
-        if (DENSE) {
-            i64 m = (i64)ch.c * v.d + j;
-            p0 = v.mom_p[m];
-            vel = v.mom_v[m];
-            v.vl[a] = vel;
-            v.vr[a] = vel;
-            T w0 = v.wp[a];
-            v.wl[a] = w0;
-            v.wr[a] = w0;
-        } else {
-            T im = ch.imm(j);
-            T z = (T)draw_z(v.rng, ch.c, ch.r.t, j, v.d);
-            p0 = sqrt((T)1 / im) * z;
-            vel = im * p0;
+    for (int jb = ch.lane; jb < v.d; jb += CH * G) {
+        T p0[CH], vel[CH], w0[CH], q0[CH], g0[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {                 // loads (and draws) of the batch first
+            const int j = jb + i * G;
+            p0[i] = 0; vel[i] = 0; w0[i] = 0; q0[i] = 0; g0[i] = 0;
+            if (j < v.d) {
+                const i64 a = ch.at(j);
+                if (DENSE) {
+                    const i64 m = (i64)ch.c * v.d + j;
+                    p0[i] = v.mom_p[m];
+                    vel[i] = v.mom_v[m];
+                    w0[i] = v.wp[a];
+                } else {
+                    const T im = ch.imm(j);
+                    const T z = (T)draw_z(v.rng, ch.c, ch.r.t, j, v.d);
+                    p0[i] = sqrt((T)1 / im) * z;
+                    vel[i] = im * p0[i];
+                }
+                q0[i] = v.qp[a]; g0[i] = v.gp[a];
+            }
         }
-        T q0 = v.qp[a], g0 = v.gp[a];
-        v.ql[a] = q0; v.qr[a] = q0;
-        v.pl[a] = p0; v.pr[a] = p0;
-        v.gl[a] = g0; v.gr[a] = g0;
-        v.pp[a] = p0;
-        v.msum[a] = p0;
-        kacc += vel * p0;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int j = jb + i * G;
+            if (j < v.d) {
+                const i64 a = ch.at(j);
+                if (DENSE) {
+                    v.vl[a] = vel[i]; v.vr[a] = vel[i];
+                    v.wl[a] = w0[i]; v.wr[a] = w0[i];
+                }
+                v.ql[a] = q0[i]; v.qr[a] = q0[i];
+                v.pl[a] = p0[i]; v.pr[a] = p0[i];
+                v.gl[a] = g0[i]; v.gr[a] = g0[i];
+                v.pp[a] = p0[i];
+                v.msum[a] = p0[i];
+                kacc += vel[i] * p0[i];
+            }
+        }
     }
     T K0 = (T)0.5 * (T)Group<G>::sum1((double)kacc, ch.red);
     T E0 = (T)ch.r.U_prop + K0;                       // nuts.py:117-119
@@ -298,24 +388,43 @@ B2H_DEVINL void begin_transition(Chain<T, G>& ch) {
 template <typename T, int G, bool DENSE, bool SPLIT, class Front>
 B2H_DEVINL void half_kick_drift(Chain<T, G>& ch, Front& f) {
     const EngineView<T>& v = ch.v;
-    T* V = ch.r.go_right ? v.vr : v.vl;     // dense only
-    T* W = ch.r.go_right ? v.wr : v.wl;     // dense only
     T e = (T)(ch.r.go_right ? ch.r.eps : -ch.r.eps);
     T he = (T)0.5 * e;
-    B2H_ELEMS(Front, ee, j, ch.lane, v.d, G) {
-        i64 a = ch.at(j);
-        T ph = f.p(ee, a) - he * f.g(ee, a);
-        f.set_p(ee, a, ph);
-        T vh;
-        if (DENSE) {
-            vh = V[a] - he * W[a];           // imm.(p - h g) by linearity
-            V[a] = vh;
-        } else {
-            vh = ch.imm(j) * ph;
+    constexpr int CH = SPLIT ? kBatch : 1;
+    constexpr int NCH = Front::kRegs ? (Front::kE + CH - 1) / CH : (1 << 28);
+#pragma unroll
+    for (int cix = 0, jb = ch.lane; cix < NCH && jb < v.d; ++cix, jb += CH * G) {
+        T pv[CH], gv[CH], vv[CH], wv[CH], qv[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {                     // loads of the batch first (see post_gradient)
+            const int ee = cix * CH + i, j = jb + i * G;
+            pv[i] = 0; gv[i] = 0; vv[i] = 0; wv[i] = 0; qv[i] = 0;
+            if (ee < Front::kE && j < v.d) {
+                const i64 a = ch.at(j);
+                pv[i] = f.p(ee, a); gv[i] = f.g(ee, a); qv[i] = f.q(ee, a);
+                if (DENSE) { vv[i] = f.vel(ee, a); wv[i] = f.w(ee, a); }
+                else vv[i] = ch.imm(j);
+            }
         }
-        T qn = f.q(ee, a) + e * vh;
-        f.set_q(ee, a, qn);
-        if (SPLIT) v.xa[(i64)ch.c * v.d + j] = qn;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int ee = cix * CH + i, j = jb + i * G;
+            if (ee < Front::kE && j < v.d) {
+                const i64 a = ch.at(j);
+                const T ph = pv[i] - he * gv[i];
+                f.set_p(ee, a, ph);
+                T vh;
+                if (DENSE) {
+                    vh = vv[i] - he * wv[i];                 // imm.(p - h g) by linearity
+                    f.set_vel(ee, a, vh);
+                } else {
+                    vh = vv[i] * ph;
+                }
+                const T qn = qv[i] + e * vh;
+                f.set_q(ee, a, qn);
+                if (SPLIT) v.xa[(i64)ch.c * v.d + j] = qn;
+            }
+        }
     }
 }
 
@@ -424,8 +533,6 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
     const EngineView<T>& v = ch.v;
     ChainRec& r = ch.r;
     const int d = v.d;
-    T* V = r.go_right ? v.vr : v.vl;     // dense only
-    T* W = r.go_right ? v.wr : v.wl;     // dense only
     const T e = (T)(r.go_right ? r.eps : -r.eps);
     const T he = (T)0.5 * e;
 
@@ -446,45 +553,102 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
     T kacc = 0, dl[LV], dr[LV];
 #pragma unroll
     for (int l = 0; l < LV; ++l) { dl[l] = 0; dr[l] = 0; }
-    B2H_ELEMS(Front, ee, j, ch.lane, d, G) {
-        i64 a = ch.at(j);
-        T p, vel, im = 0;
-        if (DENSE) {
-            T g = v.xb[(i64)ch.c * d + j], wv = v.xc[(i64)ch.c * d + j];
-            f.set_g(ee, a, g);
-            W[a] = wv;
-            p = f.p(ee, a) - he * g;
-            f.set_p(ee, a, p);
-            vel = V[a] - he * wv;            // imm p' = imm p_half - (0.5 e) imm g'
-            V[a] = vel;
-        } else {
-            T g;
-            if (SPLIT) { g = v.xb[(i64)ch.c * d + j]; f.set_g(ee, a, g); }
-            else g = f.g(ee, a);
-            p = f.p(ee, a) - he * g;
-            f.set_p(ee, a, p);
-            im = ch.imm(j);
-            vel = im * p;
-        }
-        kacc += vel * p;
-        T sm = (s == 0) ? p : v.sms[a] + p;
-        v.sms[a] = sm;
-        if (even) {
-            i64 b = ch.ck(imax, j);
-            v.mck[b] = p;
-            v.sckp[b] = sm;
-            if (DENSE) v.vck[b] = vel;
+    // Loads are issued CH elements at a time BEFORE any store of the batch: a store between two loads keeps the
+    // compiler from hoisting the second one, which would serialise one memory round trip per element.  The
+    // arithmetic per element and the accumulation order are unchanged.
+    constexpr int CH = SPLIT ? kBatch : 1;     // the persistent kernel is register-bound: one element at a time
+    constexpr int NCH = Front::kRegs ? (Front::kE + CH - 1) / CH : (1 << 28);
+    [[maybe_unused]] T smreg[Front::kRegs ? Front::kE : 1];      // sub-tree momentum sum of this lane's elements
+    const bool lev0 = nlev > 0;
+#pragma unroll
+    for (int cix = 0, jb = ch.lane; cix < NCH && jb < d; ++cix, jb += CH * G) {
+        T gx[CH], wx[CH], so[CH], pv[CH], vv[CH], imv[CH], cm[CH], cs[CH], cv[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int ee = cix * CH + i, j = jb + i * G;
+            gx[i] = 0; wx[i] = 0; so[i] = 0; pv[i] = 0; vv[i] = 0; imv[i] = 0; cm[i] = 0; cs[i] = 0; cv[i] = 0;
+            if (ee < Front::kE && j < d) {
+                const i64 a = ch.at(j), m = (i64)ch.c * d + j;
+                pv[i] = f.p(ee, a);
+                if (DENSE) { gx[i] = v.xb[m]; wx[i] = v.xc[m]; vv[i] = f.vel(ee, a); }
+                else { gx[i] = SPLIT ? v.xb[m] : f.g(ee, a); imv[i] = ch.imm(j); }
+                if (s != 0) so[i] = v.sms[a];
+                if (lev0) {
+                    const i64 b = ch.ck(imax, j);
+                    cm[i] = v.mck[b]; cs[i] = v.sckp[b];
+                    if (DENSE) cv[i] = v.vck[b];
+                }
+            }
         }
 #pragma unroll
-        for (int l = 0; l < LV; ++l) {
-            if (l < nlev) {
-                i64 b = ch.ck(imax - l, j);
-                T m = v.mck[b], sc = v.sckp[b];
-                T subsum = sm - sc + m;
-                T rho = subsum - (p + m) / (T)2;
-                T vleft = DENSE ? v.vck[b] : im * m;
-                dl[l] += vleft * rho;
-                dr[l] += vel * rho;
+        for (int i = 0; i < CH; ++i) {
+            const int ee = cix * CH + i, j = jb + i * G;
+            if (ee < Front::kE && j < d) {
+                const i64 a = ch.at(j);
+                T p, vel;
+                if (DENSE) {
+                    f.set_g(ee, a, gx[i]);
+                    f.set_w(ee, a, wx[i]);
+                    p = pv[i] - he * gx[i];
+                    f.set_p(ee, a, p);
+                    vel = vv[i] - he * wx[i];    // imm p' = imm p_half - (0.5 e) imm g'
+                    f.set_vel(ee, a, vel);
+                } else {
+                    if (SPLIT) f.set_g(ee, a, gx[i]);
+                    p = pv[i] - he * gx[i];
+                    f.set_p(ee, a, p);
+                    vel = imv[i] * p;
+                }
+                kacc += vel * p;
+                const T sm = (s == 0) ? p : so[i] + p;
+                v.sms[a] = sm;
+                if (Front::kRegs) smreg[Front::kRegs ? ee : 0] = sm;
+                if (even) {
+                    const i64 b = ch.ck(imax, j);
+                    v.mck[b] = p;
+                    v.sckp[b] = sm;
+                    if (DENSE) v.vck[b] = vel;
+                }
+                if (lev0) {
+                    const T subsum = sm - cs[i] + cm[i];
+                    const T rho = subsum - (p + cm[i]) / (T)2;
+                    const T vleft = DENSE ? cv[i] : imv[i] * cm[i];
+                    dl[0] += vleft * rho;
+                    dr[0] += vel * rho;
+                }
+            }
+        }
+    }
+    // levels 1 .. LV-1 (steps with two or more trailing one-bits: a quarter of the ticks)
+#pragma unroll
+    for (int l = 1; l < LV; ++l) {
+        if (l < nlev) {
+#pragma unroll
+            for (int cix = 0, jb = ch.lane; cix < NCH && jb < d; ++cix, jb += CH * G) {
+                T pv[CH], vv[CH], sv[CH], cm[CH], cs[CH], cv[CH];
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    const int ee = cix * CH + i, j = jb + i * G;
+                    pv[i] = 0; vv[i] = 0; sv[i] = 0; cm[i] = 0; cs[i] = 0; cv[i] = 0;
+                    if (ee < Front::kE && j < d) {
+                        const i64 a = ch.at(j), b = ch.ck(imax - l, j);
+                        pv[i] = f.p(ee, a);
+                        sv[i] = Front::kRegs ? smreg[Front::kRegs ? ee : 0] : v.sms[a];
+                        cm[i] = v.mck[b]; cs[i] = v.sckp[b];
+                        if (DENSE) { cv[i] = v.vck[b]; vv[i] = f.vel(ee, a); }
+                        else { const T im = ch.imm(j); cv[i] = im * cm[i]; vv[i] = im * pv[i]; }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    const int ee = cix * CH + i, j = jb + i * G;
+                    if (ee < Front::kE && j < d) {
+                        const T subsum = sv[i] - cs[i] + cm[i];
+                        const T rho = subsum - (pv[i] + cm[i]) / (T)2;
+                        dl[l] += cv[i] * rho;
+                        dr[l] += vv[i] * rho;
+                    }
+                }
             }
         }
     }
@@ -507,7 +671,7 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
                 T subsum = sm - sc + m;
                 T rho = subsum - (p + m) / (T)2;
                 T vleft, vright;
-                if (DENSE) { vleft = v.vck[b]; vright = V[a]; }
+                if (DENSE) { vleft = v.vck[b]; vright = f.vel(ee, a); }
                 else { T im = ch.imm(j); vleft = im * m; vright = im * p; }
                 xl += vleft * rho;
                 xr += vright * rho;
@@ -544,7 +708,7 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
         B2H_ELEMS(Front, ee, j, ch.lane, d, G) {
             i64 a = ch.at(j);
             v.qs[a] = f.q(ee, a); v.ps[a] = f.p(ee, a); v.gs[a] = f.g(ee, a);
-            if (DENSE) v.ws[a] = W[a];
+            if (DENSE) v.ws[a] = f.w(ee, a);
         }
     }
     r.sub_len = (s == 0) ? 1 : r.sub_len + 1;
@@ -569,17 +733,30 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
     // ================= end of the sub-tree: expand_once (trajectory.py:537-608) =================
     // edges are already in place; msum += sub-tree sum; top-level U-turn on (left, right, msum)
     T tl = 0, tr = 0;
-    for (int j = ch.lane; j < d; j += G) {
-        i64 a = ch.at(j);
-        T ms = v.msum[a] + v.sms[a];
-        v.msum[a] = ms;
-        T plv = v.pl[a], prv = v.pr[a];
-        T rho = ms - (prv + plv) / (T)2;
-        T vleft, vright;
-        if (DENSE) { vleft = v.vl[a]; vright = v.vr[a]; }
-        else { T im = ch.imm(j); vleft = im * plv; vright = im * prv; }
-        tl += vleft * rho;
-        tr += vright * rho;
+    for (int jb = ch.lane; jb < d; jb += CH * G) {
+        T m0[CH], m1[CH], plv[CH], prv[CH], xl[CH], xr[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int j = jb + i * G;
+            m0[i] = 0; m1[i] = 0; plv[i] = 0; prv[i] = 0; xl[i] = 0; xr[i] = 0;
+            if (j < d) {
+                const i64 a = ch.at(j);
+                m0[i] = v.msum[a]; m1[i] = v.sms[a]; plv[i] = v.pl[a]; prv[i] = v.pr[a];
+                if (DENSE) { xl[i] = v.vl[a]; xr[i] = v.vr[a]; }
+                else { const T im = ch.imm(j); xl[i] = im * plv[i]; xr[i] = im * prv[i]; }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int j = jb + i * G;
+            if (j < d) {
+                const T ms = m0[i] + m1[i];
+                v.msum[ch.at(j)] = ms;
+                const T rho = ms - (prv[i] + plv[i]) / (T)2;
+                tl += xl[i] * rho;
+                tr += xr[i] * rho;
+            }
+        }
     }
     double red2[2] = {(double)tl, (double)tr};
     Group<G>::template sum<2>(red2, ch.red);
@@ -596,10 +773,27 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
         r.slpa_prop = lae(r.slpa_sub, r.slpa_prop);             // trajectory.py:560-564
     } else {
         if (accb) {
-            for (int j = ch.lane; j < d; j += G) {
-                i64 a = ch.at(j);
-                v.qp[a] = v.qs[a]; v.pp[a] = v.ps[a]; v.gp[a] = v.gs[a];
-                if (DENSE) v.wp[a] = v.ws[a];
+            for (int jb = ch.lane; jb < d; jb += CH * G) {
+                T x0[CH], x1[CH], x2[CH], x3[CH];
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    const int j = jb + i * G;
+                    x0[i] = 0; x1[i] = 0; x2[i] = 0; x3[i] = 0;
+                    if (j < d) {
+                        const i64 a = ch.at(j);
+                        x0[i] = v.qs[a]; x1[i] = v.ps[a]; x2[i] = v.gs[a];
+                        if (DENSE) x3[i] = v.ws[a];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    const int j = jb + i * G;
+                    if (j < d) {
+                        const i64 a = ch.at(j);
+                        v.qp[a] = x0[i]; v.pp[a] = x1[i]; v.gp[a] = x2[i];
+                        if (DENSE) v.wp[a] = x3[i];
+                    }
+                }
             }
             r.E_prop = r.E_sub; r.U_prop = r.U_sub;
         }
@@ -639,11 +833,11 @@ B2H_DEVINL bool hmc_post(Chain<T, G>& ch, T U_new, Front& f) {
         if (DENSE) {
             T g = v.xb[(i64)ch.c * d + j], wv = v.xc[(i64)ch.c * d + j];
             f.set_g(ee, a, g);
-            v.wr[a] = wv;
+            f.set_w(ee, a, wv);
             T p = f.p(ee, a) - he * g;
             f.set_p(ee, a, p);
-            T vel = v.vr[a] - he * wv;
-            v.vr[a] = vel;
+            T vel = f.vel(ee, a) - he * wv;
+            f.set_vel(ee, a, vel);
             kacc += vel * p;
         } else {
             T g;
@@ -670,7 +864,7 @@ B2H_DEVINL bool hmc_post(Chain<T, G>& ch, T U_new, Front& f) {
         i64 a = ch.at(j);
         if (acc) {
             v.qp[a] = f.q(ee, a); v.pp[a] = -f.p(ee, a); v.gp[a] = f.g(ee, a);
-            if (DENSE) v.wp[a] = v.wr[a];
+            if (DENSE) v.wp[a] = f.w(ee, a);
         }
         // on reject the state keeps (q, fresh momentum, g): pp already holds p0 (hmc.py:122,195)
     }

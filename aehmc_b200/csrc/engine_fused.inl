@@ -1,0 +1,126 @@
+// The persistent fused kernel and its launch policy; included by engine_fused_f32.cu / engine_fused_f64.cu.
+#include <stdlib.h>
+
+#include "engine_host.cuh"
+#include "models.cuh"
+
+namespace b2h {
+
+template <typename T, int G, int MODEL, bool HMC, int E>
+__global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksFused)
+fused_run_kernel(EngineView<T> v, ModelDev m, i64 max_ticks) {
+    typedef typename FrontOf<T, E>::type Front;
+    __shared__ double red_s[128];
+    const int c = Geo<G>::chain();
+    if (c >= v.C) return;
+    Chain<T, G> ch(v, c, red_s);
+    ch.load();
+    Front f;
+    bool bound = false;
+    i64 tick = 0;
+    while (max_ticks <= 0 || tick < max_ticks) {
+        if (ch.r.phase == PH_DONE) break;
+        if (ch.r.phase == PH_START) {
+            if (HMC) hmc_begin<T, G, false>(ch);
+            else begin_transition<T, G, false>(ch);
+            Group<G>::sync();
+            bound = false;
+        }
+        if (!bound) { f.bind(ch); bound = Front::kRegs; }
+        half_kick_drift<T, G, false, false>(ch, f);
+        T U;
+        if constexpr (Front::kRegs) {
+            U = model_grad_front<T, G, MODEL>(m, f, ch.lane, ch.red);
+        } else {
+            Group<G>::sync();
+            U = model_grad<T, G, MODEL>(m, f.Q + ch.base, f.Gd + ch.base, v.sj, ch.lane, ch.red);
+            Group<G>::sync();
+        }
+        bool ended;
+        if (HMC) ended = hmc_post<T, G, false, false>(ch, U, f);
+        else ended = post_gradient<T, G, false, false>(ch, U, f);
+        if (ended) bound = false;
+        Group<G>::sync();
+        ++tick;
+    }
+    if (bound) f.flush(ch);                // max_ticks ran out in the middle of a sub-tree
+    ch.store();
+    if (v.counters && ch.lane == 0) atomicAdd((unsigned long long*)&v.counters[3], (unsigned long long)tick);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static ModelDev to_dev(const b2h_model* m) {
+    ModelDev d;
+    d.kind = m->kind; d.dim = m->dim; d.n_data = m->n_data;
+    d.a = m->a; d.b = m->b; d.c = m->c; d.s0 = m->s0; d.s1 = m->s1;
+    return d;
+}
+
+template <typename T, int G, bool HMC, int MODEL, int E>
+static void launch_fused_e(cudaStream_t st, const EngineView<T>& v, const ModelDev& m, i64 max_ticks) {
+    fused_run_kernel<T, G, MODEL, HMC, E><<<Geo<G>::grid(v.C), Geo<G>::kThreads, 0, st>>>(v, m, max_ticks);
+}
+
+// Register front when the chain's row fits 2, 4 or 8 elements per lane (B2H_REG_FRONT=0 disables it).
+// Measured on B200 (benchmarks/workloads.py): HMC keeps its whole trajectory in registers (c1: 0.78 -> 1.67 G
+// evals/s) and the funnel gains 33 %; NUTS on wide elementwise targets is instruction/latency bound, not memory
+// bound, and loses 10 % to the extra register pressure -- it keeps the memory front.
+template <typename T, int G, bool HMC, int MODEL>
+static void launch_fused_model(cudaStream_t st, const EngineView<T>& v, const ModelDev& m, i64 max_ticks) {
+    static int use_regs = -1;
+    if (use_regs < 0) { const char* e = getenv("B2H_REG_FRONT"); use_regs = e ? atoi(e) : 1; }
+    const int epl = (v.d + G - 1) / G;
+    if constexpr (HMC || MODEL != MODEL_IID) {
+        if (use_regs && epl <= 2) return launch_fused_e<T, G, HMC, MODEL, 2>(st, v, m, max_ticks);
+        if (use_regs && epl <= 4) return launch_fused_e<T, G, HMC, MODEL, 4>(st, v, m, max_ticks);
+        if (use_regs && epl <= 8) return launch_fused_e<T, G, HMC, MODEL, 8>(st, v, m, max_ticks);
+    }
+    (void)epl;
+    launch_fused_e<T, G, HMC, MODEL, 0>(st, v, m, max_ticks);
+}
+
+template <typename T, int G, bool HMC>
+static int launch_fused(cudaStream_t st, const EngineView<T>& v, const b2h_model* model, i64 max_ticks) {
+    ModelDev m = to_dev(model);
+    constexpr int GS = G > 8 ? 8 : G;          // funnel / eight schools are instantiated for 1 and 8 lanes only
+    switch (model->kind) {
+        case B2H_MODEL_IID_GAUSSIAN:
+            launch_fused_model<T, G, HMC, MODEL_IID>(st, v, m, max_ticks);
+            break;
+        case B2H_MODEL_FUNNEL:
+            if (G > 8) { set_error("funnel: group must be 1 or 8"); return B2H_ERR_ARG; }
+            launch_fused_model<T, GS, HMC, MODEL_FUNNEL>(st, v, m, max_ticks);
+            break;
+        case B2H_MODEL_EIGHT_SCHOOLS:
+            if (G > 8) { set_error("eight schools: group must be 1 or 8"); return B2H_ERR_ARG; }
+            launch_fused_model<T, GS, HMC, MODEL_SCHOOLS>(st, v, m, max_ticks);
+            break;
+        default:
+            set_error("model has no fused gradient");
+            return B2H_ERR_UNSUPPORTED;
+    }
+    B2H_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename T>
+int launch_fused_g(cudaStream_t st, const EngineView<T>& v, const b2h_model* model, i64 max_ticks, int G, bool hmc) {
+    if (hmc) {
+        switch (G) {
+            case 1: return launch_fused<T, 1, true>(st, v, model, max_ticks);
+            case 8: return launch_fused<T, 8, true>(st, v, model, max_ticks);
+            case 32: return launch_fused<T, 32, true>(st, v, model, max_ticks);
+            default: return launch_fused<T, 256, true>(st, v, model, max_ticks);
+        }
+    }
+    switch (G) {
+        case 1: return launch_fused<T, 1, false>(st, v, model, max_ticks);
+        case 8: return launch_fused<T, 8, false>(st, v, model, max_ticks);
+        case 32: return launch_fused<T, 32, false>(st, v, model, max_ticks);
+        default: return launch_fused<T, 256, false>(st, v, model, max_ticks);
+    }
+}
+
+}  // namespace b2h

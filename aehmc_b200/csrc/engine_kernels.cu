@@ -12,9 +12,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "engine.cuh"
-#include "launch.h"
-#include "models.cuh"
+#include "engine_host.cuh"
 
 namespace b2h {
 
@@ -31,14 +29,6 @@ struct Carver {
         off += n * sizeof(U);
         return p;
     }
-};
-
-constexpr int kRiderSplit = 5;      // split-K slices of the momentum contractions (few rows, full K)
-
-struct EnginePlan {
-    int G;
-    bool dense, split, hmc, per_chain_imm, scalar_imm;
-    size_t model_ws_off, model_ws_bytes;
 };
 
 static int auto_group(int d, long long C) {
@@ -183,294 +173,6 @@ __global__ void resume_kernel(EngineView<T> v) {
     if (v.rec[c].phase == PH_DONE) v.rec[c].phase = PH_START;
 }
 
-// ---------------------------------------------------------------------------
-// fused persistent kernel
-// ---------------------------------------------------------------------------
-template <int G>
-struct Geo {
-    static constexpr int kThreads = G > 32 ? G : 128;
-    static constexpr int kChainsPerBlock = G > 32 ? 1 : 128 / G;
-    // the per-tick (split) kernels are latency-bound streams: cap registers at 64 for 50% occupancy
-    static constexpr int kMinBlocksSplit = G > 32 ? 4 : 8;
-    // the persistent fused kernel is latency / instruction-fetch bound: favour resident warps over registers
-    static constexpr int kMinBlocksFused = G > 32 ? 3 : 5;
-    __device__ static int chain() {
-        return G > 32 ? (int)blockIdx.x : (int)(blockIdx.x * kChainsPerBlock + threadIdx.x / G);
-    }
-    static int grid(int C) { return (C + kChainsPerBlock - 1) / kChainsPerBlock; }
-};
-
-// E > 0: the integration front stays in registers (E elements per lane) between sub-tree boundaries.
-template <typename T, int E> struct FrontOf { typedef RegFront<T, E> type; };
-template <typename T> struct FrontOf<T, 0> { typedef MemFront<T> type; };
-
-template <typename T, int G, int MODEL, bool HMC, int E>
-__global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksFused)
-fused_run_kernel(EngineView<T> v, ModelDev m, i64 max_ticks) {
-    typedef typename FrontOf<T, E>::type Front;
-    __shared__ double red_s[128];
-    const int c = Geo<G>::chain();
-    if (c >= v.C) return;
-    Chain<T, G> ch(v, c, red_s);
-    ch.load();
-    Front f;
-    bool bound = false;
-    i64 tick = 0;
-    while (max_ticks <= 0 || tick < max_ticks) {
-        if (ch.r.phase == PH_DONE) break;
-        if (ch.r.phase == PH_START) {
-            if (HMC) hmc_begin<T, G, false>(ch);
-            else begin_transition<T, G, false>(ch);
-            Group<G>::sync();
-            bound = false;
-        }
-        if (!bound) { f.bind(ch); bound = Front::kRegs; }
-        half_kick_drift<T, G, false, false>(ch, f);
-        T U;
-        if constexpr (Front::kRegs) {
-            U = model_grad_front<T, G, MODEL>(m, f, ch.lane, ch.red);
-        } else {
-            Group<G>::sync();
-            U = model_grad<T, G, MODEL>(m, f.Q + ch.base, f.Gd + ch.base, v.sj, ch.lane, ch.red);
-            Group<G>::sync();
-        }
-        bool ended;
-        if (HMC) ended = hmc_post<T, G, false, false>(ch, U, f);
-        else ended = post_gradient<T, G, false, false>(ch, U, f);
-        if (ended) bound = false;
-        Group<G>::sync();
-        ++tick;
-    }
-    if (bound) f.flush(ch);                // max_ticks ran out in the middle of a sub-tree
-    ch.store();
-    if (v.counters && ch.lane == 0) atomicAdd((unsigned long long*)&v.counters[3], (unsigned long long)tick);
-}
-
-// ---------------------------------------------------------------------------
-// split-mode kernels
-// ---------------------------------------------------------------------------
-template <typename T, int G, bool DENSE, bool HMC>
-__global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksSplit) split_pre_kernel(EngineView<T> v) {
-    __shared__ double red_s[128];
-    const int c = Geo<G>::chain();
-    if (c >= v.C) return;
-    Chain<T, G> ch(v, c, red_s);
-    ch.load();
-    if (ch.r.phase == PH_DONE) return;
-    if (ch.r.phase == PH_START) {
-        if (HMC) hmc_begin<T, G, DENSE>(ch);
-        else begin_transition<T, G, DENSE>(ch);
-    }
-    MemFront<T> f;
-    f.bind(ch);
-    half_kick_drift<T, G, DENSE, true>(ch, f);
-    ch.store();
-}
-
-template <typename T, int G, bool DENSE, bool HMC>
-__global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksSplit) split_post_kernel(EngineView<T> v, int* not_done) {
-    __shared__ double red_s[128];
-    const int c = Geo<G>::chain();
-    if (c >= v.C) return;
-    Chain<T, G> ch(v, c, red_s);
-    ch.load();
-    if (ch.r.phase != PH_RUN) return;
-    const T U = v.Unew[c];
-    MemFront<T> f;
-    f.bind(ch);
-    if (HMC) hmc_post<T, G, DENSE, true>(ch, U, f);
-    else post_gradient<T, G, DENSE, true>(ch, U, f);
-    ch.store();
-    if (ch.lane == 0) {
-        if (ch.r.phase != PH_DONE && not_done) atomicAdd(not_done, 1);
-        if (v.counters) atomicAdd((unsigned long long*)&v.counters[3], 1ull);
-    }
-}
-
-// sum the split-K planes of a rider contraction and scatter the rows to their chains:
-// out[list[r]][:] = sum_s part[s][r][:] for r < *count   (two riders per launch: blockIdx.y)
-template <typename T>
-__global__ void rider_reduce_kernel(const T* part0, const int* count0, const int* list0, T* out0, const T* part1,
-                                    const int* count1, const int* list1, T* out1, int nsplit, i64 plane, int d) {
-    const T* part = blockIdx.y ? part1 : part0;
-    const int* count = blockIdx.y ? count1 : count0;
-    const int* list = blockIdx.y ? list1 : list0;
-    T* out = blockIdx.y ? out1 : out0;
-    const int r = blockIdx.x;
-    if (r >= *count) return;
-    const i64 dst = (i64)list[r] * d;
-    for (int j = threadIdx.x; j < d; j += blockDim.x) {
-        T s = 0;
-        for (int k = 0; k < nsplit; ++k) s += part[(i64)k * plane + (i64)r * d + j];
-        out[dst + j] = s;
-    }
-}
-
-// dense metric momentum at the start of a run: normals of every chain's first transition (row c of mom_z)
-template <typename T>
-__global__ void mom_init_kernel(EngineView<T> v) {
-    const int c = blockIdx.x;
-    const int t = v.rec[c].t;
-    for (int j = threadIdx.x; j < v.d; j += blockDim.x) v.mom_z[(i64)c * v.d + j] = (T)draw_z(v.rng, c, t, j, v.d);
-}
-
-// ---------------------------------------------------------------------------
-// host side
-// ---------------------------------------------------------------------------
-static ModelDev to_dev(const b2h_model* m) {
-    ModelDev d;
-    d.kind = m->kind; d.dim = m->dim; d.n_data = m->n_data;
-    d.a = m->a; d.b = m->b; d.c = m->c; d.s0 = m->s0; d.s1 = m->s1;
-    return d;
-}
-
-template <typename T, int G, bool HMC, int MODEL, int E>
-static void launch_fused_e(cudaStream_t st, const EngineView<T>& v, const ModelDev& m, i64 max_ticks) {
-    fused_run_kernel<T, G, MODEL, HMC, E><<<Geo<G>::grid(v.C), Geo<G>::kThreads, 0, st>>>(v, m, max_ticks);
-}
-
-// Register front when the chain's row fits 2, 4 or 8 elements per lane (B2H_REG_FRONT=0 disables it).
-// Measured on B200 (benchmarks/workloads.py): HMC keeps its whole trajectory in registers (c1: 0.78 -> 1.67 G
-// evals/s) and the funnel gains 33 %; NUTS on wide elementwise targets is instruction/latency bound, not memory
-// bound, and loses 10 % to the extra register pressure -- it keeps the memory front.
-template <typename T, int G, bool HMC, int MODEL>
-static void launch_fused_model(cudaStream_t st, const EngineView<T>& v, const ModelDev& m, i64 max_ticks) {
-    static int use_regs = -1;
-    if (use_regs < 0) { const char* e = getenv("B2H_REG_FRONT"); use_regs = e ? atoi(e) : 1; }
-    const int epl = (v.d + G - 1) / G;
-    if constexpr (HMC || MODEL != MODEL_IID) {
-        if (use_regs && epl <= 2) return launch_fused_e<T, G, HMC, MODEL, 2>(st, v, m, max_ticks);
-        if (use_regs && epl <= 4) return launch_fused_e<T, G, HMC, MODEL, 4>(st, v, m, max_ticks);
-        if (use_regs && epl <= 8) return launch_fused_e<T, G, HMC, MODEL, 8>(st, v, m, max_ticks);
-    }
-    (void)epl;
-    launch_fused_e<T, G, HMC, MODEL, 0>(st, v, m, max_ticks);
-}
-
-template <typename T, int G, bool HMC>
-static int launch_fused(cudaStream_t st, const EngineView<T>& v, const b2h_model* model, i64 max_ticks) {
-    ModelDev m = to_dev(model);
-    constexpr int GS = G > 8 ? 8 : G;          // funnel / eight schools are instantiated for 1 and 8 lanes only
-    switch (model->kind) {
-        case B2H_MODEL_IID_GAUSSIAN:
-            launch_fused_model<T, G, HMC, MODEL_IID>(st, v, m, max_ticks);
-            break;
-        case B2H_MODEL_FUNNEL:
-            if (G > 8) { set_error("funnel: group must be 1 or 8"); return B2H_ERR_ARG; }
-            launch_fused_model<T, GS, HMC, MODEL_FUNNEL>(st, v, m, max_ticks);
-            break;
-        case B2H_MODEL_EIGHT_SCHOOLS:
-            if (G > 8) { set_error("eight schools: group must be 1 or 8"); return B2H_ERR_ARG; }
-            launch_fused_model<T, GS, HMC, MODEL_SCHOOLS>(st, v, m, max_ticks);
-            break;
-        default:
-            set_error("model has no fused gradient");
-            return B2H_ERR_UNSUPPORTED;
-    }
-    B2H_LAUNCH_CHECK();
-    return 0;
-}
-
-template <typename T, int G, bool HMC>
-static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const b2h_model* model,
-                     const b2h_metric* metric, const b2h_cfg* cfg, i64 max_ticks, int n_transitions, void* model_ws,
-                     i64 model_ws_bytes, int* not_done_dev, int resume) {
-    cudaStream_t st = ctx->stream;
-    const int grid = Geo<G>::grid(v.C), thr = Geo<G>::kThreads;
-    const int C = v.C, d = v.d;
-    const T* imm_dense = (const T*)metric->imm;
-    const T* sqrt_t = (const T*)metric->sqrt_t;
-    i64 bound = max_ticks > 0 ? max_ticks
-                              : (i64)n_transitions * (HMC ? (i64)cfg->num_integration_steps
-                                                          : (((i64)1 << v.maxd) - 1 + v.maxd)) + 1;
-    int* host_flag = ctx->host_flag;
-    int rc = 0;
-    GemmGroup<T> none{nullptr, 0, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr};
-    int last_parity = 0;
-    if (pl.dense) {
-        B2H_CUDA(cudaMemsetAsync(v.mom_count, 0, 4 * sizeof(int), st));
-        if (!resume) {
-            // p0 = z . S^T (metrics.py:56-59,67), v0 = p0 . imm (metrics.py:71) for every chain's first transition,
-            // and w = imm . g of the starting positions
-            mom_init_kernel<T><<<C, 128, 0, st>>>(v);
-            launch_dense_apply<T>(st, v.mom_z, sqrt_t, v.mom_p, C, d, d, nullptr, nullptr);
-            launch_dense_apply<T>(st, v.mom_p, imm_dense, v.mom_v, C, d, d, nullptr, nullptr);
-            launch_dense_apply<T>(st, v.gp, imm_dense, v.wp, C, d, d, nullptr, nullptr);
-        }
-    }
-    bool side_pending[2] = {false, false};
-    static int use_side = -1;
-    if (use_side < 0) { const char* e = getenv("B2H_SIDE_STREAM"); use_side = e ? atoi(e) : 1; }
-    cudaStream_t rider_stream = use_side ? ctx->side : st;
-    for (i64 tick = 0; tick < bound; ++tick) {
-        const int b = (int)(tick & 1);
-        if (pl.dense) {
-            last_parity = b;
-            v.mom_parity = b;
-            // all momentum contractions launched so far must have landed: a chain that started a transition two
-            // ticks ago may start the next one now (its v0 came from the previous tick's side launch), and this
-            // parity's request list is about to be reused
-            for (int k = 0; k < 2; ++k)
-                if (side_pending[k]) { B2H_CUDA(cudaStreamWaitEvent(st, ctx->ev_side[k], 0)); side_pending[k] = false; }
-            B2H_CUDA(cudaMemsetAsync(v.mom_count + b, 0, sizeof(int), st));
-            split_pre_kernel<T, G, true, HMC><<<grid, thr, 0, st>>>(v);      // half kick + drift by the v/w recurrence
-            // side stream: p0 = z . S^T of the transitions queued by this pre kernel, and v0 = imm . p0 of the
-            // transitions queued one tick ago (their p0 was produced by the previous side launch)
-            if (use_side) {
-                B2H_CUDA(cudaEventRecord(ctx->ev_pre[b], st));
-                B2H_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_pre[b], 0));
-            }
-            // few rows, full reduction length: split K so that the tiles spread over all SMs, then reduce + scatter
-            const i64 plane = (i64)C * d;
-            T* part1 = v.mom_part;
-            T* part2 = v.mom_part + (size_t)kRiderSplit * plane;
-            GemmGroup<T> g1{v.mom_z + (size_t)b * C * d, (i64)d, sqrt_t, (i64)d, part1, (i64)d, C, v.mom_count + b,
-                            nullptr, nullptr, nullptr};
-            GemmGroup<T> g2{v.mom_p, (i64)d, imm_dense, (i64)d, part2, (i64)d, C, v.mom_count + (b ^ 1), nullptr,
-                            v.mom_list + (size_t)(b ^ 1) * C, nullptr};
-            launch_gemm_grouped<T>(rider_stream, g1, g2, none, d, d, kRiderSplit, plane, 0);
-            rider_reduce_kernel<T><<<dim3(C, 2), 128, 0, rider_stream>>>(
-                part1, v.mom_count + b, v.mom_list + (size_t)b * C, v.mom_p, part2, v.mom_count + (b ^ 1),
-                v.mom_list + (size_t)(b ^ 1) * C, v.mom_v, kRiderSplit, plane, d);
-            if (use_side) {
-                B2H_CUDA(cudaEventRecord(ctx->ev_side[b], ctx->side));
-                side_pending[b] = true;
-            }
-        } else {
-            split_pre_kernel<T, G, false, HMC><<<grid, thr, 0, st>>>(v);
-        }
-        rc = potential_and_grad_impl<T>(ctx, model, v.xa, v.Unew, v.xb, C, model_ws, model_ws_bytes);
-        if (rc) break;
-        const bool check = (max_ticks <= 0) && ((tick & 3) == 3 || tick + 1 == bound);
-        if (check) B2H_CUDA(cudaMemsetAsync(not_done_dev, 0, sizeof(int), st));
-        if (pl.dense) {
-            // the tick's only metric contraction on the main stream: w' = imm . g'
-            launch_dense_apply<T>(st, v.xb, imm_dense, v.xc, C, d, d, nullptr, nullptr);
-            split_post_kernel<T, G, true, HMC><<<grid, thr, 0, st>>>(v, check ? not_done_dev : nullptr);
-        } else {
-            split_post_kernel<T, G, false, HMC><<<grid, thr, 0, st>>>(v, check ? not_done_dev : nullptr);
-        }
-        if (check) {
-            cudaError_t e = cudaMemcpyAsync(host_flag, not_done_dev, sizeof(int), cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) { rc = cuda_fail(e, "tick poll"); break; }
-            if (*host_flag == 0) break;
-        }
-    }
-    if (pl.dense && rc == 0) {
-        // join the side stream, then flush: v0 of the transitions queued in the last tick, so that a resumed run
-        // starts with no request pending
-        for (int b = 0; b < 2; ++b)
-            if (side_pending[b]) B2H_CUDA(cudaStreamWaitEvent(st, ctx->ev_side[b], 0));
-        GemmGroup<T> g0{v.mom_p, (i64)d, imm_dense, (i64)d, v.mom_v, (i64)d, C, v.mom_count + last_parity, nullptr,
-                        v.mom_list + (size_t)last_parity * C, v.mom_list + (size_t)last_parity * C};
-        launch_gemm_grouped<T>(st, g0, none, none, d, d, 1, 0, 0);
-    }
-    if (rc) return rc;
-    B2H_LAUNCH_CHECK();
-    return 0;
-}
-
 template <typename T>
 static int run_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
                      const b2h_cfg* cfg, const b2h_adapt* adapt, void* q, void* p, void* U, void* g,
@@ -557,39 +259,12 @@ static int run_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* met
     B2H_LAUNCH_CHECK();
     int* not_done_dev = v.scratch;
 
-#define B2H_DISPATCH_G(FN, ...)                                          \
-    switch (pl.G) {                                                      \
-        case 1: rc = FN<T, 1, false> __VA_ARGS__; break;                 \
-        case 8: rc = FN<T, 8, false> __VA_ARGS__; break;                 \
-        case 32: rc = FN<T, 32, false> __VA_ARGS__; break;               \
-        default: rc = FN<T, 256, false> __VA_ARGS__; break;              \
-    }
-#define B2H_DISPATCH_G_HMC(FN, ...)                                      \
-    switch (pl.G) {                                                      \
-        case 1: rc = FN<T, 1, true> __VA_ARGS__; break;                  \
-        case 8: rc = FN<T, 8, true> __VA_ARGS__; break;                  \
-        case 32: rc = FN<T, 32, true> __VA_ARGS__; break;                \
-        default: rc = FN<T, 256, true> __VA_ARGS__; break;               \
-    }
-
     if (!pl.split) {
-        if (hmc) { B2H_DISPATCH_G_HMC(launch_fused, (st, v, model, max_ticks)) }
-        else { B2H_DISPATCH_G(launch_fused, (st, v, model, max_ticks)) }
+        rc = launch_fused_g<T>(st, v, model, max_ticks, pl.G, hmc);
     } else {
         if (pl.G == 1) { set_error("split mode needs group >= 8"); return B2H_ERR_ARG; }
-        if (hmc) {
-            switch (pl.G) {
-                case 8: rc = run_split<T, 8, true>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev, resume); break;
-                case 32: rc = run_split<T, 32, true>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev, resume); break;
-                default: rc = run_split<T, 256, true>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev, resume); break;
-            }
-        } else {
-            switch (pl.G) {
-                case 8: rc = run_split<T, 8, false>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev, resume); break;
-                case 32: rc = run_split<T, 32, false>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev, resume); break;
-                default: rc = run_split<T, 256, false>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev, resume); break;
-            }
-        }
+        rc = run_split_g<T>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes,
+                            not_done_dev, resume, hmc);
     }
     if (rc) return rc;
     copy_out_kernel<T><<<eg, eb, 0, st>>>(v, (T*)q, (T*)p, (T*)g, (T*)U, step_size,
@@ -776,12 +451,7 @@ static int expand_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* 
     const i64 n = C * model->dim;
     const int eb = 256, eg = (int)((n + eb - 1) / eb);
     tree_in_kernel<T><<<eg, eb, 0, st>>>(v, *tree, eps);
-    switch (pl.G) {
-        case 1: rc = launch_fused<T, 1, false>(st, v, model, 0); break;
-        case 8: rc = launch_fused<T, 8, false>(st, v, model, 0); break;
-        case 32: rc = launch_fused<T, 32, false>(st, v, model, 0); break;
-        default: rc = launch_fused<T, 256, false>(st, v, model, 0); break;
-    }
+    rc = launch_fused_g<T>(st, v, model, 0, pl.G, false);
     if (rc) return rc;
     tree_out_kernel<T><<<eg, eb, 0, st>>>(v, *tree);
     B2H_LAUNCH_CHECK();
@@ -806,12 +476,7 @@ static int subtree_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric*
     const i64 n = C * model->dim;
     const int eb = 256, eg = (int)((n + eb - 1) / eb);
     subtree_in_kernel<T><<<eg, eb, 0, st>>>(v, *sub, eps);
-    switch (pl.G) {
-        case 1: rc = launch_fused<T, 1, false>(st, v, model, 0); break;
-        case 8: rc = launch_fused<T, 8, false>(st, v, model, 0); break;
-        case 32: rc = launch_fused<T, 32, false>(st, v, model, 0); break;
-        default: rc = launch_fused<T, 256, false>(st, v, model, 0); break;
-    }
+    rc = launch_fused_g<T>(st, v, model, 0, pl.G, false);
     if (rc) return rc;
     subtree_out_kernel<T><<<eg, eb, 0, st>>>(v, *sub);
     B2H_LAUNCH_CHECK();

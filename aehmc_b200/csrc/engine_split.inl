@@ -1,0 +1,269 @@
+// The per-tick (split) kernels and their driver loop; included by engine_split_f32.cu / engine_split_f64.cu.
+#include <stdlib.h>
+
+#include "engine_host.cuh"
+
+namespace b2h {
+
+// ---------------------------------------------------------------------------
+// split-mode kernels
+// ---------------------------------------------------------------------------
+template <typename T, int G, bool DENSE, bool HMC>
+__global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksSplit) split_pre_kernel(EngineView<T> v) {
+    __shared__ double red_s[128];
+    const int c = Geo<G>::chain();
+    if (c >= v.C) return;
+    Chain<T, G> ch(v, c, red_s);
+    ch.load();
+    if (ch.r.phase == PH_DONE) return;
+    if (ch.r.phase == PH_START) {
+        if (HMC) hmc_begin<T, G, DENSE>(ch);
+        else begin_transition<T, G, DENSE>(ch);
+    }
+    MemFront<T> f;
+    f.bind(ch);
+    half_kick_drift<T, G, DENSE, true>(ch, f);
+    ch.store();
+}
+
+template <typename T, int G, bool DENSE, bool HMC>
+__global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksSplit) split_post_kernel(EngineView<T> v, int* not_done) {
+    __shared__ double red_s[128];
+    const int c = Geo<G>::chain();
+    if (c >= v.C) return;
+    Chain<T, G> ch(v, c, red_s);
+    ch.load();
+    if (ch.r.phase != PH_RUN) return;
+    const T U = v.Unew[c];
+    MemFront<T> f;
+    f.bind(ch);
+    if (HMC) hmc_post<T, G, DENSE, true>(ch, U, f);
+    else post_gradient<T, G, DENSE, true>(ch, U, f);
+    ch.store();
+    if (ch.lane == 0) {
+        if (ch.r.phase != PH_DONE && not_done) atomicAdd(not_done, 1);
+        if (v.counters) atomicAdd((unsigned long long*)&v.counters[3], 1ull);
+    }
+}
+
+// post of tick t and pre of tick t+1 in one pass with the front in registers (TickFront): q, p, g (V, W) of the
+// edge are read once and written once per tick instead of twice.
+template <typename T, int G, bool DENSE, bool HMC, int E>
+__global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksTick)
+split_postpre_kernel(EngineView<T> v, int* not_done) {
+    __shared__ double red_s[128];
+    const int c = Geo<G>::chain();
+    if (c >= v.C) return;
+    Chain<T, G> ch(v, c, red_s);
+    ch.load();
+    if (ch.r.phase == PH_DONE) return;
+    TickFront<T, E, DENSE> f;
+    bool rebind = true;
+    if (ch.r.phase == PH_RUN) {
+        f.bind_post(ch);
+        const T U = v.Unew[c];
+        bool ended;
+        if (HMC) ended = hmc_post<T, G, DENSE, true>(ch, U, f);
+        else ended = post_gradient<T, G, DENSE, true>(ch, U, f);
+        rebind = ended;                        // the front was written back (or abandoned) at a sub-tree end
+        if (ch.lane == 0) {
+            if (ch.r.phase != PH_DONE && not_done) atomicAdd(not_done, 1);
+            if (v.counters) atomicAdd((unsigned long long*)&v.counters[3], 1ull);
+        }
+        if (ch.r.phase == PH_DONE) { ch.store(); return; }
+    }
+    if (ch.r.phase == PH_START) {
+        if (HMC) hmc_begin<T, G, DENSE>(ch);
+        else begin_transition<T, G, DENSE>(ch);
+        rebind = true;
+    }
+    if (rebind) f.bind(ch);
+    half_kick_drift<T, G, DENSE, true>(ch, f);
+    f.store(ch, !rebind);                      // after a re-bind g (and W) in memory are already current
+    ch.store();
+}
+
+// sum the split-K planes of a rider contraction and scatter the rows to their chains:
+// out[list[r]][:] = sum_s part[s][r][:] for r < *count   (two riders per launch: blockIdx.y)
+template <typename T>
+__global__ void rider_reduce_kernel(const T* part0, const int* count0, const int* list0, T* out0, const T* part1,
+                                    const int* count1, const int* list1, T* out1, int nsplit, i64 plane, int d) {
+    const T* part = blockIdx.y ? part1 : part0;
+    const int* count = blockIdx.y ? count1 : count0;
+    const int* list = blockIdx.y ? list1 : list0;
+    T* out = blockIdx.y ? out1 : out0;
+    const int r = blockIdx.x;
+    if (r >= *count) return;
+    const i64 dst = (i64)list[r] * d;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        T s = 0;
+        for (int k = 0; k < nsplit; ++k) s += part[(i64)k * plane + (i64)r * d + j];
+        out[dst + j] = s;
+    }
+}
+
+// dense metric momentum at the start of a run: normals of every chain's first transition (row c of mom_z)
+template <typename T>
+__global__ void mom_init_kernel(EngineView<T> v) {
+    const int c = blockIdx.x;
+    const int t = v.rec[c].t;
+    for (int j = threadIdx.x; j < v.d; j += blockDim.x) v.mom_z[(i64)c * v.d + j] = (T)draw_z(v.rng, c, t, j, v.d);
+}
+
+template <typename T, int G, bool HMC>
+static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const b2h_model* model,
+                     const b2h_metric* metric, const b2h_cfg* cfg, i64 max_ticks, int n_transitions, void* model_ws,
+                     i64 model_ws_bytes, int* not_done_dev, int resume) {
+    cudaStream_t st = ctx->stream;
+    const int grid = Geo<G>::grid(v.C), thr = Geo<G>::kThreads;
+    const int C = v.C, d = v.d;
+    const T* imm_dense = (const T*)metric->imm;
+    const T* sqrt_t = (const T*)metric->sqrt_t;
+    i64 bound = max_ticks > 0 ? max_ticks
+                              : (i64)n_transitions * (HMC ? (i64)cfg->num_integration_steps
+                                                          : (((i64)1 << v.maxd) - 1 + v.maxd)) + 1;
+    int* host_flag = ctx->host_flag;
+    int rc = 0;
+    GemmGroup<T> none{nullptr, 0, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr};
+    int last_parity = 0;
+    if (pl.dense) {
+        B2H_CUDA(cudaMemsetAsync(v.mom_count, 0, 4 * sizeof(int), st));
+        if (!resume) {
+            // p0 = z . S^T (metrics.py:56-59,67), v0 = p0 . imm (metrics.py:71) for every chain's first transition,
+            // and w = imm . g of the starting positions
+            mom_init_kernel<T><<<C, 128, 0, st>>>(v);
+            launch_dense_apply<T>(st, v.mom_z, sqrt_t, v.mom_p, C, d, d, nullptr, nullptr);
+            launch_dense_apply<T>(st, v.mom_p, imm_dense, v.mom_v, C, d, d, nullptr, nullptr);
+            launch_dense_apply<T>(st, v.gp, imm_dense, v.wp, C, d, d, nullptr, nullptr);
+        }
+    }
+    bool side_pending[2] = {false, false};
+    static int use_side = -1, use_fuse = -1;
+    if (use_side < 0) { const char* e = getenv("B2H_SIDE_STREAM"); use_side = e ? atoi(e) : 1; }
+    if (use_fuse < 0) { const char* e = getenv("B2H_FUSE_TICK"); use_fuse = e ? atoi(e) : 1; }
+    cudaStream_t rider_stream = use_side ? ctx->side : st;
+    const int epl = (d + G - 1) / G;                 // front elements per lane
+    const bool fuse = use_fuse && epl <= 4;
+
+    // Dense metric, before the kernel that holds the pre part of tick t: all momentum contractions launched so far
+    // must have landed (a chain that started a transition two ticks ago may start the next one now: its v0 came
+    // from the previous tick's side launch), and this parity's request list is about to be reused.
+    auto pre_prologue = [&](i64 t) -> int {
+        const int b = (int)(t & 1);
+        last_parity = b;
+        v.mom_parity = b;
+        for (int k = 0; k < 2; ++k)
+            if (side_pending[k]) { B2H_CUDA(cudaStreamWaitEvent(st, ctx->ev_side[k], 0)); side_pending[k] = false; }
+        B2H_CUDA(cudaMemsetAsync(v.mom_count + b, 0, sizeof(int), st));
+        return 0;
+    };
+    // ... and after it, on the side stream: p0 = z . S^T of the transitions queued by this pre part, and
+    // v0 = imm . p0 of the transitions queued one tick ago (their p0 was produced by the previous side launch).
+    auto pre_epilogue = [&](i64 t) -> int {
+        const int b = (int)(t & 1);
+        if (use_side) {
+            B2H_CUDA(cudaEventRecord(ctx->ev_pre[b], st));
+            B2H_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_pre[b], 0));
+        }
+        // few rows, full reduction length: split K so that the tiles spread over all SMs, then reduce + scatter
+        const i64 plane = (i64)C * d;
+        T* part1 = v.mom_part;
+        T* part2 = v.mom_part + (size_t)kRiderSplit * plane;
+        GemmGroup<T> g1{v.mom_z + (size_t)b * C * d, (i64)d, sqrt_t, (i64)d, part1, (i64)d, C, v.mom_count + b,
+                        nullptr, nullptr, nullptr};
+        GemmGroup<T> g2{v.mom_p, (i64)d, imm_dense, (i64)d, part2, (i64)d, C, v.mom_count + (b ^ 1), nullptr,
+                        v.mom_list + (size_t)(b ^ 1) * C, nullptr};
+        launch_gemm_grouped<T>(rider_stream, g1, g2, none, d, d, kRiderSplit, plane, 0);
+        rider_reduce_kernel<T><<<dim3(C, 2), 128, 0, rider_stream>>>(
+            part1, v.mom_count + b, v.mom_list + (size_t)b * C, v.mom_p, part2, v.mom_count + (b ^ 1),
+            v.mom_list + (size_t)(b ^ 1) * C, v.mom_v, kRiderSplit, plane, d);
+        if (use_side) {
+            B2H_CUDA(cudaEventRecord(ctx->ev_side[b], ctx->side));
+            side_pending[b] = true;
+        }
+        return 0;
+    };
+    auto launch_pre = [&](i64 t) -> int {
+        if (pl.dense) {
+            if (int e = pre_prologue(t)) return e;
+            split_pre_kernel<T, G, true, HMC><<<grid, thr, 0, st>>>(v);      // half kick + drift by the v/w recurrence
+            return pre_epilogue(t);
+        }
+        split_pre_kernel<T, G, false, HMC><<<grid, thr, 0, st>>>(v);
+        return 0;
+    };
+    auto launch_postpre = [&](i64 t, int* nd) -> int {                       // post of tick t - 1, pre of tick t
+        if (pl.dense) {
+            if (int e = pre_prologue(t)) return e;
+            if (epl <= 1) split_postpre_kernel<T, G, true, HMC, 1><<<grid, thr, 0, st>>>(v, nd);
+            else if (epl <= 2) split_postpre_kernel<T, G, true, HMC, 2><<<grid, thr, 0, st>>>(v, nd);
+            else split_postpre_kernel<T, G, true, HMC, 4><<<grid, thr, 0, st>>>(v, nd);
+            return pre_epilogue(t);
+        }
+        if (epl <= 1) split_postpre_kernel<T, G, false, HMC, 1><<<grid, thr, 0, st>>>(v, nd);
+        else if (epl <= 2) split_postpre_kernel<T, G, false, HMC, 2><<<grid, thr, 0, st>>>(v, nd);
+        else split_postpre_kernel<T, G, false, HMC, 4><<<grid, thr, 0, st>>>(v, nd);
+        return 0;
+    };
+
+    rc = launch_pre(0);
+    for (i64 tick = 0; tick < bound && rc == 0; ++tick) {
+        rc = potential_and_grad_impl<T>(ctx, model, v.xa, v.Unew, v.xb, C, model_ws, model_ws_bytes);
+        if (rc) break;
+        const bool last = tick + 1 == bound;
+        const bool check = (max_ticks <= 0) && ((tick & 3) == 3 || last);
+        if (check) B2H_CUDA(cudaMemsetAsync(not_done_dev, 0, sizeof(int), st));
+        // the tick's only metric contraction on the main stream: w' = imm . g'
+        if (pl.dense) launch_dense_apply<T>(st, v.xb, imm_dense, v.xc, C, d, d, nullptr, nullptr);
+        int* nd = check ? not_done_dev : nullptr;
+        if (fuse && !last) {
+            rc = launch_postpre(tick + 1, nd);
+            if (rc) break;
+        } else {
+            if (pl.dense) split_post_kernel<T, G, true, HMC><<<grid, thr, 0, st>>>(v, nd);
+            else split_post_kernel<T, G, false, HMC><<<grid, thr, 0, st>>>(v, nd);
+        }
+        if (check) {
+            cudaError_t e = cudaMemcpyAsync(host_flag, not_done_dev, sizeof(int), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "tick poll"); break; }
+            if (*host_flag == 0) break;
+        }
+        if (!fuse && !last) rc = launch_pre(tick + 1);
+    }
+    if (pl.dense && rc == 0) {
+        // join the side stream, then flush: v0 of the transitions queued in the last tick, so that a resumed run
+        // starts with no request pending
+        for (int b = 0; b < 2; ++b)
+            if (side_pending[b]) B2H_CUDA(cudaStreamWaitEvent(st, ctx->ev_side[b], 0));
+        GemmGroup<T> g0{v.mom_p, (i64)d, imm_dense, (i64)d, v.mom_v, (i64)d, C, v.mom_count + last_parity, nullptr,
+                        v.mom_list + (size_t)last_parity * C, v.mom_list + (size_t)last_parity * C};
+        launch_gemm_grouped<T>(st, g0, none, none, d, d, 1, 0, 0);
+    }
+    if (rc) return rc;
+    B2H_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename T>
+int run_split_g(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const b2h_model* model, const b2h_metric* metric,
+                const b2h_cfg* cfg, i64 max_ticks, int n_transitions, void* model_ws, i64 model_ws_bytes,
+                int* not_done_dev, int resume, bool hmc) {
+#define B2H_RUN_SPLIT(G, H) \
+    run_split<T, G, H>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev, resume)
+    if (hmc) {
+        switch (pl.G) {
+            case 8: return B2H_RUN_SPLIT(8, true);
+            case 32: return B2H_RUN_SPLIT(32, true);
+            default: return B2H_RUN_SPLIT(256, true);
+        }
+    }
+    switch (pl.G) {
+        case 8: return B2H_RUN_SPLIT(8, false);
+        case 32: return B2H_RUN_SPLIT(32, false);
+        default: return B2H_RUN_SPLIT(256, false);
+    }
+#undef B2H_RUN_SPLIT
+}
+
+}  // namespace b2h
