@@ -78,6 +78,10 @@ int tc_gemm_logistic(cudaStream_t st, const void* A, long long lda, const void* 
 int tc_gemm_blocked_a(cudaStream_t st, const void* R, long long r_piece_stride, const void* B, long long ldb, float* out,
                       int M, int N, int K, int pieces, int ldo, int nsplit, long long split_stride);
 
+int tc_logistic_fused(cudaStream_t st, const void* beta_pieces, int piece_rows, const void* X, int M, int N, int dim,
+                      const float* y, float* gpart, double* upart, int* per_cta, int* planes);
+int logistic_fused_planes(int M, int N);
+
 // engine_kernels.cu
 int nuts_run_impl(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
                   const b2h_cfg* cfg, const b2h_adapt* adapt, void* q, void* p, void* U, void* g, double* step_size,

@@ -178,6 +178,86 @@ __global__ void split_reduce_f32_kernel(const float* part, T* g, i64 n, int nspl
     g[i] = (T)s;
 }
 
+
+// ---- fully fused tensor-core gradient (dim <= 128): one contraction kernel, no residual traffic ----------------
+struct LogregFusedPlan {
+    int planes;
+    size_t off_bp, off_y, off_gpart, off_U, off_upart, total;
+};
+
+static LogregFusedPlan plan_logreg_fused(const b2h_model* m, i64 C) {
+    LogregFusedPlan p;
+    p.planes = logistic_fused_planes((int)C, (int)m->n_data);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 1023) & ~(size_t)1023; return o; };
+    p.off_bp = take((size_t)3 * C * m->dim * 2);
+    p.off_y = take((size_t)m->n_data * 4);
+    p.off_gpart = take((size_t)p.planes * C * m->dim * 4);
+    p.off_U = take((size_t)C * sizeof(double));
+    p.off_upart = take((size_t)4 * 160 * C * sizeof(double));
+    p.total = off + 1024;
+    return p;
+}
+
+static bool logistic_use_fused(const b2h_model* m) { return (int)m->s1 == 2 && m->dim <= 128; }
+
+// g (T) = sum over the planes written by the CTAs that touched the chain tile (fixed order) + b / sigma^2;
+// U = sum of the CTAs' potential partials + 1/2 |b|^2 / sigma^2.  One warp per chain.
+template <typename T>
+__global__ void __launch_bounds__(128)
+logistic_fused_finish_kernel(const float* gpart, i64 plane_stride, const double* upart, const T* q, T* g, T* U,
+                             T inv_prior_var, i64 C, int d, int tiles_n, int per_cta) {
+    const i64 c = (i64)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (c >= C) return;
+    const int lane = threadIdx.x & 31;
+    const i64 mt = c / 128;
+    const int b_first = (int)((mt * tiles_n) / per_cta);
+    const int b_last = (int)(((mt + 1) * tiles_n - 1) / per_cta);
+    T acc = 0;
+    for (int j = lane; j < d; j += 32) {
+        double s = 0.0;
+        for (int b = 0; b <= b_last - b_first; ++b) s += (double)gpart[(i64)b * plane_stride + c * d + j];
+        const T bj = q[c * d + j];
+        g[c * d + j] = (T)s + inv_prior_var * bj;
+        acc += bj * bj;
+    }
+    const double nb = Group<32>::sum1((double)acc, nullptr);
+    if (lane == 0) {
+        double u = 0.0;
+        for (int t = b_first * 4; t < (b_last + 1) * 4; ++t) u += upart[(i64)t * C + c];
+        U[c] = (T)u + (T)0.5 * inv_prior_var * (T)nb;
+    }
+}
+
+template <typename T>
+static int logistic_tc_fused(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U, T* g, i64 C, void* ws, i64 ws_bytes) {
+    if (!m->x_bf16) { set_error("logistic tensor-core path needs x_bf16"); return B2H_ERR_ARG; }
+    if (m->dim % 8 || m->n_data % 8) { set_error("logistic tensor-core path needs dim and n_data multiples of 8"); return B2H_ERR_ARG; }
+    LogregFusedPlan p = plan_logreg_fused(m, C);
+    if (!ws || (size_t)ws_bytes < p.total) {
+        set_error("logistic workspace too small: need " + std::to_string(p.total) + " bytes");
+        return B2H_ERR_WORKSPACE;
+    }
+    cudaStream_t st = ctx->stream;
+    const int d = m->dim;
+    const i64 N = m->n_data;
+    char* base = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+    __nv_bfloat16* bp = (__nv_bfloat16*)(base + p.off_bp);
+    float* yf = (float*)(base + p.off_y);
+    float* gpart = (float*)(base + p.off_gpart);
+    double* upart = (double*)(base + p.off_upart);
+    const i64 ng = C * d;
+    beta_split_kernel<T><<<(int)((ng + 255) / 256), 256, 0, st>>>(q, bp, ng);
+    to_float_kernel<T><<<(int)((N + 255) / 256), 256, 0, st>>>((const T*)m->b, yf, N);
+    int per_cta = 0, planes = 0;
+    int rc = tc_logistic_fused(st, bp, (int)C, m->x_bf16, (int)C, (int)N, d, yf, gpart, upart, &per_cta, &planes);
+    if (rc < 0) return rc;
+    logistic_fused_finish_kernel<T><<<(int)((C + 3) / 4), 128, 0, st>>>(gpart, ng, upart, q, g, U, (T)m->s0, C, d,
+                                                                         (int)((N + 63) / 64), per_cta);
+    B2H_LAUNCH_CHECK();
+    return 0;
+}
+
 template <typename T>
 static int logistic_tc(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U, T* g, i64 C, void* ws, i64 ws_bytes) {
     if (!m->x_bf16 || !m->xt_bf16) { set_error("logistic tensor-core path needs x_bf16 and xt_bf16"); return B2H_ERR_ARG; }
@@ -222,14 +302,18 @@ static int logistic_tc(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U, T* g,
 }
 
 i64 logistic_workspace_bytes(const b2h_model* m, int dtype, i64 C) {
-    if ((int)m->s1 == 2) return (i64)plan_logreg_tc(m, C).total + 1024;
+    if (logistic_use_fused(m)) return (i64)plan_logreg_fused(m, C).total + 1024;
+    if ((int)m->s1 >= 2) return (i64)plan_logreg_tc(m, C).total + 1024;
     return (i64)plan_logreg(m, dtype, C).total;
 }
 
 template <typename T>
 int logistic_potential_and_grad(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U, T* g, i64 C, void* ws,
                                 i64 ws_bytes, int path) {
-    if (path == 2 || (path == 0 && (int)m->s1 == 2)) return logistic_tc<T>(ctx, m, q, U, g, C, ws, ws_bytes);
+    // model flag s1: 0 = FMA / DMMA exactness reference, 2 = tensor cores (fully fused when dim <= 128), 3 = tensor
+    // cores with the two-kernel formulation (residual pieces through memory)
+    if (path == 0 && logistic_use_fused(m)) return logistic_tc_fused<T>(ctx, m, q, U, g, C, ws, ws_bytes);
+    if (path == 2 || (path == 0 && (int)m->s1 >= 2)) return logistic_tc<T>(ctx, m, q, U, g, C, ws, ws_bytes);
     if (!m->a || !m->b || !m->c) { set_error("logistic model needs X (a), y (b) and X^T (c)"); return B2H_ERR_ARG; }
     LogregPlan p = plan_logreg(m, Num<T>::dtype, C);
     if (!ws || (size_t)ws_bytes < p.total) {

@@ -29,6 +29,8 @@
 
 namespace b2h {
 
+int logistic_fused_planes(int M, int N);
+
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 64;          // BK bf16 = one 128-byte swizzle row
@@ -453,6 +455,320 @@ tc_gemm_resident_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Fully fused logistic gradient (dim <= 128): S never leaves TMEM and the residual never leaves the SM.
+//
+// A work item is (chain tile of 128 chains, data tile of 64 rows); every CTA takes a contiguous range of items
+// (data tile fastest) and for each item runs
+//   MMA1   S[128 c x 64 n]  = sum_p Beta_p[128 c x D] . X[64 n x D]^T     Beta pieces resident in shared memory,
+//                                                                          X tile streamed once by TMA (4-stage ring)
+//   epilogue (16 warps)     r = sigmoid(s) - y split exactly into three bf16 pieces, written to shared memory in
+//                           the K-major SWIZZLE_128B operand layout; potential partial sums in registers
+//   MMA2   G[128 c x D]    += sum_p R_p[128 c x 64 n] . X[64 n x D]        A = the residual pieces just written,
+//                                                                          B = THE SAME X tile read through an
+//                                                                          MN-major descriptor (no X^T copy)
+// G accumulates in TMEM over the whole data range of the CTA and is written once per (CTA, chain tile) as an fp32
+// partial plane; a small kernel sums the planes in a fixed order (deterministic).  MMA1 of item i+1 is issued
+// before MMA2 of item i so the tensor pipe works while the epilogue of item i+1 waits for nothing but S.
+// TMEM: columns [0,64) and [64,128) = double-buffered S, [128,256) = G.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int FN = 64;                                   // data rows per item
+constexpr int F_XSTAGES = 4;
+constexpr int F_XBOX = FN * BK * 2;                      // 8 KB: 64 rows x 64 features
+constexpr int F_XSTAGE = 2 * F_XBOX;                     // 16 KB: both feature halves
+constexpr int F_RPIECE = BM * FN * 2;                    // 16 KB: 128 chains x 64 data rows
+constexpr size_t F_SMEM = (size_t)RES_A_BLOCKS * A_BYTES + (size_t)F_XSTAGES * F_XSTAGE + 3 * F_RPIECE + 1024 + 256;
+// instruction descriptors: D = F32, A = B = BF16.  MMA1: both K-major, N = 64.  MMA2: B MN-major (bit 16), N = 128.
+constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t IDESC_G = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+
+// MN-major SWIZZLE_128B operand: 128-byte rows hold 64 consecutive MN elements of one K index, 8 K rows per
+// 1024-byte atom; LBO = distance between 64-element MN atoms, SBO = distance between 8-row K groups.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+struct FusedArgs {
+    const float* y;          // [N]
+    float* gpart;            // [planes][M x dim] fp32 partial gradients
+    long long plane_stride;  // M * dim
+    double* upart;           // [gridDim.x][4][M] potential partial sums
+    int M, N, dim, piece_rows, tiles_m, tiles_n, per_cta;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __grid_constant__ CUtensorMap map_x,
+                         FusedArgs fa) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* a_res = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* x_ring = a_res + (size_t)RES_A_BLOCKS * A_BYTES;
+    uint8_t* r_buf = x_ring + (size_t)F_XSTAGES * F_XSTAGE;
+    uint64_t* bars = (uint64_t*)(r_buf + 3 * F_RPIECE);
+    uint64_t* x_full = bars;                   // [4]
+    uint64_t* x_empty = bars + 4;              // [4]
+    uint64_t* a_full = bars + 8;
+    uint64_t* a_free = bars + 9;
+    uint64_t* s_full = bars + 10;              // [2]
+    uint64_t* s_empty = bars + 12;             // [2]
+    uint64_t* r_full = bars + 14;
+    uint64_t* r_empty = bars + 15;
+    uint64_t* g_full = bars + 16;
+    uint64_t* g_empty = bars + 17;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 18);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kb_total = (fa.dim + BK - 1) / BK;                 // 1 or 2
+    const int tiles_n = fa.tiles_n;
+    const int total = fa.tiles_m * tiles_n;
+    const int t_begin = blockIdx.x * fa.per_cta;
+    const int t_end = min(total, t_begin + fa.per_cta);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_beta) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < F_XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+        mbar_init(a_full, 1); mbar_init(a_free, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], EPI_WARPS); }
+        mbar_init(r_full, EPI_WARPS); mbar_init(r_empty, 1);
+        mbar_init(g_full, 1); mbar_init(g_empty, EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer: Beta pieces once per chain tile, one X tile per item =====
+        if (lane == 0) {
+            int a_loads = 0, cur_m = -1;
+            for (int t = t_begin, L = 0; t < t_end; ++t, ++L) {
+                const int m_tile = t / tiles_n, n0 = (t % tiles_n) * FN;
+                if (m_tile != cur_m) {
+                    mbar_wait(a_free, (a_loads & 1) ^ 1);      // MMA1s of the previous chain tile retired
+                    mbar_expect_tx(a_full, (uint32_t)(3 * kb_total * A_BYTES));
+                    for (int p = 0; p < 3; ++p)
+                        for (int kb = 0; kb < kb_total; ++kb)
+                            tma_load_2d(a_res + (size_t)(p * kb_total + kb) * A_BYTES, &map_beta, a_full, kb * BK,
+                                        p * fa.piece_rows + m_tile * BM);
+                    ++a_loads;
+                    cur_m = m_tile;
+                }
+                const int s = L % F_XSTAGES, round = L / F_XSTAGES;
+                mbar_wait(&x_empty[s], (round & 1) ^ 1);
+                mbar_expect_tx(&x_full[s], (uint32_t)(kb_total * F_XBOX));
+                for (int kb = 0; kb < kb_total; ++kb)
+                    tma_load_2d(x_ring + (size_t)s * F_XSTAGE + (size_t)kb * F_XBOX, &map_x, &x_full[s], kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t r_addr = smem_u32(r_buf);
+            int a_loads = 0, cur_m = -1, segs_done = 0;
+            // second product of local item L (its residual pieces are in r_buf, its X tile still in the ring)
+            auto issue_mma2 = [&](int L) {
+                const int t = t_begin + L;
+                const int m_tile = t / tiles_n;
+                const bool first_of_seg = (L == 0) || ((t - 1) / tiles_n != m_tile);
+                const bool last_of_seg = (t + 1 >= t_end) || ((t + 1) / tiles_n != m_tile);
+                mbar_wait(r_full, L & 1);
+                if (first_of_seg && segs_done > 0) mbar_wait(g_empty, (segs_done - 1) & 1);   // G drained
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t x_addr = smem_u32(x_ring + (size_t)(L % F_XSTAGES) * F_XSTAGE);
+                const uint32_t tmem_g = tmem_base + 128u;
+                bool first = first_of_seg;
+                for (int p = 0; p < 3; ++p)
+#pragma unroll
+                    for (int k = 0; k < FN / UMMA_K; ++k) {
+                        umma_bf16(tmem_g, make_desc(r_addr + p * F_RPIECE + k * UMMA_K * 2),
+                                  make_desc_mn(x_addr + k * UMMA_K * 128, F_XBOX, 1024), IDESC_G, first ? 0u : 1u);
+                        first = false;
+                    }
+                tcgen05_commit(&x_empty[L % F_XSTAGES]);
+                tcgen05_commit(r_empty);
+                if (last_of_seg) { tcgen05_commit(g_full); ++segs_done; }
+            };
+            int L = 0;
+            for (int t = t_begin; t < t_end; ++t, ++L) {
+                const int m_tile = t / tiles_n;
+                if (m_tile != cur_m) {
+                    mbar_wait(a_full, a_loads & 1);
+                    ++a_loads;
+                    cur_m = m_tile;
+                }
+                const int buf = L & 1;
+                mbar_wait(&s_empty[buf], ((L >> 1) & 1) ^ 1);
+                mbar_wait(&x_full[L % F_XSTAGES], (L / F_XSTAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_s = tmem_base + (uint32_t)(buf * FN);
+                const uint32_t x_addr = smem_u32(x_ring + (size_t)(L % F_XSTAGES) * F_XSTAGE);
+                bool first = true;
+                for (int p = 0; p < 3; ++p)
+                    for (int kb = 0; kb < kb_total; ++kb) {
+                        const uint32_t a_addr = smem_u32(a_res + (size_t)(p * kb_total + kb) * A_BYTES);
+                        const uint32_t b_addr = x_addr + kb * F_XBOX;
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            umma_bf16(tmem_s, make_desc(a_addr + k * UMMA_K * 2), make_desc(b_addr + k * UMMA_K * 2), IDESC_S,
+                                      first ? 0u : 1u);
+                            first = false;
+                        }
+                    }
+                tcgen05_commit(&s_full[buf]);
+                const bool last_of_seg = (t + 1 >= t_end) || ((t + 1) / tiles_n != m_tile);
+                if (last_of_seg) tcgen05_commit(a_free);
+                if (L > 0) issue_mma2(L - 1);
+            }
+            if (L > 0) issue_mma2(L - 1);
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue warps: S -> residual pieces in shared memory; G -> partial plane at the end of a segment =====
+        const int q = warp & 3, part = (warp - 4) >> 2;
+        const int trow = q * 32 + lane;                        // row of the 128-chain tile = TMEM lane
+        float urun = 0.f;
+        int segs_done = 0;
+        for (int t = t_begin, L = 0; t < t_end; ++t, ++L) {
+            const int m_tile = t / tiles_n, n0 = (t % tiles_n) * FN;
+            const int buf = L & 1;
+            const int c0 = part * 16;
+            mbar_wait(&s_full[buf], (L >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t r[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * FN + c0);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[buf])) : "memory");
+
+            uint32_t p0[8], p1[8], p2[8];
+            float uacc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const int col = n0 + c0 + j;
+                float4 y4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col + 3 < fa.N) y4 = __ldg(reinterpret_cast<const float4*>(fa.y + col));
+                else {
+                    if (col < fa.N) y4.x = __ldg(fa.y + col);
+                    if (col + 1 < fa.N) y4.y = __ldg(fa.y + col + 1);
+                    if (col + 2 < fa.N) y4.z = __ldg(fa.y + col + 2);
+                }
+                const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+                float rr[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float sv = __uint_as_float(r[j + e]);
+                    const float ex = __expf(-fabsf(sv));
+                    const float inv = __fdividef(1.f, 1.f + ex);
+                    const bool ok = col + e < fa.N;
+                    uacc += ok ? fmaxf(sv, 0.f) + __logf(1.f + ex) - yv[e] * sv : 0.f;
+                    rr[e] = ok ? (sv >= 0.f ? inv : ex * inv) - yv[e] : 0.f;
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const __nv_bfloat162 a = __floats2bfloat162_rn(rr[2 * h], rr[2 * h + 1]);
+                    const float2 af = __bfloat1622float2(a);
+                    const float r1x = rr[2 * h] - af.x, r1y = rr[2 * h + 1] - af.y;
+                    const __nv_bfloat162 b = __floats2bfloat162_rn(r1x, r1y);
+                    const float2 bf = __bfloat1622float2(b);
+                    const __nv_bfloat162 c = __floats2bfloat162_rn(r1x - bf.x, r1y - bf.y);
+                    p0[(j >> 1) + h] = *reinterpret_cast<const uint32_t*>(&a);
+                    p1[(j >> 1) + h] = *reinterpret_cast<const uint32_t*>(&b);
+                    p2[(j >> 1) + h] = *reinterpret_cast<const uint32_t*>(&c);
+                }
+            }
+            urun += uacc;
+            // the second product of the previous item must have consumed the residual buffer
+            mbar_wait(r_empty, (L & 1) ^ 1);
+            {
+                uint8_t* rowp = r_buf + (trow >> 3) * 1024 + (trow & 7) * 128;
+                const int sw = trow & 7;
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    const int chunk = ((part * 2 + v) ^ sw) << 4;
+                    *reinterpret_cast<uint4*>(rowp + chunk) = make_uint4(p0[4 * v], p0[4 * v + 1], p0[4 * v + 2], p0[4 * v + 3]);
+                    *reinterpret_cast<uint4*>(rowp + F_RPIECE + chunk) =
+                        make_uint4(p1[4 * v], p1[4 * v + 1], p1[4 * v + 2], p1[4 * v + 3]);
+                    *reinterpret_cast<uint4*>(rowp + 2 * F_RPIECE + chunk) =
+                        make_uint4(p2[4 * v], p2[4 * v + 1], p2[4 * v + 2], p2[4 * v + 3]);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor-core reads
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(r_full)) : "memory");
+
+            const bool last_of_seg = (t + 1 >= t_end) || ((t + 1) / tiles_n != m_tile);
+            if (last_of_seg) {
+                // drain G: this warp's lane quadrant, columns [32 part, 32 part + 32)
+                mbar_wait(g_full, segs_done & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t gq[32];
+                const uint32_t gaddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 + part * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(gq[0]), "=r"(gq[1]), "=r"(gq[2]), "=r"(gq[3]), "=r"(gq[4]), "=r"(gq[5]), "=r"(gq[6]), "=r"(gq[7]),
+                      "=r"(gq[8]), "=r"(gq[9]), "=r"(gq[10]), "=r"(gq[11]), "=r"(gq[12]), "=r"(gq[13]), "=r"(gq[14]),
+                      "=r"(gq[15]), "=r"(gq[16]), "=r"(gq[17]), "=r"(gq[18]), "=r"(gq[19]), "=r"(gq[20]), "=r"(gq[21]),
+                      "=r"(gq[22]), "=r"(gq[23]), "=r"(gq[24]), "=r"(gq[25]), "=r"(gq[26]), "=r"(gq[27]), "=r"(gq[28]),
+                      "=r"(gq[29]), "=r"(gq[30]), "=r"(gq[31])
+                    : "r"(gaddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(g_empty)) : "memory");
+                ++segs_done;
+                const int row = m_tile * BM + trow;
+                if (row < fa.M) {
+                    // plane = position of this CTA among the CTAs that touch the chain tile
+                    const int b_first = (int)(((long long)m_tile * tiles_n) / fa.per_cta);
+                    float* orow = fa.gpart + (long long)(blockIdx.x - b_first) * fa.plane_stride + (long long)row * fa.dim;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const int col = part * 32 + j;
+                        if (col + 3 < fa.dim) {
+                            *reinterpret_cast<float4*>(orow + col) =
+                                make_float4(__uint_as_float(gq[j]), __uint_as_float(gq[j + 1]), __uint_as_float(gq[j + 2]),
+                                            __uint_as_float(gq[j + 3]));
+                        } else {
+                            for (int e = 0; e < 4; ++e)
+                                if (col + e < fa.dim) orow[col + e] = __uint_as_float(gq[j + e]);
+                        }
+                    }
+                    fa.upart[((long long)blockIdx.x * EPI_PARTS + part) * fa.M + row] = (double)urun;
+                }
+                urun = 0.f;
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host side: tensor maps through the driver entry point (no link-time dependency on libcuda)
 // ---------------------------------------------------------------------------------------------------------
@@ -472,12 +788,12 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2D bf16 row-major [rows][cols] (cols contiguous, row pitch ld elements), box = 64 x 128, 128-byte swizzle
-static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld) {
+static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows = BM) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return B2H_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -568,6 +884,53 @@ int tc_gemm_blocked_a(cudaStream_t st, const void* R, long long r_piece_stride, 
     tc::Epilogue ep{0, nullptr, nullptr, 0, 0, nullptr};
     const int piece_rows = (int)(r_piece_stride / tc::BN);
     return tc_launch(st, R, tc::BN, B, ldb, out, M, N, K, pieces, piece_rows, ldo, nsplit, split_stride, ep, 1);
+}
+
+
+// Fully fused gradient: see tc_logistic_fused_kernel.  beta_pieces: [3 * piece_rows x dim] bf16, X: [N x dim] bf16.
+// Writes gpart[plane][M x dim] (fp32) and upart[CTA][4][M]; *per_cta = items per CTA, *planes = planes a chain
+// tile can receive (the reduction kernels recompute which CTAs touched a tile from per_cta).
+int tc_logistic_fused(cudaStream_t st, const void* beta_pieces, int piece_rows, const void* X, int M, int N, int dim,
+                      const float* y, float* gpart, double* upart, int* per_cta, int* planes) {
+    using namespace tc;
+    if (dim > 2 * BK || dim % 8) { set_error("tc_logistic_fused: dim must be a multiple of 8, at most 128"); return B2H_ERR_ARG; }
+    CUtensorMap mb, mx;
+    int rc = make_map(&mb, beta_pieces, 3ll * piece_rows, dim, dim);
+    if (rc) return rc;
+    rc = make_map(&mx, X, N, dim, dim, FN);
+    if (rc) return rc;
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (sm_count <= 0) sm_count = 148;
+    }
+    FusedArgs fa;
+    fa.y = y; fa.gpart = gpart; fa.plane_stride = (long long)M * dim; fa.upart = upart;
+    fa.M = M; fa.N = N; fa.dim = dim; fa.piece_rows = piece_rows;
+    fa.tiles_m = (M + BM - 1) / BM;
+    fa.tiles_n = (N + FN - 1) / FN;
+    const long long total = (long long)fa.tiles_m * fa.tiles_n;
+    fa.per_cta = (int)((total + sm_count - 1) / sm_count);
+    const int grid = (int)((total + fa.per_cta - 1) / fa.per_cta);
+    B2H_CUDA(cudaFuncSetAttribute(tc_logistic_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+    tc_logistic_fused_kernel<<<grid, THREADS, F_SMEM, st>>>(mb, mx, fa);
+    B2H_LAUNCH_CHECK();
+    *per_cta = fa.per_cta;
+    *planes = logistic_fused_planes(M, N);
+    return 0;
+}
+
+// upper bound on the number of CTAs whose item range intersects one chain tile
+int logistic_fused_planes(int M, int N) {
+    const long long tiles_m = (M + tc::BM - 1) / tc::BM, tiles_n = (N + tc::FN - 1) / tc::FN;
+    int sm_count = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+    const long long per = (tiles_m * tiles_n + sm_count - 1) / sm_count;
+    return (int)((tiles_n + per - 1) / per + 1);
 }
 
 }  // namespace b2h

@@ -114,7 +114,9 @@ class EightSchools(Model):
 class LogisticRegression(Model):
     """``tensor_core=True`` evaluates the batched gradient X.B / X^T.R on tcgen05 tensor cores (bf16 operands,
     beta and the residuals split into three bf16 pieces, fp32 accumulation in TMEM): fp32-class accuracy.  It
-    needs X to be bf16-representable.  The default is the FP64/FP32 FMA-DMMA path (exactness reference)."""
+    needs X to be bf16-representable.  With dim <= 128 the two products and the residual run as ONE kernel (S in
+    TMEM, residual pieces in shared memory); ``tensor_core="two_kernel"`` forces the formulation that passes the
+    residual pieces through memory (any dim).  The default is the FP64/FP32 FMA-DMMA path (exactness reference)."""
     kind = _lib.MODEL_LOGISTIC
 
     def __init__(self, X, y, prior_scale=1.0, dtype=torch.float64, device=None, tensor_core=False):
@@ -125,6 +127,7 @@ class LogisticRegression(Model):
         self.inv_prior_var = 1.0 / float(prior_scale) ** 2
         self.n_data, self.dim = int(self.X.shape[0]), int(self.X.shape[1])
         self.tensor_core = bool(tensor_core)
+        self.tc_flag = 3.0 if tensor_core == "two_kernel" else (2.0 if self.tensor_core else 0.0)
         self.X_bf16 = self.Xt_bf16 = None
         if self.tensor_core:
             xb = self.X.to(torch.bfloat16)
@@ -138,5 +141,5 @@ class LogisticRegression(Model):
     def struct(self):
         p = lambda t: None if t is None else t.data_ptr()
         return _lib.Model(self.kind, self.dim, self.n_data, self.X.data_ptr(), self.y.data_ptr(),
-                          self.Xt.data_ptr(), self.inv_prior_var, 2.0 if self.tensor_core else 0.0,
+                          self.Xt.data_ptr(), self.inv_prior_var, self.tc_flag,
                           p(self.X_bf16), p(self.Xt_bf16))

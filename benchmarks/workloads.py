@@ -154,7 +154,11 @@ def c3(small):
     beta = rng.standard_normal(D) / np.sqrt(D)
     y = (rng.random(N) < 1 / (1 + np.exp(-X @ beta))).astype(np.float64)
     q0 = 0.1 * np.random.default_rng(6).standard_normal((Cn, D))
-    for dt, tcore in ((torch.float64, False), (torch.float32, False), (torch.float32, True), (torch.float64, True)):
+    cases = ((torch.float64, False), (torch.float32, False), (torch.float32, "two_kernel"), (torch.float32, True),
+             (torch.float64, True))
+    if "--tc-only" in sys.argv:
+        cases = cases[2:]
+    for dt, tcore in cases:
         model = ab.models.LogisticRegression(X, y, 1.0, dtype=dt, tensor_core=tcore)
         imm = np.full(D, 4.0 / N)
         srng = ab.RandomStream(seed=3)
@@ -165,7 +169,8 @@ def c3(small):
         (info, ex), ms = timed(run)
         leap = int(ex["counters"][0].item())
         flops = 4.0 * N * D * leap
-        path = "tcgen05 bf16x3 gradient" if tcore else "FMA/DMMA-path gradient"
+        path = ("tcgen05 bf16x3 gradient, " + ("two kernels" if tcore == "two_kernel" else "fully fused")) if tcore \
+            else "FMA/DMMA-path gradient"
         out.append({"workload": f"c3 NUTS logistic N={N} D={D} {str(dt)[6:]} ({path})", "chains": Cn,
                     "ticks": ticks, "ms_per_tick": ms / ticks, "grad_evals_per_sec": leap / (ms * 1e-3),
                     "gradient_TFLOPs_algorithmic_4ND": flops / (ms * 1e-3) / 1e12,

@@ -59,14 +59,15 @@ def _logistic_case(rng, N, d):
     return X, y
 
 
-@pytest.mark.parametrize("N, d, Cn", [(512, 64, 40), (2048, 128, 130), (20000, 128, 256)])
-def test_logistic_gradient_tensor_core_vs_fma(ab, N, d, Cn):
+@pytest.mark.parametrize("tc_mode", [True, "two_kernel"])
+@pytest.mark.parametrize("N, d, Cn", [(512, 64, 40), (2048, 128, 130), (20000, 128, 256), (1000, 96, 300), (40000, 128, 700)])
+def test_logistic_gradient_tensor_core_vs_fma(ab, N, d, Cn, tc_mode):
     rng = np.random.default_rng(N + d)
     X, y = _logistic_case(rng, N, d)
     q = 0.3 * rng.standard_normal((Cn, d))
     for dt in (torch.float64, torch.float32):
         ref_model = ab.models.LogisticRegression(X, y, 1.0, dtype=torch.float64)
-        tc_model = ab.models.LogisticRegression(X, y, 1.0, dtype=dt, tensor_core=True)
+        tc_model = ab.models.LogisticRegression(X, y, 1.0, dtype=dt, tensor_core=tc_mode)
         U0, g0 = ref_model.potential_and_grad(q)
         U1, g1 = tc_model.potential_and_grad(q)
         gs = g0.abs().max().item()
