@@ -76,6 +76,47 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     }
 }
+// spin with a short sleep: for waits that are expected to be long (a spinning warp steals issue slots from the
+// epilogue warps that share its scheduler)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(40);
+    }
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -504,6 +545,7 @@ struct FusedArgs {
     int M, N, dim, piece_rows, tiles_m, tiles_n, per_cta;
 };
 
+template <int KB>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __grid_constant__ CUtensorMap map_x,
                          FusedArgs fa) {
@@ -524,8 +566,9 @@ tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __g
     uint64_t* g_empty = bars + 17;
     uint32_t* tmem_slot = (uint32_t*)(bars + 18);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kb_total = (fa.dim + BK - 1) / BK;                 // 1 or 2
+    // the warp index goes through a shuffle so that the compiler treats role branches as warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    constexpr int kb_total = KB;                                 // 64-feature blocks: 1 or 2
     const int tiles_n = fa.tiles_n;
     const int total = fa.tiles_m * tiles_n;
     const int t_begin = blockIdx.x * fa.per_cta;
@@ -551,7 +594,7 @@ tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __g
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
         // ===== TMA producer: Beta pieces once per chain tile, one X tile per item =====
@@ -570,84 +613,104 @@ tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __g
                     cur_m = m_tile;
                 }
                 const int s = L % F_XSTAGES, round = L / F_XSTAGES;
-                mbar_wait(&x_empty[s], (round & 1) ^ 1);
+                mbar_wait_backoff(&x_empty[s], (round & 1) ^ 1);
                 mbar_expect_tx(&x_full[s], (uint32_t)(kb_total * F_XBOX));
                 for (int kb = 0; kb < kb_total; ++kb)
                     tma_load_2d(x_ring + (size_t)s * F_XSTAGE + (size_t)kb * F_XBOX, &map_x, &x_full[s], kb * BK, n0);
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t r_addr = smem_u32(r_buf);
-            int a_loads = 0, cur_m = -1, segs_done = 0;
-            // second product of local item L (its residual pieces are in r_buf, its X tile still in the ring)
-            auto issue_mma2 = [&](int L) {
-                const int t = t_begin + L;
-                const int m_tile = t / tiles_n;
-                const bool first_of_seg = (L == 0) || ((t - 1) / tiles_n != m_tile);
-                const bool last_of_seg = (t + 1 >= t_end) || ((t + 1) / tiles_n != m_tile);
-                mbar_wait(r_full, L & 1);
-                if (first_of_seg && segs_done > 0) mbar_wait(g_empty, (segs_done - 1) & 1);   // G drained
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t x_addr = smem_u32(x_ring + (size_t)(L % F_XSTAGES) * F_XSTAGE);
-                const uint32_t tmem_g = tmem_base + 128u;
-                bool first = first_of_seg;
+        // ===== MMA issuer: the whole warp runs the loop (warp-uniform control flow keeps the operand descriptors in
+        // uniform registers), one elected lane issues.  With a single diverged lane every tcgen05.mma cost ~15
+        // dependent instructions of descriptor arithmetic and the issuer, not the tensor pipe, paced the kernel. =====
+        const uint64_t a_desc0 = make_desc(smem_u32(a_res));
+        const uint64_t r_desc0 = make_desc(smem_u32(r_buf));
+        const uint32_t x_ring_addr = smem_u32(x_ring);
+        const uint32_t tmem_g = tmem_base + 128u;
+        int a_loads = 0, cur_m = -1, segs_done = 0;
+        // second product of local item L (its residual pieces are in r_buf, its X tile still in the ring)
+        auto issue_mma2 = [&](int L) {
+            const int t = t_begin + L;
+            const int m_tile = t / tiles_n;
+            const bool first_of_seg = (L == 0) || ((t - 1) / tiles_n != m_tile);
+            const bool last_of_seg = (t + 1 >= t_end) || ((t + 1) / tiles_n != m_tile);
+            mbar_wait(r_full, L & 1);
+            if (first_of_seg && segs_done > 0) mbar_wait(g_empty, (segs_done - 1) & 1);   // G drained
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int stage = L % F_XSTAGES;
+            const uint64_t xd = make_desc_mn(x_ring_addr + (uint32_t)stage * F_XSTAGE, F_XBOX, 1024);
+            if (elect_one()) {
+#pragma unroll
                 for (int p = 0; p < 3; ++p)
 #pragma unroll
-                    for (int k = 0; k < FN / UMMA_K; ++k) {
-                        umma_bf16(tmem_g, make_desc(r_addr + p * F_RPIECE + k * UMMA_K * 2),
-                                  make_desc_mn(x_addr + k * UMMA_K * 128, F_XBOX, 1024), IDESC_G, first ? 0u : 1u);
-                        first = false;
-                    }
-                tcgen05_commit(&x_empty[L % F_XSTAGES]);
+                    for (int k = 0; k < FN / UMMA_K; ++k)
+                        umma_bf16(tmem_g, r_desc0 + (uint64_t)((p * F_RPIECE + k * UMMA_K * 2) >> 4),
+                                  xd + (uint64_t)((k * UMMA_K * 128) >> 4), IDESC_G, (first_of_seg && p == 0 && k == 0) ? 0u : 1u);
+                tcgen05_commit(&x_empty[stage]);
                 tcgen05_commit(r_empty);
-                if (last_of_seg) { tcgen05_commit(g_full); ++segs_done; }
-            };
-            int L = 0;
-            for (int t = t_begin; t < t_end; ++t, ++L) {
-                const int m_tile = t / tiles_n;
-                if (m_tile != cur_m) {
-                    mbar_wait(a_full, a_loads & 1);
-                    ++a_loads;
-                    cur_m = m_tile;
-                }
-                const int buf = L & 1;
-                mbar_wait(&s_empty[buf], ((L >> 1) & 1) ^ 1);
-                mbar_wait(&x_full[L % F_XSTAGES], (L / F_XSTAGES) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t tmem_s = tmem_base + (uint32_t)(buf * FN);
-                const uint32_t x_addr = smem_u32(x_ring + (size_t)(L % F_XSTAGES) * F_XSTAGE);
-                bool first = true;
-                for (int p = 0; p < 3; ++p)
-                    for (int kb = 0; kb < kb_total; ++kb) {
-                        const uint32_t a_addr = smem_u32(a_res + (size_t)(p * kb_total + kb) * A_BYTES);
-                        const uint32_t b_addr = x_addr + kb * F_XBOX;
-#pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            umma_bf16(tmem_s, make_desc(a_addr + k * UMMA_K * 2), make_desc(b_addr + k * UMMA_K * 2), IDESC_S,
-                                      first ? 0u : 1u);
-                            first = false;
-                        }
-                    }
-                tcgen05_commit(&s_full[buf]);
-                const bool last_of_seg = (t + 1 >= t_end) || ((t + 1) / tiles_n != m_tile);
-                if (last_of_seg) tcgen05_commit(a_free);
-                if (L > 0) issue_mma2(L - 1);
+                if (last_of_seg) tcgen05_commit(g_full);
             }
+            __syncwarp();
+            if (last_of_seg) ++segs_done;
+        };
+        int L = 0;
+        for (int t = t_begin; t < t_end; ++t, ++L) {
+            const int m_tile = t / tiles_n;
+            if (m_tile != cur_m) {
+                mbar_wait(a_full, a_loads & 1);
+                ++a_loads;
+                cur_m = m_tile;
+            }
+            const int buf = L & 1;
+            const int stage = L % F_XSTAGES;
+            mbar_wait(&s_empty[buf], ((L >> 1) & 1) ^ 1);
+            mbar_wait(&x_full[stage], (L / F_XSTAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_s = tmem_base + (uint32_t)(buf * FN);
+            const uint64_t xd = make_desc(x_ring_addr + (uint32_t)stage * F_XSTAGE);
+            const bool last_of_seg = (t + 1 >= t_end) || ((t + 1) / tiles_n != m_tile);
+            if (elect_one()) {
+#pragma unroll
+                for (int p = 0; p < 3; ++p)
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_bf16(tmem_s, a_desc0 + (uint64_t)(((p * KB + kb) * A_BYTES + k * UMMA_K * 2) >> 4),
+                                      xd + (uint64_t)((kb * F_XBOX + k * UMMA_K * 2) >> 4), IDESC_S,
+                                      (p == 0 && kb == 0 && k == 0) ? 0u : 1u);
+                tcgen05_commit(&s_full[buf]);
+                if (last_of_seg) tcgen05_commit(a_free);
+            }
+            __syncwarp();
             if (L > 0) issue_mma2(L - 1);
         }
+        if (L > 0) issue_mma2(L - 1);
     } else if (warp >= 4) {
         // ===== epilogue warps: S -> residual pieces in shared memory; G -> partial plane at the end of a segment =====
         const int q = warp & 3, part = (warp - 4) >> 2;
         const int trow = q * 32 + lane;                        // row of the 128-chain tile = TMEM lane
+        const int c0 = part * 16;
         float urun = 0.f;
         int segs_done = 0;
+        int m_tile = t_begin / tiles_n, n_tile = t_begin - m_tile * tiles_n;
         for (int t = t_begin, L = 0; t < t_end; ++t, ++L) {
-            const int m_tile = t / tiles_n, n0 = (t % tiles_n) * FN;
+            const int n0 = n_tile * FN;
             const int buf = L & 1;
-            const int c0 = part * 16;
-            mbar_wait(&s_full[buf], (L >> 1) & 1);
+            const bool full = n0 + FN <= fa.N;
+            // responses of this thread's 16 data rows (warp-uniform addresses), requested before S is waited for
+            float yv[16];
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 y4 = __ldg(reinterpret_cast<const float4*>(fa.y + n0 + c0 + j));
+                    yv[j] = y4.x; yv[j + 1] = y4.y; yv[j + 2] = y4.z; yv[j + 3] = y4.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) yv[j] = (n0 + c0 + j < fa.N) ? __ldg(fa.y + n0 + c0 + j) : 0.f;
+            }
+            mbar_wait_backoff(&s_full[buf], (L >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t r[16];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * FN + c0);
@@ -662,42 +725,39 @@ tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __g
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[buf])) : "memory");
 
             uint32_t p0[8], p1[8], p2[8];
-            float uacc = 0.f;
+            float ua[4] = {0.f, 0.f, 0.f, 0.f};
+            float rr[16];
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-                const int col = n0 + c0 + j;
-                float4 y4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (col + 3 < fa.N) y4 = __ldg(reinterpret_cast<const float4*>(fa.y + col));
-                else {
-                    if (col < fa.N) y4.x = __ldg(fa.y + col);
-                    if (col + 1 < fa.N) y4.y = __ldg(fa.y + col + 1);
-                    if (col + 2 < fa.N) y4.z = __ldg(fa.y + col + 2);
-                }
-                const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
-                float rr[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float sv = __uint_as_float(r[j + e]);
-                    const float ex = __expf(-fabsf(sv));
-                    const float inv = __fdividef(1.f, 1.f + ex);
-                    const bool ok = col + e < fa.N;
-                    uacc += ok ? fmaxf(sv, 0.f) + __logf(1.f + ex) - yv[e] * sv : 0.f;
-                    rr[e] = ok ? (sv >= 0.f ? inv : ex * inv) - yv[e] : 0.f;
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const __nv_bfloat162 a = __floats2bfloat162_rn(rr[2 * h], rr[2 * h + 1]);
-                    const float2 af = __bfloat1622float2(a);
-                    const float r1x = rr[2 * h] - af.x, r1y = rr[2 * h + 1] - af.y;
-                    const __nv_bfloat162 b = __floats2bfloat162_rn(r1x, r1y);
-                    const float2 bf = __bfloat1622float2(b);
-                    const __nv_bfloat162 c = __floats2bfloat162_rn(r1x - bf.x, r1y - bf.y);
-                    p0[(j >> 1) + h] = *reinterpret_cast<const uint32_t*>(&a);
-                    p1[(j >> 1) + h] = *reinterpret_cast<const uint32_t*>(&b);
-                    p2[(j >> 1) + h] = *reinterpret_cast<const uint32_t*>(&c);
-                }
+            for (int j = 0; j < 16; ++j) {
+                // softplus(s) - y s and sigmoid(s) - y from one ex2, one rcp and one lg2 (ftz approximations,
+                // arguments are in (0, 2]: no range fix-ups needed)
+                const float sv = __uint_as_float(r[j]);
+                const float ex = ex2_approx(fabsf(sv) * -1.4426950408889634f);
+                const float den = 1.f + ex;
+                const float inv = rcp_approx(den);
+                const float sp = fmaf(lg2_approx(den), 0.6931471805599453f, fmaxf(sv, 0.f));
+                ua[j & 3] += fmaf(-yv[j], sv, sp);
+                rr[j] = (sv >= 0.f ? 1.f : ex) * inv - yv[j];
             }
-            urun += uacc;
+            if (!full) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (n0 + c0 + j >= fa.N) { rr[j] = 0.f; ua[j & 3] -= 0.6931471805599453f; }   // s = 0, y = 0 there
+            }
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                // exact three-way split, two data rows per packed conversion
+                const __nv_bfloat162 a = __floats2bfloat162_rn(rr[2 * h], rr[2 * h + 1]);
+                const float2 af = __bfloat1622float2(a);
+                const float r1x = rr[2 * h] - af.x, r1y = rr[2 * h + 1] - af.y;
+                const __nv_bfloat162 b = __floats2bfloat162_rn(r1x, r1y);
+                const float2 bf = __bfloat1622float2(b);
+                const __nv_bfloat162 c = __floats2bfloat162_rn(r1x - bf.x, r1y - bf.y);
+                p0[h] = *reinterpret_cast<const uint32_t*>(&a);
+                p1[h] = *reinterpret_cast<const uint32_t*>(&b);
+                p2[h] = *reinterpret_cast<const uint32_t*>(&c);
+            }
+            urun += (ua[0] + ua[1]) + (ua[2] + ua[3]);
             // the second product of the previous item must have consumed the residual buffer
             mbar_wait(r_empty, (L & 1) ^ 1);
             {
@@ -717,7 +777,7 @@ tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __g
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(r_full)) : "memory");
 
-            const bool last_of_seg = (t + 1 >= t_end) || ((t + 1) / tiles_n != m_tile);
+            const bool last_of_seg = (t + 1 >= t_end) || (n_tile + 1 == tiles_n);
             if (last_of_seg) {
                 // drain G: this warp's lane quadrant, columns [32 part, 32 part + 32)
                 mbar_wait(g_full, segs_done & 1);
@@ -759,6 +819,7 @@ tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __g
                 }
                 urun = 0.f;
             }
+            if (++n_tile == tiles_n) { n_tile = 0; ++m_tile; }
         }
     }
 
@@ -914,8 +975,13 @@ int tc_logistic_fused(cudaStream_t st, const void* beta_pieces, int piece_rows, 
     const long long total = (long long)fa.tiles_m * fa.tiles_n;
     fa.per_cta = (int)((total + sm_count - 1) / sm_count);
     const int grid = (int)((total + fa.per_cta - 1) / fa.per_cta);
-    B2H_CUDA(cudaFuncSetAttribute(tc_logistic_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
-    tc_logistic_fused_kernel<<<grid, THREADS, F_SMEM, st>>>(mb, mx, fa);
+    if (dim > BK) {
+        B2H_CUDA(cudaFuncSetAttribute(tc_logistic_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+        tc_logistic_fused_kernel<2><<<grid, THREADS, F_SMEM, st>>>(mb, mx, fa);
+    } else {
+        B2H_CUDA(cudaFuncSetAttribute(tc_logistic_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+        tc_logistic_fused_kernel<1><<<grid, THREADS, F_SMEM, st>>>(mb, mx, fa);
+    }
     B2H_LAUNCH_CHECK();
     *per_cta = fa.per_cta;
     *planes = logistic_fused_planes(M, N);
