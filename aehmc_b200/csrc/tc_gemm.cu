@@ -23,6 +23,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "launch.h"
@@ -498,28 +499,32 @@ tc_gemm_resident_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 
 
 // ---------------------------------------------------------------------------------------------------------
-// Fully fused logistic gradient (dim <= 128): S never leaves TMEM and the residual never leaves the SM.
+// Fully fused logistic gradient (dim <= 128): S and the residual never leave tensor memory.
 //
 // A work item is (chain tile of 128 chains, data tile of 64 rows); every CTA takes a contiguous range of items
 // (data tile fastest) and for each item runs
-//   MMA1   S[128 c x 64 n]  = sum_p Beta_p[128 c x D] . X[64 n x D]^T     Beta pieces resident in shared memory,
-//                                                                          X tile streamed once by TMA (4-stage ring)
-//   epilogue (16 warps)     r = sigmoid(s) - y split exactly into three bf16 pieces, written to shared memory in
-//                           the K-major SWIZZLE_128B operand layout; potential partial sums in registers
-//   MMA2   G[128 c x D]    += sum_p R_p[128 c x 64 n] . X[64 n x D]        A = the residual pieces just written,
-//                                                                          B = THE SAME X tile read through an
-//                                                                          MN-major descriptor (no X^T copy)
+//   MMA1 (warp 1)   S[128 c x 64 n]  = sum_p Beta_p[128 c x D] . X[64 n x D]^T   Beta pieces resident in shared memory,
+//                                                                                X tile streamed once by TMA (6-stage ring)
+//   epilogue (16 warps)  r = sigmoid(s) - y split exactly into three bf16 pieces and stored straight back to TENSOR
+//                        MEMORY (tcgen05.st) as the A operand of the second product; potential partial sums in registers
+//   MMA2 (warp 3)   G[128 c x D]    += sum_p R_p[128 c x 64 n] . X[64 n x D]     A from TMEM (no shared-memory traffic
+//                                                                                for the residual), B = THE SAME X tile
+//                                                                                read through an MN-major descriptor
 // G accumulates in TMEM over the whole data range of the CTA and is written once per (CTA, chain tile) as an fp32
-// partial plane; a small kernel sums the planes in a fixed order (deterministic).  MMA1 of item i+1 is issued
-// before MMA2 of item i so the tensor pipe works while the epilogue of item i+1 waits for nothing but S.
-// TMEM: columns [0,64) and [64,128) = double-buffered S, [128,256) = G.
+// partial plane; a small kernel sums the planes in a fixed order (deterministic).  The two products have separate
+// issuing warps, so the first product runs ahead (bounded by the two S buffers) instead of queueing behind the
+// residual hand-off of the previous item.  Why A-from-TMEM: with both operands in shared memory the kernel was bound
+// by shared-memory bandwidth (an M128 N64 K16 step reads 6 KB in 32 tensor cycles, plus the epilogue's own stores).
+// TMEM columns: [0,64) [64,128) = S double buffer, [128,256) = G, [256,352) [352,448) = residual pieces double buffer
+// (per piece 32 columns: two bf16 data rows per 32-bit cell, lane = chain).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int FN = 64;                                   // data rows per item
-constexpr int F_XSTAGES = 4;
+constexpr int F_XSTAGES = 6;
 constexpr int F_XBOX = FN * BK * 2;                      // 8 KB: 64 rows x 64 features
 constexpr int F_XSTAGE = 2 * F_XBOX;                     // 16 KB: both feature halves
-constexpr int F_RPIECE = BM * FN * 2;                    // 16 KB: 128 chains x 64 data rows
-constexpr size_t F_SMEM = (size_t)RES_A_BLOCKS * A_BYTES + (size_t)F_XSTAGES * F_XSTAGE + 3 * F_RPIECE + 1024 + 256;
+constexpr int F_TMEM_COLS = 512;
+constexpr uint32_t F_COL_G = 128, F_COL_R = 256, F_RBUF_COLS = 96, F_RPIECE_COLS = 32;
+constexpr size_t F_SMEM = (size_t)RES_A_BLOCKS * A_BYTES + (size_t)F_XSTAGES * F_XSTAGE + 1024 + 512;
 // instruction descriptors: D = F32, A = B = BF16.  MMA1: both K-major, N = 64.  MMA2: B MN-major (bit 16), N = 128.
 constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 constexpr uint32_t IDESC_G = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
@@ -536,6 +541,19 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lb
     d |= (uint64_t)2 << 61;
     return d;
 }
+// A operand in tensor memory (lane = row, two 16-bit K elements per 32-bit column)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 
 struct FusedArgs {
     const float* y;          // [N]
@@ -545,30 +563,28 @@ struct FusedArgs {
     int M, N, dim, piece_rows, tiles_m, tiles_n, per_cta;
 };
 
-template <int KB>
+template <int KB, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __grid_constant__ CUtensorMap map_x,
                          FusedArgs fa) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* a_res = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* x_ring = a_res + (size_t)RES_A_BLOCKS * A_BYTES;
-    uint8_t* r_buf = x_ring + (size_t)F_XSTAGES * F_XSTAGE;
-    uint64_t* bars = (uint64_t*)(r_buf + 3 * F_RPIECE);
-    uint64_t* x_full = bars;                   // [4]
-    uint64_t* x_empty = bars + 4;              // [4]
-    uint64_t* a_full = bars + 8;
-    uint64_t* a_free = bars + 9;
-    uint64_t* s_full = bars + 10;              // [2]
-    uint64_t* s_empty = bars + 12;             // [2]
-    uint64_t* r_full = bars + 14;
-    uint64_t* r_empty = bars + 15;
-    uint64_t* g_full = bars + 16;
-    uint64_t* g_empty = bars + 17;
-    uint32_t* tmem_slot = (uint32_t*)(bars + 18);
+    uint64_t* bars = (uint64_t*)(x_ring + (size_t)F_XSTAGES * F_XSTAGE);
+    uint64_t* x_full = bars;                          // [6]
+    uint64_t* x_empty = bars + F_XSTAGES;             // [6]
+    uint64_t* a_full = bars + 2 * F_XSTAGES;
+    uint64_t* a_free = a_full + 1;
+    uint64_t* s_full = a_full + 2;                    // [2]
+    uint64_t* s_empty = a_full + 4;                   // [2]
+    uint64_t* r_full = a_full + 6;                    // [2]
+    uint64_t* r_empty = a_full + 8;                   // [2]
+    uint64_t* g_full = a_full + 10;
+    uint64_t* g_empty = a_full + 11;
+    uint32_t* tmem_slot = (uint32_t*)(a_full + 12);
 
     // the warp index goes through a shuffle so that the compiler treats role branches as warp-uniform
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    constexpr int kb_total = KB;                                 // 64-feature blocks: 1 or 2
     const int tiles_n = fa.tiles_n;
     const int total = fa.tiles_m * tiles_n;
     const int t_begin = blockIdx.x * fa.per_cta;
@@ -581,14 +597,16 @@ tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __g
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < F_XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
         mbar_init(a_full, 1); mbar_init(a_free, 1);
-        for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], EPI_WARPS); }
-        mbar_init(r_full, EPI_WARPS); mbar_init(r_empty, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], EPI_WARPS);
+            mbar_init(&r_full[b], EPI_WARPS); mbar_init(&r_empty[b], 1);
+        }
         mbar_init(g_full, 1); mbar_init(g_empty, EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "n"(TMEM_COLS) : "memory");
+                     "n"(F_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -600,62 +618,35 @@ tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __g
         // ===== TMA producer: Beta pieces once per chain tile, one X tile per item =====
         if (lane == 0) {
             int a_loads = 0, cur_m = -1;
+            int m_tile = t_begin / tiles_n, n_tile = t_begin - m_tile * tiles_n;
             for (int t = t_begin, L = 0; t < t_end; ++t, ++L) {
-                const int m_tile = t / tiles_n, n0 = (t % tiles_n) * FN;
                 if (m_tile != cur_m) {
-                    mbar_wait(a_free, (a_loads & 1) ^ 1);      // MMA1s of the previous chain tile retired
-                    mbar_expect_tx(a_full, (uint32_t)(3 * kb_total * A_BYTES));
+                    mbar_wait(a_free, (a_loads & 1) ^ 1);      // first products of the previous chain tile retired
+                    mbar_expect_tx(a_full, (uint32_t)(3 * KB * A_BYTES));
                     for (int p = 0; p < 3; ++p)
-                        for (int kb = 0; kb < kb_total; ++kb)
-                            tma_load_2d(a_res + (size_t)(p * kb_total + kb) * A_BYTES, &map_beta, a_full, kb * BK,
+                        for (int kb = 0; kb < KB; ++kb)
+                            tma_load_2d(a_res + (size_t)(p * KB + kb) * A_BYTES, &map_beta, a_full, kb * BK,
                                         p * fa.piece_rows + m_tile * BM);
                     ++a_loads;
                     cur_m = m_tile;
                 }
                 const int s = L % F_XSTAGES, round = L / F_XSTAGES;
                 mbar_wait_backoff(&x_empty[s], (round & 1) ^ 1);
-                mbar_expect_tx(&x_full[s], (uint32_t)(kb_total * F_XBOX));
-                for (int kb = 0; kb < kb_total; ++kb)
-                    tma_load_2d(x_ring + (size_t)s * F_XSTAGE + (size_t)kb * F_XBOX, &map_x, &x_full[s], kb * BK, n0);
+                mbar_expect_tx(&x_full[s], (uint32_t)(KB * F_XBOX));
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_load_2d(x_ring + (size_t)s * F_XSTAGE + (size_t)kb * F_XBOX, &map_x, &x_full[s], kb * BK, n_tile * FN);
+                if (++n_tile == tiles_n) { n_tile = 0; ++m_tile; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: the whole warp runs the loop (warp-uniform control flow keeps the operand descriptors in
-        // uniform registers), one elected lane issues.  With a single diverged lane every tcgen05.mma cost ~15
-        // dependent instructions of descriptor arithmetic and the issuer, not the tensor pipe, paced the kernel. =====
+        // ===== issuer of the first product.  The whole warp runs the loop (warp-uniform control flow keeps the operand
+        // descriptors in uniform registers), one elected lane issues: with a single diverged lane every tcgen05.mma
+        // cost ~15 dependent instructions of descriptor arithmetic and the issuer paced the kernel. =====
         const uint64_t a_desc0 = make_desc(smem_u32(a_res));
-        const uint64_t r_desc0 = make_desc(smem_u32(r_buf));
         const uint32_t x_ring_addr = smem_u32(x_ring);
-        const uint32_t tmem_g = tmem_base + 128u;
-        int a_loads = 0, cur_m = -1, segs_done = 0;
-        // second product of local item L (its residual pieces are in r_buf, its X tile still in the ring)
-        auto issue_mma2 = [&](int L) {
-            const int t = t_begin + L;
-            const int m_tile = t / tiles_n;
-            const bool first_of_seg = (L == 0) || ((t - 1) / tiles_n != m_tile);
-            const bool last_of_seg = (t + 1 >= t_end) || ((t + 1) / tiles_n != m_tile);
-            mbar_wait(r_full, L & 1);
-            if (first_of_seg && segs_done > 0) mbar_wait(g_empty, (segs_done - 1) & 1);   // G drained
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int stage = L % F_XSTAGES;
-            const uint64_t xd = make_desc_mn(x_ring_addr + (uint32_t)stage * F_XSTAGE, F_XBOX, 1024);
-            if (elect_one()) {
-#pragma unroll
-                for (int p = 0; p < 3; ++p)
-#pragma unroll
-                    for (int k = 0; k < FN / UMMA_K; ++k)
-                        umma_bf16(tmem_g, r_desc0 + (uint64_t)((p * F_RPIECE + k * UMMA_K * 2) >> 4),
-                                  xd + (uint64_t)((k * UMMA_K * 128) >> 4), IDESC_G, (first_of_seg && p == 0 && k == 0) ? 0u : 1u);
-                tcgen05_commit(&x_empty[stage]);
-                tcgen05_commit(r_empty);
-                if (last_of_seg) tcgen05_commit(g_full);
-            }
-            __syncwarp();
-            if (last_of_seg) ++segs_done;
-        };
-        int L = 0;
-        for (int t = t_begin; t < t_end; ++t, ++L) {
-            const int m_tile = t / tiles_n;
+        int a_loads = 0, cur_m = -1;
+        int m_tile = t_begin / tiles_n, n_tile = t_begin - m_tile * tiles_n;
+        for (int t = t_begin, L = 0; t < t_end; ++t, ++L) {
             if (m_tile != cur_m) {
                 mbar_wait(a_full, a_loads & 1);
                 ++a_loads;
@@ -668,7 +659,7 @@ tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __g
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tmem_s = tmem_base + (uint32_t)(buf * FN);
             const uint64_t xd = make_desc(x_ring_addr + (uint32_t)stage * F_XSTAGE);
-            const bool last_of_seg = (t + 1 >= t_end) || ((t + 1) / tiles_n != m_tile);
+            const bool last_of_seg = (t + 1 >= t_end) || (n_tile + 1 == tiles_n);
             if (elect_one()) {
 #pragma unroll
                 for (int p = 0; p < 3; ++p)
@@ -683,14 +674,47 @@ tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __g
                 if (last_of_seg) tcgen05_commit(a_free);
             }
             __syncwarp();
-            if (L > 0) issue_mma2(L - 1);
+            if (++n_tile == tiles_n) { n_tile = 0; ++m_tile; }
         }
-        if (L > 0) issue_mma2(L - 1);
+    } else if (warp == 3) {
+        // ===== issuer of the second product: A = residual pieces in tensor memory, B = the item's X tile (MN-major) =====
+        const uint32_t x_ring_addr = smem_u32(x_ring);
+        const uint32_t tmem_g = tmem_base + F_COL_G;
+        int segs_done = 0;
+        int m_tile = t_begin / tiles_n, n_tile = t_begin - m_tile * tiles_n;
+        bool first_of_seg = true;
+        for (int t = t_begin, L = 0; t < t_end; ++t, ++L) {
+            const bool last_of_seg = (t + 1 >= t_end) || (n_tile + 1 == tiles_n);
+            const int rb = L & 1, stage = L % F_XSTAGES;
+            mbar_wait(&r_full[rb], (L >> 1) & 1);
+            mbar_wait(&x_full[stage], (L / F_XSTAGES) & 1);               // already complete; orders this warp after the TMA
+            if (first_of_seg && segs_done > 0) mbar_wait(g_empty, (segs_done - 1) & 1);   // G drained
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t xd = make_desc_mn(x_ring_addr + (uint32_t)stage * F_XSTAGE, F_XBOX, 1024);
+            const uint32_t tmem_r = tmem_base + F_COL_R + (uint32_t)rb * F_RBUF_COLS;
+            if (elect_one()) {
+#pragma unroll
+                for (int p = 0; p < 3; ++p)
+#pragma unroll
+                    for (int k = 0; k < FN / UMMA_K; ++k)
+                        umma_bf16_ts(tmem_g, tmem_r + (uint32_t)(p * F_RPIECE_COLS + k * (UMMA_K / 2)),
+                                     xd + (uint64_t)((k * UMMA_K * 128) >> 4), IDESC_G,
+                                     (first_of_seg && p == 0 && k == 0) ? 0u : 1u);
+                tcgen05_commit(&x_empty[stage]);
+                tcgen05_commit(&r_empty[rb]);
+                if (last_of_seg) tcgen05_commit(g_full);
+            }
+            __syncwarp();
+            first_of_seg = last_of_seg;
+            if (last_of_seg) ++segs_done;
+            if (++n_tile == tiles_n) { n_tile = 0; ++m_tile; }
+        }
     } else if (warp >= 4) {
-        // ===== epilogue warps: S -> residual pieces in shared memory; G -> partial plane at the end of a segment =====
+        // ===== epilogue warps: S -> residual pieces back into tensor memory; G -> partial plane at the end of a segment =====
         const int q = warp & 3, part = (warp - 4) >> 2;
         const int trow = q * 32 + lane;                        // row of the 128-chain tile = TMEM lane
         const int c0 = part * 16;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         float urun = 0.f;
         int segs_done = 0;
         int m_tile = t_begin / tiles_n, n_tile = t_begin - m_tile * tiles_n;
@@ -708,74 +732,106 @@ tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __g
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) yv[j] = (n0 + c0 + j < fa.N) ? __ldg(fa.y + n0 + c0 + j) : 0.f;
+                for (int j = 0; j < 16; ++j) yv[j] = (n0 + c0 + j < fa.N) ? __ldg(fa.y + n0 + c0 + j) : 0.5f;
             }
             mbar_wait_backoff(&s_full[buf], (L >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t r[16];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * FN + c0);
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                : "r"(taddr));
+                : "r"(lane_addr + (uint32_t)(buf * FN + c0)));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[buf])) : "memory");
 
             uint32_t p0[8], p1[8], p2[8];
-            float ua[4] = {0.f, 0.f, 0.f, 0.f};
-            float rr[16];
+            float uacc;
+            if constexpr (EPI == 0) {
+                // one ex2, one rcp and one lg2 per element; rounding three-way split
+                float ua[4] = {0.f, 0.f, 0.f, 0.f};
+                float rr[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                // softplus(s) - y s and sigmoid(s) - y from one ex2, one rcp and one lg2 (ftz approximations,
-                // arguments are in (0, 2]: no range fix-ups needed)
-                const float sv = __uint_as_float(r[j]);
-                const float ex = ex2_approx(fabsf(sv) * -1.4426950408889634f);
-                const float den = 1.f + ex;
-                const float inv = rcp_approx(den);
-                const float sp = fmaf(lg2_approx(den), 0.6931471805599453f, fmaxf(sv, 0.f));
-                ua[j & 3] += fmaf(-yv[j], sv, sp);
-                rr[j] = (sv >= 0.f ? 1.f : ex) * inv - yv[j];
-            }
-            if (!full) {
+                for (int j = 0; j < 16; ++j) {
+                    const float sv = __uint_as_float(r[j]);
+                    const float ex = ex2_approx(fabsf(sv) * -1.4426950408889634f);
+                    const float den = 1.f + ex;
+                    const float inv = rcp_approx(den);
+                    const float sp = fmaf(lg2_approx(den), 0.6931471805599453f, fmaxf(sv, 0.f));
+                    ua[j & 3] += fmaf(-yv[j], sv, sp);
+                    rr[j] = (sv >= 0.f ? 1.f : ex) * inv - yv[j];
+                }
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (n0 + c0 + j >= fa.N) { rr[j] = 0.f; ua[j & 3] -= 0.6931471805599453f; }   // s = 0, y = 0 there
-            }
+                for (int h = 0; h < 8; ++h) {
+                    const __nv_bfloat162 a = __floats2bfloat162_rn(rr[2 * h], rr[2 * h + 1]);
+                    const float2 af = __bfloat1622float2(a);
+                    const float r1x = rr[2 * h] - af.x, r1y = rr[2 * h + 1] - af.y;
+                    const __nv_bfloat162 b = __floats2bfloat162_rn(r1x, r1y);
+                    const float2 bf = __bfloat1622float2(b);
+                    const __nv_bfloat162 c = __floats2bfloat162_rn(r1x - bf.x, r1y - bf.y);
+                    p0[h] = *reinterpret_cast<const uint32_t*>(&a);
+                    p1[h] = *reinterpret_cast<const uint32_t*>(&b);
+                    p2[h] = *reinterpret_cast<const uint32_t*>(&c);
+                }
+                uacc = (ua[0] + ua[1]) + (ua[2] + ua[3]);
+            } else {
+                // MUFU is a quarter-rate pipe and this loop is its only user, so the special functions are batched:
+                // one ex2 per element, one rcp per PAIR (1/a = b / (a b)) and one lg2 per 16 elements (sum of logs =
+                // log of the product; every factor is in (1, 2], the product <= 65536); truncating split.
+                float rr[16], den[16];
+                float ua0 = 0.f, ua1 = 0.f;
 #pragma unroll
-            for (int h = 0; h < 8; ++h) {
-                // exact three-way split, two data rows per packed conversion
-                const __nv_bfloat162 a = __floats2bfloat162_rn(rr[2 * h], rr[2 * h + 1]);
-                const float2 af = __bfloat1622float2(a);
-                const float r1x = rr[2 * h] - af.x, r1y = rr[2 * h + 1] - af.y;
-                const __nv_bfloat162 b = __floats2bfloat162_rn(r1x, r1y);
-                const float2 bf = __bfloat1622float2(b);
-                const __nv_bfloat162 c = __floats2bfloat162_rn(r1x - bf.x, r1y - bf.y);
-                p0[h] = *reinterpret_cast<const uint32_t*>(&a);
-                p1[h] = *reinterpret_cast<const uint32_t*>(&b);
-                p2[h] = *reinterpret_cast<const uint32_t*>(&c);
-            }
-            urun += (ua[0] + ua[1]) + (ua[2] + ua[3]);
-            // the second product of the previous item must have consumed the residual buffer
-            mbar_wait(r_empty, (L & 1) ^ 1);
-            {
-                uint8_t* rowp = r_buf + (trow >> 3) * 1024 + (trow & 7) * 128;
-                const int sw = trow & 7;
+                for (int j = 0; j < 16; ++j) {
+                    const float sv = __uint_as_float(r[j]);
+                    const float ex = ex2_approx(fabsf(sv) * -1.4426950408889634f);
+                    den[j] = 1.f + ex;
+                    rr[j] = sv >= 0.f ? 1.f : ex;                            // numerator of sigmoid(s)
+                    if (j & 1) ua1 += fmaf(-yv[j], sv, fmaxf(sv, 0.f));
+                    else ua0 += fmaf(-yv[j], sv, fmaxf(sv, 0.f));
+                }
+                float pp[8];
 #pragma unroll
-                for (int v = 0; v < 2; ++v) {
-                    const int chunk = ((part * 2 + v) ^ sw) << 4;
-                    *reinterpret_cast<uint4*>(rowp + chunk) = make_uint4(p0[4 * v], p0[4 * v + 1], p0[4 * v + 2], p0[4 * v + 3]);
-                    *reinterpret_cast<uint4*>(rowp + F_RPIECE + chunk) =
-                        make_uint4(p1[4 * v], p1[4 * v + 1], p1[4 * v + 2], p1[4 * v + 3]);
-                    *reinterpret_cast<uint4*>(rowp + 2 * F_RPIECE + chunk) =
-                        make_uint4(p2[4 * v], p2[4 * v + 1], p2[4 * v + 2], p2[4 * v + 3]);
+                for (int h = 0; h < 8; ++h) {
+                    pp[h] = den[2 * h] * den[2 * h + 1];
+                    const float rp = rcp_approx(pp[h]);
+                    rr[2 * h] = fmaf(rr[2 * h], den[2 * h + 1] * rp, -yv[2 * h]);
+                    rr[2 * h + 1] = fmaf(rr[2 * h + 1], den[2 * h] * rp, -yv[2 * h + 1]);
+                }
+                const float prod = ((pp[0] * pp[1]) * (pp[2] * pp[3])) * ((pp[4] * pp[5]) * (pp[6] * pp[7]));
+                uacc = fmaf(lg2_approx(prod), 0.6931471805599453f, ua0 + ua1);
+#pragma unroll
+                for (int h = 0; h < 8; ++h) {
+                    // exact three-way split by truncation (8 + 8 + 8 significant bits), two data rows per packed word
+                    const uint32_t a0 = __float_as_uint(rr[2 * h]), b0 = __float_as_uint(rr[2 * h + 1]);
+                    const float a1 = rr[2 * h] - __uint_as_float(a0 & 0xffff0000u);
+                    const float b1 = rr[2 * h + 1] - __uint_as_float(b0 & 0xffff0000u);
+                    const uint32_t a1u = __float_as_uint(a1), b1u = __float_as_uint(b1);
+                    const float a2 = a1 - __uint_as_float(a1u & 0xffff0000u);
+                    const float b2 = b1 - __uint_as_float(b1u & 0xffff0000u);
+                    p0[h] = __byte_perm(a0, b0, 0x7632);
+                    p1[h] = __byte_perm(a1u, b1u, 0x7632);
+                    p2[h] = __byte_perm(__float_as_uint(a2), __float_as_uint(b2), 0x7632);
                 }
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor-core reads
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(r_full)) : "memory");
+            // rows past the end of the data (s = 0 from the zero-filled X rows, y loaded as 1/2): the residual is
+            // 0 by construction and each such row added log 2 to the potential
+            if (!full) uacc -= 0.6931471805599453f * (float)min(16, max(0, n0 + c0 + 16 - fa.N));
+            urun += uacc;
+            // residual pieces -> tensor memory (the second product of item L - 2 must have consumed this buffer)
+            {
+                const int rb = L & 1;
+                mbar_wait(&r_empty[rb], ((L >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t raddr = lane_addr + F_COL_R + (uint32_t)rb * F_RBUF_COLS + (uint32_t)(part * 8);
+                tmem_st8(raddr, p0);
+                tmem_st8(raddr + F_RPIECE_COLS, p1);
+                tmem_st8(raddr + 2 * F_RPIECE_COLS, p2);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&r_full[rb])) : "memory");
+            }
 
             const bool last_of_seg = (t + 1 >= t_end) || (n_tile + 1 == tiles_n);
             if (last_of_seg) {
@@ -783,7 +839,6 @@ tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __g
                 mbar_wait(g_full, segs_done & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t gq[32];
-                const uint32_t gaddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 + part * 32);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -793,7 +848,7 @@ tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __g
                       "=r"(gq[15]), "=r"(gq[16]), "=r"(gq[17]), "=r"(gq[18]), "=r"(gq[19]), "=r"(gq[20]), "=r"(gq[21]),
                       "=r"(gq[22]), "=r"(gq[23]), "=r"(gq[24]), "=r"(gq[25]), "=r"(gq[26]), "=r"(gq[27]), "=r"(gq[28]),
                       "=r"(gq[29]), "=r"(gq[30]), "=r"(gq[31])
-                    : "r"(gaddr));
+                    : "r"(lane_addr + F_COL_G + (uint32_t)(part * 32)));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(g_empty)) : "memory");
@@ -826,7 +881,7 @@ tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __g
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(F_TMEM_COLS) : "memory");
     }
 }
 
@@ -975,13 +1030,17 @@ int tc_logistic_fused(cudaStream_t st, const void* beta_pieces, int piece_rows, 
     const long long total = (long long)fa.tiles_m * fa.tiles_n;
     fa.per_cta = (int)((total + sm_count - 1) / sm_count);
     const int grid = (int)((total + fa.per_cta - 1) / fa.per_cta);
-    if (dim > BK) {
-        B2H_CUDA(cudaFuncSetAttribute(tc_logistic_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
-        tc_logistic_fused_kernel<2><<<grid, THREADS, F_SMEM, st>>>(mb, mx, fa);
-    } else {
-        B2H_CUDA(cudaFuncSetAttribute(tc_logistic_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
-        tc_logistic_fused_kernel<1><<<grid, THREADS, F_SMEM, st>>>(mb, mx, fa);
-    }
+    // epilogue arithmetic variant (development switch, default 1 = batched special functions)
+    static int epi = -1;
+    if (epi < 0) { const char* e = getenv("B2H_FUSED_EPI"); epi = e ? atoi(e) : 1; }
+    auto launch = [&](auto kern) -> int {
+        B2H_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+        kern<<<grid, THREADS, F_SMEM, st>>>(mb, mx, fa);
+        return 0;
+    };
+    if (dim > BK) rc = epi ? launch(tc_logistic_fused_kernel<2, 1>) : launch(tc_logistic_fused_kernel<2, 0>);
+    else rc = epi ? launch(tc_logistic_fused_kernel<1, 1>) : launch(tc_logistic_fused_kernel<1, 0>);
+    if (rc) return rc;
     B2H_LAUNCH_CHECK();
     *per_cta = fa.per_cta;
     *planes = logistic_fused_planes(M, N);
