@@ -21,7 +21,8 @@ RNG_PHILOX, RNG_INJECTED = 0, 1
 class Model(C.Structure):
     _fields_ = [("kind", C.c_int32), ("dim", C.c_int32), ("n_data", C.c_int64), ("a", C.c_void_p),
                 ("b", C.c_void_p), ("c", C.c_void_p), ("s0", C.c_double), ("s1", C.c_double),
-                ("x_bf16", C.c_void_p), ("xt_bf16", C.c_void_p)]
+                ("x_bf16", C.c_void_p), ("xt_bf16", C.c_void_p), ("x_f16", C.c_void_p), ("x_f16_shift", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class Metric(C.Structure):

@@ -9,6 +9,7 @@
 // chunked over the data dimension so that S never exceeds a bounded scratch,
 // with a deterministic split-K reduction for the tall-skinny second product.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "launch.h"
@@ -199,14 +200,17 @@ static LogregFusedPlan plan_logreg_fused(const b2h_model* m, i64 C) {
     return p;
 }
 
-static bool logistic_use_fused(const b2h_model* m) { return (int)m->s1 == 2 && m->dim <= 128; }
+static bool logistic_use_fused16(const b2h_model* m) { return (int)m->s1 == 4 && m->dim <= 128 && m->x_f16; }
+static bool logistic_use_fused(const b2h_model* m) {
+    return ((int)m->s1 == 2 || (int)m->s1 == 4) && m->dim <= 128;
+}
 
 // g (T) = sum over the planes written by the CTAs that touched the chain tile (fixed order) + b / sigma^2;
 // U = sum of the CTAs' potential partials + 1/2 |b|^2 / sigma^2.  One warp per chain.
 template <typename T>
 __global__ void __launch_bounds__(128)
 logistic_fused_finish_kernel(const float* gpart, i64 plane_stride, const double* upart, const T* q, T* g, T* U,
-                             T inv_prior_var, i64 C, int d, int tiles_n, int per_cta) {
+                             T inv_prior_var, i64 C, int d, int tiles_n, int per_cta, double g_scale) {
     const i64 c = (i64)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (c >= C) return;
     const int lane = threadIdx.x & 31;
@@ -218,7 +222,7 @@ logistic_fused_finish_kernel(const float* gpart, i64 plane_stride, const double*
         double s = 0.0;
         for (int b = 0; b <= b_last - b_first; ++b) s += (double)gpart[(i64)b * plane_stride + c * d + j];
         const T bj = q[c * d + j];
-        g[c * d + j] = (T)s + inv_prior_var * bj;
+        g[c * d + j] = (T)(s * g_scale) + inv_prior_var * bj;
         acc += bj * bj;
     }
     const double nb = Group<32>::sum1((double)acc, nullptr);
@@ -253,7 +257,55 @@ static int logistic_tc_fused(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U,
     int rc = tc_logistic_fused(st, bp, (int)C, m->x_bf16, (int)C, (int)N, d, yf, gpart, upart, &per_cta, &planes);
     if (rc < 0) return rc;
     logistic_fused_finish_kernel<T><<<(int)((C + 3) / 4), 128, 0, st>>>(gpart, ng, upart, q, g, U, (T)m->s0, C, d,
-                                                                         (int)((N + 63) / 64), per_cta);
+                                                                         (int)((N + 63) / 64), per_cta, 1.0);
+    B2H_LAUNCH_CHECK();
+    return 0;
+}
+
+
+// beta[C x d] (T) -> two stacked fp16 pieces of beta * 2^8 (22 significant bits; clamped to the fp16 range)
+template <typename T>
+__global__ void beta_split16_kernel(const T* q, __half* bp, i64 n) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x = (double)q[i] * 256.0;
+    x = fmin(fmax(x, -65000.0), 65000.0);
+    const __half a = __double2half(x);
+    bp[i] = a;
+    bp[n + i] = __double2half(x - (double)__half2float(a));
+}
+
+template <typename T>
+__global__ void to_float_scaled_kernel(const T* x, float* y, i64 n, float scale) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = (float)x[i] * scale;
+}
+
+template <typename T>
+static int logistic_tc_fused16(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U, T* g, i64 C, void* ws, i64 ws_bytes) {
+    if (m->dim % 8 || m->n_data % 8) { set_error("logistic tensor-core path needs dim and n_data multiples of 8"); return B2H_ERR_ARG; }
+    LogregFusedPlan p = plan_logreg_fused(m, C);
+    if (!ws || (size_t)ws_bytes < p.total) {
+        set_error("logistic workspace too small: need " + std::to_string(p.total) + " bytes");
+        return B2H_ERR_WORKSPACE;
+    }
+    cudaStream_t st = ctx->stream;
+    const int d = m->dim;
+    const i64 N = m->n_data;
+    char* base = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+    __half* bp = (__half*)(base + p.off_bp);                 // the plan reserves three 16-bit pieces; two are used
+    float* yf = (float*)(base + p.off_y);
+    float* gpart = (float*)(base + p.off_gpart);
+    double* upart = (double*)(base + p.off_upart);
+    const i64 ng = C * d;
+    beta_split16_kernel<T><<<(int)((ng + 255) / 256), 256, 0, st>>>(q, bp, ng);
+    to_float_scaled_kernel<T><<<(int)((N + 255) / 256), 256, 0, st>>>((const T*)m->b, yf, N, 1024.f);
+    int per_cta = 0;
+    int rc = tc_logistic_fused16(st, bp, m->x_f16, m->x_f16_shift, (int)C, (int)N, d, yf, gpart, upart, &per_cta);
+    if (rc < 0) return rc;
+    logistic_fused_finish_kernel<T><<<(int)((C + 3) / 4), 128, 0, st>>>(gpart, ng, upart, q, g, U, (T)m->s0, C, d,
+                                                                         (int)((N + 63) / 64), per_cta,
+                                                                         ldexp(1.0, -(10 + m->x_f16_shift)));
     B2H_LAUNCH_CHECK();
     return 0;
 }
@@ -312,6 +364,7 @@ int logistic_potential_and_grad(b2h_ctx* ctx, const b2h_model* m, const T* q, T*
                                 i64 ws_bytes, int path) {
     // model flag s1: 0 = FMA / DMMA exactness reference, 2 = tensor cores (fully fused when dim <= 128), 3 = tensor
     // cores with the two-kernel formulation (residual pieces through memory)
+    if (path == 0 && logistic_use_fused16(m)) return logistic_tc_fused16<T>(ctx, m, q, U, g, C, ws, ws_bytes);
     if (path == 0 && logistic_use_fused(m)) return logistic_tc_fused<T>(ctx, m, q, U, g, C, ws, ws_bytes);
     if (path == 2 || (path == 0 && (int)m->s1 >= 2)) return logistic_tc<T>(ctx, m, q, U, g, C, ws, ws_bytes);
     if (!m->a || !m->b || !m->c) { set_error("logistic model needs X (a), y (b) and X^T (c)"); return B2H_ERR_ARG; }

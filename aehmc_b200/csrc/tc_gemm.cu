@@ -21,6 +21,7 @@
 //                             so S is never written to memory
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -886,6 +887,325 @@ tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __g
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// fp16 x 2 variant of the fused gradient: beta and the residual are carried as TWO fp16 pieces (22 significant
+// bits; the hardware does not mix an fp16 A with a bf16 B inside kind::f16, so X is read from an exact fp16 copy
+// X * 2^shift).  Two thirds of the tensor work of the bf16 x 3 kernel, and small enough for BOTH products to take
+// their A operand from tensor memory: the beta pieces of the CTA's chain tile are stored to TMEM once per segment by
+// the epilogue warps, so shared memory carries nothing but the X ring.
+// Scales (powers of two, exact): beta pieces hold beta * 2^8, X holds X * 2^shift, so S_acc = s * 2^(8 + shift);
+// the residual pieces hold r * 2^10 (keeps the low piece out of the fp16 subnormals), so G_acc = g * 2^(10 + shift).
+// TMEM columns: [0,128) S double buffer, [128,256) G, [256,384) residual double buffer (2 x 2 pieces x 32),
+// [384,512) beta (2 pieces x 64).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int H_XSTAGES = 8;
+constexpr uint32_t H_COL_R = 256, H_RBUF_COLS = 64, H_RPIECE_COLS = 32, H_COL_B = 384, H_BPIECE_COLS = 64;
+constexpr size_t H_SMEM = (size_t)H_XSTAGES * F_XSTAGE + 1024 + 512;
+constexpr uint32_t IDESC_S16 = (1u << 4) | ((uint32_t)(FN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t IDESC_G16 = (1u << 4) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct Fused16Args {
+    const float* y1024;      // [N] responses * 1024
+    const __half* beta;      // [2][M x dim] fp16 pieces of beta * 2^8
+    float* gpart;            // [planes][M x dim] fp32 partial gradients (scaled by 2^(10 + shift))
+    long long plane_stride;  // M * dim
+    double* upart;           // [gridDim.x][4][M] potential partial sums
+    float s_scale;           // 2^-(8 + shift)
+    int M, N, dim, tiles_m, tiles_n, per_cta;
+};
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+
+template <int KB>
+__global__ void __launch_bounds__(THREADS, 1)
+tc_logistic_fused16_kernel(const __grid_constant__ CUtensorMap map_x, Fused16Args fa) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* x_ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(x_ring + (size_t)H_XSTAGES * F_XSTAGE);
+    uint64_t* x_full = bars;                          // [8]
+    uint64_t* x_empty = bars + H_XSTAGES;             // [8]
+    uint64_t* a_full = bars + 2 * H_XSTAGES;
+    uint64_t* a_free = a_full + 1;
+    uint64_t* s_full = a_full + 2;                    // [2]
+    uint64_t* s_empty = a_full + 4;                   // [2]
+    uint64_t* r_full = a_full + 6;                    // [2]
+    uint64_t* r_empty = a_full + 8;                   // [2]
+    uint64_t* g_full = a_full + 10;
+    uint64_t* g_empty = a_full + 11;
+    uint32_t* tmem_slot = (uint32_t*)(a_full + 12);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int tiles_n = fa.tiles_n;
+    const int total = fa.tiles_m * tiles_n;
+    const int t_begin = blockIdx.x * fa.per_cta;
+    const int t_end = min(total, t_begin + fa.per_cta);
+
+    if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < H_XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+        mbar_init(a_full, EPI_WARPS); mbar_init(a_free, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], EPI_WARPS);
+            mbar_init(&r_full[b], EPI_WARPS); mbar_init(&r_empty[b], 1);
+        }
+        mbar_init(g_full, 1); mbar_init(g_empty, EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(F_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    if (warp == 0) {
+        // ===== TMA producer: one X tile per item =====
+        if (lane == 0) {
+            int n_tile = t_begin % tiles_n;
+            for (int t = t_begin, L = 0; t < t_end; ++t, ++L) {
+                const int s = L % H_XSTAGES, round = L / H_XSTAGES;
+                mbar_wait_backoff(&x_empty[s], (round & 1) ^ 1);
+                mbar_expect_tx(&x_full[s], (uint32_t)(KB * F_XBOX));
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_load_2d(x_ring + (size_t)s * F_XSTAGE + (size_t)kb * F_XBOX, &map_x, &x_full[s], kb * BK, n_tile * FN);
+                if (++n_tile == tiles_n) n_tile = 0;
+            }
+        }
+    } else if (warp == 1) {
+        // ===== issuer of the first product: A = beta pieces in tensor memory, B = X tile (K-major) =====
+        const uint32_t x_ring_addr = smem_u32(x_ring);
+        const uint32_t tmem_b = tmem_base + H_COL_B;
+        int seg = 0;
+        int n_tile = t_begin % tiles_n;
+        bool first_of_seg = true;
+        for (int t = t_begin, L = 0; t < t_end; ++t, ++L) {
+            if (first_of_seg) { mbar_wait(a_full, seg & 1); ++seg; }
+            const int buf = L & 1;
+            const int stage = L % H_XSTAGES;
+            mbar_wait(&s_empty[buf], ((L >> 1) & 1) ^ 1);
+            mbar_wait(&x_full[stage], (L / H_XSTAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_s = tmem_base + (uint32_t)(buf * FN);
+            const uint64_t xd = make_desc(x_ring_addr + (uint32_t)stage * F_XSTAGE);
+            const bool last_of_seg = (t + 1 >= t_end) || (n_tile + 1 == tiles_n);
+            if (elect_one()) {
+#pragma unroll
+                for (int p = 0; p < 2; ++p)
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_bf16_ts(tmem_s, tmem_b + (uint32_t)(p * H_BPIECE_COLS + kb * (BK / 2) + k * (UMMA_K / 2)),
+                                         xd + (uint64_t)((kb * F_XBOX + k * UMMA_K * 2) >> 4), IDESC_S16,
+                                         (p == 0 && kb == 0 && k == 0) ? 0u : 1u);
+                tcgen05_commit(&s_full[buf]);
+                if (last_of_seg) tcgen05_commit(a_free);
+            }
+            __syncwarp();
+            first_of_seg = last_of_seg;
+            if (++n_tile == tiles_n) n_tile = 0;
+        }
+    } else if (warp == 3) {
+        // ===== issuer of the second product: A = residual pieces in tensor memory, B = the item's X tile (MN-major) =====
+        const uint32_t x_ring_addr = smem_u32(x_ring);
+        const uint32_t tmem_g = tmem_base + F_COL_G;
+        int segs_done = 0;
+        int n_tile = t_begin % tiles_n;
+        bool first_of_seg = true;
+        for (int t = t_begin, L = 0; t < t_end; ++t, ++L) {
+            const bool last_of_seg = (t + 1 >= t_end) || (n_tile + 1 == tiles_n);
+            const int rb = L & 1, stage = L % H_XSTAGES;
+            mbar_wait(&r_full[rb], (L >> 1) & 1);
+            mbar_wait(&x_full[stage], (L / H_XSTAGES) & 1);               // already complete; orders this warp after the TMA
+            if (first_of_seg && segs_done > 0) mbar_wait(g_empty, (segs_done - 1) & 1);   // G drained
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t xd = make_desc_mn(x_ring_addr + (uint32_t)stage * F_XSTAGE, F_XBOX, 1024);
+            const uint32_t tmem_r = tmem_base + H_COL_R + (uint32_t)rb * H_RBUF_COLS;
+            if (elect_one()) {
+#pragma unroll
+                for (int p = 0; p < 2; ++p)
+#pragma unroll
+                    for (int k = 0; k < FN / UMMA_K; ++k)
+                        umma_bf16_ts(tmem_g, tmem_r + (uint32_t)(p * H_RPIECE_COLS + k * (UMMA_K / 2)),
+                                     xd + (uint64_t)((k * UMMA_K * 128) >> 4), IDESC_G16,
+                                     (first_of_seg && p == 0 && k == 0) ? 0u : 1u);
+                tcgen05_commit(&x_empty[stage]);
+                tcgen05_commit(&r_empty[rb]);
+                if (last_of_seg) tcgen05_commit(g_full);
+            }
+            __syncwarp();
+            first_of_seg = last_of_seg;
+            if (last_of_seg) ++segs_done;
+            if (++n_tile == tiles_n) n_tile = 0;
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue warps =====
+        const int q = warp & 3, part = (warp - 4) >> 2;
+        const int trow = q * 32 + lane;                        // row of the 128-chain tile = TMEM lane
+        const int c0 = part * 16;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const float ex_scale = -1.4426950408889634f * fa.s_scale;
+        float urun = 0.f;
+        int segs_done = 0;
+        int m_tile = t_begin / tiles_n, n_tile = t_begin - m_tile * tiles_n;
+        bool first_of_seg = true;
+        for (int t = t_begin, L = 0; t < t_end; ++t, ++L) {
+            if (first_of_seg) {
+                // beta pieces of this chain tile -> tensor memory (the first products of the previous segment retired)
+                mbar_wait(a_free, (segs_done & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int row = m_tile * BM + trow;
+                if (part * 32 < KB * BK) {
+#pragma unroll
+                    for (int p = 0; p < 2; ++p) {
+                        uint32_t bw[16];
+                        const __half* src = fa.beta + (long long)p * fa.plane_stride + (long long)row * fa.dim + part * 32;
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            uint4 w = make_uint4(0u, 0u, 0u, 0u);
+                            if (row < fa.M && part * 32 + v * 8 < fa.dim) w = __ldg(reinterpret_cast<const uint4*>(src + v * 8));
+                            bw[4 * v] = w.x; bw[4 * v + 1] = w.y; bw[4 * v + 2] = w.z; bw[4 * v + 3] = w.w;
+                        }
+                        tmem_st16(lane_addr + H_COL_B + (uint32_t)(p * H_BPIECE_COLS + part * 16), bw);
+                    }
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(a_full)) : "memory");
+            }
+            const int n0 = n_tile * FN;
+            const int buf = L & 1;
+            const bool full = n0 + FN <= fa.N;
+            float yv[16];                                      // 1024 y
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 y4 = __ldg(reinterpret_cast<const float4*>(fa.y1024 + n0 + c0 + j));
+                    yv[j] = y4.x; yv[j + 1] = y4.y; yv[j + 2] = y4.z; yv[j + 3] = y4.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) yv[j] = (n0 + c0 + j < fa.N) ? __ldg(fa.y1024 + n0 + c0 + j) : 512.f;
+            }
+            mbar_wait_backoff(&s_full[buf], (L >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t r[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(lane_addr + (uint32_t)(buf * FN + c0)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[buf])) : "memory");
+
+            // batched special functions (see the bf16 kernel); sv below is s * 2^(8 + shift)
+            uint32_t p0[8], p1[8];
+            float rr[16], den[16];
+            float ua0 = 0.f, ua1 = 0.f, ub0 = 0.f, ub1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float sv = __uint_as_float(r[j]);
+                const float ex = ex2_approx(fabsf(sv) * ex_scale);
+                den[j] = 1.f + ex;
+                rr[j] = sv >= 0.f ? 1.f : ex;                            // numerator of sigmoid(s)
+                if (j & 1) { ua1 += fmaxf(sv, 0.f); ub1 = fmaf(yv[j], sv, ub1); }
+                else { ua0 += fmaxf(sv, 0.f); ub0 = fmaf(yv[j], sv, ub0); }
+            }
+            float pp[8];
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                pp[h] = den[2 * h] * den[2 * h + 1];
+                const float rp = rcp_approx(pp[h]) * 1024.f;
+                rr[2 * h] = fmaf(rr[2 * h], den[2 * h + 1] * rp, -yv[2 * h]);              // 1024 (sigmoid(s) - y)
+                rr[2 * h + 1] = fmaf(rr[2 * h + 1], den[2 * h] * rp, -yv[2 * h + 1]);
+            }
+            const float prod = ((pp[0] * pp[1]) * (pp[2] * pp[3])) * ((pp[4] * pp[5]) * (pp[6] * pp[7]));
+            float uacc = fmaf(lg2_approx(prod), 0.6931471805599453f,
+                              fa.s_scale * fmaf(ub0 + ub1, -0.0009765625f, ua0 + ua1));
+            if (!full) uacc -= 0.6931471805599453f * (float)min(16, max(0, n0 + c0 + 16 - fa.N));
+            urun += uacc;
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                const __half2 hi = __floats2half2_rn(rr[2 * h], rr[2 * h + 1]);
+                const float2 hf = __half22float2(hi);
+                const __half2 lo = __floats2half2_rn(rr[2 * h] - hf.x, rr[2 * h + 1] - hf.y);
+                p0[h] = *reinterpret_cast<const uint32_t*>(&hi);
+                p1[h] = *reinterpret_cast<const uint32_t*>(&lo);
+            }
+            {
+                const int rb = L & 1;
+                mbar_wait(&r_empty[rb], ((L >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t raddr = lane_addr + H_COL_R + (uint32_t)rb * H_RBUF_COLS + (uint32_t)(part * 8);
+                tmem_st8(raddr, p0);
+                tmem_st8(raddr + H_RPIECE_COLS, p1);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&r_full[rb])) : "memory");
+            }
+
+            const bool last_of_seg = (t + 1 >= t_end) || (n_tile + 1 == tiles_n);
+            if (last_of_seg) {
+                mbar_wait(g_full, segs_done & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t gq[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(gq[0]), "=r"(gq[1]), "=r"(gq[2]), "=r"(gq[3]), "=r"(gq[4]), "=r"(gq[5]), "=r"(gq[6]), "=r"(gq[7]),
+                      "=r"(gq[8]), "=r"(gq[9]), "=r"(gq[10]), "=r"(gq[11]), "=r"(gq[12]), "=r"(gq[13]), "=r"(gq[14]),
+                      "=r"(gq[15]), "=r"(gq[16]), "=r"(gq[17]), "=r"(gq[18]), "=r"(gq[19]), "=r"(gq[20]), "=r"(gq[21]),
+                      "=r"(gq[22]), "=r"(gq[23]), "=r"(gq[24]), "=r"(gq[25]), "=r"(gq[26]), "=r"(gq[27]), "=r"(gq[28]),
+                      "=r"(gq[29]), "=r"(gq[30]), "=r"(gq[31])
+                    : "r"(lane_addr + F_COL_G + (uint32_t)(part * 32)));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(g_empty)) : "memory");
+                ++segs_done;
+                const int row = m_tile * BM + trow;
+                if (row < fa.M) {
+                    const int b_first = (int)(((long long)m_tile * tiles_n) / fa.per_cta);
+                    float* orow = fa.gpart + (long long)(blockIdx.x - b_first) * fa.plane_stride + (long long)row * fa.dim;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const int col = part * 32 + j;
+                        if (col + 3 < fa.dim) {
+                            *reinterpret_cast<float4*>(orow + col) =
+                                make_float4(__uint_as_float(gq[j]), __uint_as_float(gq[j + 1]), __uint_as_float(gq[j + 2]),
+                                            __uint_as_float(gq[j + 3]));
+                        } else {
+                            for (int e = 0; e < 4; ++e)
+                                if (col + e < fa.dim) orow[col + e] = __uint_as_float(gq[j + e]);
+                        }
+                    }
+                    fa.upart[((long long)blockIdx.x * EPI_PARTS + part) * fa.M + row] = (double)urun;
+                }
+                urun = 0.f;
+            }
+            first_of_seg = last_of_seg;
+            if (++n_tile == tiles_n) { n_tile = 0; ++m_tile; }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(F_TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host side: tensor maps through the driver entry point (no link-time dependency on libcuda)
 // ---------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -904,14 +1224,15 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2D bf16 row-major [rows][cols] (cols contiguous, row pitch ld elements), box = 64 x 128, 128-byte swizzle
-static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows = BM) {
+static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows = BM,
+                    CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return B2H_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); return B2H_ERR_CUDA; }
@@ -1044,6 +1365,43 @@ int tc_logistic_fused(cudaStream_t st, const void* beta_pieces, int piece_rows, 
     B2H_LAUNCH_CHECK();
     *per_cta = fa.per_cta;
     *planes = logistic_fused_planes(M, N);
+    return 0;
+}
+
+// fp16 x 2 fused gradient: see tc_logistic_fused16_kernel.  beta_pieces: [2][M x dim] fp16 (beta * 2^8),
+// X16: [N x dim] fp16 = X * 2^shift, y1024: responses * 1024.  gpart comes out scaled by 2^(10 + shift).
+int tc_logistic_fused16(cudaStream_t st, const void* beta_pieces, const void* X16, int shift, int M, int N, int dim,
+                        const float* y1024, float* gpart, double* upart, int* per_cta) {
+    using namespace tc;
+    if (dim > 2 * BK || dim % 8) { set_error("tc_logistic_fused16: dim must be a multiple of 8, at most 128"); return B2H_ERR_ARG; }
+    CUtensorMap mx;
+    int rc = make_map(&mx, X16, N, dim, dim, FN, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    if (rc) return rc;
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (sm_count <= 0) sm_count = 148;
+    }
+    Fused16Args fa;
+    fa.y1024 = y1024; fa.beta = (const __half*)beta_pieces; fa.gpart = gpart; fa.plane_stride = (long long)M * dim;
+    fa.upart = upart; fa.s_scale = ldexpf(1.f, -(8 + shift));
+    fa.M = M; fa.N = N; fa.dim = dim;
+    fa.tiles_m = (M + BM - 1) / BM;
+    fa.tiles_n = (N + FN - 1) / FN;
+    const long long total = (long long)fa.tiles_m * fa.tiles_n;
+    fa.per_cta = (int)((total + sm_count - 1) / sm_count);
+    const int grid = (int)((total + fa.per_cta - 1) / fa.per_cta);
+    if (dim > BK) {
+        B2H_CUDA(cudaFuncSetAttribute(tc_logistic_fused16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H_SMEM));
+        tc_logistic_fused16_kernel<2><<<grid, THREADS, H_SMEM, st>>>(mx, fa);
+    } else {
+        B2H_CUDA(cudaFuncSetAttribute(tc_logistic_fused16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H_SMEM));
+        tc_logistic_fused16_kernel<1><<<grid, THREADS, H_SMEM, st>>>(mx, fa);
+    }
+    B2H_LAUNCH_CHECK();
+    *per_cta = fa.per_cta;
     return 0;
 }
 

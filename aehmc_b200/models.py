@@ -9,6 +9,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import math
+
 import numpy as np
 import torch
 
@@ -115,8 +117,12 @@ class LogisticRegression(Model):
     """``tensor_core=True`` evaluates the batched gradient X.B / X^T.R on tcgen05 tensor cores (bf16 operands,
     beta and the residuals split into three bf16 pieces, fp32 accumulation in TMEM): fp32-class accuracy.  It
     needs X to be bf16-representable.  With dim <= 128 the two products and the residual run as ONE kernel (S in
-    TMEM, residual pieces in shared memory); ``tensor_core="two_kernel"`` forces the formulation that passes the
-    residual pieces through memory (any dim).  The default is the FP64/FP32 FMA-DMMA path (exactness reference)."""
+    TMEM, residual pieces written back to TMEM as the A operand of the second product).  When, in addition,
+    X * 2^k is exactly representable in fp16 for some k (true for bf16 data spanning less than 2^32 in magnitude),
+    beta and the residual are carried as TWO fp16 pieces (22 significant bits) with beta resident in TMEM: two
+    thirds of the tensor work.  ``tensor_core="bf16x3"`` forces the three-piece bf16 kernel,
+    ``tensor_core="two_kernel"`` the formulation that passes the residual pieces through memory (any dim).
+    The default (``False``) is the FP64/FP32 FMA-DMMA path (exactness reference)."""
     kind = _lib.MODEL_LOGISTIC
 
     def __init__(self, X, y, prior_scale=1.0, dtype=torch.float64, device=None, tensor_core=False):
@@ -128,7 +134,8 @@ class LogisticRegression(Model):
         self.n_data, self.dim = int(self.X.shape[0]), int(self.X.shape[1])
         self.tensor_core = bool(tensor_core)
         self.tc_flag = 3.0 if tensor_core == "two_kernel" else (2.0 if self.tensor_core else 0.0)
-        self.X_bf16 = self.Xt_bf16 = None
+        self.X_bf16 = self.Xt_bf16 = self.X_f16 = None
+        self.x_f16_shift = 0
         if self.tensor_core:
             xb = self.X.to(torch.bfloat16)
             if not torch.equal(xb.to(self.dtype), self.X):
@@ -137,9 +144,18 @@ class LogisticRegression(Model):
                 raise ValueError("tensor_core=True needs n_data and dim to be multiples of 8 (16-byte TMA pitches)")
             self.X_bf16 = xb.contiguous()
             self.Xt_bf16 = xb.t().contiguous()
+            if tensor_core is True and self.dim <= 128:
+                # fp16 copy X * 2^shift (exact): largest magnitude just below 2^15
+                amax = float(self.X.abs().max())
+                if amax > 0.0 and math.isfinite(amax):
+                    shift = 14 - int(math.floor(math.log2(amax)))
+                    xs = torch.ldexp(self.X.double(), torch.tensor(shift, device=self.device))
+                    xh = xs.to(torch.float16)
+                    if bool(torch.isfinite(xh).all()) and torch.equal(xh.double(), xs):
+                        self.X_f16, self.x_f16_shift, self.tc_flag = xh.contiguous(), shift, 4.0
 
     def struct(self):
         p = lambda t: None if t is None else t.data_ptr()
         return _lib.Model(self.kind, self.dim, self.n_data, self.X.data_ptr(), self.y.data_ptr(),
                           self.Xt.data_ptr(), self.inv_prior_var, self.tc_flag,
-                          p(self.X_bf16), p(self.Xt_bf16))
+                          p(self.X_bf16), p(self.Xt_bf16), p(self.X_f16), self.x_f16_shift, 0)

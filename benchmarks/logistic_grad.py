@@ -11,6 +11,7 @@ ap.add_argument("--n", type=int, default=100000)
 ap.add_argument("--d", type=int, default=128)
 ap.add_argument("--reps", type=int, default=200)
 ap.add_argument("--two-kernel", action="store_true")
+ap.add_argument("--bf16x3", action="store_true")
 ap.add_argument("--f64", action="store_true")
 a = ap.parse_args()
 rng = np.random.default_rng(4)
@@ -18,7 +19,7 @@ X = torch.tensor(rng.standard_normal((a.n, a.d)), dtype=torch.float32).bfloat16(
 beta = rng.standard_normal(a.d) / np.sqrt(a.d)
 y = (rng.random(a.n) < 1 / (1 + np.exp(-X @ beta))).astype(np.float64)
 dt = torch.float64 if a.f64 else torch.float32
-model = ab.models.LogisticRegression(X, y, 1.0, dtype=dt, tensor_core="two_kernel" if a.two_kernel else True)
+model = ab.models.LogisticRegression(X, y, 1.0, dtype=dt, tensor_core="two_kernel" if a.two_kernel else ("bf16x3" if a.bf16x3 else True))
 q = torch.tensor(0.1 * np.random.default_rng(6).standard_normal((a.chains, a.d)), dtype=dt, device="cuda")
 for _ in range(5):
     model.potential_and_grad(q)
@@ -43,7 +44,7 @@ e1.record(); torch.cuda.synchronize()
 stop = True; th.join(timeout=1)
 ms = e0.elapsed_time(e1) / a.reps
 flops = 4.0 * a.n * a.d * a.chains
-print(json.dumps({"workload": f"logistic gradient N={a.n} D={a.d} chains={a.chains} {'two-kernel' if a.two_kernel else 'fused'} "
+print(json.dumps({"workload": f"logistic gradient N={a.n} D={a.d} chains={a.chains} {'two-kernel' if a.two_kernel else 'fused'} path={model.tc_flag} "
                   f"epi={os.environ.get('B2H_FUSED_EPI', 'default')}", "ms_per_gradient": ms,
                   "evals_per_sec": a.chains / (ms * 1e-3), "TFLOPs_algorithmic": flops / (ms * 1e-3) / 1e12,
                   "TFLOPs_issued_x3": 3 * flops / (ms * 1e-3) / 1e12,

@@ -46,7 +46,10 @@ enum {
     B2H_MODEL_EIGHT_SCHOOLS = 3, /* non-centred; a=y[d-2], b=inv_var[d-2]                          */
     B2H_MODEL_LOGISTIC = 4       /* a=X[n_data x d] row-major, b=y[n_data], c=X^T[d x n_data], s0 = 1/prior_scale^2;
                                     s1 = gradient path: 0 FMA/DMMA exactness reference, 2 tcgen05 tensor core
-                                    (needs x_bf16 = X and xt_bf16 = X^T as bf16, X bf16-representable)         */
+                                    (needs x_bf16 = X and xt_bf16 = X^T as bf16, X bf16-representable; one fused
+                                    kernel when dim <= 128), 3 = tensor core, two-kernel formulation (any dim),
+                                    4 = fused kernel on two fp16 pieces (needs x_f16 = X * 2^x_f16_shift exactly
+                                    representable as fp16, dim <= 128)                                          */
 };
 
 typedef struct {
@@ -60,6 +63,9 @@ typedef struct {
     double s1;
     const void* x_bf16;  /* device, logistic tensor-core path: X   [n_data x d] as bf16 */
     const void* xt_bf16; /* device, logistic tensor-core path: X^T [d x n_data] as bf16 */
+    const void* x_f16;   /* device, logistic fp16 path: X * 2^x_f16_shift [n_data x d] as fp16 (exact) */
+    int32_t x_f16_shift;
+    int32_t reserved;
 } b2h_model;
 
 /* ---- gaussian metric (reference metrics.py:10-106) ---- */

@@ -59,7 +59,7 @@ def _logistic_case(rng, N, d):
     return X, y
 
 
-@pytest.mark.parametrize("tc_mode", [True, "two_kernel"])
+@pytest.mark.parametrize("tc_mode", [True, "bf16x3", "two_kernel"])
 @pytest.mark.parametrize("N, d, Cn", [(512, 64, 40), (2048, 128, 130), (20000, 128, 256), (1000, 96, 300), (40000, 128, 700)])
 def test_logistic_gradient_tensor_core_vs_fma(ab, N, d, Cn, tc_mode):
     rng = np.random.default_rng(N + d)
@@ -79,7 +79,8 @@ def test_logistic_gradient_tensor_core_vs_fma(ab, N, d, Cn, tc_mode):
     np.testing.assert_allclose(g1[0].double().cpu().numpy(), go, atol=2e-5 * gs)
 
 
-def test_nuts_logistic_tensor_core_float32_parity(ab):
+@pytest.mark.parametrize("tc_mode", [True, "bf16x3"])
+def test_nuts_logistic_tensor_core_float32_parity(ab, tc_mode):
     """north star: FP32 bar -- positions within 1e-4 of the oracle per transition, tree shapes equal
     (a near-tie U-turn test may flip in float32: >= 90 % must be identical)."""
     from aehmc_b200 import _engine
@@ -90,7 +91,8 @@ def test_nuts_logistic_tensor_core_float32_parity(ab):
     imm = np.full(d, 4.0 / N)
     draws = parity.random_draws(rng, Cn, T, d)
     ref = parity.oracle_nuts(o_models.LogisticRegression(X, y, 1.0), q0, 0.4, imm, draws, T)
-    model = ab.models.LogisticRegression(X, y, 1.0, dtype=torch.float32, tensor_core=True)
+    model = ab.models.LogisticRegression(X, y, 1.0, dtype=torch.float32, tensor_core=tc_mode)
+    assert model.tc_flag == (4.0 if tc_mode is True else 2.0)
     srng = ab.InjectedDraws(draws["z"], draws["u_dir"], draws["u_biased"], draws["u_uniform"])
     info, extras = _engine.run("nuts", model, imm, srng, ab.nuts.new_state(q0, model), 0.4, n_transitions=T)
     nd = info.num_doublings.cpu().numpy()
