@@ -22,7 +22,7 @@ class Model(C.Structure):
     _fields_ = [("kind", C.c_int32), ("dim", C.c_int32), ("n_data", C.c_int64), ("a", C.c_void_p),
                 ("b", C.c_void_p), ("c", C.c_void_p), ("s0", C.c_double), ("s1", C.c_double),
                 ("x_bf16", C.c_void_p), ("xt_bf16", C.c_void_p), ("x_f16", C.c_void_p), ("x_f16_shift", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("u_lin", C.c_void_p)]
 
 
 class Metric(C.Structure):

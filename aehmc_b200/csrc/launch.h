@@ -82,7 +82,7 @@ int tc_logistic_fused(cudaStream_t st, const void* beta_pieces, int piece_rows, 
                       const float* y, float* gpart, double* upart, int* per_cta, int* planes);
 int logistic_fused_planes(int M, int N);
 int tc_logistic_fused16(cudaStream_t st, const void* beta_pieces, const void* X16, int shift, int M, int N, int dim,
-                        const float* y1024, float* gpart, double* upart, int* per_cta);
+                        const float* y, float* gpart, double* upart, int* per_cta);
 
 // engine_kernels.cu
 int nuts_run_impl(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,

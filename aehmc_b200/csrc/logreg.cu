@@ -200,7 +200,7 @@ static LogregFusedPlan plan_logreg_fused(const b2h_model* m, i64 C) {
     return p;
 }
 
-static bool logistic_use_fused16(const b2h_model* m) { return (int)m->s1 == 4 && m->dim <= 128 && m->x_f16; }
+static bool logistic_use_fused16(const b2h_model* m) { return (int)m->s1 == 4 && m->dim <= 128 && m->x_f16 && m->u_lin; }
 static bool logistic_use_fused(const b2h_model* m) {
     return ((int)m->s1 == 2 || (int)m->s1 == 4) && m->dim <= 128;
 }
@@ -210,7 +210,8 @@ static bool logistic_use_fused(const b2h_model* m) {
 template <typename T>
 __global__ void __launch_bounds__(128)
 logistic_fused_finish_kernel(const float* gpart, i64 plane_stride, const double* upart, const T* q, T* g, T* U,
-                             T inv_prior_var, i64 C, int d, int tiles_n, int per_cta, double g_scale) {
+                             T inv_prior_var, i64 C, int d, int tiles_n, int per_cta, double g_scale,
+                             const double* u_lin) {
     const i64 c = (i64)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (c >= C) return;
     const int lane = threadIdx.x & 31;
@@ -218,16 +219,19 @@ logistic_fused_finish_kernel(const float* gpart, i64 plane_stride, const double*
     const int b_first = (int)((mt * tiles_n) / per_cta);
     const int b_last = (int)(((mt + 1) * tiles_n - 1) / per_cta);
     T acc = 0;
+    double lin = 0.0;
     for (int j = lane; j < d; j += 32) {
         double s = 0.0;
         for (int b = 0; b <= b_last - b_first; ++b) s += (double)gpart[(i64)b * plane_stride + c * d + j];
         const T bj = q[c * d + j];
         g[c * d + j] = (T)(s * g_scale) + inv_prior_var * bj;
         acc += bj * bj;
+        if (u_lin) lin += (double)bj * u_lin[j];
     }
     const double nb = Group<32>::sum1((double)acc, nullptr);
+    if (u_lin) lin = Group<32>::sum1(lin, nullptr);
     if (lane == 0) {
-        double u = 0.0;
+        double u = lin;
         for (int t = b_first * 4; t < (b_last + 1) * 4; ++t) u += upart[(i64)t * C + c];
         U[c] = (T)u + (T)0.5 * inv_prior_var * (T)nb;
     }
@@ -257,7 +261,7 @@ static int logistic_tc_fused(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U,
     int rc = tc_logistic_fused(st, bp, (int)C, m->x_bf16, (int)C, (int)N, d, yf, gpart, upart, &per_cta, &planes);
     if (rc < 0) return rc;
     logistic_fused_finish_kernel<T><<<(int)((C + 3) / 4), 128, 0, st>>>(gpart, ng, upart, q, g, U, (T)m->s0, C, d,
-                                                                         (int)((N + 63) / 64), per_cta, 1.0);
+                                                                         (int)((N + 63) / 64), per_cta, 1.0, nullptr);
     B2H_LAUNCH_CHECK();
     return 0;
 }
@@ -273,12 +277,6 @@ __global__ void beta_split16_kernel(const T* q, __half* bp, i64 n) {
     const __half a = __double2half(x);
     bp[i] = a;
     bp[n + i] = __double2half(x - (double)__half2float(a));
-}
-
-template <typename T>
-__global__ void to_float_scaled_kernel(const T* x, float* y, i64 n, float scale) {
-    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) y[i] = (float)x[i] * scale;
 }
 
 template <typename T>
@@ -299,13 +297,13 @@ static int logistic_tc_fused16(b2h_ctx* ctx, const b2h_model* m, const T* q, T* 
     double* upart = (double*)(base + p.off_upart);
     const i64 ng = C * d;
     beta_split16_kernel<T><<<(int)((ng + 255) / 256), 256, 0, st>>>(q, bp, ng);
-    to_float_scaled_kernel<T><<<(int)((N + 255) / 256), 256, 0, st>>>((const T*)m->b, yf, N, 1024.f);
+    to_float_kernel<T><<<(int)((N + 255) / 256), 256, 0, st>>>((const T*)m->b, yf, N);
     int per_cta = 0;
     int rc = tc_logistic_fused16(st, bp, m->x_f16, m->x_f16_shift, (int)C, (int)N, d, yf, gpart, upart, &per_cta);
     if (rc < 0) return rc;
     logistic_fused_finish_kernel<T><<<(int)((C + 3) / 4), 128, 0, st>>>(gpart, ng, upart, q, g, U, (T)m->s0, C, d,
                                                                          (int)((N + 63) / 64), per_cta,
-                                                                         ldexp(1.0, -(10 + m->x_f16_shift)));
+                                                                         ldexp(1.0, -m->x_f16_shift), m->u_lin);
     B2H_LAUNCH_CHECK();
     return 0;
 }

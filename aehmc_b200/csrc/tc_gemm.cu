@@ -893,7 +893,8 @@ tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __g
 // their A operand from tensor memory: the beta pieces of the CTA's chain tile are stored to TMEM once per segment by
 // the epilogue warps, so shared memory carries nothing but the X ring.
 // Scales (powers of two, exact): beta pieces hold beta * 2^8, X holds X * 2^shift, so S_acc = s * 2^(8 + shift);
-// the residual pieces hold r * 2^10 (keeps the low piece out of the fp16 subnormals), so G_acc = g * 2^(10 + shift).
+// the residual pieces hold r itself (the low piece may be an fp16 subnormal: absolute error <= 2^-25, what an fp32
+// residual has anyway), so G_acc = g * 2^shift.
 // TMEM columns: [0,128) S double buffer, [128,256) G, [256,384) residual double buffer (2 x 2 pieces x 32),
 // [384,512) beta (2 pieces x 64).
 // ---------------------------------------------------------------------------------------------------------
@@ -904,9 +905,9 @@ constexpr uint32_t IDESC_S16 = (1u << 4) | ((uint32_t)(FN >> 3) << 17) | ((uint3
 constexpr uint32_t IDESC_G16 = (1u << 4) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 struct Fused16Args {
-    const float* y1024;      // [N] responses * 1024
+    const float* y;          // [N] responses
     const __half* beta;      // [2][M x dim] fp16 pieces of beta * 2^8
-    float* gpart;            // [planes][M x dim] fp32 partial gradients (scaled by 2^(10 + shift))
+    float* gpart;            // [planes][M x dim] fp32 partial gradients (scaled by 2^shift)
     long long plane_stride;  // M * dim
     double* upart;           // [gridDim.x][4][M] potential partial sums
     float s_scale;           // 2^-(8 + shift)
@@ -1051,7 +1052,7 @@ tc_logistic_fused16_kernel(const __grid_constant__ CUtensorMap map_x, Fused16Arg
         const int trow = q * 32 + lane;                        // row of the 128-chain tile = TMEM lane
         const int c0 = part * 16;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const float ex_scale = -1.4426950408889634f * fa.s_scale;
+        const float ex_scale = -1.4426950408889634f * fa.s_scale, half_scale = 0.5f * fa.s_scale;
         float urun = 0.f;
         int segs_done = 0;
         int m_tile = t_begin / tiles_n, n_tile = t_begin - m_tile * tiles_n;
@@ -1084,16 +1085,16 @@ tc_logistic_fused16_kernel(const __grid_constant__ CUtensorMap map_x, Fused16Arg
             const int n0 = n_tile * FN;
             const int buf = L & 1;
             const bool full = n0 + FN <= fa.N;
-            float yv[16];                                      // 1024 y
+            float yv[16];
             if (full) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
-                    const float4 y4 = __ldg(reinterpret_cast<const float4*>(fa.y1024 + n0 + c0 + j));
+                    const float4 y4 = __ldg(reinterpret_cast<const float4*>(fa.y + n0 + c0 + j));
                     yv[j] = y4.x; yv[j + 1] = y4.y; yv[j + 2] = y4.z; yv[j + 3] = y4.w;
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) yv[j] = (n0 + c0 + j < fa.N) ? __ldg(fa.y1024 + n0 + c0 + j) : 512.f;
+                for (int j = 0; j < 16; ++j) yv[j] = (n0 + c0 + j < fa.N) ? __ldg(fa.y + n0 + c0 + j) : 0.5f;
             }
             mbar_wait_backoff(&s_full[buf], (L >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1108,30 +1109,31 @@ tc_logistic_fused16_kernel(const __grid_constant__ CUtensorMap map_x, Fused16Arg
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[buf])) : "memory");
 
-            // batched special functions (see the bf16 kernel); sv below is s * 2^(8 + shift)
+            // batched special functions (see the bf16 kernel); sv below is s * 2^(8 + shift).  softplus(s) - y s =
+            // 1/2 |s| + log(1 + exp(-|s|)) + (1/2 - y) s: the last term is linear in beta and is added by the finish
+            // kernel as beta . X^T (1/2 - y), so the potential costs one add per element here.
             uint32_t p0[8], p1[8];
             float rr[16], den[16];
-            float ua0 = 0.f, ua1 = 0.f, ub0 = 0.f, ub1 = 0.f;
+            float ua0 = 0.f, ua1 = 0.f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const float sv = __uint_as_float(r[j]);
                 const float ex = ex2_approx(fabsf(sv) * ex_scale);
                 den[j] = 1.f + ex;
                 rr[j] = sv >= 0.f ? 1.f : ex;                            // numerator of sigmoid(s)
-                if (j & 1) { ua1 += fmaxf(sv, 0.f); ub1 = fmaf(yv[j], sv, ub1); }
-                else { ua0 += fmaxf(sv, 0.f); ub0 = fmaf(yv[j], sv, ub0); }
+                if (j & 1) ua1 += fabsf(sv);
+                else ua0 += fabsf(sv);
             }
             float pp[8];
 #pragma unroll
             for (int h = 0; h < 8; ++h) {
                 pp[h] = den[2 * h] * den[2 * h + 1];
-                const float rp = rcp_approx(pp[h]) * 1024.f;
-                rr[2 * h] = fmaf(rr[2 * h], den[2 * h + 1] * rp, -yv[2 * h]);              // 1024 (sigmoid(s) - y)
+                const float rp = rcp_approx(pp[h]);
+                rr[2 * h] = fmaf(rr[2 * h], den[2 * h + 1] * rp, -yv[2 * h]);              // sigmoid(s) - y
                 rr[2 * h + 1] = fmaf(rr[2 * h + 1], den[2 * h] * rp, -yv[2 * h + 1]);
             }
             const float prod = ((pp[0] * pp[1]) * (pp[2] * pp[3])) * ((pp[4] * pp[5]) * (pp[6] * pp[7]));
-            float uacc = fmaf(lg2_approx(prod), 0.6931471805599453f,
-                              fa.s_scale * fmaf(ub0 + ub1, -0.0009765625f, ua0 + ua1));
+            float uacc = fmaf(lg2_approx(prod), 0.6931471805599453f, half_scale * (ua0 + ua1));
             if (!full) uacc -= 0.6931471805599453f * (float)min(16, max(0, n0 + c0 + 16 - fa.N));
             urun += uacc;
 #pragma unroll
@@ -1369,9 +1371,10 @@ int tc_logistic_fused(cudaStream_t st, const void* beta_pieces, int piece_rows, 
 }
 
 // fp16 x 2 fused gradient: see tc_logistic_fused16_kernel.  beta_pieces: [2][M x dim] fp16 (beta * 2^8),
-// X16: [N x dim] fp16 = X * 2^shift, y1024: responses * 1024.  gpart comes out scaled by 2^(10 + shift).
+// X16: [N x dim] fp16 = X * 2^shift.  gpart comes out scaled by 2^shift; the potential partials lack the part
+// that is linear in beta (see the kernel).
 int tc_logistic_fused16(cudaStream_t st, const void* beta_pieces, const void* X16, int shift, int M, int N, int dim,
-                        const float* y1024, float* gpart, double* upart, int* per_cta) {
+                        const float* y, float* gpart, double* upart, int* per_cta) {
     using namespace tc;
     if (dim > 2 * BK || dim % 8) { set_error("tc_logistic_fused16: dim must be a multiple of 8, at most 128"); return B2H_ERR_ARG; }
     CUtensorMap mx;
@@ -1385,7 +1388,7 @@ int tc_logistic_fused16(cudaStream_t st, const void* beta_pieces, const void* X1
         if (sm_count <= 0) sm_count = 148;
     }
     Fused16Args fa;
-    fa.y1024 = y1024; fa.beta = (const __half*)beta_pieces; fa.gpart = gpart; fa.plane_stride = (long long)M * dim;
+    fa.y = y; fa.beta = (const __half*)beta_pieces; fa.gpart = gpart; fa.plane_stride = (long long)M * dim;
     fa.upart = upart; fa.s_scale = ldexpf(1.f, -(8 + shift));
     fa.M = M; fa.N = N; fa.dim = dim;
     fa.tiles_m = (M + BM - 1) / BM;

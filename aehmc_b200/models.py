@@ -134,7 +134,7 @@ class LogisticRegression(Model):
         self.n_data, self.dim = int(self.X.shape[0]), int(self.X.shape[1])
         self.tensor_core = bool(tensor_core)
         self.tc_flag = 3.0 if tensor_core == "two_kernel" else (2.0 if self.tensor_core else 0.0)
-        self.X_bf16 = self.Xt_bf16 = self.X_f16 = None
+        self.X_bf16 = self.Xt_bf16 = self.X_f16 = self.u_lin = None
         self.x_f16_shift = 0
         if self.tensor_core:
             xb = self.X.to(torch.bfloat16)
@@ -153,9 +153,11 @@ class LogisticRegression(Model):
                     xh = xs.to(torch.float16)
                     if bool(torch.isfinite(xh).all()) and torch.equal(xh.double(), xs):
                         self.X_f16, self.x_f16_shift, self.tc_flag = xh.contiguous(), shift, 4.0
+                        # sum_n (1/2 - y_n) x_n: the potential's part that is linear in beta
+                        self.u_lin = (self.X.double().t() @ (0.5 - self.y.double())).contiguous()
 
     def struct(self):
         p = lambda t: None if t is None else t.data_ptr()
         return _lib.Model(self.kind, self.dim, self.n_data, self.X.data_ptr(), self.y.data_ptr(),
                           self.Xt.data_ptr(), self.inv_prior_var, self.tc_flag,
-                          p(self.X_bf16), p(self.Xt_bf16), p(self.X_f16), self.x_f16_shift, 0)
+                          p(self.X_bf16), p(self.Xt_bf16), p(self.X_f16), self.x_f16_shift, 0, p(self.u_lin))

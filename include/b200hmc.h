@@ -66,6 +66,8 @@ typedef struct {
     const void* x_f16;   /* device, logistic fp16 path: X * 2^x_f16_shift [n_data x d] as fp16 (exact) */
     int32_t x_f16_shift;
     int32_t reserved;
+    const double* u_lin; /* device, logistic fp16 path: X^T (1/2 - y) [d] in float64: the part of the potential that is
+                            linear in beta, sum_n (1/2 - y_n) x_n . beta, is added outside the contraction kernel */
 } b2h_model;
 
 /* ---- gaussian metric (reference metrics.py:10-106) ---- */
