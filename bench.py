@@ -305,16 +305,20 @@ def logistic_roofline(model, Cn, d, n, ticks, step_ms, peaks, dev, dtype):
     flops = 4.0 * n * d * Cn
     achieved = flops / (ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", 1389.0))
+    pieces = 2 if getattr(model, "tc_flag", 0.0) == 4.0 else 3
     return {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        # dram bytes of one launch at 4096 chains, profiles/r01_ncu_tc_fused_summary.md (ncu --set full): X once + y
-        "traffic": 29.2e6 if (Cn, d, n) == (4096, 128, 100000) else None,
-        "kernel": "tc_logistic_fused_kernel (tcgen05.mma kind::f16, TMA, TMEM): S = B X^T, residual epilogue into "
-                  "TMEM, G += R X; 1 launch per tick",
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 4096 chains (ncu --set full,
+        # profiles/r01_ncu_tc_fused_summary.md): X once + the responses; everything else stays on chip
+        "traffic": 28.12e6 if (Cn, d, n) == (4096, 128, 100000) else None,
+        "kernel": ("tc_logistic_fused16_kernel" if pieces == 2 else "tc_logistic_fused_kernel") +
+                  " (tcgen05.mma kind::f16 with both A operands in TMEM, TMA, one launch per tick): S = B X^T, "
+                  "residual epilogue back into TMEM, G += R X",
         "flops_per_launch": flops, "avg_launch_ms": ms,
-        "what": "ALGORITHMIC flops (4 N D per chain-gradient).  beta and the residual are carried as three bf16 "
-                "pieces for fp32-class accuracy, so the tensor pipe issues 3x these flops",
-        "issued_tflops": 3.0 * achieved, "issued_frac": 3.0 * achieved / peak,
+        "what": f"ALGORITHMIC flops (4 N D per chain-gradient).  beta and the residual are carried as {pieces} "
+                f"{'fp16' if pieces == 2 else 'bf16'} pieces for fp32-class accuracy, so the tensor pipe issues "
+                f"{pieces}x these flops; timed through b2h_potential_and_grad (includes 3 small side kernels)",
+        "issued_tflops": pieces * achieved, "issued_frac": pieces * achieved / peak,
         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
         "launches_per_tick": 1, "share_of_step": ticks * ms / step_ms}
 
