@@ -9,6 +9,6 @@ happens in libb200hmc.so (hand-written sm_100a CUDA) through its C-ABI; there is
 from . import _lib  # noqa: F401
 from .random import InjectedDraws, RandomStream  # noqa: F401
 from . import (algorithms, diagnostics, hmc, integrators, mass_matrix, metrics, models, nuts, sampling, step_size,  # noqa: F401
-               termination, trajectory, window_adaptation, proposals)
+               termination, trajectory, utils, window_adaptation, proposals)
 
 __version__ = "0.1.0"
