@@ -109,6 +109,23 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// packed f32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2, one issue slot for two lanes of work)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -1052,7 +1069,7 @@ tc_logistic_fused16_kernel(const __grid_constant__ CUtensorMap map_x, Fused16Arg
         const int trow = q * 32 + lane;                        // row of the 128-chain tile = TMEM lane
         const int c0 = part * 16;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const float ex_scale = -1.4426950408889634f * fa.s_scale, half_scale = 0.5f * fa.s_scale;
+        const float l2_scale = 1.4426950408889634f * fa.s_scale;     // accumulator -> s log2(e)
         float urun = 0.f;
         int segs_done = 0;
         int m_tile = t_begin / tiles_n, n_tile = t_begin - m_tile * tiles_n;
@@ -1112,35 +1129,42 @@ tc_logistic_fused16_kernel(const __grid_constant__ CUtensorMap map_x, Fused16Arg
             // batched special functions (see the bf16 kernel); sv below is s * 2^(8 + shift).  softplus(s) - y s =
             // 1/2 |s| + log(1 + exp(-|s|)) + (1/2 - y) s: the last term is linear in beta and is added by the finish
             // kernel as beta . X^T (1/2 - y), so the potential costs one add per element here.
+            // Packed f32x2 arithmetic (FMUL2 / FADD2 / FFMA2 on sm_100): the epilogue is issue-bound, one instruction
+            // per PAIR of data rows wherever the operation has no operand modifier.
             uint32_t p0[8], p1[8];
-            float rr[16], den[16];
-            float ua0 = 0.f, ua1 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float sv = __uint_as_float(r[j]);
-                const float ex = ex2_approx(fabsf(sv) * ex_scale);
-                den[j] = 1.f + ex;
-                rr[j] = sv >= 0.f ? 1.f : ex;                            // numerator of sigmoid(s)
-                if (j & 1) ua1 += fabsf(sv);
-                else ua0 += fabsf(sv);
-            }
+            float2 pacc = make_float2(0.f, 0.f);
+            float2 den2[8], num2[8];
             float pp[8];
+            const float2 lscale = make_float2(l2_scale, l2_scale), one2 = make_float2(1.f, 1.f);
 #pragma unroll
             for (int h = 0; h < 8; ++h) {
-                pp[h] = den[2 * h] * den[2 * h + 1];
+                const float2 sv2 = make_float2(__uint_as_float(r[2 * h]), __uint_as_float(r[2 * h + 1]));
+                const float2 t2 = fmul2(sv2, lscale);                    // s log2(e)
+                const float2 e2 = make_float2(ex2_approx(-fabsf(t2.x)), ex2_approx(-fabsf(t2.y)));
+                den2[h] = fadd2(e2, one2);
+                num2[h] = make_float2(sv2.x >= 0.f ? 1.f : e2.x, sv2.y >= 0.f ? 1.f : e2.y);   // numerator of sigmoid(s)
+                pacc.x += fabsf(t2.x);
+                pacc.y += fabsf(t2.y);
+                pp[h] = den2[h].x * den2[h].y;
+            }
+            float2 rr2[8];
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
                 const float rp = rcp_approx(pp[h]);
-                rr[2 * h] = fmaf(rr[2 * h], den[2 * h + 1] * rp, -yv[2 * h]);              // sigmoid(s) - y
-                rr[2 * h + 1] = fmaf(rr[2 * h + 1], den[2 * h] * rp, -yv[2 * h + 1]);
+                const float2 inv2 = fmul2(make_float2(den2[h].y, den2[h].x), make_float2(rp, rp));   // 1/a = b / (a b)
+                rr2[h] = ffma2(num2[h], inv2, make_float2(-yv[2 * h], -yv[2 * h + 1]));               // sigmoid(s) - y
             }
             const float prod = ((pp[0] * pp[1]) * (pp[2] * pp[3])) * ((pp[4] * pp[5]) * (pp[6] * pp[7]));
-            float uacc = fmaf(lg2_approx(prod), 0.6931471805599453f, half_scale * (ua0 + ua1));
+            // sum of 1/2 |s| + log(1 + exp(-|s|)):  |s| = |t| ln 2
+            float uacc = 0.6931471805599453f * fmaf(0.5f, pacc.x + pacc.y, lg2_approx(prod));
             if (!full) uacc -= 0.6931471805599453f * (float)min(16, max(0, n0 + c0 + 16 - fa.N));
             urun += uacc;
 #pragma unroll
             for (int h = 0; h < 8; ++h) {
-                const __half2 hi = __floats2half2_rn(rr[2 * h], rr[2 * h + 1]);
+                const __half2 hi = __floats2half2_rn(rr2[h].x, rr2[h].y);
                 const float2 hf = __half22float2(hi);
-                const __half2 lo = __floats2half2_rn(rr[2 * h] - hf.x, rr[2 * h + 1] - hf.y);
+                const float2 lo2 = fadd2(rr2[h], make_float2(-hf.x, -hf.y));
+                const __half2 lo = __floats2half2_rn(lo2.x, lo2.y);
                 p0[h] = *reinterpret_cast<const uint32_t*>(&hi);
                 p1[h] = *reinterpret_cast<const uint32_t*>(&lo);
             }
