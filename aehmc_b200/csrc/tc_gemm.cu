@@ -931,6 +931,11 @@ struct Fused16Args {
     int M, N, dim, tiles_m, tiles_n, per_cta;
 };
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
@@ -1070,6 +1075,43 @@ tc_logistic_fused16_kernel(const __grid_constant__ CUtensorMap map_x, Fused16Arg
         const int c0 = part * 16;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const float l2_scale = 1.4426950408889634f * fa.s_scale;     // accumulator -> s log2(e)
+        uint32_t ra[8], rb8[8];
+        // 8 accumulator columns (s * 2^(8 + shift)) -> 4 + 4 packed fp16 residual words; returns the potential terms.
+        // Packed f32x2 arithmetic (FMUL2 / FADD2 / FFMA2 on sm_100) wherever the operation has no operand modifier;
+        // special functions batched: one ex2 per element, one rcp per PAIR (1/a = b / (a b)), one lg2 per 8 elements
+        // (sum of logs = log of the product; every factor is in (1, 2]).
+        auto half_item = [&](const uint32_t* r, const float* y, uint32_t* q0, uint32_t* q1) -> float {
+            float2 pacc = make_float2(0.f, 0.f);
+            float2 den2[4], num2[4];
+            float pp[4];
+            const float2 lscale = make_float2(l2_scale, l2_scale), one2 = make_float2(1.f, 1.f);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const float2 sv2 = make_float2(__uint_as_float(r[2 * h]), __uint_as_float(r[2 * h + 1]));
+                const float2 t2 = fmul2(sv2, lscale);                    // s log2(e)
+                const float2 e2 = make_float2(ex2_approx(-fabsf(t2.x)), ex2_approx(-fabsf(t2.y)));
+                den2[h] = fadd2(e2, one2);
+                num2[h] = make_float2(sv2.x >= 0.f ? 1.f : e2.x, sv2.y >= 0.f ? 1.f : e2.y);   // numerator of sigmoid(s)
+                pacc.x += fabsf(t2.x);
+                pacc.y += fabsf(t2.y);
+                pp[h] = den2[h].x * den2[h].y;
+            }
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const float rp = rcp_approx(pp[h]);
+                const float2 inv2 = fmul2(make_float2(den2[h].y, den2[h].x), make_float2(rp, rp));
+                const float2 rr = ffma2(num2[h], inv2, make_float2(-y[2 * h], -y[2 * h + 1]));     // sigmoid(s) - y
+                const __half2 hi = __floats2half2_rn(rr.x, rr.y);
+                const float2 hf = __half22float2(hi);
+                const float2 lo2 = fadd2(rr, make_float2(-hf.x, -hf.y));
+                const __half2 lo = __floats2half2_rn(lo2.x, lo2.y);
+                q0[h] = *reinterpret_cast<const uint32_t*>(&hi);
+                q1[h] = *reinterpret_cast<const uint32_t*>(&lo);
+            }
+            const float prod = (pp[0] * pp[1]) * (pp[2] * pp[3]);
+            // sum of 1/2 |s| + log(1 + exp(-|s|)):  |s| = |t| ln 2
+            return 0.6931471805599453f * fmaf(0.5f, pacc.x + pacc.y, lg2_approx(prod));
+        };
         float urun = 0.f;
         int segs_done = 0;
         int m_tile = t_begin / tiles_n, n_tile = t_begin - m_tile * tiles_n;
@@ -1113,61 +1155,31 @@ tc_logistic_fused16_kernel(const __grid_constant__ CUtensorMap map_x, Fused16Arg
 #pragma unroll
                 for (int j = 0; j < 16; ++j) yv[j] = (n0 + c0 + j < fa.N) ? __ldg(fa.y + n0 + c0 + j) : 0.5f;
             }
-            mbar_wait_backoff(&s_full[buf], (L >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t r[16];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                : "r"(lane_addr + (uint32_t)(buf * FN + c0)));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // The 16 accumulator columns of this thread are read as two halves so that the tensor-memory read of one
+            // half (TMEM reads run at ~64 B/clk per SM: 32 KB per item) overlaps the arithmetic of the other; the
+            // first half of the NEXT item is requested before the second half of this one is processed.
+            uint32_t p0[8], p1[8];
+            float uacc = 0.f;
+            if (first_of_seg) {          // nothing was requested ahead (the beta pieces had to be in place first)
+                mbar_wait_backoff(&s_full[buf], (L >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                tmem_ld8(lane_addr + (uint32_t)(buf * FN + c0), ra);
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");          // ra = columns [c0, c0 + 8) of S(L)
+            tmem_ld8(lane_addr + (uint32_t)(buf * FN + c0 + 8), rb8);
+            uacc += half_item(ra, yv, p0, p1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");          // rb8 = columns [c0 + 8, c0 + 16)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[buf])) : "memory");
-
-            // batched special functions (see the bf16 kernel); sv below is s * 2^(8 + shift).  softplus(s) - y s =
-            // 1/2 |s| + log(1 + exp(-|s|)) + (1/2 - y) s: the last term is linear in beta and is added by the finish
-            // kernel as beta . X^T (1/2 - y), so the potential costs one add per element here.
-            // Packed f32x2 arithmetic (FMUL2 / FADD2 / FFMA2 on sm_100): the epilogue is issue-bound, one instruction
-            // per PAIR of data rows wherever the operation has no operand modifier.
-            uint32_t p0[8], p1[8];
-            float2 pacc = make_float2(0.f, 0.f);
-            float2 den2[8], num2[8];
-            float pp[8];
-            const float2 lscale = make_float2(l2_scale, l2_scale), one2 = make_float2(1.f, 1.f);
-#pragma unroll
-            for (int h = 0; h < 8; ++h) {
-                const float2 sv2 = make_float2(__uint_as_float(r[2 * h]), __uint_as_float(r[2 * h + 1]));
-                const float2 t2 = fmul2(sv2, lscale);                    // s log2(e)
-                const float2 e2 = make_float2(ex2_approx(-fabsf(t2.x)), ex2_approx(-fabsf(t2.y)));
-                den2[h] = fadd2(e2, one2);
-                num2[h] = make_float2(sv2.x >= 0.f ? 1.f : e2.x, sv2.y >= 0.f ? 1.f : e2.y);   // numerator of sigmoid(s)
-                pacc.x += fabsf(t2.x);
-                pacc.y += fabsf(t2.y);
-                pp[h] = den2[h].x * den2[h].y;
+            if (t + 1 < t_end && n_tile + 1 != tiles_n) {      // next item of the same segment
+                const int nbuf = (L + 1) & 1;
+                mbar_wait_backoff(&s_full[nbuf], ((L + 1) >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                tmem_ld8(lane_addr + (uint32_t)(nbuf * FN + c0), ra);
             }
-            float2 rr2[8];
-#pragma unroll
-            for (int h = 0; h < 8; ++h) {
-                const float rp = rcp_approx(pp[h]);
-                const float2 inv2 = fmul2(make_float2(den2[h].y, den2[h].x), make_float2(rp, rp));   // 1/a = b / (a b)
-                rr2[h] = ffma2(num2[h], inv2, make_float2(-yv[2 * h], -yv[2 * h + 1]));               // sigmoid(s) - y
-            }
-            const float prod = ((pp[0] * pp[1]) * (pp[2] * pp[3])) * ((pp[4] * pp[5]) * (pp[6] * pp[7]));
-            // sum of 1/2 |s| + log(1 + exp(-|s|)):  |s| = |t| ln 2
-            float uacc = 0.6931471805599453f * fmaf(0.5f, pacc.x + pacc.y, lg2_approx(prod));
+            uacc += half_item(rb8, yv + 8, p0 + 4, p1 + 4);
             if (!full) uacc -= 0.6931471805599453f * (float)min(16, max(0, n0 + c0 + 16 - fa.N));
             urun += uacc;
-#pragma unroll
-            for (int h = 0; h < 8; ++h) {
-                const __half2 hi = __floats2half2_rn(rr2[h].x, rr2[h].y);
-                const float2 hf = __half22float2(hi);
-                const float2 lo2 = fadd2(rr2[h], make_float2(-hf.x, -hf.y));
-                const __half2 lo = __floats2half2_rn(lo2.x, lo2.y);
-                p0[h] = *reinterpret_cast<const uint32_t*>(&hi);
-                p1[h] = *reinterpret_cast<const uint32_t*>(&lo);
-            }
             {
                 const int rb = L & 1;
                 mbar_wait(&r_empty[rb], ((L >> 1) & 1) ^ 1);
