@@ -84,6 +84,10 @@ int logistic_fused_planes(int M, int N);
 int tc_logistic_fused16(cudaStream_t st, const void* beta_pieces, const void* X16, int shift, int M, int N, int dim,
                         const float* y, float* gpart, double* upart, int* per_cta);
 
+// user_model.cu (NVRTC-compiled user log-density, thread per chain)
+template <typename T>
+int user_potential_and_grad(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U, T* g, i64 C);
+
 // engine_kernels.cu
 int nuts_run_impl(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
                   const b2h_cfg* cfg, const b2h_adapt* adapt, void* q, void* p, void* U, void* g, double* step_size,

@@ -73,6 +73,8 @@ int potential_and_grad_impl(b2h_ctx* ctx, const b2h_model* model, const T* q, T*
             break;
         case B2H_MODEL_LOGISTIC:
             return logistic_potential_and_grad<T>(ctx, model, q, U, g, C, ws, ws_bytes, 0);
+        case B2H_MODEL_USER:
+            return user_potential_and_grad<T>(ctx, model, q, U, g, C);
         default:
             set_error("unknown model kind");
             return B2H_ERR_ARG;

@@ -161,3 +161,44 @@ class LogisticRegression(Model):
         return _lib.Model(self.kind, self.dim, self.n_data, self.X.data_ptr(), self.y.data_ptr(),
                           self.Xt.data_ptr(), self.inv_prior_var, self.tc_flag,
                           p(self.X_bf16), p(self.Xt_bf16), p(self.X_f16), self.x_f16_shift, 0, p(self.u_lin))
+
+
+class UserModel(Model):
+    """A log-density written by the user as CUDA C++ (the reference's arbitrary ``logprob_fn``).
+
+    ``source`` must define::
+
+        template <typename T>
+        __device__ T potential_and_grad(const T* q, T* g, int d, const T* data);   // returns U = -logprob, writes dU/dq
+
+    It is compiled once with NVRTC for sm_100a (``b2h_user_model_create``) and evaluated one thread per chain; the
+    sampler runs it in split mode (one gradient launch per leapfrog tick).  ``data`` is an optional flat array of
+    constants handed to the function in the model's dtype.  ``host_fn(q[d]) -> (U, g)`` is an optional NumPy
+    counterpart (used by the tests as the oracle's model); it is never called by the sampler."""
+    kind = _lib.MODEL_USER
+
+    def __init__(self, source, dim, data=None, dtype=torch.float64, device=None, host_fn=None):
+        super().__init__(dtype, device)
+        self.dim = int(dim)
+        self.source = str(source)
+        self.host_fn = host_fn
+        self.data = None if data is None else backend.as_device(np.asarray(data, dtype=np.float64).ravel(), self.dtype,
+                                                                self.device)
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            handle = C.c_void_p()
+            _lib.check(lib.b2h_user_model_create(self.source.encode(), C.byref(handle)))
+        self._handle = handle
+        self._lib = lib
+
+    def struct(self):
+        return _lib.Model(self.kind, self.dim, 0, self._handle.value, None if self.data is None else self.data.data_ptr(),
+                          None, 0.0, 0.0, None, None)
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h is not None and h.value:
+            try:
+                self._lib.b2h_user_model_destroy(h)
+            except Exception:
+                pass

@@ -50,6 +50,9 @@ enum {
                                     kernel when dim <= 128), 3 = tensor core, two-kernel formulation (any dim),
                                     4 = fused kernel on two fp16 pieces (needs x_f16 = X * 2^x_f16_shift exactly
                                     representable as fp16, dim <= 128)                                          */
+    ,
+    B2H_MODEL_USER = 5           /* user-written device function compiled by b2h_user_model_create:
+                                    a = the b2h_user_model* handle, b = user data [any length], dtype of the call */
 };
 
 typedef struct {
@@ -156,6 +159,15 @@ int b2h_ctx_destroy(b2h_ctx* ctx);
 int b2h_ctx_sync(b2h_ctx* ctx); /* cudaStreamSynchronize */
 
 /* hmc.new_state (reference hmc.py:16-40): U[C] = -logp(q), g[C x d] = dU/dq */
+/* User log-density (the reference's arbitrary Python logprob_fn + aesara.grad, hmc.py:33-34): CUDA C++ source
+ * that defines
+ *     template <typename T> __device__ T potential_and_grad(const T* q, T* g, int d, const T* data);
+ * (returns U(q) = -logprob(q), writes dU/dq into g[0..d)).  Compiled with NVRTC for sm_100a on the current device;
+ * the handle goes into b2h_model.a of a B2H_MODEL_USER model.  The compile log is in b2h_last_error() on failure. */
+typedef struct b2h_user_model b2h_user_model;
+int b2h_user_model_create(const char* cuda_source, b2h_user_model** out);
+int b2h_user_model_destroy(b2h_user_model* model);
+
 int b2h_potential_and_grad(b2h_ctx*, const b2h_model*, int dtype, const void* q, void* U, void* g, int64_t C,
                            void* workspace, int64_t workspace_bytes);
 int64_t b2h_potential_workspace_bytes(const b2h_model*, int dtype, int64_t C);
