@@ -66,6 +66,7 @@ struct OutView {
     void* draws;             // [n_store][C][d] row-major, dtype T
     double* draw_stats;      // [n_store][C][4]
     int n_store;
+    int thin;                // keep every thin-th transition of the call (<= 1: all)
     double* acceptance_probability;
     int32_t* num_doublings;
     uint8_t *is_turning, *is_diverging;
@@ -504,13 +505,15 @@ B2H_DEVINL void end_transition(Chain<T, G>& ch, int num_doublings, bool is_turni
     ch.r.last_nd = num_doublings;
     ch.r.last_flags = (is_turning ? 1 : 0) | (is_diverging ? 2 : 0) | (ch.r.sub_term ? 4 : 0);
     ch.r.last_nleap = ch.r.nleap;
-    if (tl < v.out.n_store) {
+    const int thin = v.out.thin > 1 ? v.out.thin : 1;
+    const int slot = tl / thin;
+    if (slot < v.out.n_store && slot * thin == tl) {
         if (v.out.draws) {
-            T* dr = (T*)v.out.draws + ((i64)tl * v.C + ch.c) * v.d;
+            T* dr = (T*)v.out.draws + ((i64)slot * v.C + ch.c) * v.d;
             for (int j = ch.lane; j < v.d; j += G) dr[j] = v.qp[ch.at(j)];
         }
         if (v.out.draw_stats && ch.lane == 0) {
-            double* ds = v.out.draw_stats + ((i64)tl * v.C + ch.c) * 4;
+            double* ds = v.out.draw_stats + ((i64)slot * v.C + ch.c) * 4;
             ds[0] = ch.r.accept_prob; ds[1] = (double)num_doublings; ds[2] = (double)ch.r.nleap;
             ds[3] = (double)ch.r.last_flags;
         }

@@ -232,7 +232,7 @@ static int run_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* met
         v.adapt.da_step = (i64*)adapt->da_step; v.adapt.da_x = adapt->da_x; v.adapt.da_x_avg = adapt->da_x_avg;
         v.adapt.da_g_avg = adapt->da_g_avg; v.adapt.da_mu = adapt->da_mu; v.adapt.wc_n = (i64*)adapt->wc_n;
     }
-    v.out.draws = draws; v.out.draw_stats = draw_stats; v.out.n_store = n_store;
+    v.out.draws = draws; v.out.draw_stats = draw_stats; v.out.n_store = n_store; v.out.thin = cfg->thin;
     if (diag) {
         v.out.acceptance_probability = diag->acceptance_probability; v.out.num_doublings = diag->num_doublings;
         v.out.is_turning = diag->is_turning; v.out.is_diverging = diag->is_diverging;

@@ -146,7 +146,8 @@ typedef struct {
     int32_t num_integration_steps;/* HMC only (hmc.py:81) */
     int32_t group;                /* threads per chain: 0 = auto, else 1,2,4,8,16,32,128,256 */
     int32_t gradient_path;        /* logistic: 0 auto, 1 FFMA exactness reference, 2 tcgen05 tensor core */
-    int32_t reserved;
+    int32_t thin;                 /* draw storage: keep every thin-th transition of the call (0 or 1: all); slot k of
+                                     draws / draw_stats holds transition k * thin */
 } b2h_cfg;
 
 /* ======================================================================== */

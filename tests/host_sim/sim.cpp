@@ -84,7 +84,7 @@ extern "C" int sim_run(int model_kind, int hmc, int C, int d, int maxd, const do
     v.rng.mode = 1; v.rng.n_injected = n_inj; v.rng.z = z; v.rng.u_dir = u_dir; v.rng.u_biased = u_biased;
     v.rng.u_uniform = u_uniform; v.rng.u_accept = u_accept;
     v.div_thr = div_thr; v.n_transitions = n_transitions; v.hmc_L = hmc_L;
-    v.out.draws = draws; v.out.n_store = n_store;
+    v.out.draws = draws; v.out.n_store = n_store; v.out.thin = 1;
     std::vector<long long> da_step(C, 1), wc_n(C, 0);
     std::vector<double> da_x(C, 0.0), da_xa(C, 0.0), da_g(C, 0.0), da_mu(C, init_step_size), wc_mean(n, 0.0), wc_m2(n, 0.0);
     if (adapt_steps > 0) {
