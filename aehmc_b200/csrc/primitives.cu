@@ -386,6 +386,155 @@ iterative_turning_kernel(ImmView iv, const T* mck, const T* sck, const int64_t* 
 }
 
 // ---------------------------------------------------------------------------
+// 128-bit vectorised variants of the metric / U-turn primitives (warp per chain, lane = one 16-byte chunk, two
+// chunks in flight per array): used when the rows are 16-byte aligned and the metric is scalar or has unit stride.
+// ---------------------------------------------------------------------------
+template <typename T> struct V16;
+template <> struct V16<double> { static constexpr int N = 2; using type = double2; };
+template <> struct V16<float> { static constexpr int N = 4; using type = float4; };
+
+template <typename T>
+B2H_DEVINL void ld16(const T* p, T (&v)[V16<T>::N]) {
+    const typename V16<T>::type w = *reinterpret_cast<const typename V16<T>::type*>(p);
+    const T* e = reinterpret_cast<const T*>(&w);
+#pragma unroll
+    for (int i = 0; i < V16<T>::N; ++i) v[i] = e[i];
+}
+template <typename T>
+B2H_DEVINL void st16(T* p, const T (&v)[V16<T>::N]) {
+    typename V16<T>::type w;
+    T* e = reinterpret_cast<T*>(&w);
+#pragma unroll
+    for (int i = 0; i < V16<T>::N; ++i) e[i] = v[i];
+    *reinterpret_cast<typename V16<T>::type*>(p) = w;
+}
+template <typename T>
+B2H_DEVINL void imm16(const ImmView& iv, i64 c, int j, T (&v)[V16<T>::N]) {
+    if (iv.kind == B2H_IMM_SCALAR) {
+#pragma unroll
+        for (int i = 0; i < V16<T>::N; ++i) v[i] = (T)iv.scalar;
+    } else {
+        ld16<T>((const T*)iv.imm + c * iv.sc + j, v);
+    }
+}
+static bool vec_ok(const ImmView& iv, i64 d, int dtype, std::initializer_list<const void*> ptrs) {
+    const int n = 16 / (int)dtype_size(dtype);
+    if (d % n) return false;
+    if (iv.kind != B2H_IMM_SCALAR && (iv.sj != 1 || ((uintptr_t)iv.imm & 15) || (iv.sc % n))) return false;
+    for (const void* p : ptrs)
+        if (p && ((uintptr_t)p & 15)) return false;
+    return true;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) kinetic_vec_kernel(ImmView iv, const T* p, const T* vel, T* K, i64 C, int d) {
+    constexpr int N = V16<T>::N;
+    const i64 c = PGeo<32>::chain();
+    if (c >= C) return;
+    const int lane = threadIdx.x & 31;
+    T acc = 0;
+#pragma unroll 2
+    for (int j = lane * N; j < d; j += 32 * N) {
+        T pj[N], vj[N];
+        ld16<T>(p + c * d + j, pj);
+        if (vel) ld16<T>(vel + c * d + j, vj);
+        else imm16<T>(iv, c, j, vj);
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc += (vel ? vj[i] : vj[i] * pj[i]) * pj[i];
+    }
+    double s = Group<32>::sum1((double)acc, nullptr);
+    if (lane == 0) K[c] = (T)0.5 * (T)s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) turning_vec_kernel(ImmView iv, const T* pl, const T* pr, const T* ps, const T* vl,
+                                                          const T* vr, uint8_t* out, i64 C, int d) {
+    constexpr int N = V16<T>::N;
+    const i64 c = PGeo<32>::chain();
+    if (c >= C) return;
+    const int lane = threadIdx.x & 31;
+    T dl = 0, dr = 0;
+#pragma unroll 2
+    for (int j = lane * N; j < d; j += 32 * N) {
+        const i64 a = c * d + j;
+        T l[N], r[N], sm[N], a0[N], a1[N];
+        ld16<T>(pl + a, l); ld16<T>(pr + a, r); ld16<T>(ps + a, sm);
+        if (vl) { ld16<T>(vl + a, a0); ld16<T>(vr + a, a1); }
+        else imm16<T>(iv, c, j, a0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const T rho = sm[i] - (r[i] + l[i]) / (T)2;
+            const T vleft = vl ? a0[i] : a0[i] * l[i], vright = vl ? a1[i] : a0[i] * r[i];
+            dl += vleft * rho;
+            dr += vright * rho;
+        }
+    }
+    double red[2] = {(double)dl, (double)dr};
+    Group<32>::sum<2>(red, nullptr);
+    if (lane == 0) out[c] = ((T)red[0] <= (T)0 || (T)red[1] <= (T)0) ? 1 : 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+termination_update_vec_kernel(T* mck, T* sck, int64_t* imin, int64_t* imax, const T* msum, const T* mom,
+                              const int64_t* step, i64 C, int d, int maxd) {
+    constexpr int N = V16<T>::N;
+    const i64 c = PGeo<32>::chain();
+    if (c >= C) return;
+    const int lane = threadIdx.x & 31;
+    const int s = (int)step[c];
+    int lo, hi;
+    if (s == 0) { lo = (int)imin[c]; hi = (int)imax[c]; }        // stale indices (Q2)
+    else storage_indices(s, lo, hi);
+    if ((s & 1) == 0 && hi >= 0 && hi < maxd) {
+#pragma unroll 2
+        for (int j = lane * N; j < d; j += 32 * N) {
+            const i64 b = (c * maxd + hi) * d + j;
+            T m[N], ms[N];
+            ld16<T>(mom + c * d + j, m); ld16<T>(msum + c * d + j, ms);
+            st16<T>(mck + b, m); st16<T>(sck + b, ms);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) { imin[c] = lo; imax[c] = hi; }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+iterative_turning_vec_kernel(ImmView iv, const T* mck, const T* sck, const int64_t* imin, const int64_t* imax,
+                             const T* msum, const T* mom, uint8_t* out, i64 C, int d, int maxd) {
+    constexpr int N = V16<T>::N;
+    const i64 c = PGeo<32>::chain();
+    if (c >= C) return;
+    const int lane = threadIdx.x & 31;
+    const int lo = (int)imin[c], hi = (int)imax[c];
+    bool term = false;
+    if (hi >= lo) {
+        for (int i = hi; i >= lo; --i) {
+            T dl = 0, dr = 0;
+#pragma unroll 2
+            for (int j = lane * N; j < d; j += 32 * N) {
+                const i64 a = c * d + j, b = (c * maxd + i) * d + j;
+                T mm[N], pp[N], ss[N], sc[N], im[N];
+                ld16<T>(mck + b, mm); ld16<T>(sck + b, sc); ld16<T>(mom + a, pp); ld16<T>(msum + a, ss);
+                imm16<T>(iv, c, j, im);
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    const T subsum = ss[k] - sc[k] + mm[k];
+                    const T rho = subsum - (pp[k] + mm[k]) / (T)2;
+                    dl += (im[k] * mm[k]) * rho;
+                    dr += (im[k] * pp[k]) * rho;
+                }
+            }
+            double red[2] = {(double)dl, (double)dr};
+            Group<32>::sum<2>(red, nullptr);
+            if ((T)red[0] <= (T)0 || (T)red[1] <= (T)0) { term = true; break; }
+        }
+    }
+    if (lane == 0) out[c] = term ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------
 // adaptation algorithms (algorithms.py:79-115,166-202; mass_matrix.py:81-118)
 // ---------------------------------------------------------------------------
 __global__ void dual_averaging_kernel(const double* p_accept, double target, double gamma, double t0, double kappa,
@@ -612,10 +761,12 @@ int b2h_kinetic_energy(b2h_ctx* ctx, const b2h_metric* metric, int dtype, const 
     const int grid = PGeo<32>::grid(C);
     if (dtype == B2H_F64) {
         if (dense) launch_dense_apply<double>(st, (const double*)p, (const double*)metric->imm, (double*)ws, (int)C, (int)d, (int)d, nullptr, nullptr);
-        kinetic_kernel<double><<<grid, 128, 0, st>>>(iv, (const double*)p, dense ? (const double*)ws : nullptr, (double*)K, C, (int)d);
+        if (vec_ok(iv, d, dtype, {p, dense ? ws : nullptr})) kinetic_vec_kernel<double><<<grid, 128, 0, st>>>(iv, (const double*)p, dense ? (const double*)ws : nullptr, (double*)K, C, (int)d);
+        else kinetic_kernel<double><<<grid, 128, 0, st>>>(iv, (const double*)p, dense ? (const double*)ws : nullptr, (double*)K, C, (int)d);
     } else if (dtype == B2H_F32) {
         if (dense) launch_dense_apply<float>(st, (const float*)p, (const float*)metric->imm, (float*)ws, (int)C, (int)d, (int)d, nullptr, nullptr);
-        kinetic_kernel<float><<<grid, 128, 0, st>>>(iv, (const float*)p, dense ? (const float*)ws : nullptr, (float*)K, C, (int)d);
+        if (vec_ok(iv, d, dtype, {p, dense ? ws : nullptr})) kinetic_vec_kernel<float><<<grid, 128, 0, st>>>(iv, (const float*)p, dense ? (const float*)ws : nullptr, (float*)K, C, (int)d);
+        else kinetic_kernel<float><<<grid, 128, 0, st>>>(iv, (const float*)p, dense ? (const float*)ws : nullptr, (float*)K, C, (int)d);
     } else { set_error("bad dtype"); return B2H_ERR_ARG; }
     B2H_LAUNCH_CHECK();
     return 0;
@@ -637,14 +788,16 @@ int b2h_is_turning(b2h_ctx* ctx, const b2h_metric* metric, int dtype, const void
             launch_dense_apply<double>(st, (const double*)pl, (const double*)metric->imm, vl, (int)C, (int)d, (int)d, nullptr, nullptr);
             launch_dense_apply<double>(st, (const double*)pr, (const double*)metric->imm, vr, (int)C, (int)d, (int)d, nullptr, nullptr);
         }
-        turning_kernel<double><<<grid, 128, 0, st>>>(iv, (const double*)pl, (const double*)pr, (const double*)ps, vl, vr, out, C, (int)d);
+        if (vec_ok(iv, d, dtype, {pl, pr, ps, vl, vr})) turning_vec_kernel<double><<<grid, 128, 0, st>>>(iv, (const double*)pl, (const double*)pr, (const double*)ps, vl, vr, out, C, (int)d);
+        else turning_kernel<double><<<grid, 128, 0, st>>>(iv, (const double*)pl, (const double*)pr, (const double*)ps, vl, vr, out, C, (int)d);
     } else if (dtype == B2H_F32) {
         float* vl = dense ? (float*)ws : nullptr; float* vr = dense ? vl + n : nullptr;
         if (dense) {
             launch_dense_apply<float>(st, (const float*)pl, (const float*)metric->imm, vl, (int)C, (int)d, (int)d, nullptr, nullptr);
             launch_dense_apply<float>(st, (const float*)pr, (const float*)metric->imm, vr, (int)C, (int)d, (int)d, nullptr, nullptr);
         }
-        turning_kernel<float><<<grid, 128, 0, st>>>(iv, (const float*)pl, (const float*)pr, (const float*)ps, vl, vr, out, C, (int)d);
+        if (vec_ok(iv, d, dtype, {pl, pr, ps, vl, vr})) turning_vec_kernel<float><<<grid, 128, 0, st>>>(iv, (const float*)pl, (const float*)pr, (const float*)ps, vl, vr, out, C, (int)d);
+        else turning_kernel<float><<<grid, 128, 0, st>>>(iv, (const float*)pl, (const float*)pr, (const float*)ps, vl, vr, out, C, (int)d);
     } else { set_error("bad dtype"); return B2H_ERR_ARG; }
     B2H_LAUNCH_CHECK();
     return 0;
@@ -671,6 +824,15 @@ int b2h_termination_update(b2h_ctx* ctx, int dtype, void* mck, void* sck, int64_
                            const void* mom, const int64_t* step, int64_t C, int64_t d, int32_t maxd) {
     B2H_CHECK_CTX();
     const int grid = PGeo<32>::grid(C);
+    ImmView none{};
+    none.kind = B2H_IMM_SCALAR;
+    if (vec_ok(none, d, dtype, {mck, sck, msum, mom})) {
+        B2H_TYPED(dtype,
+                  (termination_update_vec_kernel<float><<<grid, 128, 0, ctx->stream>>>((float*)mck, (float*)sck, imin, imax, (const float*)msum, (const float*)mom, step, C, (int)d, maxd)),
+                  (termination_update_vec_kernel<double><<<grid, 128, 0, ctx->stream>>>((double*)mck, (double*)sck, imin, imax, (const double*)msum, (const double*)mom, step, C, (int)d, maxd)));
+        B2H_LAUNCH_CHECK();
+        return 0;
+    }
     B2H_TYPED(dtype,
               (termination_update_kernel<float><<<grid, 128, 0, ctx->stream>>>((float*)mck, (float*)sck, imin, imax, (const float*)msum, (const float*)mom, step, C, (int)d, maxd)),
               (termination_update_kernel<double><<<grid, 128, 0, ctx->stream>>>((double*)mck, (double*)sck, imin, imax, (const double*)msum, (const double*)mom, step, C, (int)d, maxd)));
@@ -685,6 +847,13 @@ int b2h_is_iterative_turning(b2h_ctx* ctx, const b2h_metric* metric, int dtype, 
     if (metric->kind == B2H_IMM_DENSE) { set_error("is_iterative_turning primitive: dense metric not supported (use nuts_run)"); return B2H_ERR_UNSUPPORTED; }
     ImmView iv = imm_view(metric, d);
     const int grid = PGeo<32>::grid(C);
+    if (vec_ok(iv, d, dtype, {mck, sck, msum, mom})) {
+        B2H_TYPED(dtype,
+                  (iterative_turning_vec_kernel<float><<<grid, 128, 0, ctx->stream>>>(iv, (const float*)mck, (const float*)sck, imin, imax, (const float*)msum, (const float*)mom, out, C, (int)d, maxd)),
+                  (iterative_turning_vec_kernel<double><<<grid, 128, 0, ctx->stream>>>(iv, (const double*)mck, (const double*)sck, imin, imax, (const double*)msum, (const double*)mom, out, C, (int)d, maxd)));
+        B2H_LAUNCH_CHECK();
+        return 0;
+    }
     B2H_TYPED(dtype,
               (iterative_turning_kernel<float><<<grid, 128, 0, ctx->stream>>>(iv, (const float*)mck, (const float*)sck, imin, imax, (const float*)msum, (const float*)mom, out, C, (int)d, maxd)),
               (iterative_turning_kernel<double><<<grid, 128, 0, ctx->stream>>>(iv, (const double*)mck, (const double*)sck, imin, imax, (const double*)msum, (const double*)mom, out, C, (int)d, maxd)));

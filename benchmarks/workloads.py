@@ -90,6 +90,58 @@ def leapfrog(small):
     return out
 
 
+def uturn(small):
+    """Stand-alone metric / U-turn primitives (b2h_kinetic_energy, b2h_is_turning, b2h_termination_update,
+    b2h_is_iterative_turning): achieved GB/s by their algorithmic bytes (streaming formulation)."""
+    out = []
+    lib = _lib.load()
+    for dt, s in ((torch.float64, 8), (torch.float32, 4)):
+        Cn, d, maxd = (65536, 128, 10) if small else (262144, 128, 10)
+        code = backend.code(dt)
+        imm = torch.rand(d, dtype=torch.float64).add(0.5).numpy()
+        metric = ab.metrics.GaussianMetric(imm, dt, torch.device("cuda"))
+        mt = metric.struct()
+        ctx = backend.context(torch.device("cuda"))
+        g = torch.Generator(device="cuda").manual_seed(1)
+        rnd = lambda *shape: torch.randn(shape, dtype=dt, device="cuda", generator=g)
+        p, pl, pr, ps = rnd(Cn, d), rnd(Cn, d), rnd(Cn, d), rnd(Cn, d)
+        mck, sck = rnd(Cn, maxd, d), rnd(Cn, maxd, d)
+        K = torch.empty(Cn, dtype=dt, device="cuda")
+        flag = torch.empty(Cn, dtype=torch.uint8, device="cuda")
+        imin = torch.zeros(Cn, dtype=torch.int64, device="cuda")
+        imax = torch.zeros(Cn, dtype=torch.int64, device="cuda")
+        step = torch.full((Cn,), 6, dtype=torch.int64, device="cuda")            # even step: one checkpoint row written
+        n64 = C.c_int64
+        calls = {
+            "kinetic_energy": (lambda: lib.b2h_kinetic_energy(ctx, C.byref(mt), code, backend.ptr(p), backend.ptr(K), n64(Cn),
+                                                              n64(d), None, n64(0)), 1 * d * s),
+            "is_turning": (lambda: lib.b2h_is_turning(ctx, C.byref(mt), code, backend.ptr(pl), backend.ptr(pr), backend.ptr(ps),
+                                                      backend.ptr(flag), n64(Cn), n64(d), None, n64(0)), 3 * d * s),
+            "termination_update (even step)": (lambda: lib.b2h_termination_update(
+                ctx, code, backend.ptr(mck), backend.ptr(sck), backend.ptr(imin), backend.ptr(imax), backend.ptr(ps),
+                backend.ptr(p), backend.ptr(step), n64(Cn), n64(d), C.c_int32(maxd)), 4 * d * s),
+        }
+        for levels in (1, 3):
+            imin.zero_(); imax.fill_(levels - 1)
+            lo, hi = imin.clone(), imax.clone()
+            # make the criterion hold at every level so that all `levels` rows are read: msum far along +p
+            big = (p * 1000.0).contiguous()
+            mck.copy_(p.unsqueeze(1).expand(Cn, maxd, d)); sck.zero_()
+            calls[f"is_iterative_turning ({levels} level{'s' if levels > 1 else ''})"] = (
+                (lambda lo=lo, hi=hi, big=big: lib.b2h_is_iterative_turning(
+                    ctx, C.byref(mt), code, backend.ptr(mck), backend.ptr(sck), backend.ptr(lo), backend.ptr(hi),
+                    backend.ptr(big), backend.ptr(p), backend.ptr(flag), n64(Cn), n64(d), C.c_int32(maxd))),
+                (2 + 2 * levels) * d * s)
+        for name, (fn, bytes_chain) in calls.items():
+            for _ in range(3):
+                _lib.check(fn())
+            _, ms = timed(lambda: _lib.check(fn()), 20)
+            gbs = bytes_chain * Cn / (ms * 1e-3) / 1e9
+            out.append({"workload": f"{name} d={d} {str(dt)[6:]}", "chains": Cn, "ms": ms, "achieved_GBs": gbs,
+                        "hbm_frac": gbs / PEAK_HBM, "algorithmic_bytes_per_chain": bytes_chain})
+    return out
+
+
 def c4(small):
     """config 3: window_adaptation (1000 steps) + 1000 NUTS draws, 10-dim funnel and eight schools, 65536 chains."""
     out = []
@@ -183,5 +235,5 @@ if __name__ == "__main__":
     small = "--small" in sys.argv
     names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["leapfrog", "c1", "wide", "c4", "c3"]
     for n in names:
-        for line in {"c1": c1, "c3": c3, "c4": c4, "leapfrog": leapfrog, "wide": wide}[n](small):
+        for line in {"c1": c1, "c3": c3, "c4": c4, "leapfrog": leapfrog, "wide": wide, "uturn": uturn}[n](small):
             print(json.dumps(line), flush=True)
