@@ -117,11 +117,15 @@ def _cpu_worker(args):
     return n_leap, dt
 
 
-def cpu_transitions(name):
+def cpu_transitions(name, n_samples=1):
+    """NUTS transitions per oracle chain in one CPU sample; shrunk when many samples are requested so that the
+    whole reference arm stays within a few minutes (about 0.3 s per c2 transition, 0.2 s per c3 transition)."""
     kind, _, d, _, n = WORKLOADS[name]
     if kind == "dense":
-        return 30 if d >= 1000 else 60
-    return 20 if n >= 100000 else 60
+        full = 30 if d >= 1000 else 60
+        return max(4, min(full, (8 * full) // max(n_samples, 1)))
+    full = 20 if n >= 100000 else 60
+    return max(3, min(full, (8 * full) // max(n_samples, 1)))
 
 
 def cpu_reference_sample(name, cores, n_transitions):
@@ -142,9 +146,9 @@ def run_reference_arm(args):
         return
     kind, _, d, _, n = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    n_tr = cpu_transitions(args.workload)
-    vals = []
     warm = min(args.warmup, 1)
+    n_tr = cpu_transitions(args.workload, warm + args.steps)
+    vals = []
     for i in range(warm + args.steps):
         v, n_leap, wall = cpu_reference_sample(args.workload, cores, n_tr)
         if i >= warm:
