@@ -442,7 +442,7 @@ def run_gpu_arm(args):
     roofline_elementwise = None
     if kind == "dense":
         roofline, roofline_elementwise = dense_roofline(metric, Cn, d, ticks, step_ms, hbm_peak, dev)
-        kernels_per_tick = 5          # post+pre, gradient apply, potential, imm.g apply + the momentum side launch
+        kernels_per_tick = 6          # post+pre, gradient apply, potential, imm.g apply, momentum rider GEMM + its reduce
     else:
         roofline = logistic_roofline(model, Cn, d, n_data, ticks, step_ms, peaks, dev, dtype)
         kernels_per_tick = 5          # post+pre, beta split, response convert, fused gradient, finish
