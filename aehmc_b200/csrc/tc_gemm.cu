@@ -581,7 +581,7 @@ struct FusedArgs {
     int M, N, dim, piece_rows, tiles_m, tiles_n, per_cta;
 };
 
-template <int KB, int EPI>
+template <int KB>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __grid_constant__ CUtensorMap map_x,
                          FusedArgs fa) {
@@ -767,34 +767,7 @@ tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __g
 
             uint32_t p0[8], p1[8], p2[8];
             float uacc;
-            if constexpr (EPI == 0) {
-                // one ex2, one rcp and one lg2 per element; rounding three-way split
-                float ua[4] = {0.f, 0.f, 0.f, 0.f};
-                float rr[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float sv = __uint_as_float(r[j]);
-                    const float ex = ex2_approx(fabsf(sv) * -1.4426950408889634f);
-                    const float den = 1.f + ex;
-                    const float inv = rcp_approx(den);
-                    const float sp = fmaf(lg2_approx(den), 0.6931471805599453f, fmaxf(sv, 0.f));
-                    ua[j & 3] += fmaf(-yv[j], sv, sp);
-                    rr[j] = (sv >= 0.f ? 1.f : ex) * inv - yv[j];
-                }
-#pragma unroll
-                for (int h = 0; h < 8; ++h) {
-                    const __nv_bfloat162 a = __floats2bfloat162_rn(rr[2 * h], rr[2 * h + 1]);
-                    const float2 af = __bfloat1622float2(a);
-                    const float r1x = rr[2 * h] - af.x, r1y = rr[2 * h + 1] - af.y;
-                    const __nv_bfloat162 b = __floats2bfloat162_rn(r1x, r1y);
-                    const float2 bf = __bfloat1622float2(b);
-                    const __nv_bfloat162 c = __floats2bfloat162_rn(r1x - bf.x, r1y - bf.y);
-                    p0[h] = *reinterpret_cast<const uint32_t*>(&a);
-                    p1[h] = *reinterpret_cast<const uint32_t*>(&b);
-                    p2[h] = *reinterpret_cast<const uint32_t*>(&c);
-                }
-                uacc = (ua[0] + ua[1]) + (ua[2] + ua[3]);
-            } else {
+            {
                 // MUFU is a quarter-rate pipe and this loop is its only user, so the special functions are batched:
                 // one ex2 per element, one rcp per PAIR (1/a = b / (a b)) and one lg2 per 16 elements (sum of logs =
                 // log of the product; every factor is in (1, 2], the product <= 65536); truncating split.
@@ -1389,16 +1362,12 @@ int tc_logistic_fused(cudaStream_t st, const void* beta_pieces, int piece_rows, 
     const long long total = (long long)fa.tiles_m * fa.tiles_n;
     fa.per_cta = (int)((total + sm_count - 1) / sm_count);
     const int grid = (int)((total + fa.per_cta - 1) / fa.per_cta);
-    // epilogue arithmetic variant (development switch, default 1 = batched special functions)
-    static int epi = -1;
-    if (epi < 0) { const char* e = getenv("B2H_FUSED_EPI"); epi = e ? atoi(e) : 1; }
     auto launch = [&](auto kern) -> int {
         B2H_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
         kern<<<grid, THREADS, F_SMEM, st>>>(mb, mx, fa);
         return 0;
     };
-    if (dim > BK) rc = epi ? launch(tc_logistic_fused_kernel<2, 1>) : launch(tc_logistic_fused_kernel<2, 0>);
-    else rc = epi ? launch(tc_logistic_fused_kernel<1, 1>) : launch(tc_logistic_fused_kernel<1, 0>);
+    rc = dim > BK ? launch(tc_logistic_fused_kernel<2>) : launch(tc_logistic_fused_kernel<1>);
     if (rc) return rc;
     B2H_LAUNCH_CHECK();
     *per_cta = fa.per_cta;
