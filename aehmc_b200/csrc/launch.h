@@ -81,7 +81,7 @@ int tc_gemm_blocked_a(cudaStream_t st, const void* R, long long r_piece_stride, 
 int tc_logistic_fused(cudaStream_t st, const void* beta_pieces, int piece_rows, const void* X, int M, int N, int dim,
                       const float* y, float* gpart, double* upart, int* per_cta, int* planes);
 int logistic_fused_planes(int M, int N);
-int tc_logistic_fused16(cudaStream_t st, const void* beta_pieces, const void* X16, int shift, int M, int N, int dim,
+int tc_logistic_fused16(cudaStream_t st, const void* beta_pieces, const void* X16, int acc_exp, int M, int N, int dim,
                         const float* y, float* gpart, double* upart, int* per_cta);
 
 // user_model.cu (NVRTC-compiled user log-density, thread per chain)

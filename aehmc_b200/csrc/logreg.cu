@@ -211,7 +211,7 @@ template <typename T>
 __global__ void __launch_bounds__(128)
 logistic_fused_finish_kernel(const float* gpart, i64 plane_stride, const double* upart, const T* q, T* g, T* U,
                              T inv_prior_var, i64 C, int d, int tiles_n, int per_cta, double g_scale,
-                             const double* u_lin) {
+                             const double* u_lin, double beta_limit) {
     const i64 c = (i64)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (c >= C) return;
     const int lane = threadIdx.x & 31;
@@ -227,6 +227,7 @@ logistic_fused_finish_kernel(const float* gpart, i64 plane_stride, const double*
         g[c * d + j] = (T)(s * g_scale) + inv_prior_var * bj;
         acc += bj * bj;
         if (u_lin) lin += (double)bj * u_lin[j];
+        if (fabs((double)bj) > beta_limit) lin = INFINITY;       // outside the fp16 pieces' range: reject the state
     }
     const double nb = Group<32>::sum1((double)acc, nullptr);
     if (u_lin) lin = Group<32>::sum1(lin, nullptr);
@@ -261,18 +262,19 @@ static int logistic_tc_fused(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U,
     int rc = tc_logistic_fused(st, bp, (int)C, m->x_bf16, (int)C, (int)N, d, yf, gpart, upart, &per_cta, &planes);
     if (rc < 0) return rc;
     logistic_fused_finish_kernel<T><<<(int)((C + 3) / 4), 128, 0, st>>>(gpart, ng, upart, q, g, U, (T)m->s0, C, d,
-                                                                         (int)((N + 63) / 64), per_cta, 1.0, nullptr);
+                                                                         (int)((N + 63) / 64), per_cta, 1.0, nullptr, INFINITY);
     B2H_LAUNCH_CHECK();
     return 0;
 }
 
 
-// beta[C x d] (T) -> two stacked fp16 pieces of beta * 2^8 (22 significant bits; clamped to the fp16 range)
+// beta[C x d] (T) -> two stacked fp16 pieces of beta * scale (22 significant bits; clamped to the fp16 range: the
+// finish kernel turns a chain that left the range into a divergence)
 template <typename T>
-__global__ void beta_split16_kernel(const T* q, __half* bp, i64 n) {
+__global__ void beta_split16_kernel(const T* q, __half* bp, i64 n, double scale) {
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double x = (double)q[i] * 256.0;
+    double x = (double)q[i] * scale;
     x = fmin(fmax(x, -65000.0), 65000.0);
     const __half a = __double2half(x);
     bp[i] = a;
@@ -296,14 +298,18 @@ static int logistic_tc_fused16(b2h_ctx* ctx, const b2h_model* m, const T* q, T* 
     float* gpart = (float*)(base + p.off_gpart);
     double* upart = (double*)(base + p.off_upart);
     const i64 ng = C * d;
-    beta_split16_kernel<T><<<(int)((ng + 255) / 256), 256, 0, st>>>(q, bp, ng);
+    // Scales are powers of two tied together: X16 = X * 2^shift (largest entry just below 2^15), beta pieces hold
+    // beta * 2^(20 - shift), so the accumulator is always s * 2^20 and the representable |beta| grows as X shrinks
+    // (|beta| < 255 for data of unit scale).
+    const int beta_exp = 20 - m->x_f16_shift;
+    beta_split16_kernel<T><<<(int)((ng + 255) / 256), 256, 0, st>>>(q, bp, ng, ldexp(1.0, beta_exp));
     to_float_kernel<T><<<(int)((N + 255) / 256), 256, 0, st>>>((const T*)m->b, yf, N);
     int per_cta = 0;
-    int rc = tc_logistic_fused16(st, bp, m->x_f16, m->x_f16_shift, (int)C, (int)N, d, yf, gpart, upart, &per_cta);
+    int rc = tc_logistic_fused16(st, bp, m->x_f16, 20, (int)C, (int)N, d, yf, gpart, upart, &per_cta);
     if (rc < 0) return rc;
     logistic_fused_finish_kernel<T><<<(int)((C + 3) / 4), 128, 0, st>>>(gpart, ng, upart, q, g, U, (T)m->s0, C, d,
                                                                          (int)((N + 63) / 64), per_cta,
-                                                                         ldexp(1.0, -m->x_f16_shift), m->u_lin);
+                                                                         ldexp(1.0, -m->x_f16_shift), m->u_lin, 65000.0 * ldexp(1.0, -beta_exp));
     B2H_LAUNCH_CHECK();
     return 0;
 }

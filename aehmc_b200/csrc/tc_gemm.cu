@@ -882,7 +882,7 @@ tc_logistic_fused_kernel(const __grid_constant__ CUtensorMap map_beta, const __g
 // X * 2^shift).  Two thirds of the tensor work of the bf16 x 3 kernel, and small enough for BOTH products to take
 // their A operand from tensor memory: the beta pieces of the CTA's chain tile are stored to TMEM once per segment by
 // the epilogue warps, so shared memory carries nothing but the X ring.
-// Scales (powers of two, exact): beta pieces hold beta * 2^8, X holds X * 2^shift, so S_acc = s * 2^(8 + shift);
+// Scales (powers of two, exact): X holds X * 2^shift, the beta pieces hold beta * 2^(20 - shift), so S_acc = s * 2^20;
 // the residual pieces hold r itself (the low piece may be an fp16 subnormal: absolute error <= 2^-25, what an fp32
 // residual has anyway), so G_acc = g * 2^shift.
 // TMEM columns: [0,128) S double buffer, [128,256) G, [256,384) residual double buffer (2 x 2 pieces x 32),
@@ -896,11 +896,11 @@ constexpr uint32_t IDESC_G16 = (1u << 4) | (1u << 16) | ((uint32_t)(BN >> 3) << 
 
 struct Fused16Args {
     const float* y;          // [N] responses
-    const __half* beta;      // [2][M x dim] fp16 pieces of beta * 2^8
+    const __half* beta;      // [2][M x dim] fp16 pieces of beta * 2^(acc_exp - shift)
     float* gpart;            // [planes][M x dim] fp32 partial gradients (scaled by 2^shift)
     long long plane_stride;  // M * dim
     double* upart;           // [gridDim.x][4][M] potential partial sums
-    float s_scale;           // 2^-(8 + shift)
+    float s_scale;           // 2^-acc_exp: accumulator -> s
     int M, N, dim, tiles_m, tiles_n, per_cta;
 };
 
@@ -1049,7 +1049,7 @@ tc_logistic_fused16_kernel(const __grid_constant__ CUtensorMap map_x, Fused16Arg
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const float l2_scale = 1.4426950408889634f * fa.s_scale;     // accumulator -> s log2(e)
         uint32_t ra[8], rb8[8];
-        // 8 accumulator columns (s * 2^(8 + shift)) -> 4 + 4 packed fp16 residual words; returns the potential terms.
+        // 8 accumulator columns (s * 2^20) -> 4 + 4 packed fp16 residual words; returns the potential terms.
         // Packed f32x2 arithmetic (FMUL2 / FADD2 / FFMA2 on sm_100) wherever the operation has no operand modifier;
         // special functions batched: one ex2 per element, one rcp per PAIR (1/a = b / (a b)), one lg2 per 8 elements
         // (sum of logs = log of the product; every factor is in (1, 2]).
@@ -1375,10 +1375,10 @@ int tc_logistic_fused(cudaStream_t st, const void* beta_pieces, int piece_rows, 
     return 0;
 }
 
-// fp16 x 2 fused gradient: see tc_logistic_fused16_kernel.  beta_pieces: [2][M x dim] fp16 (beta * 2^8),
+// fp16 x 2 fused gradient: see tc_logistic_fused16_kernel.  beta_pieces: [2][M x dim] fp16 (beta * 2^(acc_exp - shift)),
 // X16: [N x dim] fp16 = X * 2^shift.  gpart comes out scaled by 2^shift; the potential partials lack the part
 // that is linear in beta (see the kernel).
-int tc_logistic_fused16(cudaStream_t st, const void* beta_pieces, const void* X16, int shift, int M, int N, int dim,
+int tc_logistic_fused16(cudaStream_t st, const void* beta_pieces, const void* X16, int acc_exp, int M, int N, int dim,
                         const float* y, float* gpart, double* upart, int* per_cta) {
     using namespace tc;
     if (dim > 2 * BK || dim % 8) { set_error("tc_logistic_fused16: dim must be a multiple of 8, at most 128"); return B2H_ERR_ARG; }
@@ -1394,7 +1394,7 @@ int tc_logistic_fused16(cudaStream_t st, const void* beta_pieces, const void* X1
     }
     Fused16Args fa;
     fa.y = y; fa.beta = (const __half*)beta_pieces; fa.gpart = gpart; fa.plane_stride = (long long)M * dim;
-    fa.upart = upart; fa.s_scale = ldexpf(1.f, -(8 + shift));
+    fa.upart = upart; fa.s_scale = ldexpf(1.f, -acc_exp);
     fa.M = M; fa.N = N; fa.dim = dim;
     fa.tiles_m = (M + BM - 1) / BM;
     fa.tiles_n = (N + FN - 1) / FN;

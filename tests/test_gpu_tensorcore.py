@@ -101,3 +101,34 @@ def test_nuts_logistic_tensor_core_float32_parity(ab, tc_mode):
     assert same.mean() >= 0.9
     q = info.state.position.double().cpu().numpy()
     np.testing.assert_allclose(q[same], ref["q"][same], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("scale_exp", [-10, 6])
+def test_logistic_fp16_path_follows_the_data_scale(ab, scale_exp):
+    """X * 2^k with beta * 2^-k is the same model: the fp16 pieces' scales are tied to the data scale, so the
+    gradient (which scales by 2^k) keeps its accuracy for small and large features."""
+    rng = np.random.default_rng(3)
+    N, d, Cn = 4096, 128, 64
+    X, y = _logistic_case(rng, N, d)
+    q = 0.3 * rng.standard_normal((Cn, d))
+    k = 2.0 ** scale_exp
+    ref_model = ab.models.LogisticRegression(X * k, y, 1e6, dtype=torch.float64)           # flat prior: pure likelihood
+    tc_model = ab.models.LogisticRegression(X * k, y, 1e6, dtype=torch.float32, tensor_core=True)
+    assert tc_model.tc_flag == 4.0
+    U0, g0 = ref_model.potential_and_grad(q / k)
+    U1, g1 = tc_model.potential_and_grad(q / k)
+    assert (g1.double() - g0).abs().max().item() < 2e-5 * g0.abs().max().item()
+    assert ((U1.double() - U0).abs() / U0.abs()).max().item() < 2e-6
+
+
+def test_logistic_fp16_path_rejects_out_of_range_beta(ab):
+    """|beta| beyond what the fp16 pieces can carry (255 for unit-scale data) must not give a silently wrong gradient:
+    the state gets U = +inf, which the sampler treats as a divergence."""
+    rng = np.random.default_rng(4)
+    X, y = _logistic_case(rng, 1024, 64)
+    model = ab.models.LogisticRegression(X, y, 1.0, dtype=torch.float64, tensor_core=True)
+    q = 0.1 * rng.standard_normal((8, 64))
+    q[3, 5] = 400.0
+    U, g = model.potential_and_grad(q)
+    assert torch.isinf(U[3]) and U[3] > 0
+    assert torch.isfinite(torch.cat([U[:3], U[4:]])).all()
