@@ -132,3 +132,19 @@ def test_logistic_fp16_path_rejects_out_of_range_beta(ab):
     U, g = model.potential_and_grad(q)
     assert torch.isinf(U[3]) and U[3] > 0
     assert torch.isfinite(torch.cat([U[:3], U[4:]])).all()
+
+
+@pytest.mark.parametrize("tc_mode", [True, "bf16x3"])
+@pytest.mark.parametrize("N, d, Cn", [(256, 64, 20000), (192, 128, 40000)])
+def test_logistic_fused_many_chain_tiles_per_cta(ab, N, d, Cn, tc_mode):
+    """Few data tiles, many chain tiles: every CTA walks several (chain tile) segments -- beta reload, G drain and the
+    partial-plane bookkeeping at each boundary (the c5 shape has ~7 segments per CTA)."""
+    rng = np.random.default_rng(N + Cn)
+    X, y = _logistic_case(rng, N, d)
+    q = 0.3 * rng.standard_normal((Cn, d))
+    ref_model = ab.models.LogisticRegression(X, y, 1.0, dtype=torch.float64)
+    tc_model = ab.models.LogisticRegression(X, y, 1.0, dtype=torch.float32, tensor_core=tc_mode)
+    U0, g0 = ref_model.potential_and_grad(q)
+    U1, g1 = tc_model.potential_and_grad(q)
+    assert (g1.double() - g0).abs().max().item() < 2e-5 * g0.abs().max().item()
+    assert ((U1.double() - U0).abs() / U0.abs()).max().item() < 5e-6
