@@ -45,7 +45,7 @@ class AdaptState:
 
 def run(kind, model, metric, srng, state, step_size, *, n_transitions=1, max_num_expansions=10,
         divergence_threshold=1000.0, num_integration_steps=0, adapt=None, store_draws=0, max_ticks=0,
-        resume=False, group=0, workspace_key=None, return_counters=False, thin=1):
+        resume=False, group=0, workspace_key=None, return_counters=False, thin=1, exact_doubling=False):
     """Run ``n_transitions`` HMC/NUTS transitions of every chain (or ``max_ticks`` leapfrog ticks).
     ``store_draws`` slots are filled with every ``thin``-th transition of the call (slot k = transition k * thin).
     Returns (Diagnostics of the last transition, extras dict)."""
@@ -67,7 +67,7 @@ def run(kind, model, metric, srng, state, step_size, *, n_transitions=1, max_num
     p = torch.empty_like(q)
     eps = _per_chain(step_size, Cn, dev).clone()
     cfg = _lib.Cfg(backend.code(dt), int(max_num_expansions), float(divergence_threshold),
-                   int(num_integration_steps), int(group), 0, int(thin))
+                   int(num_integration_steps), int(group), 0, int(thin), 1 if exact_doubling else 0, 0)
     m, mt = model.struct(), metric.struct()
     rng, keep = srng.struct(n_transitions)
     acc = torch.empty(Cn, dtype=torch.float64, device=dev)

@@ -74,7 +74,7 @@ class Subtree(C.Structure):
 class Cfg(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("max_num_expansions", C.c_int32), ("divergence_threshold", C.c_double),
                 ("num_integration_steps", C.c_int32), ("group", C.c_int32), ("gradient_path", C.c_int32),
-                ("thin", C.c_int32)]
+                ("thin", C.c_int32), ("exact_doubling", C.c_int32), ("reserved", C.c_int32)]
 
 
 # every symbol include/b200hmc.h declares (tests check the .so exports all of them)

@@ -109,6 +109,7 @@ struct EngineView {
     int n_transitions;                   // per chain; <=0 : free running
     int hmc_L;
     int sub_max_steps;                   // > 0: stand-alone dynamic_integration: scan length of the one sub-tree
+    int exact_doubling;                  // 1: sub-trees of 2**k leapfrogs instead of the reference's 2**k + 1 (Q1)
     int stop_at_subtree_end;             // stand-alone dynamic_integration: stop instead of running expand_once
     i64* counters;                       // [0] leapfrogs [1] transitions [2] ticks [3] active chain-ticks
 };
@@ -719,7 +720,7 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
     r.total_leap += 1;
     r.U_front = (double)U_new;
 
-    const int sub_limit = v.sub_max_steps > 0 ? v.sub_max_steps : (1 << k);
+    const int sub_limit = v.sub_max_steps > 0 ? v.sub_max_steps : (1 << k) - (v.exact_doubling ? 1 : 0);
     const bool end_sub = div || term || (s == sub_limit);      // Q1: 2**k more steps after step 0
     if (!end_sub) { r.s = s + 1; return false; }
     f.flush(ch);                                                // the edge arrays must be current from here on

@@ -212,6 +212,7 @@ static int run_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* met
     carve<T>(v, (char*)ws, pl, model, C, d, maxd, adapting, model_ws_bytes, &model_ws_off);
     void* model_ws = model_ws_bytes ? (char*)ws + model_ws_off : nullptr;
     v.C = C; v.d = d; v.maxd = maxd;
+    v.exact_doubling = cfg->exact_doubling ? 1 : 0;
     if (pl.G == 1) { v.sc = 1; v.sj = C; v.sck = 1; }
     else { v.sc = d; v.sj = 1; v.sck = (i64)maxd * d; }
     v.imm_kind = metric->kind;
@@ -415,6 +416,7 @@ static int tree_setup(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* me
     if (!ws || (size_t)ws_bytes < need) { set_error("workspace too small: need " + std::to_string(need) + " bytes"); return B2H_ERR_WORKSPACE; }
     carve<T>(v, (char*)ws, pl, model, C, d, maxd, false, 0, nullptr);
     v.C = C; v.d = d; v.maxd = maxd;
+    v.exact_doubling = cfg->exact_doubling ? 1 : 0;
     if (pl.G == 1) { v.sc = 1; v.sj = C; v.sck = 1; }
     else { v.sc = d; v.sj = 1; v.sck = (i64)maxd * d; }
     v.imm_kind = metric->kind;

@@ -23,6 +23,7 @@ def sample(kernel, state, step_size, inverse_mass_matrix, num_samples, *, num_in
               store_draws=n_slots if store_draws else 0, group=group, thin=thin)
     if spec["kind"] == "nuts":
         kw["max_num_expansions"] = spec["max_num_expansions"]
+        kw["exact_doubling"] = spec.get("exact_doubling", False)
     else:
         kw["num_integration_steps"] = int(num_integration_steps)
     info, extras = _engine.run(spec["kind"], spec["model"], inverse_mass_matrix, spec["srng"], state, step_size, **kw)

@@ -110,7 +110,7 @@ def dynamic_integration(srng, integrator, kinetic_energy, update_termination_sta
                            weight.data_ptr(), slpa.data_ptr(), msum.data_ptr(), mck.data_ptr(), sck.data_ptr(),
                            imin.data_ptr(), imax.data_ptr(), E0.data_ptr(), n_steps, int(k), length.data_ptr(),
                            div.data_ptr(), term.data_ptr())
-        cfg = _lib.Cfg(backend.code(dt), maxd, float(divergence_threshold), 0, int(group), 0, 0)
+        cfg = _lib.Cfg(backend.code(dt), maxd, float(divergence_threshold), 0, int(group), 0, 0, 0, 0)
         m, mt = model.struct(), metric.struct()
         rng, keep = srng.struct(1)
         w = _tree_workspace(lib, ws, m, mt, cfg, Cn, dev)
@@ -173,7 +173,7 @@ def multiplicative_expansion(srng, trajectory_integrator, uturn_check_fn, max_nu
         tree = _lib.Tree(_state_struct(prop), energy.data_ptr(), weight.data_ptr(), slpa.data_ptr(),
                          _state_struct(left), _state_struct(right), msum.data_ptr(), mck.data_ptr(), sck.data_ptr(),
                          imin.data_ptr(), imax.data_ptr(), E0.data_ptr())
-        cfg = _lib.Cfg(backend.code(dt), maxd, thr, 0, group, 0, 0)
+        cfg = _lib.Cfg(backend.code(dt), maxd, thr, 0, group, 0, 0, 0, 0)
         m, mt = model.struct(), metric.struct()
         rng, keep = srng.struct(1)
         w = _tree_workspace(lib, ws, m, mt, cfg, Cn, dev)

@@ -57,6 +57,7 @@ def run(kernel, initial_state: IntegratorState, num_steps=1000, *, is_mass_matri
     kw = dict(n_transitions=num_steps, divergence_threshold=spec["divergence_threshold"], adapt=adapt)
     if spec["kind"] == "nuts":
         kw["max_num_expansions"] = spec["max_num_expansions"]
+        kw["exact_doubling"] = spec.get("exact_doubling", False)
     else:
         if num_integration_steps is None:
             raise ValueError("HMC warm-up needs num_integration_steps")

@@ -148,6 +148,10 @@ typedef struct {
     int32_t gradient_path;        /* logistic: 0 auto, 1 FFMA exactness reference, 2 tcgen05 tensor core */
     int32_t thin;                 /* draw storage: keep every thin-th transition of the call (0 or 1: all); slot k of
                                      draws / draw_stats holds transition k * thin */
+    int32_t exact_doubling;       /* 0 (default): the reference's sub-trees of 2**k + 1 leapfrogs (trajectory.py:276,302,307),
+                                     reproduced decision for decision.  1: balanced sub-trees of 2**k leapfrogs, for which
+                                     the iterative U-turn / biased progressive sampling leave the target invariant */
+    int32_t reserved;
 } b2h_cfg;
 
 /* ======================================================================== */

@@ -58,7 +58,7 @@ def hmc_new_kernel(srng, logprob_fn, divergence_threshold=1000):
     return step
 
 
-def nuts_new_kernel(srng, logprob_fn, max_num_expansions=10, divergence_threshold=1000):
+def nuts_new_kernel(srng, logprob_fn, max_num_expansions=10, divergence_threshold=1000, exact_doubling=False):
     """reference nuts.py:17-155.  ``step`` returns (Diagnostics, extras)."""
     potential_fn = logprob_fn.potential_and_grad
 
@@ -76,7 +76,7 @@ def nuts_new_kernel(srng, logprob_fn, max_num_expansions=10, divergence_threshol
             divergence_threshold,
         )
         expand = tree.multiplicative_expansion(
-            srng, trajectory_integrator, uturn_check_fn, max_num_expansions
+            srng, trajectory_integrator, uturn_check_fn, max_num_expansions, exact_doubling
         )
 
         initial_state = state._replace(momentum=momentum_generator(srng))     # :113

@@ -254,9 +254,12 @@ class ExpansionTrace(NamedTuple):
     proposal_position: object
 
 
-def multiplicative_expansion(draws, trajectory_integrator, uturn_check_fn, max_num_expansions):
+def multiplicative_expansion(draws, trajectory_integrator, uturn_check_fn, max_num_expansions, exact_doubling=False):
     """reference trajectory.py:396-714.  Returns the values of the LAST executed
-    expansion (what nuts.py:138-151 extracts) plus a per-expansion trace."""
+    expansion (what nuts.py:138-151 extracts) plus a per-expansion trace.
+    ``exact_doubling`` is NOT reference behaviour: it shortens every sub-tree from the reference's ``2**k + 1``
+    leapfrogs to the balanced ``2**k`` (the checker of the engine option of the same name)."""
+    sub_steps = (lambda step: 2 ** step - 1) if exact_doubling else (lambda step: 2 ** step)
 
     def expand(proposal, left_state, right_state, momentum_sum, termination_state,
                initial_energy, step_size):
@@ -269,7 +272,7 @@ def multiplicative_expansion(draws, trajectory_integrator, uturn_check_fn, max_n
             direction = 1.0 if do_go_right else -1.0
             start_state = right_state if do_go_right else left_state
             sub, _ = trajectory_integrator(
-                start_state, direction, termination_state, 2 ** step, step_size, initial_energy,
+                start_state, direction, termination_state, sub_steps(step), step_size, initial_energy,
                 expansion=step,
             )
             new_proposal, new_state = sub.proposal, sub.state

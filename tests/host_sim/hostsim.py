@@ -25,11 +25,12 @@ def _p(a, t=ctypes.c_double):
 
 
 def run(model_kind, a, b, s0, imm, q, eps, draws, n_transitions, *, hmc_L=0, maxd=10, div_thr=1000.0,
-        n_store=0, schedule=None, target=0.8, init_step_size=1.0, reg_front=False):
+        n_store=0, schedule=None, target=0.8, init_step_size=1.0, reg_front=False, exact_doubling=False):
     """draws: dict of arrays [C, T, ...].  Returns dict of outputs.  reg_front: keep the integration front
     in "registers" (engine.cuh RegFront) instead of the edge arrays."""
     lib = ctypes.CDLL(build())
     lib.sim_set_reg_front(ctypes.c_int(16 if reg_front else 0))
+    lib.sim_set_exact_doubling(ctypes.c_int(1 if exact_doubling else 0))
     q = np.ascontiguousarray(q, dtype=np.float64).copy()
     C, d = q.shape
     imm = np.asarray(imm, dtype=np.float64)

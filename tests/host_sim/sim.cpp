@@ -50,6 +50,8 @@ static void run_chain(EngineView<double>& v, const ModelDev& m, int c, long long
 }
 
 extern "C" void sim_set_reg_front(int on) { g_reg_front = on; }
+static int g_exact_doubling = 0;
+extern "C" void sim_set_exact_doubling(int on) { g_exact_doubling = on; }
 
 extern "C" int sim_run(int model_kind, int hmc, int C, int d, int maxd, const double* a, const double* b, double s0,
                        int imm_kind, const double* imm, double imm_scalar, double* q, double* p, double* U, double* g,
@@ -66,6 +68,7 @@ extern "C" int sim_run(int model_kind, int hmc, int C, int d, int maxd, const do
     auto mk = [&](size_t k) { store.emplace_back(k, 0.0); return store.back().data(); };
     store.reserve(64);
     v.C = C; v.d = d; v.maxd = hmc ? 1 : maxd;
+    v.exact_doubling = g_exact_doubling;
     v.sc = 1; v.sj = C; v.sck = 1;
     v.ql = mk(n); v.pl = mk(n); v.gl = mk(n); v.qr = mk(n); v.pr = mk(n); v.gr = mk(n);
     v.qs = mk(n); v.ps = mk(n); v.gs = mk(n); v.qp = mk(n); v.pp = mk(n); v.gp = mk(n);

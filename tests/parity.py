@@ -22,7 +22,7 @@ def chain_draws(draws, c):
 
 
 def oracle_nuts(model, q0, eps, imm, draws, n_transitions, maxd=10, div_thr=1000.0, schedule_steps=0,
-                target=0.8, init_step_size=1.0, per_chain_imm=False):
+                target=0.8, init_step_size=1.0, per_chain_imm=False, exact_doubling=False):
     """Per-chain oracle run.  imm: 0-d / [d] / [C,d] / [d,d].  Returns dict of stacked outputs."""
     q0 = np.asarray(q0, dtype=np.float64)
     C, d = q0.shape
@@ -34,7 +34,7 @@ def oracle_nuts(model, q0, eps, imm, draws, n_transitions, maxd=10, div_thr=1000
                            "is_diverging", "n_leapfrog", "draws", "eps", "imm", "hist")}
     for c in range(C):
         srng = chain_draws(draws, c)
-        kernel = kernels.nuts_new_kernel(srng, model, maxd, div_thr)
+        kernel = kernels.nuts_new_kernel(srng, model, maxd, div_thr, exact_doubling)
         state = kernels.new_state(q0[c].copy(), model)
         imm_c = imm[c] if per_chain_imm else imm
         pos, hist = [], []

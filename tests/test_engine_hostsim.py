@@ -198,3 +198,58 @@ def test_register_front_matches_oracle(case):
         got = hostsim.run(0, mu, model.inv_var, 0.0, sigma ** 2, q0, 0.4, draws, T, hmc_L=L, n_store=T, reg_front=True)
         for k in ("q", "p", "g", "U", "acceptance_probability"):
             np.testing.assert_allclose(got[k], ref[k], rtol=1e-11, atol=1e-13, err_msg=k)
+
+
+@pytest.mark.parametrize("model_name, eps", [("iid", 0.4), ("iid", 1.7), ("funnel", 0.3)])
+def test_exact_doubling_engine_matches_oracle(model_name, eps):
+    """The non-reference option `exact_doubling` (sub-trees of 2**k leapfrogs): the engine code and the oracle's
+    variant agree decision for decision, and the trajectories really are balanced (2**depth - 1 leapfrogs when
+    nothing stopped a sub-tree early)."""
+    rng = np.random.default_rng(31)
+    C, T = 16, 3
+    if model_name == "iid":
+        d = 5
+        mu, sigma = rng.standard_normal(d), np.exp(0.5 * rng.standard_normal(d))
+        model, args = models.IIDGaussian(mu, sigma), (0, mu, 1.0 / sigma ** 2, 0.0)
+        q0 = mu + sigma * rng.standard_normal((C, d))
+    else:
+        d = 10
+        model, args = models.NealFunnel(d), (2, None, None, 0.0)
+        q0 = rng.standard_normal((C, d))
+    imm = np.ones(d)
+    draws = parity.random_draws(rng, C, T, d)
+    ref = parity.oracle_nuts(model, q0, eps, imm, draws, T, exact_doubling=True)
+    got = hostsim.run(*args, imm, q0, eps, draws, T, n_store=T, exact_doubling=True)
+    parity.assert_nuts_parity(got, ref, rtol=1e-10, what=f"exact doubling {model_name}")
+    ref_q = parity.oracle_nuts(model, q0, eps, imm, draws, T)          # the reference's 2**k + 1 behaviour differs
+    assert not np.array_equal(ref_q["n_leapfrog"], ref["n_leapfrog"])
+    clean = ~ref["is_diverging"].astype(bool)
+    assert np.all(ref["n_leapfrog"][clean] <= 2 ** ref["num_doublings"][clean] - 1)
+
+
+def test_exact_doubling_removes_the_reference_bias():
+    """Oracle-level statement of DESIGN.md 2.1 on the reference's own 1-d test target, logprob = -2 (x - 1)^2
+    (tests/test_step_size.py:15-16; true variance 1/4) at eps = 0.5: the reference's 2**k + 1 sub-trees resonate with
+    the oscillator and give variance ~0.002, balanced sub-trees give the posterior."""
+    from oracle import kernels, streams
+
+    class Quad:
+        def potential_and_grad(self, q):
+            r = q - 1.0
+            return float(2.0 * np.sum(r * r)), 4.0 * r
+
+    def long_run_variance(exact):
+        xs = []
+        for seed in range(24):
+            srng = streams.StreamDraws(seed, "nuts")
+            k = kernels.nuts_new_kernel(srng, Quad(), exact_doubling=exact)
+            st = kernels.new_state(np.zeros(1), Quad())
+            for t in range(70):
+                info, _ = k(st, 0.5, np.ones(1))
+                st = info.state._replace(momentum=None)
+                if t >= 20:
+                    xs.append(info.state.position[0])
+        return np.var(xs)
+
+    assert long_run_variance(False) < 0.02
+    assert 0.19 < long_run_variance(True) < 0.31
