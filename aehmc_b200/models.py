@@ -171,15 +171,23 @@ class UserModel(Model):
         template <typename T>
         __device__ T potential_and_grad(const T* q, T* g, int d, const T* data);   // returns U = -logprob, writes dU/dq
 
-    It is compiled once with NVRTC for sm_100a (``b2h_user_model_create``) and evaluated one thread per chain; the
-    sampler runs it in split mode (one gradient launch per leapfrog tick).  ``data`` is an optional flat array of
+    or, with ``autodiff=True``, only the log-density::
+
+        template <typename S, typename T>
+        __device__ S log_density(const S* q, int d, const T* data);                 // returns logprob
+
+    written with ordinary arithmetic and exp / log / log1p / sqrt / tanh / sin / cos / square / pow / softplus: the
+    gradient then comes from forward-mode dual numbers (the role of ``aesara.grad``; O(dim) per operation, dim <= 64).
+    It is compiled once with NVRTC for sm_100a (``b2h_user_model_create[_ad]``) and evaluated one thread per chain;
+    the sampler runs it in split mode (one gradient launch per leapfrog tick).  ``data`` is an optional flat array of
     constants handed to the function in the model's dtype.  ``host_fn(q[d]) -> (U, g)`` is an optional NumPy
     counterpart (used by the tests as the oracle's model); it is never called by the sampler."""
     kind = _lib.MODEL_USER
 
-    def __init__(self, source, dim, data=None, dtype=torch.float64, device=None, host_fn=None):
+    def __init__(self, source, dim, data=None, dtype=torch.float64, device=None, host_fn=None, autodiff=False):
         super().__init__(dtype, device)
         self.dim = int(dim)
+        self.autodiff = bool(autodiff)
         self.source = str(source)
         self.host_fn = host_fn
         self.data = None if data is None else backend.as_device(np.asarray(data, dtype=np.float64).ravel(), self.dtype,
@@ -187,7 +195,10 @@ class UserModel(Model):
         lib = _lib.load()
         with torch.cuda.device(self.device):
             handle = C.c_void_p()
-            _lib.check(lib.b2h_user_model_create(self.source.encode(), C.byref(handle)))
+            if self.autodiff:
+                _lib.check(lib.b2h_user_model_create_ad(self.source.encode(), C.c_int32(self.dim), C.byref(handle)))
+            else:
+                _lib.check(lib.b2h_user_model_create(self.source.encode(), C.byref(handle)))
         self._handle = handle
         self._lib = lib
 

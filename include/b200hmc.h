@@ -171,6 +171,12 @@ int b2h_ctx_sync(b2h_ctx* ctx); /* cudaStreamSynchronize */
  * the handle goes into b2h_model.a of a B2H_MODEL_USER model.  The compile log is in b2h_last_error() on failure. */
 typedef struct b2h_user_model b2h_user_model;
 int b2h_user_model_create(const char* cuda_source, b2h_user_model** out);
+/* Same, but the source defines only the log-density,
+ *     template <typename S, typename T> __device__ S log_density(const S* q, int d, const T* data);
+ * written with ordinary arithmetic and exp / log / log1p / sqrt / tanh / sin / cos / square / pow(x, T) / softplus; the
+ * gradient comes from forward-mode dual numbers S = Dual<T, dim> (the role of aesara.grad; O(dim) per operation,
+ * dim <= 64). */
+int b2h_user_model_create_ad(const char* cuda_source, int32_t dim, b2h_user_model** out);
 int b2h_user_model_destroy(b2h_user_model* model);
 
 int b2h_potential_and_grad(b2h_ctx*, const b2h_model*, int dtype, const void* q, void* U, void* g, int64_t C,

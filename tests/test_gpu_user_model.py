@@ -119,3 +119,77 @@ def test_user_model_compile_error_is_reported(ab):
     with pytest.raises(B200HMCError) as e:
         ab.models.UserModel("template <typename T> __device__ T potential_and_grad(const T* q, T* g, int d, const T* data) { return undefined_symbol; }", 3)
     assert "undefined_symbol" in str(e.value)
+
+
+FUNNEL_DENSITY = r"""
+template <typename S, typename T>
+__device__ S log_density(const S* q, int d, const T* data) {
+    // Neal's funnel: v ~ N(0, 3), x_i ~ N(0, exp(v / 2)); constants dropped
+    const S v = q[0];
+    S lp = (T)(-0.5) * square(v) / (T)9;
+    const S inv_var = exp(-v);
+    for (int i = 1; i < d; ++i) lp += (T)(-0.5) * square(q[i]) * inv_var - (T)0.5 * v;
+    return lp;
+}
+"""
+
+LOGISTIC_DENSITY = r"""
+template <typename S, typename T>
+__device__ S log_density(const S* q, int d, const T* data) {
+    // tiny Bayesian logistic regression: data = [n, X (n x d, row-major), y (n)], standard normal prior
+    const int n = (int)data[0];
+    const T* X = data + 1;
+    const T* y = X + n * d;
+    S lp = (T)0;
+    for (int j = 0; j < d; ++j) lp -= (T)0.5 * square(q[j]);
+    for (int i = 0; i < n; ++i) {
+        S s = (T)0;
+        for (int j = 0; j < d; ++j) s += q[j] * X[i * d + j];
+        lp -= softplus(s) - s * y[i];
+    }
+    return lp;
+}
+"""
+
+
+def test_autodiff_density_matches_builtin_funnel(ab):
+    """Only the log-density is written; forward-mode duals supply the gradient (the reference's logprob_fn + aesara.grad)."""
+    from oracle import models as o_models
+    rng = np.random.default_rng(1)
+    d = 10
+    q = rng.standard_normal((50, d))
+    model = ab.models.UserModel(FUNNEL_DENSITY, d, autodiff=True)
+    builtin = ab.models.NealFunnel(d)
+    U, g = model.potential_and_grad(q)
+    U0, g0 = builtin.potential_and_grad(q)
+    np.testing.assert_allclose(U.cpu().numpy(), U0.cpu().numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(g.cpu().numpy(), g0.cpu().numpy(), rtol=1e-11, atol=1e-12)
+    ref = [o_models.NealFunnel(d).potential_and_grad(q[c]) for c in range(5)]
+    np.testing.assert_allclose(g[:5].cpu().numpy(), np.stack([r[1] for r in ref]), rtol=1e-11, atol=1e-12)
+
+
+def test_autodiff_density_nuts_parity_and_logistic(ab):
+    from aehmc_b200 import _engine
+    from oracle import models as o_models
+    rng = np.random.default_rng(2)
+    # NUTS on the autodiff funnel against the oracle's funnel under injected draws
+    d, Cn, T = 6, 24, 2
+    q0 = rng.standard_normal((Cn, d))
+    draws = parity.random_draws(rng, Cn, T, d)
+    ref = parity.oracle_nuts(o_models.NealFunnel(d), q0, 0.2, np.ones(d), draws, T)
+    model = ab.models.UserModel(FUNNEL_DENSITY, d, autodiff=True)
+    srng = ab.InjectedDraws(draws["z"], draws["u_dir"], draws["u_biased"], draws["u_uniform"])
+    info, extras = _engine.run("nuts", model, np.ones(d), srng, ab.nuts.new_state(q0, model), 0.2, n_transitions=T)
+    assert np.array_equal(info.num_doublings.cpu().numpy(), ref["num_doublings"])
+    assert np.array_equal(extras["n_leapfrog"].cpu().numpy(), ref["n_leapfrog"])
+    np.testing.assert_allclose(info.state.position.cpu().numpy(), ref["q"], rtol=1e-9, atol=1e-11)
+    # a data-carrying density: small logistic regression against the oracle's model
+    n, dd = 40, 5
+    X = rng.standard_normal((n, dd)); y = (rng.random(n) < 0.5).astype(np.float64)
+    lm = ab.models.UserModel(LOGISTIC_DENSITY, dd, data=np.concatenate([[n], X.ravel(), y]), autodiff=True)
+    beta = 0.5 * rng.standard_normal((7, dd))
+    U, g = lm.potential_and_grad(beta)
+    om = o_models.LogisticRegression(X, y, 1.0)
+    refs = [om.potential_and_grad(beta[c]) for c in range(7)]
+    np.testing.assert_allclose(U.cpu().numpy(), [r[0] for r in refs], rtol=1e-12)
+    np.testing.assert_allclose(g.cpu().numpy(), np.stack([r[1] for r in refs]), rtol=1e-10, atol=1e-12)
