@@ -1,0 +1,35 @@
+"""The README quick start runs as written (smaller sizes)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def test_readme_quick_start(cuda_device):
+    import aehmc_b200 as ab
+
+    model = ab.models.IIDGaussian([0.0], [1.0])
+    srng = ab.RandomStream(seed=0)
+    kernel = ab.nuts.new_kernel(srng, model)
+    state = ab.nuts.new_state(np.zeros((2048, 1)), model)
+    info, updates = kernel(state, 1e-2, 1.0)
+    assert info.state.position.shape == (2048, 1) and "n_leapfrog" in updates
+
+    state, (step_size, imm), _ = ab.window_adaptation.run(kernel, state, num_steps=200)
+    info, draws, stats, _ = ab.sampling.sample(kernel, state, step_size, ab.metrics.per_chain(imm), 100, thin=10)
+    assert draws.shape == (10, 2048, 1)
+    rhat, ess = ab.diagnostics.rhat(draws), ab.diagnostics.ess(draws)
+    assert abs(float(rhat[0]) - 1.0) < 0.05 and float(ess[0]) > 2000
+
+    funnel = ab.models.UserModel(r'''
+template <typename S, typename T>
+__device__ S log_density(const S* q, int d, const T* data) {
+    const S v = q[0];
+    S lp = (T)(-0.5) * square(v) / (T)9;
+    for (int i = 1; i < d; ++i) lp += (T)(-0.5) * square(q[i]) * exp(-v) - (T)0.5 * v;
+    return lp;
+}''', dim=10, autodiff=True)
+    k2 = ab.nuts.new_kernel(ab.RandomStream(seed=1), funnel)
+    info2, _ = k2(ab.nuts.new_state(np.zeros((64, 10)), funnel), 0.1, np.ones(10))
+    assert torch.isfinite(info2.state.position).all()
