@@ -220,22 +220,24 @@ logistic_fused_finish_kernel(const float* gpart, i64 plane_stride, const double*
     const int b_last = (int)(((mt + 1) * tiles_n - 1) / per_cta);
     T acc = 0;
     double lin = 0.0;
+    const int np = b_last - b_first + 1;
+#pragma unroll 4
     for (int j = lane; j < d; j += 32) {
         double s = 0.0;
-        for (int b = 0; b <= b_last - b_first; ++b) s += (double)gpart[(i64)b * plane_stride + c * d + j];
+#pragma unroll 2
+        for (int b = 0; b < np; ++b) s += (double)gpart[(i64)b * plane_stride + c * d + j];
         const T bj = q[c * d + j];
         g[c * d + j] = (T)(s * g_scale) + inv_prior_var * bj;
         acc += bj * bj;
         if (u_lin) lin += (double)bj * u_lin[j];
         if (fabs((double)bj) > beta_limit) lin = INFINITY;       // outside the fp16 pieces' range: reject the state
     }
-    const double nb = Group<32>::sum1((double)acc, nullptr);
-    if (u_lin) lin = Group<32>::sum1(lin, nullptr);
-    if (lane == 0) {
-        double u = lin;
-        for (int t = b_first * 4; t < (b_last + 1) * 4; ++t) u += upart[(i64)t * C + c];
-        U[c] = (T)u + (T)0.5 * inv_prior_var * (T)nb;
-    }
+    // potential partials of the CTAs that touched the chain tile: the lanes share the loads (fixed order: deterministic)
+    double u = 0.0;
+    for (int t = b_first * 4 + lane; t < (b_last + 1) * 4; t += 32) u += upart[(i64)t * C + c];
+    double red[3] = {(double)acc, lin, u};
+    Group<32>::sum<3>(red, nullptr);
+    if (lane == 0) U[c] = (T)(red[1] + red[2]) + (T)0.5 * inv_prior_var * (T)red[0];
 }
 
 template <typename T>
@@ -303,7 +305,8 @@ static int logistic_tc_fused16(b2h_ctx* ctx, const b2h_model* m, const T* q, T* 
     // (|beta| < 255 for data of unit scale).
     const int beta_exp = 20 - m->x_f16_shift;
     beta_split16_kernel<T><<<(int)((ng + 255) / 256), 256, 0, st>>>(q, bp, ng, ldexp(1.0, beta_exp));
-    to_float_kernel<T><<<(int)((N + 255) / 256), 256, 0, st>>>((const T*)m->b, yf, N);
+    if (sizeof(T) == sizeof(float)) yf = (float*)m->b;           // the responses are float already
+    else to_float_kernel<T><<<(int)((N + 255) / 256), 256, 0, st>>>((const T*)m->b, yf, N);
     int per_cta = 0;
     int rc = tc_logistic_fused16(st, bp, m->x_f16, 20, (int)C, (int)N, d, yf, gpart, upart, &per_cta);
     if (rc < 0) return rc;
