@@ -30,7 +30,7 @@ WORKLOADS = {
     "c2": ("dense", 4096, 1000, 24, 0),
     "c2small": ("dense", 512, 256, 8, 0),
     "c3": ("logistic", 4096, 128, 24, 100000),
-    "c5": ("logistic", 131072, 128, 4, 100000),
+    "c5": ("logistic", 131072, 128, 8, 100000),
     "c3small": ("logistic", 512, 64, 8, 4096),
 }
 EPS = {"dense": 0.25, "logistic": 0.4}
