@@ -151,6 +151,32 @@ def rhat(draws, dims=None, distributed=True):
     return rhat_from_statistics(stats)
 
 
+def gather_draws(draws, dims=None, thin=1):
+    """All-gather (thinned, dimension-selected) draws over the ranks: [T, C_local, d] -> [T', C_total, len(dims)] on
+    every rank, chains in global order (BASELINE.json configs[4]: "NCCL gather of draws for R-hat / ESS").  The
+    sufficient-statistics all-reduce of :func:`ess` / :func:`rhat` moves (2 + lags) * d doubles instead and is what the
+    benchmark uses; the gather is for consumers that need the draws themselves (plots, rank-normalised diagnostics).
+    A full gather at the c5 size is 1 GB per stored draw: select dimensions and thin."""
+    import torch.distributed as dist
+    x = draws if isinstance(draws, torch.Tensor) else torch.as_tensor(np.asarray(draws))
+    x = x[::max(int(thin), 1)]
+    if dims is not None:
+        x = x[:, :, dims]
+    x = x.contiguous()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return x
+    world = dist.get_world_size()
+    counts = torch.zeros(world, dtype=torch.int64, device=x.device)
+    counts[dist.get_rank()] = x.shape[1]
+    dist.all_reduce(counts)
+    cmax = int(counts.max())
+    pad = x if x.shape[1] == cmax else torch.cat(
+        [x, x.new_zeros((x.shape[0], cmax - x.shape[1], x.shape[2]))], dim=1)
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad.contiguous())
+    return torch.cat([p[:, :int(n)] for p, n in zip(parts, counts.tolist())], dim=1)
+
+
 def ess_bulk_single_chain(x):
     """arviz.ess(method="bulk") for ONE chain x[T] as the reference's tests call it: split the chain in two,
     rank-normalise over all draws, then the estimator above."""

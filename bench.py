@@ -448,7 +448,7 @@ def run_gpu_arm(args):
         kernels_per_tick = 5          # post+pre, beta split, response convert, fused gradient, finish
 
     # ---- second metric of BASELINE.json: NUTS ESS/s (min over the monitored dims, all chains, all ranks) ----
-    ess_per_s = rhat_max = None
+    ess_per_s = rhat_max = gathered = None
     if not args.no_ess:
         n_tr = args.ess_transitions
         st0 = ab.nuts.new_state(q_host.to(dev), model)
@@ -469,6 +469,15 @@ def run_gpu_arm(args):
         rhat = ab.diagnostics.rhat(ex["draws"][burn:], dims=dims)
         ess_per_s = float(np.nanmin(ess)) / (t_ess.item() * 1e-3)
         rhat_max = float(np.nanmax(rhat))
+        gathered = None
+        if world > 1:
+            # configs[4] words it as a "gather of draws": all-gather the monitored coordinates (NCCL) and recompute
+            # R-hat from the gathered tensor; it must agree with the all-reduced sufficient statistics
+            g = ab.diagnostics.gather_draws(ex["draws"][burn:], dims=dims)
+            r2 = ab.diagnostics.rhat(g, distributed=False)
+            gathered = {"shape": list(g.shape), "bytes": int(g.numel() * g.element_size()),
+                        "rhat_max": float(np.nanmax(r2))}
+            del g
         del ex
 
     if rank == 0:
@@ -488,7 +497,7 @@ def run_gpu_arm(args):
                     "what": "pinned host positions -> device, new_state, TICKS ticks, position + acceptance back to pinned host"},
             "gpu_launches": int(args.steps * (ticks * kernels_per_tick + 3)),
             "clocks": clocks,
-            "nuts_ess_per_sec": ess_per_s, "rhat_max": rhat_max,
+            "nuts_ess_per_sec": ess_per_s, "rhat_max": rhat_max, "gathered_draws": gathered if not args.no_ess else None,
             "ess_how": None if ess_per_s is None else
             f"{args.ess_transitions} NUTS transitions per chain from the initial positions, first quarter discarded, "
             "multi-chain ESS (Stan/arviz estimator, no rank normalisation) of the first 8 coordinates, minimum, "

@@ -69,7 +69,12 @@ def _worker(rank, world, port, q):
     off, cnt = diag.shard_chains(12)
     local = diag.sufficient_statistics_numpy(x[:, off:off + cnt], 150)
     merged = diag.all_reduce_statistics(local)
-    q.put((rank, float(diag.ess_from_statistics(merged)[0]), float(diag.rhat_from_statistics(merged)[0]), off, cnt))
+    import torch
+    off7, cnt7 = diag.shard_chains(7)              # uneven shards: 4 + 3 chains
+    y = _ar1(np.random.default_rng(9), 0.3, 20, 7)
+    gathered = diag.gather_draws(torch.from_numpy(y[:, off7:off7 + cnt7]), dims=[0], thin=2)
+    ok = bool(torch.equal(gathered, torch.from_numpy(y[::2, :, :1])))
+    q.put((rank, float(diag.ess_from_statistics(merged)[0]), float(diag.rhat_from_statistics(merged)[0]), off, cnt, ok))
     dist.destroy_process_group()
 
 
@@ -90,6 +95,7 @@ def test_sharded_statistics_reduce_to_the_global_answer_gloo():
     x = _ar1(np.random.default_rng(5), 0.6, 800, 12)
     full = diag.sufficient_statistics_numpy(x, 150)
     ess, rhat = diag.ess_from_statistics(full)[0], diag.rhat_from_statistics(full)[0]
-    assert [r[3:] for r in res] == [(0, 6), (6, 6)]
+    assert [r[3:5] for r in res] == [(0, 6), (6, 6)]
+    assert all(r[5] for r in res)                  # gather_draws: global chain order, uneven shards, thinned
     for r in res:
         assert r[1] == pytest.approx(ess, rel=1e-12) and r[2] == pytest.approx(rhat, rel=1e-12)
