@@ -84,3 +84,29 @@ def test_product_does_not_import_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "host_sim" not in text, f
+
+
+def test_user_model_sources_compile_without_a_gpu():
+    """NVRTC needs no device: a valid user source (hand-written gradient, or density-only with the forward-mode dual
+    header) gets through compilation and fails only at loading the code (no GPU here); a broken one reports the
+    compiler log.  On a GPU box the same calls succeed (tests/test_gpu_user_model.py)."""
+    import ctypes as C
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("meant for machines without a GPU")
+    from aehmc_b200 import _lib
+    lib = _lib.load()
+    good = b"""template <typename T> __device__ T potential_and_grad(const T* q, T* g, int d, const T* data) {
+        T U = 0; for (int i = 0; i < d; ++i) { U += (T)0.5 * q[i] * q[i]; g[i] = q[i]; } return U; }"""
+    good_ad = b"""template <typename S, typename T> __device__ S log_density(const S* q, int d, const T* data) {
+        S lp = (T)0; for (int i = 0; i < d; ++i) lp -= softplus(q[i]) + square(q[i]) * exp(-q[0]) / (T)3 + log1p(square(q[i])); return lp; }"""
+    h = C.c_void_p()
+    for call, text in ((lambda: lib.b2h_user_model_create(good, C.byref(h)), "loading"),
+                       (lambda: lib.b2h_user_model_create_ad(good_ad, C.c_int32(6), C.byref(h)), "loading"),
+                       (lambda: lib.b2h_user_model_create(b"this is not CUDA", C.byref(h)), "does not compile"),
+                       (lambda: lib.b2h_user_model_create_ad(good_ad, C.c_int32(1000), C.byref(h)), "dim must be")):
+        assert call() != 0
+        msg = lib.b2h_last_error().decode()
+        if "libnvrtc" in msg:
+            pytest.skip("NVRTC is not installed on this machine")
+        assert text in msg, msg
