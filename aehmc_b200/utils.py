@@ -41,7 +41,8 @@ def _spec(p, index):
 
 
 class RaveledParamsMap:
-    """Maps a set of parameters to a vector of their raveled values (reference utils.py:22-74).
+    """Bidirectional map between a list of named, shaped parameters and one flat vector per chain (the job of the
+    reference class of the same name, utils.py:22-74).
 
     ``ref_params``: iterable of templates or ``ParamSpec``s; the objects themselves are the keys of the dict
     returned by :meth:`unravel_params` (like the reference, which keys by the reference variables)."""
@@ -61,7 +62,7 @@ class RaveledParamsMap:
         self.size = ends[-1] if ends else 0
 
     def ravel_params(self, params: Sequence):
-        """Concatenate the raveled vectors of each parameter (reference utils.py:54-56).  Every parameter has
+        """Flatten every parameter and join the pieces in declaration order (reference utils.py:54-56).  Every parameter has
         either its reference shape (result ``[dim]``) or one extra leading chains axis (result ``[chains, dim]``)."""
         if len(params) != len(self.specs):
             raise ValueError(f"expected {len(self.specs)} parameters, got {len(params)}")
@@ -94,7 +95,7 @@ class RaveledParamsMap:
         return np.concatenate(cols, axis=-1)
 
     def unravel_params(self, raveled_params) -> Dict[object, object]:
-        """Unravel a concatenated set of raveled parameters (reference utils.py:58-71): ``[dim]`` gives the
+        """Cut a flat vector back into the declared parameters (reference utils.py:58-71): ``[dim]`` gives the
         reference shapes, ``[chains, dim]`` gives ``[chains, *shape]``; values are cast to the reference dtypes."""
         q = raveled_params
         is_torch = torch is not None and isinstance(q, torch.Tensor)
