@@ -301,3 +301,39 @@ def test_native_rng_replays_through_injected_draws(ab):
     ref = parity.oracle_nuts(o_models.NealFunnel(d), q0, 0.3, np.ones(d), draws, T)
     np.testing.assert_array_equal(_np(native.num_doublings), ref["num_doublings"])
     np.testing.assert_allclose(_np(native.state.position), ref["q"], rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize("which", ["logistic", "user"])
+def test_window_adaptation_in_split_mode(ab, which):
+    """Warm-up in the per-tick (split) engine: logistic regression (FMA path) and a user-written model go through the
+    same dual-averaging / Welford schedule as the oracle under injected draws (short run: adaptation is a feedback
+    loop)."""
+    rng = np.random.default_rng(23)
+    C, W = 6, 22
+    if which == "logistic":
+        N, d = 96, 4
+        X = rng.standard_normal((N, d))
+        y = (rng.random(N) < 0.5).astype(np.float64)
+        o_model = o_models.LogisticRegression(X, y, 1.0)
+        model = ab.models.LogisticRegression(X, y, 1.0)
+    else:
+        d = 4
+        src = r"""
+        template <typename S, typename T>
+        __device__ S log_density(const S* q, int d, const T* data) {
+            S lp = (T)0;
+            for (int i = 0; i < d; ++i) lp -= (T)0.5 * square(q[i] - data[i]) * data[d + i];
+            return lp;
+        }"""
+        mu, sigma = rng.standard_normal(d), np.exp(0.5 * rng.standard_normal(d))
+        o_model = o_models.IIDGaussian(mu, sigma)
+        model = ab.models.UserModel(src, d, data=np.concatenate([mu, 1.0 / sigma ** 2]), autodiff=True)
+    q0 = 0.5 * rng.standard_normal((C, d))
+    draws = parity.random_draws(rng, C, W, d)
+    ref = parity.oracle_nuts(o_model, q0, 1.0, np.ones(d), draws, W, schedule_steps=W)
+    srng = ab.InjectedDraws(**{k: draws[k] for k in ("z", "u_dir", "u_biased", "u_uniform")})
+    kernel = ab.nuts.new_kernel(srng, model)
+    state, (step_size, imm_out), _ = ab.window_adaptation.run(kernel, ab.nuts.new_state(q0, model), W)
+    np.testing.assert_allclose(_np(step_size), ref["eps"], rtol=1e-6)
+    np.testing.assert_allclose(_np(imm_out), ref["imm"], rtol=1e-6)
+    np.testing.assert_allclose(_np(state.position), ref["q"], rtol=1e-5, atol=1e-8)
