@@ -122,12 +122,17 @@ class LogisticRegression(Model):
     beta and the residual are carried as TWO fp16 pieces (22 significant bits) with beta resident in TMEM: two
     thirds of the tensor work.  ``tensor_core="bf16x3"`` forces the three-piece bf16 kernel,
     ``tensor_core="two_kernel"`` the formulation that passes the residual pieces through memory (any dim).
+    Real-valued features are not bf16-representable: ``round_features=True`` rounds X to bf16 once, up front, so that
+    the model itself is defined on the rounded features (a relative perturbation of at most 2^-9 per entry).
     The default (``False``) is the FP64/FP32 FMA-DMMA path (exactness reference)."""
     kind = _lib.MODEL_LOGISTIC
 
-    def __init__(self, X, y, prior_scale=1.0, dtype=torch.float64, device=None, tensor_core=False):
+    def __init__(self, X, y, prior_scale=1.0, dtype=torch.float64, device=None, tensor_core=False, round_features=False):
         super().__init__(dtype, device)
         self.X = backend.as_device(X, self.dtype, self.device)
+        if round_features:
+            # the MODEL becomes the one with bf16-rounded features (every gradient path then sees the same X)
+            self.X = self.X.to(torch.bfloat16).to(self.dtype)
         self.Xt = self.X.t().contiguous()
         self.y = backend.as_device(y, self.dtype, self.device)
         self.inv_prior_var = 1.0 / float(prior_scale) ** 2

@@ -148,3 +148,20 @@ def test_logistic_fused_many_chain_tiles_per_cta(ab, N, d, Cn, tc_mode):
     U1, g1 = tc_model.potential_and_grad(q)
     assert (g1.double() - g0).abs().max().item() < 2e-5 * g0.abs().max().item()
     assert ((U1.double() - U0).abs() / U0.abs()).max().item() < 5e-6
+
+
+def test_logistic_round_features_option(ab):
+    """Arbitrary float features: tensor_core=True refuses them unless round_features=True defines the model on the
+    bf16-rounded X, in which case every gradient path sees the same matrix."""
+    rng = np.random.default_rng(8)
+    X = rng.standard_normal((512, 64))                       # not bf16-representable
+    y = (rng.random(512) < 0.5).astype(np.float64)
+    with pytest.raises(ValueError):
+        ab.models.LogisticRegression(X, y, 1.0, tensor_core=True)
+    tc = ab.models.LogisticRegression(X, y, 1.0, dtype=torch.float32, tensor_core=True, round_features=True)
+    ref = ab.models.LogisticRegression(X, y, 1.0, dtype=torch.float64, round_features=True)
+    assert tc.tc_flag == 4.0 and torch.equal(tc.X.double(), ref.X)
+    q = 0.3 * rng.standard_normal((16, 64))
+    (U0, g0), (U1, g1) = ref.potential_and_grad(q), tc.potential_and_grad(q)
+    assert (g1.double() - g0).abs().max().item() < 2e-5 * g0.abs().max().item()
+    assert ((U1.double() - U0).abs() / U0.abs()).max().item() < 5e-6
