@@ -337,3 +337,38 @@ def test_window_adaptation_in_split_mode(ab, which):
     np.testing.assert_allclose(_np(step_size), ref["eps"], rtol=1e-6)
     np.testing.assert_allclose(_np(imm_out), ref["imm"], rtol=1e-6)
     np.testing.assert_allclose(_np(state.position), ref["q"], rtol=1e-5, atol=1e-8)
+
+
+def test_aesara_op_shim_perform_marshals_to_the_kernels(ab, monkeypatch):
+    """Aesara is not installable here, but `perform` (the only logic-free marshalling of aesara_ops.py) can be driven
+    directly: NumPy in, NumPy out, identical to the kernel called through the Python API."""
+    from aehmc_b200 import aesara_ops
+    monkeypatch.setattr(aesara_ops, "HAVE_AESARA", True)
+    rng = np.random.default_rng(41)
+    C, d = 9, 4
+    mu, sigma = rng.standard_normal(d), np.exp(0.3 * rng.standard_normal(d))
+    model = ab.models.IIDGaussian(mu, sigma)
+    q0 = rng.standard_normal((C, d))
+    draws = parity.random_draws(rng, C, 1, d)
+    mk = lambda: ab.InjectedDraws(**{k: draws[k] for k in ("z", "u_dir", "u_biased", "u_uniform", "u_accept")})
+    U0, g0 = model.potential_and_grad(q0)
+    pot = aesara_ops.PotentialAndGradOp(model)
+    store = [[None], [None]]
+    pot.perform(None, [q0], store)
+    np.testing.assert_array_equal(store[0][0], _np(U0))
+    np.testing.assert_array_equal(store[1][0], _np(g0))
+
+    op = aesara_ops.NUTSStepOp(mk(), model)
+    out = [[None] for _ in range(8)]
+    op.perform(None, [q0, _np(U0), _np(g0), np.full(C, 0.3), sigma ** 2], out)
+    info, _ = ab.nuts.new_kernel(mk(), model)(ab.nuts.new_state(q0, model), 0.3, sigma ** 2)
+    np.testing.assert_array_equal(out[0][0], _np(info.state.position))
+    np.testing.assert_array_equal(out[4][0], _np(info.acceptance_probability))
+    np.testing.assert_array_equal(out[5][0], _np(info.num_doublings))
+
+    hop = aesara_ops.HMCStepOp(mk(), model, num_integration_steps=5)
+    hout = [[None] for _ in range(6)]
+    hop.perform(None, [q0, _np(U0), _np(g0), np.full(C, 0.2), sigma ** 2], hout)
+    hinfo, _ = ab.hmc.new_kernel(mk(), model)(ab.hmc.new_state(q0, model), 0.2, sigma ** 2, 5)
+    np.testing.assert_array_equal(hout[0][0], _np(hinfo.state.position))
+    np.testing.assert_array_equal(hout[5][0], _np(hinfo.is_diverging))
