@@ -402,19 +402,25 @@ __global__ void subtree_out_kernel(EngineView<T> v, b2h_subtree t) {
     }
 }
 
-// shared set-up of the two entry points: fused models, diagonal-family metrics
+// shared set-up of the two entry points: every model, scalar / diagonal metrics (the tree state of the reference's
+// closures carries no velocities, which the dense-metric engine needs)
 template <typename T>
 static int tree_setup(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng, const b2h_cfg* cfg,
-                      i64 C64, void* ws, i64 ws_bytes, EngineView<T>& v, EnginePlan& pl) {
+                      i64 C64, void* ws, i64 ws_bytes, EngineView<T>& v, EnginePlan& pl, void** model_ws,
+                      size_t* model_ws_bytes) {
     int rc = make_plan(model, metric, cfg, pl, C64);
     if (rc) return rc;
-    if (pl.split) { set_error("stand-alone trajectory builders support the fused models with scalar/diagonal metrics"); return B2H_ERR_UNSUPPORTED; }
+    if (pl.dense) { set_error("stand-alone trajectory builders need a scalar or diagonal metric (use nuts_run for a dense one)"); return B2H_ERR_UNSUPPORTED; }
     const int C = (int)C64, d = model->dim, maxd = cfg->max_num_expansions;
     if (maxd < 1 || maxd > 24) { set_error("max_num_expansions must be in [1, 24]"); return B2H_ERR_ARG; }
     memset(&v, 0, sizeof(v));
-    size_t need = carve<T>(v, nullptr, pl, model, C, d, maxd, false, 0, nullptr);
+    const size_t mws = pl.split ? (size_t)potential_workspace_bytes_impl(model, Num<T>::dtype, C) : 0;
+    size_t mws_off = 0;
+    size_t need = carve<T>(v, nullptr, pl, model, C, d, maxd, false, mws, &mws_off);
     if (!ws || (size_t)ws_bytes < need) { set_error("workspace too small: need " + std::to_string(need) + " bytes"); return B2H_ERR_WORKSPACE; }
-    carve<T>(v, (char*)ws, pl, model, C, d, maxd, false, 0, nullptr);
+    carve<T>(v, (char*)ws, pl, model, C, d, maxd, false, mws, &mws_off);
+    *model_ws = mws ? (char*)ws + mws_off : nullptr;
+    *model_ws_bytes = mws;
     v.C = C; v.d = d; v.maxd = maxd;
     v.exact_doubling = cfg->exact_doubling ? 1 : 0;
     if (pl.G == 1) { v.sc = 1; v.sj = C; v.sck = 1; }
@@ -443,7 +449,9 @@ static int expand_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* 
                         const b2h_cfg* cfg, b2h_tree* tree, const double* eps, i64 C, b2h_diag* diag, void* ws, i64 ws_bytes) {
     EngineView<T> v;
     EnginePlan pl;
-    int rc = tree_setup<T>(ctx, model, metric, rng, cfg, C, ws, ws_bytes, v, pl);
+    void* model_ws = nullptr;
+    size_t model_ws_bytes = 0;
+    int rc = tree_setup<T>(ctx, model, metric, rng, cfg, C, ws, ws_bytes, v, pl, &model_ws, &model_ws_bytes);
     if (rc) return rc;
     if (diag) {
         v.out.acceptance_probability = diag->acceptance_probability; v.out.num_doublings = diag->num_doublings;
@@ -453,7 +461,8 @@ static int expand_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* 
     const i64 n = C * model->dim;
     const int eb = 256, eg = (int)((n + eb - 1) / eb);
     tree_in_kernel<T><<<eg, eb, 0, st>>>(v, *tree, eps);
-    rc = launch_fused_g<T>(st, v, model, 0, pl.G, false);
+    if (pl.split) rc = run_split_g<T>(ctx, v, pl, model, metric, cfg, 0, 1, model_ws, (i64)model_ws_bytes, v.scratch, 0, false);
+    else rc = launch_fused_g<T>(st, v, model, 0, pl.G, false);
     if (rc) return rc;
     tree_out_kernel<T><<<eg, eb, 0, st>>>(v, *tree);
     B2H_LAUNCH_CHECK();
@@ -465,7 +474,9 @@ static int subtree_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric*
                          const b2h_cfg* cfg, b2h_subtree* sub, const double* eps, i64 C, void* ws, i64 ws_bytes) {
     EngineView<T> v;
     EnginePlan pl;
-    int rc = tree_setup<T>(ctx, model, metric, rng, cfg, C, ws, ws_bytes, v, pl);
+    void* model_ws = nullptr;
+    size_t model_ws_bytes = 0;
+    int rc = tree_setup<T>(ctx, model, metric, rng, cfg, C, ws, ws_bytes, v, pl, &model_ws, &model_ws_bytes);
     if (rc) return rc;
     if (sub->max_num_steps < 1 || sub->expansion < 0 ||
         ((i64)1 << sub->expansion) - 1 + sub->max_num_steps > ((i64)1 << cfg->max_num_expansions) - 1) {
@@ -478,7 +489,8 @@ static int subtree_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric*
     const i64 n = C * model->dim;
     const int eb = 256, eg = (int)((n + eb - 1) / eb);
     subtree_in_kernel<T><<<eg, eb, 0, st>>>(v, *sub, eps);
-    rc = launch_fused_g<T>(st, v, model, 0, pl.G, false);
+    if (pl.split) rc = run_split_g<T>(ctx, v, pl, model, metric, cfg, 0, 1, model_ws, (i64)model_ws_bytes, v.scratch, 0, false);
+    else rc = launch_fused_g<T>(st, v, model, 0, pl.G, false);
     if (rc) return rc;
     subtree_out_kernel<T><<<eg, eb, 0, st>>>(v, *sub);
     B2H_LAUNCH_CHECK();

@@ -235,7 +235,8 @@ int b2h_nuts_run(b2h_ctx*, const b2h_model*, const b2h_metric*, const b2h_rng*, 
 int64_t b2h_nuts_workspace_bytes(const b2h_model*, const b2h_metric*, const b2h_cfg*, int64_t C);
 int64_t b2h_hmc_workspace_bytes(const b2h_model*, const b2h_metric*, const b2h_cfg*, int64_t C);
 
-/* ---- stand-alone trajectory builders with caller-supplied tree state (fused models, diagonal-family metrics) ---- */
+/* ---- stand-alone trajectory builders with caller-supplied tree state (every model; scalar / diagonal metrics: the
+ *      reference's tree state carries no velocities, which the dense-metric engine needs -- use b2h_nuts_run) ---- */
 typedef struct {
     void *q, *p, *g; /* [C x d] */
     void* U;         /* [C]     */

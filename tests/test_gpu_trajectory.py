@@ -308,3 +308,86 @@ def test_proposal_primitives(ab):
     np.testing.assert_array_equal(_np(sel.weight), np.where(mask, w1, w2))
     upd = ab.proposals.maybe_update_proposal(cu(mask), a, b)
     np.testing.assert_array_equal(_np(upd.state.momentum), np.where(mask[:, None], p + 1.0, p))
+
+
+@pytest.mark.parametrize("kind", ["corr", "logistic"])
+def test_standalone_builders_split_models(ab, kind):
+    """dynamic_integration / multiplicative_expansion as stand-alone closures for models that run in the per-tick
+    (split) engine: correlated Gaussian and logistic regression with a diagonal metric."""
+    rng = np.random.default_rng(77)
+    C, maxd, d = 20, 6, 6
+    if kind == "corr":
+        A = rng.standard_normal((d, d))
+        cov = A @ A.T / d + 0.3 * np.eye(d)
+        mu = 0.2 * rng.standard_normal(d)
+        om = o_models.CorrelatedGaussian(mu, np.linalg.inv(cov))
+        gm = ab.models.CorrelatedGaussian(mu, np.linalg.inv(cov))
+    else:
+        X = rng.standard_normal((80, d)); y = (rng.random(80) < 0.5).astype(np.float64)
+        om = o_models.LogisticRegression(X, y, 1.0)
+        gm = ab.models.LogisticRegression(X, y, 1.0)
+    imm = np.exp(0.2 * rng.standard_normal(d))
+    q0 = 0.5 * rng.standard_normal((C, d))
+    p0 = rng.standard_normal((C, d)) / np.sqrt(imm)
+    eps = 0.15 + 0.2 * rng.random(C)
+    eps[::6] = 20.0                                                    # some chains diverge
+    draws = parity.random_draws(rng, C, 1, d, maxd)
+
+    # --- the whole doubling loop
+    ref = []
+    for c in range(C):
+        srng = parity.chain_draws(draws, c)
+        srng.begin_transition()
+        mg, ke, ut, new_ts, ti = _oracle_parts(om, imm, srng)
+        expand = o_tree.multiplicative_expansion(srng, ti, ut, maxd)
+        U, g = om.potential_and_grad(q0[c])
+        st = o_ham.IntegratorState(q0[c], p0[c], U, g)
+        E0 = U + ke(p0[c])
+        with np.errstate(all="ignore"):
+            ref.append(expand(o_tree.ProposalState(st, E0, 0.0, -np.inf), st, st, st.momentum, new_ts(st.position, maxd), E0,
+                              float(eps[c])))
+    srng = ab.InjectedDraws(None, draws["u_dir"], draws["u_biased"], draws["u_uniform"], None)
+    mg, ke, ut, new_ts, ti = _gpu_parts(ab, gm, imm, srng)
+    expand = ab.trajectory.multiplicative_expansion(srng, ti, ut, maxd)
+    U, g = gm.potential_and_grad(q0)
+    st = ab.integrators.IntegratorState(torch.as_tensor(q0).cuda(), torch.as_tensor(p0).cuda(), U, g)
+    E0 = U + ke(st.momentum)
+    prop = ab.proposals.ProposalState(st, E0, torch.zeros(C, dtype=torch.float64).cuda(),
+                                      torch.full((C,), -np.inf, dtype=torch.float64).cuda())
+    res, _ = expand(prop, st, st, st.momentum, new_ts(st.position, maxd), E0, eps)
+    dg = res.diagnostics
+    np.testing.assert_array_equal(_np(dg.num_doublings[-1]), [r[0].num_doublings for r in ref])
+    np.testing.assert_array_equal(_np(dg.is_turning[-1]), [bool(r[0].is_turning) for r in ref])
+    np.testing.assert_array_equal(_np(dg.is_diverging[-1]), [bool(r[0].is_diverging) for r in ref])
+    ok = ~_np(dg.is_diverging[-1])
+    assert ok.any() and (~ok).any()
+    for name, got, want in [
+        ("proposal.q", res.proposals.state.position[-1], [r[1]["proposal"].state.position for r in ref]),
+        ("left.q", res.left_states.position[-1], [r[1]["left_state"].position for r in ref]),
+        ("right.g", res.right_states.potential_energy_grad[-1], [r[1]["right_state"].potential_energy_grad for r in ref]),
+        ("momentum_sum", res.momentum_sums[-1], [r[1]["momentum_sum"] for r in ref]),
+        ("acceptance", dg.acceptance_probability[-1], [r[0].acceptance_probability for r in ref]),
+    ]:
+        np.testing.assert_allclose(_np(got)[ok], np.asarray(want, dtype=np.float64)[ok], err_msg=name, rtol=1e-9, atol=1e-11)
+
+    # --- one sub-tree
+    dirs = np.where(rng.random(C) < 0.5, 1, -1).astype(np.int8)
+    refs = []
+    for c in range(C):
+        srng = parity.chain_draws(draws, c)
+        srng.begin_transition()
+        mg_o, ke_o, ut_o, new_ts_o, ti_o = _oracle_parts(om, imm, srng)
+        U, g = om.potential_and_grad(q0[c])
+        st_o = o_ham.IntegratorState(q0[c], p0[c], U, g)
+        with np.errstate(all="ignore"):
+            sub, _ = ti_o(st_o, float(dirs[c]), new_ts_o(st_o.position, maxd), 4, float(eps[c]), U + ke_o(p0[c]), expansion=2)
+        refs.append(sub)
+    srng = ab.InjectedDraws(None, draws["u_dir"], draws["u_biased"], draws["u_uniform"], None)
+    mg, ke, ut, new_ts, ti = _gpu_parts(ab, gm, imm, srng, expansion=2)
+    (prop2, last, msum, ts2, length, div, term), _ = ti(st, dirs, new_ts(st.position, maxd), 4, eps, E0)
+    np.testing.assert_array_equal(_np(length), [r.trajectory_length for r in refs])
+    np.testing.assert_array_equal(_np(div), [bool(r.is_diverging) for r in refs])
+    ok = ~_np(div)
+    np.testing.assert_allclose(_np(last.position)[ok], np.asarray([r.state.position for r in refs])[ok], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(_np(prop2.state.position)[ok], np.asarray([r.proposal.state.position for r in refs])[ok],
+                               rtol=1e-9, atol=1e-11)
