@@ -402,6 +402,14 @@ __global__ void subtree_out_kernel(EngineView<T> v, b2h_subtree t) {
     }
 }
 
+template <typename T>
+__global__ void imm_in_kernel(EngineView<T> v, const T* imm_user) {
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (i64)v.C * v.d) return;
+    const int c = (int)(idx / v.d), j = (int)(idx % v.d);
+    v.imm[(i64)c * v.sc + (i64)j * v.sj] = imm_user[idx];
+}
+
 // shared set-up of the two entry points: every model, scalar / diagonal metrics (the tree state of the reference's
 // closures carries no velocities, which the dense-metric engine needs)
 template <typename T>
@@ -432,7 +440,11 @@ static int tree_setup(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* me
         B2H_CUDA(cudaMemcpyAsync(v.imm, &val, sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
         B2H_CUDA(cudaStreamSynchronize(ctx->stream));
     } else if (metric->kind == B2H_IMM_DIAG) { v.imm = (T*)metric->imm; v.imm_sc = 0; v.imm_sj = 1; }
-    else { set_error("per-chain metrics are not supported here"); return B2H_ERR_UNSUPPORTED; }
+    else {                                   // per-chain diagonal: the caller's [C x d] rows into the engine layout
+        v.imm_sc = v.sc; v.imm_sj = v.sj;
+        const i64 n = (i64)C * d;
+        imm_in_kernel<T><<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(v, (const T*)metric->imm);
+    }
     v.rng.mode = rng->mode;
     v.rng.key.k0 = (uint32_t)rng->seed; v.rng.key.k1 = (uint32_t)(rng->seed >> 32);
     v.rng.chain_offset = rng->chain_offset; v.rng.transition_offset = rng->transition_offset;

@@ -391,3 +391,43 @@ def test_standalone_builders_split_models(ab, kind):
     np.testing.assert_allclose(_np(last.position)[ok], np.asarray([r.state.position for r in refs])[ok], rtol=1e-9, atol=1e-11)
     np.testing.assert_allclose(_np(prop2.state.position)[ok], np.asarray([r.proposal.state.position for r in refs])[ok],
                                rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize("group", [1, 8])
+def test_expand_with_per_chain_diagonal_metric(ab, group):
+    """every chain with its own diagonal inverse mass matrix (what per-chain window adaptation produces)."""
+    rng = np.random.default_rng(91)
+    C, maxd, d = 16, 6, 5
+    mu, sigma = 0.3 * rng.standard_normal(d), np.exp(0.3 * rng.standard_normal(d))
+    imm = np.exp(0.4 * rng.standard_normal((C, d)))
+    q0 = mu + sigma * rng.standard_normal((C, d))
+    p0 = rng.standard_normal((C, d)) / np.sqrt(imm)
+    eps = 0.2 + 0.3 * rng.random(C)
+    draws = parity.random_draws(rng, C, 1, d, maxd)
+    om = o_models.IIDGaussian(mu, sigma)
+    gm = ab.models.IIDGaussian(mu, sigma)
+    ref = []
+    for c in range(C):
+        srng = parity.chain_draws(draws, c)
+        srng.begin_transition()
+        mg, ke, ut, new_ts, ti = _oracle_parts(om, imm[c], srng)
+        expand = o_tree.multiplicative_expansion(srng, ti, ut, maxd)
+        U, g = om.potential_and_grad(q0[c])
+        st = o_ham.IntegratorState(q0[c], p0[c], U, g)
+        E0 = U + ke(p0[c])
+        ref.append(expand(o_tree.ProposalState(st, E0, 0.0, -np.inf), st, st, st.momentum, new_ts(st.position, maxd), E0,
+                          float(eps[c])))
+    srng = ab.InjectedDraws(None, draws["u_dir"], draws["u_biased"], draws["u_uniform"], None)
+    mg, ke, ut, new_ts, ti = _gpu_parts(ab, gm, ab.metrics.per_chain(torch.as_tensor(imm).cuda()), srng, group=group)
+    expand = ab.trajectory.multiplicative_expansion(srng, ti, ut, maxd)
+    U, g = gm.potential_and_grad(q0)
+    st = ab.integrators.IntegratorState(torch.as_tensor(q0).cuda(), torch.as_tensor(p0).cuda(), U, g)
+    E0 = U + ke(st.momentum)
+    prop = ab.proposals.ProposalState(st, E0, torch.zeros(C, dtype=torch.float64).cuda(),
+                                      torch.full((C,), -np.inf, dtype=torch.float64).cuda())
+    res, _ = expand(prop, st, st, st.momentum, new_ts(st.position, maxd), E0, eps)
+    np.testing.assert_array_equal(_np(res.diagnostics.num_doublings[-1]), [r[0].num_doublings for r in ref])
+    np.testing.assert_array_equal(_np(res.diagnostics.is_turning[-1]), [bool(r[0].is_turning) for r in ref])
+    np.testing.assert_allclose(_np(res.proposals.state.position[-1]), [r[1]["proposal"].state.position for r in ref],
+                               rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(_np(res.momentum_sums[-1]), [r[1]["momentum_sum"] for r in ref], rtol=1e-10, atol=1e-11)
