@@ -206,8 +206,8 @@ def c3(small):
     beta = rng.standard_normal(D) / np.sqrt(D)
     y = (rng.random(N) < 1 / (1 + np.exp(-X @ beta))).astype(np.float64)
     q0 = 0.1 * np.random.default_rng(6).standard_normal((Cn, D))
-    cases = ((torch.float64, False), (torch.float32, False), (torch.float32, "two_kernel"), (torch.float32, True),
-             (torch.float64, True))
+    cases = ((torch.float64, False), (torch.float32, False), (torch.float32, "two_kernel"), (torch.float32, "bf16x3"),
+             (torch.float32, True), (torch.float64, True))
     if "--tc-only" in sys.argv:
         cases = cases[2:]
     for dt, tcore in cases:
@@ -221,12 +221,13 @@ def c3(small):
         (info, ex), ms = timed(run)
         leap = int(ex["counters"][0].item())
         flops = 4.0 * N * D * leap
-        path = ("tcgen05 bf16x3 gradient, " + ("two kernels" if tcore == "two_kernel" else "fully fused")) if tcore \
-            else "FMA/DMMA-path gradient"
+        pieces = 2 if getattr(model, "tc_flag", 0.0) == 4.0 else 3
+        path = {0.0: "FMA/DMMA-path gradient", 2.0: "tcgen05 bf16x3 gradient, fully fused", 3.0: "tcgen05 bf16x3 gradient, two kernels",
+                4.0: "tcgen05 fp16x2 gradient, fully fused, A operands in TMEM"}[getattr(model, "tc_flag", 0.0)]
         out.append({"workload": f"c3 NUTS logistic N={N} D={D} {str(dt)[6:]} ({path})", "chains": Cn,
                     "ticks": ticks, "ms_per_tick": ms / ticks, "grad_evals_per_sec": leap / (ms * 1e-3),
                     "gradient_TFLOPs_algorithmic_4ND": flops / (ms * 1e-3) / 1e12,
-                    "tensor_TFLOPs_issued": (3.0 * flops / (ms * 1e-3) / 1e12) if tcore else None,
+                    "tensor_TFLOPs_issued": (pieces * flops / (ms * 1e-3) / 1e12) if tcore else None,
                     "mean_accept": float(info.acceptance_probability.mean())})
     return out
 
