@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import torch
 
@@ -11,19 +12,39 @@ from .metrics import GaussianMetric
 from .trajectory import Diagnostics
 
 _workspaces = {}
+_resume_offsets = {}
 
 
-def _workspace(key, nbytes, dev):
+def _evict(key):
+    _workspaces.pop(key, None)
+    _resume_offsets.pop(key, None)
+
+
+def _workspace(key, nbytes, dev, owner=None):
+    """Engine workspace of one (model, chain count): freed with the model that owns it (an explicit
+    ``workspace_key`` lives until ``release_workspace(key)``)."""
     ws = _workspaces.get(key)
     if ws is None:
         ws = _workspaces[key] = backend.Workspace()
+        if owner is not None:
+            try:
+                weakref.finalize(owner, _evict, key)
+            except TypeError:
+                pass
     return ws.get(nbytes, dev)
+
+
+def release_workspace(key):
+    """Drop the workspace (and the chain state machines kept in it) of an explicit ``workspace_key``."""
+    _evict(key)
 
 
 class AdaptState:
     """Device arrays of the per-chain warm-up state (b2h_adapt)."""
 
-    def __init__(self, Cn, schedule, dev, target=0.8, initial_step_size=1.0, gamma=0.05, t0=10, kappa=0.75):
+    def __init__(self, Cn, schedule, dev, target=0.8, initial_step_size=1.0, gamma=0.05, t0=10, kappa=0.75,
+                 pooled=False):
+        self.pooled, self.step_offset = bool(pooled), 0
         self.num_steps = len(schedule)
         self.stage = torch.tensor([s for s, _ in schedule], dtype=torch.uint8, device=dev)
         self.window_end = torch.tensor([1 if e else 0 for _, e in schedule], dtype=torch.uint8, device=dev)
@@ -40,7 +61,8 @@ class AdaptState:
         return _lib.Adapt(1, self.num_steps, self.stage.data_ptr(), self.window_end.data_ptr(), self.target,
                           self.gamma, self.t0, self.kappa, self.initial_step_size, self.da_step.data_ptr(),
                           self.da_x.data_ptr(), self.da_x_avg.data_ptr(), self.da_g_avg.data_ptr(),
-                          self.da_mu.data_ptr(), None, None, self.wc_n.data_ptr())
+                          self.da_mu.data_ptr(), None, None, self.wc_n.data_ptr(), 1 if self.pooled else 0,
+                          int(self.step_offset))
 
 
 def run(kind, model, metric, srng, state, step_size, *, n_transitions=1, max_num_expansions=10,
@@ -84,7 +106,15 @@ def run(kind, model, metric, srng, state, step_size, *, n_transitions=1, max_num
     nbytes = lib.b2h_nuts_workspace_bytes(C.byref(m), C.byref(mt), C.byref(cfg), C.c_int64(Cn))
     if nbytes < 0:
         _lib.check(-1)
-    ws = _workspace(workspace_key or (kind, id(model), Cn, dev.index), nbytes, dev)
+    key = workspace_key or (kind, id(model), Cn, dev.index)
+    ws = _workspace(key, nbytes, dev, owner=None if workspace_key else model)
+    # a resumed call continues the transitions in flight: it keeps the Philox transition offset of the call that
+    # started the run (the chain records count transitions cumulatively), so draws stay a pure function of
+    # (seed, chain, transition) however the run is chunked
+    if resume and key in _resume_offsets:
+        rng.transition_offset = _resume_offsets[key]
+    else:
+        _resume_offsets[key] = int(rng.transition_offset)
     ad = adapt.struct() if adapt is not None else None
     ctx = backend.context(dev)
     if kind == "nuts":

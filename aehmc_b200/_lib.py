@@ -27,7 +27,7 @@ class Model(C.Structure):
 
 class Metric(C.Structure):
     _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("scalar", C.c_double), ("imm", C.c_void_p),
-                ("sqrt_t", C.c_void_p)]
+                ("sqrt_t", C.c_void_p), ("chol_t", C.c_void_p)]
 
 
 class Rng(C.Structure):
@@ -48,7 +48,7 @@ class Adapt(C.Structure):
                 ("t0", C.c_double), ("kappa", C.c_double), ("initial_step_size", C.c_double),
                 ("da_step", C.c_void_p), ("da_x", C.c_void_p), ("da_x_avg", C.c_void_p),
                 ("da_g_avg", C.c_void_p), ("da_mu", C.c_void_p), ("wc_mean", C.c_void_p),
-                ("wc_m2", C.c_void_p), ("wc_n", C.c_void_p)]
+                ("wc_m2", C.c_void_p), ("wc_n", C.c_void_p), ("pooled", C.c_int32), ("step_offset", C.c_int32)]
 
 
 class State(C.Structure):
@@ -86,6 +86,7 @@ EXPORTS = [
     "b2h_hmc_workspace_bytes", "b2h_dual_averaging_update", "b2h_welford_update", "b2h_mass_matrix_final",
     "b2h_philox_fill", "b2h_dense_apply", "b2h_chain_moments", "b2h_chain_autocov", "b2h_tc_gemm_bf16", "b2h_nuts_expand", "b2h_nuts_subtree", "b2h_proposal_update",
     "b2h_progressive_sampling", "b2h_select_rows", "b2h_user_model_create", "b2h_user_model_create_ad", "b2h_user_model_destroy",
+    "b2h_hmc_accept", "b2h_welford_pooled_update", "b2h_welford_pooled_workspace_bytes", "b2h_welford_merge",
 ]
 
 _lib = None
@@ -107,7 +108,8 @@ def load():
             "aehmc_b200 has no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     lib.b2h_last_error.restype = C.c_char_p
-    for name in ("b2h_potential_workspace_bytes", "b2h_nuts_workspace_bytes", "b2h_hmc_workspace_bytes"):
+    for name in ("b2h_potential_workspace_bytes", "b2h_nuts_workspace_bytes", "b2h_hmc_workspace_bytes",
+                 "b2h_welford_pooled_workspace_bytes"):
         getattr(lib, name).restype = C.c_int64
     _lib = lib
     return lib

@@ -54,6 +54,8 @@ struct RngView {
 
 struct AdaptView {
     int enabled, num_steps;
+    int pooled;              // 1: dual averaging only; the caller re-estimates the shared metric from pooled statistics
+    int step_offset;         // schedule index of this call's first transition
     const uint8_t *stage, *window_end;
     double target, gamma, t0, kappa;
     i64* da_step;
@@ -119,7 +121,7 @@ struct EngineView {
 // ---------------------------------------------------------------------------
 B2H_DEVINL double draw_u(const RngView& r, int kind, int c, int t, int idx, int maxd) {
     if (r.mode == 1) {
-        i64 row = (i64)c * r.n_injected + t;
+        i64 row = (i64)c * r.n_injected + t + (i64)r.transition_offset;
         if (kind == DRAW_DIR) return r.u_dir[row * maxd + idx];
         if (kind == DRAW_BIASED) return r.u_biased[row * maxd + idx];
         if (kind == DRAW_UNIFORM) return r.u_uniform[row * (((i64)1 << maxd) - 1) + idx];
@@ -130,7 +132,7 @@ B2H_DEVINL double draw_u(const RngView& r, int kind, int c, int t, int idx, int 
 }
 
 B2H_DEVINL double draw_z(const RngView& r, int c, int t, int j, int d) {
-    if (r.mode == 1) return r.z[((i64)c * r.n_injected + t) * d + j];
+    if (r.mode == 1) return r.z[((i64)c * r.n_injected + t + (i64)r.transition_offset) * d + j];
     return philox_normal(r.key, r.chain_offset + (uint64_t)c, (uint32_t)(r.transition_offset + (uint64_t)t),
                          (uint32_t)j);
 }
@@ -367,7 +369,8 @@ B2H_DEVINL void begin_transition(Chain<T, G>& ch) {
     ch.r.nleap = 0;
     ch.r.phase = PH_RUN;
     if (DENSE) {
-        // queue the momentum of the NEXT transition (consumed at the earliest two ticks from now)
+        // queue the momentum of the NEXT transition: (p0, v0) land before the next tick's pre part, so a
+        // transition that lasts a single tick (HMC with L = 1, a first-step divergence) finds them ready
         int slot = 0;
         if (ch.lane == 0) {
             slot = atomicAdd(v.mom_count + v.mom_parity, 1);
@@ -375,7 +378,7 @@ B2H_DEVINL void begin_transition(Chain<T, G>& ch) {
         }
         slot = Group<G>::bcast(slot, ch.red);
         const int tn = ch.r.t + 1;
-        const bool have = (v.rng.mode == 0) || (tn < v.rng.n_injected);
+        const bool have = (v.rng.mode == 0) || (tn + (i64)v.rng.transition_offset < v.rng.n_injected);
         T* zrow = v.mom_z + ((i64)v.mom_parity * v.C + slot) * v.d;
         for (int j = ch.lane; j < v.d; j += G) zrow[j] = have ? (T)draw_z(v.rng, ch.c, tn, j, v.d) : (T)0;
     }
@@ -452,11 +455,11 @@ B2H_DEVINL void adapt_update(Chain<T, G>& ch, int step, double p_accept) {
     dstep += 1;
     double eps = exp(new_x);
 
-    const bool slow = ad.stage[step] != 0;
+    const bool slow = ad.stage[step] != 0 && !ad.pooled;
     const bool wend = ad.window_end[step] != 0;
     T* mean = (T*)ad.wc_mean;
     T* m2 = (T*)ad.wc_m2;
-    i64 n = ad.wc_n[c];
+    i64 n = ad.pooled ? 0 : ad.wc_n[c];
     if (slow) {
         n += 1;
         for (int j = ch.lane; j < v.d; j += G) {
@@ -471,14 +474,17 @@ B2H_DEVINL void adapt_update(Chain<T, G>& ch, int step, double p_accept) {
     }
     if (wend) {
         // imm = (n/(n+5)) * m2/(n-1) + 1e-3 * (5/(n+5));  Welford re-init; da re-init with mu = step size
-        T scale = (T)((double)n / ((double)n + 5.0));
-        T shrink = (T)(1e-3 * (5.0 / ((double)n + 5.0)));
-        for (int j = ch.lane; j < v.d; j += G) {
-            i64 a = ch.at(j);
-            T cov = m2[a] / (T)(n - 1);
-            v.imm[(i64)c * v.imm_sc + (i64)j * v.imm_sj] = scale * cov + shrink;
-            mean[a] = 0;
-            m2[a] = 0;
+        // (pooled: the caller rebuilds the shared metric between two calls; only the dual averaging restarts here)
+        if (!ad.pooled) {
+            T scale = (T)((double)n / ((double)n + 5.0));
+            T shrink = (T)(1e-3 * (5.0 / ((double)n + 5.0)));
+            for (int j = ch.lane; j < v.d; j += G) {
+                i64 a = ch.at(j);
+                T cov = m2[a] / (T)(n - 1);
+                v.imm[(i64)c * v.imm_sc + (i64)j * v.imm_sj] = scale * cov + shrink;
+                mean[a] = 0;
+                m2[a] = 0;
+            }
         }
         n = 0;
         mu = eps;
@@ -489,7 +495,7 @@ B2H_DEVINL void adapt_update(Chain<T, G>& ch, int step, double p_accept) {
     if (ch.lane == 0) {
         ad.da_step[c] = dstep; ad.da_x[c] = new_x; ad.da_x_avg[c] = new_xavg; ad.da_g_avg[c] = new_gavg;
         ad.da_mu[c] = mu;
-        ad.wc_n[c] = n;
+        if (!ad.pooled) ad.wc_n[c] = n;
     }
     ch.r.eps = eps;
 }
@@ -519,7 +525,8 @@ B2H_DEVINL void end_transition(Chain<T, G>& ch, int num_doublings, bool is_turni
             ds[3] = (double)ch.r.last_flags;
         }
     }
-    if (v.adapt.enabled && t < v.adapt.num_steps) adapt_update(ch, t, ch.r.accept_prob);
+    if (v.adapt.enabled && t + v.adapt.step_offset < v.adapt.num_steps)
+        adapt_update(ch, t + v.adapt.step_offset, ch.r.accept_prob);
     ch.r.t = t + 1;
     ch.r.phase = (v.n_transitions > 0 && (ch.r.t - ch.r.t_base) >= v.n_transitions) ? PH_DONE : PH_START;
 }

@@ -119,18 +119,18 @@ __global__ void copy_in_kernel(EngineView<T> v, const T* q, const T* g, const T*
     v.qp[a] = q[idx];
     v.gp[a] = g[idx];
     if (imm_user) v.imm[a] = imm_user[idx];
-    if (v.adapt.enabled) { ((T*)v.adapt.wc_mean)[a] = 0; ((T*)v.adapt.wc_m2)[a] = 0; }
+    if (v.adapt.enabled && v.adapt.wc_mean) { ((T*)v.adapt.wc_mean)[a] = 0; ((T*)v.adapt.wc_m2)[a] = 0; }
     if (j == 0) {
         ChainRec r;
         memset(&r, 0, sizeof(r));
         r.phase = PH_START;
         r.U_prop = (double)U[c];
         r.eps = eps[c];
-        if (v.adapt.enabled) {
+        if (v.adapt.enabled && v.adapt.step_offset == 0) {
             // window_adaptation.init (window_adaptation.py:132-144): mu = initial step size, step size = exp(0)
             v.adapt.da_step[c] = 1; v.adapt.da_x[c] = 0.0; v.adapt.da_x_avg[c] = 0.0; v.adapt.da_g_avg[c] = 0.0;
             v.adapt.da_mu[c] = init_step_size;
-            v.adapt.wc_n[c] = 0;
+            if (!v.adapt.pooled) v.adapt.wc_n[c] = 0;
             r.eps = 1.0;
         }
         v.rec[c] = r;
@@ -186,14 +186,19 @@ static int run_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* met
     const int maxd = hmc ? 1 : cfg->max_num_expansions;
     if (!hmc && (maxd < 1 || maxd > 24)) { set_error("max_num_expansions must be in [1, 24]"); return B2H_ERR_ARG; }
     const bool adapting = adapt && adapt->enabled;
-    if (adapting && !pl.per_chain_imm) {
-        set_error("window adaptation needs a DIAG_PER_CHAIN inverse mass matrix (adapted in place)");
+    const bool pooled = adapting && adapt->pooled;
+    if (adapting && !pooled && !pl.per_chain_imm) {
+        set_error("per-chain window adaptation needs a DIAG_PER_CHAIN inverse mass matrix (adapted in place)");
         return B2H_ERR_ARG;
     }
-    if (pl.dense && (!metric->imm || !metric->sqrt_t)) { set_error("dense metric needs imm and sqrt_t"); return B2H_ERR_ARG; }
+    if (adapting && (adapt->step_offset < 0 || adapt->step_offset >= adapt->num_steps)) {
+        set_error("adapt.step_offset must be in [0, num_steps)");
+        return B2H_ERR_ARG;
+    }
+    if (pl.dense && (!metric->imm || !metric->sqrt_t || !metric->chol_t)) { set_error("dense metric needs imm, sqrt_t and chol_t"); return B2H_ERR_ARG; }
     if (rng->mode == B2H_RNG_INJECTED) {
-        if (!rng->z || rng->n_injected < n_transitions || n_transitions <= 0) {
-            set_error("injected draws need z and n_injected >= n_transitions > 0");
+        if (!rng->z || rng->n_injected < (i64)rng->transition_offset + n_transitions || n_transitions <= 0) {
+            set_error("injected draws need z and n_injected >= transition_offset + n_transitions, n_transitions > 0");
             return B2H_ERR_ARG;
         }
         if (!hmc && (!rng->u_dir || !rng->u_biased || !rng->u_uniform)) { set_error("NUTS needs u_dir/u_biased/u_uniform"); return B2H_ERR_ARG; }
@@ -204,12 +209,12 @@ static int run_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* met
     memset(&v, 0, sizeof(v));
     size_t model_ws_bytes = pl.split ? (size_t)potential_workspace_bytes_impl(model, Num<T>::dtype, C) : 0;
     size_t model_ws_off = 0;
-    size_t need = carve<T>(v, nullptr, pl, model, C, d, maxd, adapting, model_ws_bytes, &model_ws_off);
+    size_t need = carve<T>(v, nullptr, pl, model, C, d, maxd, adapting && !pooled, model_ws_bytes, &model_ws_off);
     if (!ws || (size_t)ws_bytes < need) {
         set_error("workspace too small: need " + std::to_string(need) + " bytes");
         return B2H_ERR_WORKSPACE;
     }
-    carve<T>(v, (char*)ws, pl, model, C, d, maxd, adapting, model_ws_bytes, &model_ws_off);
+    carve<T>(v, (char*)ws, pl, model, C, d, maxd, adapting && !pooled, model_ws_bytes, &model_ws_off);
     void* model_ws = model_ws_bytes ? (char*)ws + model_ws_off : nullptr;
     v.C = C; v.d = d; v.maxd = maxd;
     v.exact_doubling = cfg->exact_doubling ? 1 : 0;
@@ -227,6 +232,7 @@ static int run_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* met
     v.rng.u_accept = rng->u_accept;
     v.adapt.enabled = adapting ? 1 : 0;
     if (adapting) {
+        v.adapt.pooled = pooled ? 1 : 0; v.adapt.step_offset = adapt->step_offset;
         v.adapt.num_steps = adapt->num_steps; v.adapt.stage = adapt->stage; v.adapt.window_end = adapt->window_end;
         v.adapt.target = adapt->target_acceptance_rate; v.adapt.gamma = adapt->gamma; v.adapt.t0 = adapt->t0;
         v.adapt.kappa = adapt->kappa;

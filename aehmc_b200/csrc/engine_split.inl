@@ -119,6 +119,7 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
     const int C = v.C, d = v.d;
     const T* imm_dense = (const T*)metric->imm;
     const T* sqrt_t = (const T*)metric->sqrt_t;
+    const T* chol_t = (const T*)metric->chol_t;
     i64 bound = max_ticks > 0 ? max_ticks
                               : (i64)n_transitions * (HMC ? (i64)cfg->num_integration_steps
                                                           : (((i64)1 << v.maxd) - 1 + v.maxd)) + 1;
@@ -129,11 +130,11 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
     if (pl.dense) {
         B2H_CUDA(cudaMemsetAsync(v.mom_count, 0, 4 * sizeof(int), st));
         if (!resume) {
-            // p0 = z . S^T (metrics.py:56-59,67), v0 = p0 . imm (metrics.py:71) for every chain's first transition,
-            // and w = imm . g of the starting positions
+            // p0 = z . S^T (metrics.py:56-59,67), v0 = imm . p0 = z . L^T (metrics.py:71 with imm = L L^T, S = L^-T)
+            // for every chain's first transition, and w = imm . g of the starting positions
             mom_init_kernel<T><<<C, 128, 0, st>>>(v);
             launch_dense_apply<T>(st, v.mom_z, sqrt_t, v.mom_p, C, d, d, nullptr, nullptr);
-            launch_dense_apply<T>(st, v.mom_p, imm_dense, v.mom_v, C, d, d, nullptr, nullptr);
+            launch_dense_apply<T>(st, v.mom_z, chol_t, v.mom_v, C, d, d, nullptr, nullptr);
             launch_dense_apply<T>(st, v.gp, imm_dense, v.wp, C, d, d, nullptr, nullptr);
         }
     }
@@ -146,8 +147,9 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
     const bool fuse = use_fuse && epl <= 4;
 
     // Dense metric, before the kernel that holds the pre part of tick t: all momentum contractions launched so far
-    // must have landed (a chain that started a transition two ticks ago may start the next one now: its v0 came
-    // from the previous tick's side launch), and this parity's request list is about to be reused.
+    // must have landed (a chain that started a transition one tick ago -- HMC with L = 1, a first-step divergence --
+    // may start the next one now: p0 and v0 both came from the previous tick's side launch), and this parity's
+    // request list is about to be reused.
     auto pre_prologue = [&](i64 t) -> int {
         const int b = (int)(t & 1);
         last_parity = b;
@@ -157,8 +159,8 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
         B2H_CUDA(cudaMemsetAsync(v.mom_count + b, 0, sizeof(int), st));
         return 0;
     };
-    // ... and after it, on the side stream: p0 = z . S^T of the transitions queued by this pre part, and
-    // v0 = imm . p0 of the transitions queued one tick ago (their p0 was produced by the previous side launch).
+    // ... and after it, on the side stream: p0 = z . S^T and v0 = imm . p0 = z . L^T of the transitions queued by
+    // this pre part, both from the same normals in one grouped launch.
     auto pre_epilogue = [&](i64 t) -> int {
         const int b = (int)(t & 1);
         if (use_side) {
@@ -171,12 +173,12 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
         T* part2 = v.mom_part + (size_t)kRiderSplit * plane;
         GemmGroup<T> g1{v.mom_z + (size_t)b * C * d, (i64)d, sqrt_t, (i64)d, part1, (i64)d, C, v.mom_count + b,
                         nullptr, nullptr, nullptr};
-        GemmGroup<T> g2{v.mom_p, (i64)d, imm_dense, (i64)d, part2, (i64)d, C, v.mom_count + (b ^ 1), nullptr,
-                        v.mom_list + (size_t)(b ^ 1) * C, nullptr};
+        GemmGroup<T> g2{v.mom_z + (size_t)b * C * d, (i64)d, chol_t, (i64)d, part2, (i64)d, C, v.mom_count + b,
+                        nullptr, nullptr, nullptr};
         launch_gemm_grouped<T>(rider_stream, g1, g2, none, d, d, kRiderSplit, plane, 0);
         rider_reduce_kernel<T><<<dim3(C, 2), 128, 0, rider_stream>>>(
-            part1, v.mom_count + b, v.mom_list + (size_t)b * C, v.mom_p, part2, v.mom_count + (b ^ 1),
-            v.mom_list + (size_t)(b ^ 1) * C, v.mom_v, kRiderSplit, plane, d);
+            part1, v.mom_count + b, v.mom_list + (size_t)b * C, v.mom_p, part2, v.mom_count + b,
+            v.mom_list + (size_t)b * C, v.mom_v, kRiderSplit, plane, d);
         if (use_side) {
             B2H_CUDA(cudaEventRecord(ctx->ev_side[b], ctx->side));
             side_pending[b] = true;
@@ -232,14 +234,11 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
         if (!fuse && !last) rc = launch_pre(tick + 1);
     }
     if (pl.dense && rc == 0) {
-        // join the side stream, then flush: v0 of the transitions queued in the last tick, so that a resumed run
-        // starts with no request pending
+        // join the side stream so that a resumed run (or the caller) starts with no momentum request pending
         for (int b = 0; b < 2; ++b)
             if (side_pending[b]) B2H_CUDA(cudaStreamWaitEvent(st, ctx->ev_side[b], 0));
-        GemmGroup<T> g0{v.mom_p, (i64)d, imm_dense, (i64)d, v.mom_v, (i64)d, C, v.mom_count + last_parity, nullptr,
-                        v.mom_list + (size_t)last_parity * C, v.mom_list + (size_t)last_parity * C};
-        launch_gemm_grouped<T>(st, g0, none, none, d, d, 1, 0, 0);
     }
+    (void)last_parity;
     if (rc) return rc;
     B2H_LAUNCH_CHECK();
     return 0;

@@ -630,6 +630,35 @@ __global__ void select_rows_kernel(const uint8_t* mask, const T* a, const T* b, 
     out[idx] = mask[idx / d] ? a[idx] : b[idx];
 }
 
+// hmc_proposal.propose after the integration (hmc.py:183-204): one warp per chain.  The integrated state gets its
+// momentum flipped; energies E = U + K (K(-p) = K(p)); delta = E_old - E_new (NaN -> -inf); diverging = |delta| >
+// threshold (Q15: a divergent transition is NOT force-rejected); p_accept = clip(exp(delta), 0, 1); accept from the
+// uniform with numpy's binomial(1, p) rule; the final state overwrites the `new` arrays.
+template <typename T>
+__global__ void __launch_bounds__(128)
+hmc_accept_kernel(const T* q0, const T* p0, const T* g0, const T* U0, T* q1, T* p1, T* g1, T* U1, const T* K0,
+                  const T* K1, const double* u, double thr, double* p_accept, uint8_t* diverging, i64 C, int d) {
+    const i64 c = (i64)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (c >= C) return;
+    const int lane = threadIdx.x & 31;
+    const T E0 = U0[c] + K0[c];
+    const T E1 = U1[c] + K1[c];
+    double delta = (double)(E0 - E1);
+    if (isnan(delta)) delta = -INFINITY;
+    const double pa = fmin(fmax(exp(delta), 0.0), 1.0);
+    const bool acc = bern(u[c], pa);
+    for (int j = lane; j < d; j += 32) {
+        const i64 a = c * d + j;
+        if (acc) p1[a] = -p1[a];
+        else { q1[a] = q0[a]; p1[a] = p0[a]; g1[a] = g0[a]; }
+    }
+    if (lane == 0) {
+        if (!acc) U1[c] = U0[c];
+        p_accept[c] = pa;
+        diverging[c] = fabs(delta) > thr ? 1 : 0;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // native draws exported in the injected layout
 // ---------------------------------------------------------------------------
@@ -952,6 +981,20 @@ int b2h_select_rows(b2h_ctx* ctx, int dtype, const uint8_t* mask, const void* a,
     B2H_TYPED(dtype,
               (select_rows_kernel<float><<<grid, 256, 0, ctx->stream>>>(mask, (const float*)a, (const float*)b, (float*)out, C, (int)d)),
               (select_rows_kernel<double><<<grid, 256, 0, ctx->stream>>>(mask, (const double*)a, (const double*)b, (double*)out, C, (int)d)));
+    B2H_LAUNCH_CHECK();
+    return 0;
+}
+
+int b2h_hmc_accept(b2h_ctx* ctx, int dtype, const b2h_state* old_state, b2h_state* new_state, const void* K_old,
+                   const void* K_new, const double* u, double threshold, double* p_accept, uint8_t* is_diverging,
+                   int64_t C, int64_t d) {
+    B2H_CHECK_CTX();
+    if (!old_state || !new_state || !K_old || !K_new || !u || !p_accept || !is_diverging) { set_error("null argument"); return B2H_ERR_ARG; }
+    const int grid = (int)((C + 3) / 4);
+    const b2h_state &o = *old_state, &n = *new_state;
+    B2H_TYPED(dtype,
+              (hmc_accept_kernel<float><<<grid, 128, 0, ctx->stream>>>((const float*)o.q, (const float*)o.p, (const float*)o.g, (const float*)o.U, (float*)n.q, (float*)n.p, (float*)n.g, (float*)n.U, (const float*)K_old, (const float*)K_new, u, threshold, p_accept, is_diverging, C, (int)d)),
+              (hmc_accept_kernel<double><<<grid, 128, 0, ctx->stream>>>((const double*)o.q, (const double*)o.p, (const double*)o.g, (const double*)o.U, (double*)n.q, (double*)n.p, (double*)n.g, (double*)n.U, (const double*)K_old, (const double*)K_new, u, threshold, p_accept, is_diverging, C, (int)d)));
     B2H_LAUNCH_CHECK();
     return 0;
 }

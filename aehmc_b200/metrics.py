@@ -37,7 +37,7 @@ class GaussianMetric:
         self.dtype = backend.torch_dtype(dtype or torch.float64)
         self.device = backend.device(device)
         ndim = imm.ndim if isinstance(imm, torch.Tensor) else np.ndim(imm)
-        self.scalar, self.imm, self.sqrt_t = 0.0, None, None
+        self.scalar, self.imm, self.sqrt_t, self.chol_t = 0.0, None, None, None
         if pc:
             if ndim != 2:
                 raise ValueError("per_chain() expects a [chains, dim] tensor")
@@ -62,6 +62,8 @@ class GaussianMetric:
             self.kind = _lib.IMM_DENSE
             self.imm = backend.as_device(a, self.dtype, self.device)
             self.sqrt_t = backend.as_device(np.ascontiguousarray(sqrt.T), self.dtype, self.device)
+            # imm . (L^-T z) = L z: the engine draws a transition's momentum and its velocity from the same normals
+            self.chol_t = backend.as_device(np.ascontiguousarray(L.T), self.dtype, self.device)
             self.dim = int(a.shape[0])
         else:
             raise ValueError(f"Expected a mass matrix of dimension 1 (diagonal) or 2, got {ndim}")
@@ -69,7 +71,7 @@ class GaussianMetric:
 
     def struct(self):
         p = lambda t: None if t is None else t.data_ptr()
-        return _lib.Metric(self.kind, 0, self.scalar, p(self.imm), p(self.sqrt_t))
+        return _lib.Metric(self.kind, 0, self.scalar, p(self.imm), p(self.sqrt_t), p(self.chol_t))
 
     def _ws_for(self, n_elems):
         nbytes = n_elems * (8 if self.dtype == torch.float64 else 4) + 512
@@ -90,8 +92,7 @@ def gaussian_metric(inverse_mass_matrix, dtype=None, device=None):
         p = torch.empty((Cn, d), dtype=metric.dtype, device=metric.device)
         rng, keep = srng.struct()
         t = srng.transition if transition is None else transition
-        if rng.mode == _lib.RNG_PHILOX:
-            rng.transition_offset = 0
+        rng.transition_offset = 0                  # the transition is passed explicitly
         ws = metric._ws_for(Cn * d)
         m = metric.struct()
         _lib.check(lib.b2h_sample_momentum(backend.context(metric.device), C.byref(m), C.byref(rng), code,

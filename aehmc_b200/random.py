@@ -54,11 +54,12 @@ class InjectedDraws:
         self._cursor = 0
 
     def struct(self, n_transitions=1):
-        if self.transition != 0:
-            raise ValueError("injected draws are consumed from transition 0: use a fresh InjectedDraws per run")
+        if self.transition + int(n_transitions) > self.n_injected:
+            raise ValueError(f"injected draws exhausted: {self.n_injected} transitions injected, "
+                             f"{self.transition} consumed, {n_transitions} requested")
         keep = (self.z, self.u_dir, self.u_biased, self.u_uniform, self.u_accept)
         p = lambda t: None if t is None else t.data_ptr()
-        return _lib.Rng(_lib.RNG_INJECTED, 0, 0, 0, 0, self.n_injected, p(self.z), p(self.u_dir),
+        return _lib.Rng(_lib.RNG_INJECTED, 0, 0, 0, self.transition, self.n_injected, p(self.z), p(self.u_dir),
                         p(self.u_biased), p(self.u_uniform), p(self.u_accept)), keep
 
     def advance(self, n):

@@ -5,11 +5,13 @@ from __future__ import annotations
 
 import torch
 
-from . import _engine
+from . import _engine, _lib, metrics
 from .integrators import IntegratorState
 from .random import RandomStream
 
-CHECKPOINT_VERSION = 1
+CHECKPOINT_VERSION = 2
+_KIND_NAMES = {_lib.IMM_SCALAR: "scalar", _lib.IMM_DIAG: "diag", _lib.IMM_DIAG_PER_CHAIN: "per_chain",
+               _lib.IMM_DENSE: "dense"}
 
 
 def sample(kernel, state, step_size, inverse_mass_matrix, num_samples, *, num_integration_steps=None,
@@ -45,15 +47,29 @@ def checkpoint(state, srng, step_size, inverse_mass_matrix):
             t = torch.from_numpy(np.asarray(t, dtype=np.float64).copy())
         return t.detach().to("cpu").clone()
 
+    # the inverse mass matrix keeps its kind: a [C, d] per-chain diagonal (what window adaptation returns) must not
+    # come back as a dense [d, d] matrix
+    imm = inverse_mass_matrix
+    if isinstance(imm, metrics.GaussianMetric):
+        kind = _KIND_NAMES[imm.kind]
+        imm = torch.tensor(imm.scalar, dtype=torch.float64) if kind == "scalar" else imm.imm
+    elif isinstance(imm, metrics.per_chain):
+        kind, imm = "per_chain", imm.imm
+    else:
+        imm = cpu(imm)
+        if imm.ndim > 2:
+            raise ValueError(f"Expected a mass matrix of dimension 1 (diagonal) or 2, got {imm.ndim}")
+        kind = ("scalar", "diag", "dense")[imm.ndim]
     return {"version": CHECKPOINT_VERSION,
             "position": cpu(state.position), "potential_energy": cpu(state.potential_energy),
             "potential_energy_grad": cpu(state.potential_energy_grad),
-            "step_size": cpu(step_size), "inverse_mass_matrix": cpu(inverse_mass_matrix),
+            "step_size": cpu(step_size), "inverse_mass_matrix": cpu(imm), "inverse_mass_matrix_kind": kind,
             "seed": srng.seed, "chain_offset": srng.chain_offset, "transition": srng.transition}
 
 
 def restore(ckpt, device=None):
-    """Inverse of :func:`checkpoint`: returns (state, srng, step_size, inverse_mass_matrix) on ``device``."""
+    """Inverse of :func:`checkpoint`: returns (state, srng, step_size, inverse_mass_matrix) on ``device``; a
+    per-chain diagonal inverse mass matrix comes back wrapped in ``metrics.per_chain``."""
     if ckpt.get("version") != CHECKPOINT_VERSION:
         raise ValueError(f"unknown checkpoint version {ckpt.get('version')}")
     dev = torch.device("cuda" if device is None else device)
@@ -61,4 +77,7 @@ def restore(ckpt, device=None):
     state = IntegratorState(up(ckpt["position"]), None, up(ckpt["potential_energy"]), up(ckpt["potential_energy_grad"]))
     srng = RandomStream(ckpt["seed"], ckpt["chain_offset"])
     srng.transition = int(ckpt["transition"])
-    return state, srng, up(ckpt["step_size"]), up(ckpt["inverse_mass_matrix"])
+    imm = up(ckpt["inverse_mass_matrix"])
+    if ckpt["inverse_mass_matrix_kind"] == "per_chain":
+        imm = metrics.per_chain(imm)
+    return state, srng, up(ckpt["step_size"]), imm

@@ -43,12 +43,23 @@ def build_schedule(num_steps: int, initial_buffer_size: int = 75, final_buffer_s
 
 
 def run(kernel, initial_state: IntegratorState, num_steps=1000, *, is_mass_matrix_full=False,
-        initial_step_size=1.0, target_acceptance_rate=0.80, num_integration_steps=None):
-    """reference window_adaptation.py:17-116 -> (last_chain_state, (step_size[C], imm[C, d]), updates)."""
+        initial_step_size=1.0, target_acceptance_rate=0.80, num_integration_steps=None, pooled=False,
+        max_chunk_bytes=2 << 30):
+    """reference window_adaptation.py:17-116 -> (last_chain_state, (step_size[C], imm[C, d]), updates).
+
+    ``pooled=True`` (not in the reference, which adapts one chain at a time): the chains sample the same target, so
+    the inverse mass matrix is ONE matrix -- diagonal [d] or, with ``is_mass_matrix_full``, dense [d, d] -- estimated
+    at each slow-window end from the positions of all chains of all ranks (Welford states merged over NCCL); step
+    sizes stay per chain.  Returns (state, (step_size[C], imm[d] or imm[d, d]), updates)."""
     spec = getattr(kernel, "spec", None)
+    if pooled:
+        if spec is None:
+            raise ValueError("pooled warm-up needs a kernel from nuts.new_kernel / hmc.new_kernel")
+        return _run_pooled(spec, initial_state, num_steps, is_mass_matrix_full, initial_step_size,
+                           target_acceptance_rate, num_integration_steps, max_chunk_bytes)
     if spec is None or is_mass_matrix_full:
         return _run_composed(kernel, initial_state, num_steps, is_mass_matrix_full, initial_step_size,
-                             target_acceptance_rate)
+                             target_acceptance_rate, num_integration_steps)
     model = spec["model"]
     Cn, d = initial_state.position.shape
     schedule = build_schedule(num_steps)
@@ -100,19 +111,76 @@ def window_adaptation(num_steps, is_mass_matrix_full=False, initial_step_size=1.
     return init, update
 
 
-def _run_composed(kernel, initial_state, num_steps, is_mass_matrix_full, initial_step_size, target):
+def _run_composed(kernel, initial_state, num_steps, is_mass_matrix_full, initial_step_size, target,
+                  num_integration_steps=None):
     init_adapt, update_adapt = window_adaptation(num_steps, is_mass_matrix_full, initial_step_size, target)
     warmup_state, parameters = init_adapt(initial_state)
     Cn = initial_state.position.shape[0]
     if is_mass_matrix_full and Cn != 1:
         raise NotImplementedError("dense mass-matrix adaptation is per chain; a dense metric is shared by all chains, "
                                   "so is_mass_matrix_full=True needs a single chain")
+    spec = getattr(kernel, "spec", None)
+    is_hmc = (spec is not None and spec.get("kind") == "hmc") or (spec is None and num_integration_steps is not None)
+    if is_hmc and num_integration_steps is None:
+        raise ValueError("HMC warm-up needs num_integration_steps")
     state = initial_state
     for step in range(num_steps):
         step_size, imm = parameters
         arg = imm[0] if is_mass_matrix_full else metrics.per_chain(imm)
-        info, _ = kernel(state, step_size, arg)
+        if is_hmc:
+            info, _ = kernel(state, step_size, arg, num_integration_steps)
+        else:
+            info, _ = kernel(state, step_size, arg)
         warmup_state, parameters = update_adapt(step, warmup_state, parameters, info)
         s = info.state
         state = IntegratorState(s.position, None, s.potential_energy, s.potential_energy_grad)
     return state, parameters, {}
+
+
+def _run_pooled(spec, initial_state, num_steps, is_mass_matrix_full, initial_step_size, target, num_integration_steps,
+                max_chunk_bytes):
+    """Warm-up with cross-chain statistics.  The engine runs the transitions of a chunk (per-chain dual averaging on
+    the device, window_adaptation.py:194-215); between chunks the draws of the slow stage are folded into the pooled
+    Welford state, and at a window end (window_adaptation.py:165-190) the per-rank states are merged over the process
+    group and every rank rebuilds the same shared metric."""
+    from .mass_matrix import PooledWelford
+    model = spec["model"]
+    dev, dt = model.device, model.dtype
+    Cn, d = initial_state.position.shape
+    schedule = build_schedule(num_steps)
+    adapt = _engine.AdaptState(Cn, schedule, dev, target, float(initial_step_size), pooled=True)
+    imm = torch.eye(d, dtype=dt, device=dev) if is_mass_matrix_full else torch.ones(d, dtype=dt, device=dev)
+    pool = PooledWelford(d, is_mass_matrix_full, dev)
+    kw = dict(divergence_threshold=spec["divergence_threshold"], adapt=adapt)
+    if spec["kind"] == "nuts":
+        kw["max_num_expansions"] = spec["max_num_expansions"]
+        kw["exact_doubling"] = spec.get("exact_doubling", False)
+    else:
+        if num_integration_steps is None:
+            raise ValueError("HMC warm-up needs num_integration_steps")
+        kw["num_integration_steps"] = num_integration_steps
+    chunk_max = max(1, int(max_chunk_bytes) // max(Cn * d * initial_state.position.element_size(), 1))
+    state, eps, step, n_leap = initial_state, 1.0, 0, None
+    windows = []
+    while step < num_steps:
+        end = step
+        while end < num_steps - 1 and not schedule[end][1] and end - step + 1 < chunk_max:
+            end += 1
+        n = end - step + 1
+        slow = [i - step for i in range(step, end + 1) if schedule[i][0] == 1]
+        adapt.step_offset = step
+        info, extras = _engine.run(spec["kind"], model, imm, spec["srng"], state, eps, n_transitions=n,
+                                   store_draws=n if slow else 0, **kw)
+        eps = extras["step_size"]
+        if slow:
+            pool.update(extras["draws"][slow[0]:slow[-1] + 1])          # the slow stage is one contiguous range
+        if schedule[end][1]:
+            pool.all_reduce()
+            windows.append(pool.n)
+            imm = pool.final(dt)
+            pool.reset()
+        st = info.state
+        state = IntegratorState(st.position, None, st.potential_energy, st.potential_energy_grad)
+        n_leap = extras["n_leapfrog"]
+        step = end + 1
+    return state, (eps, imm), {"n_leapfrog": n_leap, "pooled_window_sizes": windows}

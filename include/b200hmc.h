@@ -88,6 +88,9 @@ typedef struct {
     const void* imm;    /* device; dense: symmetric [d x d] */
     const void* sqrt_t; /* device, dense only: TRANSPOSE of mass_matrix_sqrt = solve_triangular(chol(imm), I,
                            lower, trans) (metrics.py:56-58), row-major [d x d]: p_row = z_row . sqrt_t       */
+    const void* chol_t; /* device, dense only: TRANSPOSE of L = chol(imm), row-major [d x d].  imm . p = L L^T L^-T z
+                           = L z, so the velocity of a fresh momentum is v_row = z_row . chol_t: the sampler draws p0 and
+                           imm . p0 of a transition from the same normals in ONE grouped contraction               */
 } b2h_metric;
 
 /* ---- random draws: native Philox4x32-10 or injected (validation mode) ---- */
@@ -98,7 +101,8 @@ typedef struct {
     int32_t reserved;
     uint64_t seed;
     uint64_t chain_offset;      /* global id of local chain 0 (multi-GPU sharding)               */
-    uint64_t transition_offset; /* global index of the first transition of this call             */
+    uint64_t transition_offset; /* global index of the first transition of this call (injected mode:
+                                   index of its first row within the T injected transitions)           */
     /* injected draws, float64, device; T = n_injected transitions per chain                     */
     int64_t n_injected;
     const double* z;         /* [C][T][d]                 standard normals (momentum)            */
@@ -136,6 +140,10 @@ typedef struct {
     void* wc_mean;              /* [C x d] dtype */
     void* wc_m2;                /* [C x d] dtype */
     int64_t* wc_n;              /* [C] */
+    int32_t pooled;             /* 1: the inverse mass matrix is shared and re-estimated by the CALLER from the pooled
+                                   statistics of all chains at each window end (b2h_welford_pooled_update): the engine
+                                   runs the per-chain dual averaging only and never touches the metric; any metric kind */
+    int32_t step_offset;        /* schedule index of the call's first transition (a warm-up run in several calls)    */
 } b2h_adapt;
 
 /* ---- sampler configuration ---- */
@@ -296,6 +304,14 @@ int b2h_progressive_sampling(b2h_ctx*, int biased, const double* w_old, const do
 int b2h_select_rows(b2h_ctx*, int dtype, const uint8_t* mask, const void* a, const void* b, void* out, int64_t C,
                     int64_t d);
 
+/* hmc.hmc_proposal(...).propose after the static integration (hmc.py:183-204): flips the momentum of the integrated
+ * state, delta = (U + K)_old - (U + K)_new (NaN -> -inf), is_diverging = |delta| > threshold, p_accept =
+ * clip(exp(delta), 0, 1), Metropolis accept from the uniform u[C] (numpy's binomial(1, p) decision rule).  new_state
+ * is overwritten with the final state (the flipped new state, or old_state). */
+int b2h_hmc_accept(b2h_ctx*, int dtype, const b2h_state* old_state, b2h_state* new_state, const void* K_old,
+                   const void* K_new, const double* u, double threshold, double* p_accept, uint8_t* is_diverging,
+                   int64_t C, int64_t d);
+
 /* algorithms.dual_averaging update (algorithms.py:79-115) with gradient = target - p_accept
  * (step_size.py:97); in place on the [C] state arrays. */
 int b2h_dual_averaging_update(b2h_ctx*, const double* p_accept, double target, double gamma, double t0, double kappa,
@@ -306,6 +322,18 @@ int b2h_welford_update(b2h_ctx*, int dtype, const void* value, void* mean, void*
                        int64_t d, int32_t full);
 int b2h_mass_matrix_final(b2h_ctx*, int dtype, const void* m2, const int64_t* n, void* imm_out, int64_t C, int64_t d,
                           int32_t full);
+
+/* Pooled (cross-chain) Welford statistics: the positions of ALL chains in a slow window are one sample of the same
+ * target.  Folds a block of draws [T][C][d] into the running float64 state (n, mean[d], m2[d] or, full != 0,
+ * m2[d x d]) with the group form of welford_covariance.update (algorithms.py:166-197; Chan's pairwise update), fixed
+ * summation order.  n is the number of rows already in the state (host value; the caller adds T * C afterwards). */
+int b2h_welford_pooled_update(b2h_ctx*, int dtype, const void* draws, int64_t T, int64_t C, int64_t d, int32_t full,
+                              int64_t n, double* mean, double* m2, void* workspace, int64_t workspace_bytes);
+int64_t b2h_welford_pooled_workspace_bytes(int64_t T, int64_t C, int64_t d, int32_t full);
+/* (n_a, mean_a, m2_a) <- merge with (n_b, mean_b, m2_b): the states of two groups of chains, e.g. two ranks after
+ * the all-gather of the adaptation statistics.  scratch_mean: [d] float64. */
+int b2h_welford_merge(b2h_ctx*, int64_t d, int32_t full, int64_t n_a, double* mean_a, double* m2_a, int64_t n_b,
+                      const double* mean_b, const double* m2_b, double* scratch_mean);
 
 /* Native-RNG draws exported in the injected layout (so a Philox run can be replayed by the oracle). */
 int b2h_philox_fill(b2h_ctx*, uint64_t seed, uint64_t chain_offset, uint64_t transition_offset, int64_t C,

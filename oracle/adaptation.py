@@ -201,3 +201,55 @@ def run(kernel, initial_state, num_steps=1000, *, is_mass_matrix_full=False,
         if trace is not None:
             trace.append((chain_info, extras, parameters))
     return chain_state, parameters, {}
+
+
+def merge_welford(n_a, mean_a, m2_a, n_b, mean_b, m2_b):
+    """Chan's pairwise merge of two Welford states: what folding the second group's values one by one with
+    welford_covariance.update (reference algorithms.py:187-197) converges to, in one step."""
+    if n_b == 0:
+        return n_a, mean_a, m2_a
+    if n_a == 0:
+        return n_b, np.array(mean_b, dtype=np.float64), np.array(m2_b, dtype=np.float64)
+    n = n_a + n_b
+    delta = mean_b - mean_a
+    cross = np.outer(delta, delta) if np.ndim(m2_a) == 2 else delta * delta
+    return n, mean_a + delta * (n_b / n), m2_a + m2_b + cross * (n_a * n_b / n)
+
+
+def run_pooled(kernels, initial_states, num_steps, *, is_mass_matrix_full=False, initial_step_size=1.0,
+               target_acceptance_rate=0.80, trace=None):
+    """Pooled warm-up of many chains of one target (beyond the reference, which adapts one chain at a time): per-chain
+    dual averaging exactly as window_adaptation.update (reference window_adaptation.py:194-227), ONE inverse mass matrix
+    re-estimated at each slow-window end from the slow-stage positions of all chains with the reference's own
+    welford_covariance / covariance_adaptation.final (values folded one by one: the defining recurrence)."""
+    mm_init, mm_update, mm_final = covariance_adaptation(is_mass_matrix_full)
+    da_init, da_update = dual_averaging_adaptation(target_acceptance_rate)
+    schedule = build_schedule(num_steps)
+    n_chains = len(kernels)
+    d = np.asarray(initial_states[0].position).shape[0]
+    imm, mm_state = mm_init(d)
+    da_states = [da_init(initial_step_size) for _ in range(n_chains)]
+    step_sizes = [math.exp(s.iterates) for s in da_states]
+    states = list(initial_states)
+    for step in range(num_steps):
+        stage, is_end = schedule[step]
+        infos = []
+        for c in range(n_chains):
+            info, extras = kernels[c](states[c], step_sizes[c], imm)
+            infos.append((info, extras))
+            da_states[c] = da_update(info.acceptance_probability, da_states[c])
+            step_sizes[c] = math.exp(da_states[c].iterates)
+            states[c] = IntegratorState(info.state.position, None, info.state.potential_energy,
+                                        info.state.potential_energy_grad)
+        if stage == 1:
+            for c in range(n_chains):
+                mm_state = mm_update(infos[c][0].state.position, mm_state)
+        if is_end:
+            imm = mm_final(mm_state)
+            _, mm_state = mm_init(d)
+            da_states = [da_init(step_sizes[c]) for c in range(n_chains)]
+        if step == num_steps - 1:
+            step_sizes = [math.exp(s.iterates_avg) for s in da_states]
+        if trace is not None:
+            trace.append((infos, list(step_sizes), imm))
+    return states, (np.array(step_sizes), imm), {}

@@ -266,6 +266,80 @@ def test_hmc_dense_metric_correlated_gaussian(ab):
         np.testing.assert_allclose(got[k], ref[k], rtol=1e-9, atol=1e-11, err_msg=k)
 
 
+@pytest.mark.parametrize("L", [1, 2])
+def test_hmc_dense_metric_single_tick_transitions(ab, L):
+    """A dense-metric transition that lasts ONE tick (HMC with L = 1) starts the next one on the following tick:
+    the look-ahead momentum p0 AND its velocity imm.p0 must both have landed by then (they come from the same
+    normals in one grouped launch, v0 = z.L^T)."""
+    rng = np.random.default_rng(32 + L)
+    C, T, d = 8, 5, 12
+    mu, cov, prec = _corr_case(rng, d)
+    q0 = mu + rng.standard_normal((C, d))
+    draws = parity.random_draws(rng, C, T, d)
+    ref = parity.oracle_hmc(o_models.CorrelatedGaussian(mu, prec), q0, 0.2, cov, draws, T, L)
+    got = gpu_hmc(ab, ab.models.CorrelatedGaussian(mu, prec), cov, q0, 0.2, draws, T, L)
+    for k in ("q", "p", "g", "U", "acceptance_probability"):
+        np.testing.assert_allclose(got[k], ref[k], rtol=1e-9, atol=1e-11, err_msg=k)
+    np.testing.assert_allclose(got["draws"], ref["draws"], rtol=1e-9, atol=1e-11)
+
+
+def test_nuts_dense_metric_first_step_divergence(ab):
+    """NUTS with a dense metric where the very first leapfrog diverges (huge step size, low threshold): every
+    transition is one tick long and still uses the momentum / velocity of its OWN transition."""
+    from aehmc_b200 import _engine
+    rng = np.random.default_rng(41)
+    C, T, d = 6, 4, 10
+    mu, cov, prec = _corr_case(rng, d)
+    q0 = mu + rng.standard_normal((C, d))
+    draws = parity.random_draws(rng, C, T, d)
+    eps = np.array([50.0, 0.2, 50.0, 0.3, 50.0, 50.0])
+    ref = parity.oracle_nuts(o_models.CorrelatedGaussian(mu, prec), q0, eps, cov, draws, T, div_thr=10.0)
+    assert ref["is_diverging"].astype(bool).sum() >= 3 and (ref["n_leapfrog"] == 1).sum() >= 3
+    model = ab.models.CorrelatedGaussian(mu, prec)
+    srng = ab.InjectedDraws(draws["z"], draws["u_dir"], draws["u_biased"], draws["u_uniform"])
+    info, extras = _engine.run("nuts", model, cov, srng, ab.nuts.new_state(q0, model),
+                               torch.as_tensor(eps, dtype=torch.float64), n_transitions=T, divergence_threshold=10.0,
+                               store_draws=T)
+    np.testing.assert_array_equal(_np(info.num_doublings), ref["num_doublings"])
+    np.testing.assert_array_equal(_np(extras["n_leapfrog"]), ref["n_leapfrog"])
+    np.testing.assert_array_equal(_np(info.is_diverging).astype(bool), ref["is_diverging"].astype(bool))
+    np.testing.assert_allclose(_np(extras["draws"]), ref["draws"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(_np(info.state.momentum), ref["p"], rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize("metric_kind", ["diag", "dense"])
+def test_hmc_proposal_closure_matches_oracle(ab, metric_kind):
+    """hmc.hmc_proposal(integrator, kinetic_energy, L, threshold) -> propose(srng, state, step_size)
+    (reference hmc.py:129-206), composed the way hmc.new_kernel.step composes it (hmc.py:110-123)."""
+    rng = np.random.default_rng(51)
+    C, T, L, d = 9, 3, 6, 7
+    mu, cov, prec = _corr_case(rng, d)
+    imm = cov if metric_kind == "dense" else np.diag(cov).copy()
+    q0 = mu + rng.standard_normal((C, d))
+    draws = parity.random_draws(rng, C, T, d)
+    ref = parity.oracle_hmc(o_models.CorrelatedGaussian(mu, prec), q0, 0.3, imm, draws, T, L, div_thr=0.05)
+    model = ab.models.CorrelatedGaussian(mu, prec)
+    momentum_generator, kinetic_energy, _ = ab.metrics.gaussian_metric(imm)
+    integrator = ab.integrators.velocity_verlet(model, kinetic_energy)
+    propose = ab.hmc.hmc_proposal(integrator, kinetic_energy, L, 0.05)
+    srng = ab.InjectedDraws(z=draws["z"], u_accept=draws["u_accept"])
+    state = ab.hmc.new_state(q0, model)
+    for t in range(T):
+        state = state._replace(momentum=momentum_generator(srng, num_chains=C, dim=d, transition=t))
+        info, updates = propose(srng, state, 0.3)
+        np.testing.assert_allclose(_np(info.state.position), ref["draws"][t], rtol=1e-9, atol=1e-11)
+        state = info.state
+    assert info.num_doublings is None and info.is_turning is None and updates == {}
+    np.testing.assert_allclose(_np(info.state.momentum), ref["p"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(_np(info.state.potential_energy), ref["U"], rtol=1e-9)
+    np.testing.assert_allclose(_np(info.state.potential_energy_grad), ref["g"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(_np(info.acceptance_probability), ref["acceptance_probability"], rtol=1e-9)
+    np.testing.assert_array_equal(_np(info.is_diverging).astype(bool), ref["is_diverging"].astype(bool))
+    assert ref["is_diverging"].any() and not ref["is_diverging"].all()
+    with pytest.raises(ValueError):
+        propose(srng, ab.hmc.new_state(q0, model), 0.3)
+
+
 def test_hmc_public_kernel_signature(ab):
     """hmc.new_kernel(srng, logprob_fn)(state, step_size, imm, L) -> (Diagnostics, updates)."""
     model = ab.models.IIDGaussian(np.zeros(3), np.ones(3))

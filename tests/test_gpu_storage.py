@@ -61,3 +61,24 @@ def test_checkpoint_resume_is_bit_exact(ab, split):
     second = ab.sampling.sample(ab.nuts.new_kernel(srng2, model), state, eps, imm2, 3)
     assert torch.equal(torch.cat([first[1], second[1]]), whole[1])
     assert torch.equal(second[0].state.position, whole[0].state.position)
+
+
+def test_checkpoint_after_window_adaptation_is_bit_exact(ab):
+    """The README workflow: warm up, checkpoint (per-chain step sizes + per-chain diagonal inverse mass matrix),
+    restore, keep sampling -- equal to sampling straight on, bit for bit."""
+    rng = np.random.default_rng(3)
+    Cn, d = 64, 10
+    model = ab.models.NealFunnel(d)
+    q0 = rng.standard_normal((Cn, d))
+    srng = ab.RandomStream(seed=21)
+    kernel = ab.nuts.new_kernel(srng, model)
+    state, (eps, imm), _ = ab.window_adaptation.run(kernel, ab.nuts.new_state(q0, model), 60)
+    assert imm.shape == (Cn, d)
+    buf = io.BytesIO()
+    torch.save(ab.sampling.checkpoint(state, srng, eps, ab.metrics.per_chain(imm)), buf)
+    buf.seek(0)
+    whole = ab.sampling.sample(kernel, state, eps, ab.metrics.per_chain(imm), 5)
+    state2, srng2, eps2, imm2 = ab.sampling.restore(torch.load(buf, weights_only=False), device="cuda:0")
+    assert isinstance(imm2, ab.metrics.per_chain) and srng2.transition == 60
+    again = ab.sampling.sample(ab.nuts.new_kernel(srng2, model), state2, eps2, imm2, 5)
+    assert torch.equal(again[1], whole[1]) and torch.equal(again[0].state.position, whole[0].state.position)

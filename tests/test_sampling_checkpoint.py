@@ -30,3 +30,21 @@ def test_checkpoint_round_trip_cpu():
         sampling.restore({**ck, "version": 99}, device="cpu")
     with pytest.raises(TypeError):
         sampling.checkpoint(state, InjectedDraws.__new__(InjectedDraws), 0.3, 1.0)
+
+
+def test_checkpoint_keeps_the_metric_kind_cpu():
+    """window adaptation returns a [C, d] per-chain diagonal: it must come back as per_chain, never as a dense matrix."""
+    from aehmc_b200 import metrics, sampling
+    from aehmc_b200.integrators import IntegratorState
+    from aehmc_b200.random import RandomStream
+    q = torch.zeros((4, 4), dtype=torch.float64)
+    state = IntegratorState(q, None, torch.zeros(4, dtype=torch.float64), q.clone())
+    imm = torch.rand((4, 4), dtype=torch.float64) + 0.5            # C == d: the ambiguous case
+    ck = sampling.checkpoint(state, RandomStream(1), torch.full((4,), 0.1, dtype=torch.float64), metrics.per_chain(imm))
+    assert ck["inverse_mass_matrix_kind"] == "per_chain"
+    _, _, eps, imm2 = sampling.restore(ck, device="cpu")
+    assert isinstance(imm2, metrics.per_chain) and torch.equal(imm2.imm, imm) and eps.shape == (4,)
+    for raw, kind in ((2.0, "scalar"), (np.ones(4), "diag"), (np.eye(4), "dense")):
+        assert sampling.checkpoint(state, RandomStream(1), 0.1, raw)["inverse_mass_matrix_kind"] == kind
+    with pytest.raises(ValueError):
+        sampling.checkpoint(state, RandomStream(1), 0.1, np.ones((2, 2, 2)))
