@@ -136,19 +136,112 @@ def sufficient_statistics(draws, max_lag=None, dims=None):
             "sum_mean_sq": (mean * mean).sum(0).cpu().numpy(), "sum_acov": acov.sum(0).cpu().numpy()}
 
 
-def ess(draws, max_lag=None, dims=None, distributed=True):
-    """Effective sample size per dimension over all chains (and all ranks when distributed)."""
-    stats = sufficient_statistics(draws, max_lag, dims)
+def ess(draws, max_lag=None, dims=None, distributed=True, method="bulk"):
+    """Effective sample size per dimension over all chains (and all ranks when distributed).
+    ``method="bulk"`` (default, what ``arviz.ess`` computes by default and the reference's tests use,
+    tests/test_hmc.py:158-167): chains split in halves, draws rank-normalised over the whole pool, then the
+    multi-chain autocorrelation estimator.  ``method="mean"``: the same estimator on the raw draws, no split."""
+    if method == "bulk":
+        z = rank_normalized_split(draws, dims, distributed)
+        if max_lag is None:
+            max_lag = min(z.shape[0] - 1, 200)
+        stats = sufficient_statistics(z, max_lag)
+    elif method == "mean":
+        stats = sufficient_statistics(draws, max_lag, dims)
+    else:
+        raise ValueError("method must be 'bulk' or 'mean'")
     if distributed:
         stats = all_reduce_statistics(stats, draws.device if isinstance(draws, torch.Tensor) and draws.is_cuda else None)
     return ess_from_statistics(stats)
 
 
-def rhat(draws, dims=None, distributed=True):
-    stats = sufficient_statistics(draws, 1, dims)
-    if distributed:
-        stats = all_reduce_statistics(stats, draws.device if isinstance(draws, torch.Tensor) and draws.is_cuda else None)
-    return rhat_from_statistics(stats)
+def rhat(draws, dims=None, distributed=True, method="rank"):
+    """Potential scale reduction per dimension.  ``method="rank"`` (default, ``arviz.rhat``'s default; Vehtari et al.
+    2021): the larger of the split-R-hat of the rank-normalised draws and of the rank-normalised folded draws
+    |x - median|.  ``method="split"``: split chains, raw draws.  ``method="identity"``: raw chains."""
+    cuda_dev = draws.device if isinstance(draws, torch.Tensor) and draws.is_cuda else None
+
+    def from_draws(x):
+        stats = sufficient_statistics(x, 1)
+        if distributed:
+            stats = all_reduce_statistics(stats, cuda_dev)
+        return rhat_from_statistics(stats)
+
+    if method == "rank":
+        bulk = from_draws(rank_normalized_split(draws, dims, distributed))
+        tail = from_draws(rank_normalized_split(draws, dims, distributed, fold=True))
+        return np.maximum(bulk, tail)
+    if method == "split":
+        x = _as_tensor(draws)
+        if dims is not None:
+            x = x[:, :, dims]
+        return from_draws(split_chains(x))
+    if method == "identity":
+        stats = sufficient_statistics(draws, 1, dims)
+        if distributed:
+            stats = all_reduce_statistics(stats, cuda_dev)
+        return rhat_from_statistics(stats)
+    raise ValueError("method must be 'rank', 'split' or 'identity'")
+
+
+# ------------------------------------------------------------------------------------------------
+# split chains + rank normalisation (arviz _split_chains / _z_scale), on the device of the draws
+# ------------------------------------------------------------------------------------------------
+def _as_tensor(draws):
+    return draws if isinstance(draws, torch.Tensor) else torch.as_tensor(np.asarray(draws))
+
+
+def split_chains(x):
+    """[T, C, d] -> [T // 2, 2 C, d]: first and last half of every chain as separate chains."""
+    half = x.shape[0] // 2
+    return torch.cat([x[:half], x[x.shape[0] - half:]], dim=1)
+
+
+def _gather_sorted(v):
+    """Sorted values of every rank ([n_r] each).  Without a process group: just the local ones."""
+    import torch.distributed as dist
+    s = torch.sort(v).values
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [s]
+    world = dist.get_world_size()
+    counts = torch.zeros(world, dtype=torch.int64, device=v.device)
+    counts[dist.get_rank()] = s.numel()
+    dist.all_reduce(counts)
+    nmax = int(counts.max())
+    pad = s if s.numel() == nmax else torch.cat([s, s.new_full((nmax - s.numel(),), float("inf"))])
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)                       # the "gather of draws" of BASELINE.json configs[4]
+    return [p[:int(n)] for p, n in zip(parts, counts.tolist())]
+
+
+def rank_normalized_split(draws, dims=None, distributed=True, fold=False):
+    """z-scores of the split chains: z = Phi^-1((rank - 3/8) / (S + 1/4)), average ranks over the pool of ALL draws of
+    all chains (of all ranks when ``distributed``: every rank sorts its own values, the sorted runs are all-gathered,
+    and each rank ranks its own draws against all runs).  ``fold``: ranks of |x - median| (tail R-hat).
+    Returns [T // 2, 2 C, d'] float64 on the device of ``draws``."""
+    x = _as_tensor(draws)
+    if dims is not None:
+        x = x[:, :, dims]
+    x = split_chains(x).to(torch.float64)
+    out = torch.empty_like(x)
+    for j in range(x.shape[2]):
+        v = x[:, :, j].reshape(-1).contiguous()
+        runs = _gather_sorted(v) if distributed else [torch.sort(v).values]
+        if fold:
+            allv = torch.sort(torch.cat(runs)).values
+            n = allv.numel()
+            med = allv[n // 2] if n % 2 else 0.5 * (allv[n // 2 - 1] + allv[n // 2])
+            v = (v - med).abs()
+            runs = [torch.sort((r - med).abs()).values for r in runs]
+        total = sum(int(r.numel()) for r in runs)
+        less = torch.zeros_like(v)
+        leq = torch.zeros_like(v)
+        for r in runs:
+            less += torch.searchsorted(r, v, right=False).to(torch.float64)
+            leq += torch.searchsorted(r, v, right=True).to(torch.float64)
+        rank = 0.5 * (less + leq + 1.0)                # average rank, 1-based (scipy.stats.rankdata "average")
+        out[:, :, j] = torch.special.ndtri((rank - 0.375) / (total + 0.25)).reshape(x.shape[0], x.shape[1])
+    return out
 
 
 def gather_draws(draws, dims=None, thin=1):
@@ -182,8 +275,9 @@ def ess_bulk_single_chain(x):
     rank-normalise over all draws, then the estimator above."""
     from scipy import stats as sstats
     x = np.asarray(x, dtype=np.float64)
-    n = (x.shape[0] // 2) * 2
-    halves = x[:n].reshape(2, n // 2)
+    half = x.shape[0] // 2
+    n = 2 * half
+    halves = np.stack([x[:half], x[x.shape[0] - half:]])        # arviz _split_chains: an odd middle draw is dropped
     ranks = sstats.rankdata(halves.ravel(), method="average").reshape(halves.shape)
     z = sstats.norm.ppf((ranks - 0.375) / (halves.size + 0.25))
     st = sufficient_statistics_numpy(z.T[:, :, None], n // 2 - 1)

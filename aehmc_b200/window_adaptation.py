@@ -44,19 +44,23 @@ def build_schedule(num_steps: int, initial_buffer_size: int = 75, final_buffer_s
 
 def run(kernel, initial_state: IntegratorState, num_steps=1000, *, is_mass_matrix_full=False,
         initial_step_size=1.0, target_acceptance_rate=0.80, num_integration_steps=None, pooled=False,
-        max_chunk_bytes=2 << 30):
+        max_chunk_bytes=2 << 30, initial_inverse_mass_matrix=None):
     """reference window_adaptation.py:17-116 -> (last_chain_state, (step_size[C], imm[C, d]), updates).
 
     ``pooled=True`` (not in the reference, which adapts one chain at a time): the chains sample the same target, so
     the inverse mass matrix is ONE matrix -- diagonal [d] or, with ``is_mass_matrix_full``, dense [d, d] -- estimated
     at each slow-window end from the positions of all chains of all ranks (Welford states merged over NCCL); step
-    sizes stay per chain.  Returns (state, (step_size[C], imm[d] or imm[d, d]), updates)."""
+    sizes stay per chain.  ``initial_inverse_mass_matrix`` (pooled mode only; the reference always starts from the
+    identity) is the metric used until the first window end.  Returns (state, (step_size[C], imm[d] or imm[d, d]),
+    updates)."""
     spec = getattr(kernel, "spec", None)
     if pooled:
         if spec is None:
             raise ValueError("pooled warm-up needs a kernel from nuts.new_kernel / hmc.new_kernel")
         return _run_pooled(spec, initial_state, num_steps, is_mass_matrix_full, initial_step_size,
-                           target_acceptance_rate, num_integration_steps, max_chunk_bytes)
+                           target_acceptance_rate, num_integration_steps, max_chunk_bytes, initial_inverse_mass_matrix)
+    if initial_inverse_mass_matrix is not None:
+        raise ValueError("initial_inverse_mass_matrix needs pooled=True (per-chain warm-up starts from the identity)")
     if spec is None or is_mass_matrix_full:
         return _run_composed(kernel, initial_state, num_steps, is_mass_matrix_full, initial_step_size,
                              target_acceptance_rate, num_integration_steps)
@@ -138,7 +142,7 @@ def _run_composed(kernel, initial_state, num_steps, is_mass_matrix_full, initial
 
 
 def _run_pooled(spec, initial_state, num_steps, is_mass_matrix_full, initial_step_size, target, num_integration_steps,
-                max_chunk_bytes):
+                max_chunk_bytes, initial_imm=None):
     """Warm-up with cross-chain statistics.  The engine runs the transitions of a chunk (per-chain dual averaging on
     the device, window_adaptation.py:194-215); between chunks the draws of the slow stage are folded into the pooled
     Welford state, and at a window end (window_adaptation.py:165-190) the per-rank states are merged over the process
@@ -150,6 +154,11 @@ def _run_pooled(spec, initial_state, num_steps, is_mass_matrix_full, initial_ste
     schedule = build_schedule(num_steps)
     adapt = _engine.AdaptState(Cn, schedule, dev, target, float(initial_step_size), pooled=True)
     imm = torch.eye(d, dtype=dt, device=dev) if is_mass_matrix_full else torch.ones(d, dtype=dt, device=dev)
+    if initial_imm is not None:
+        imm0 = backend.as_device(initial_imm, dt, dev)
+        if imm0.shape != imm.shape:
+            raise ValueError(f"initial_inverse_mass_matrix must have shape {tuple(imm.shape)}")
+        imm = imm0
     pool = PooledWelford(d, is_mass_matrix_full, dev)
     kw = dict(divergence_threshold=spec["divergence_threshold"], adapt=adapt)
     if spec["kind"] == "nuts":

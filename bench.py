@@ -1,19 +1,25 @@
 #!/usr/bin/env python
-"""Throughput benchmark of the many-chain NUTS hot path (BASELINE.json metric: leapfrog gradient evals/s).
+"""Throughput benchmark of the many-chain NUTS hot path (BASELINE.json metric: leapfrog gradient evals/s and
+NUTS ESS/s, whole box).
 
-Default workload (N=1): BASELINE.json configs[1] ("c2") -- NUTS on a 1000-dim correlated Gaussian with a dense
-inverse mass matrix, 4096 chains per GPU (synthetic inputs of SURVEY.md section 8d).  Other workloads:
-"c3" = configs[2] (NUTS Bayesian logistic regression, N = 100k, D = 128, 4096 chains, tcgen05 gradient) and
-"c5" = configs[4] (the same model with 131072 chains per GPU = 1M chains on 8 GPUs).  A "step" is TICKS engine
-ticks in free-running mode; every tick is one velocity-Verlet step (one gradient evaluation) of every chain,
-with chains finishing and restarting NUTS transitions independently.  N>1: chains are sharded (Philox keyed by
-global chain id), no data-path collective ("weak" scaling); the only collective is the all-reduce of the
-R-hat / ESS sufficient statistics.
+Default workload: BASELINE.json configs[4] ("c5") -- chain-sharded NUTS Bayesian logistic regression, N = 100k,
+D = 128, 131072 chains per GPU (1M chains on 8 GPUs), float32 state, gradient on the fused tcgen05 / TMA / TMEM
+kernel.  A "step" is TICKS engine ticks in free-running mode; every tick is one velocity-Verlet step (one gradient
+evaluation) of every chain, chains finishing and restarting NUTS transitions independently.  At N = 1 the same JSON
+line carries the other BASELINE configurations as `secondary`: c3 (configs[2], 4096 chains), c2 (configs[1], d = 1000
+dense metric, float64), c4 (configs[3], window adaptation + NUTS on the funnel / eight schools, 65536 chains) and c1
+(configs[0], HMC on a 100-dim Gaussian), each with its own value / ms / roofline.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|c5|c2small|c3small]
+N > 1: chains are sharded (Philox keyed by global chain id), no data-path collective ("weak" scaling).  The
+collectives are the adaptation-statistic exchange of the pooled warm-up and the diagnostics exchange (all-gather of
+the sorted monitored draws for the rank normalisation, all-reduce of the ESS / R-hat sufficient statistics); both are
+inside the timed `e2e_with_diagnostics` number.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c5|c3|c2|c3small|c2small]
 """
 import argparse
 import json
+import math
 import multiprocessing as mp
 import os
 import sys
@@ -27,15 +33,16 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (kind, chains per GPU, dim, ticks per step, data rows)
+    "c5": ("logistic", 131072, 128, 16, 100000),
+    "c3": ("logistic", 4096, 128, 24, 100000),
     "c2": ("dense", 4096, 1000, 24, 0),
     "c2small": ("dense", 512, 256, 8, 0),
-    "c3": ("logistic", 4096, 128, 24, 100000),
-    "c5": ("logistic", 131072, 128, 8, 100000),
     "c3small": ("logistic", 512, 64, 8, 4096),
 }
 EPS = {"dense": 0.25, "logistic": 0.4}
 METRIC = "leapfrog_gradient_evals_per_sec"
 UNIT = "gradient evals/s"
+MIN_TIMED_S = 2.0          # secondary workloads choose their step count so that the timed region lasts this long
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -68,6 +75,13 @@ def make_logistic_problem(n, d):
     return X, y, np.full(d, 4.0 / n)
 
 
+def make_c1_problem():
+    """config 0: mu = 0, sigma_i = exp(N(0, 0.5^2)) (seed 1), imm = sigma^2, HMC L = 10, eps = 0.25."""
+    d = 100
+    sigma = np.exp(0.5 * np.random.default_rng(1).standard_normal(d))
+    return d, sigma
+
+
 def initial_positions(kind, C, d, chain_offset=0):
     if kind == "dense":
         return np.random.default_rng([5, chain_offset]).standard_normal((C, d))
@@ -82,6 +96,15 @@ def describe(name):
     which = {"c3": " (BASELINE.json configs[2])", "c5": " (BASELINE.json configs[4]: 1M chains on 8 GPUs)"}.get(name, "")
     return (f"{name}: NUTS, Bayesian logistic regression N={n} D={d}, diagonal inverse mass matrix, "
             f"{Cn} chains per GPU{which}")
+
+
+def host_ess(draws):
+    """bulk-ESS (arviz default: split, rank-normalised) of host draws [T, C, d'], min over dims; NumPy/torch-CPU."""
+    import torch
+    from aehmc_b200 import diagnostics
+    if draws.shape[0] < 4:
+        return None
+    return float(np.nanmin(diagnostics.ess(torch.from_numpy(np.ascontiguousarray(draws)), distributed=False)))
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -106,15 +129,17 @@ def _cpu_worker(args):
     kernel = kernels.nuts_new_kernel(srng, model)
     q0 = initial_positions(kind, 1, d, seed)[0]
     state = kernels.new_state(q0, model)
-    n_leap = 0
+    n_leap, pos, acc = 0, [], []
     t0 = time.perf_counter()
     for _ in range(n_transitions):
         info, extras = kernel(state, EPS[kind], imm)
         n_leap += extras["n_leapfrog"]
+        pos.append(np.asarray(info.state.position)[:8].copy())
+        acc.append(float(info.acceptance_probability))
         state = info.state._replace(momentum=None)
     dt = time.perf_counter() - t0
     del limiter
-    return n_leap, dt
+    return n_leap, dt, np.array(pos), float(np.mean(acc))
 
 
 def cpu_transitions(name, n_samples=1):
@@ -129,7 +154,7 @@ def cpu_transitions(name, n_samples=1):
 
 
 def cpu_reference_sample(name, cores, n_transitions):
-    """All host cores, one oracle chain each; returns (evals/s aggregate, leapfrogs, wall seconds)."""
+    """All host cores, one oracle chain each; returns a dict (evals/s aggregate, leapfrogs, wall seconds, ESS/s)."""
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
@@ -137,7 +162,41 @@ def cpu_reference_sample(name, cores, n_transitions):
     wall = time.perf_counter() - t0
     n_leap = sum(r[0] for r in res)
     busy = max(r[1] for r in res)
-    return n_leap / busy, n_leap, wall
+    draws = np.stack([r[2] for r in res], axis=1)                    # [T, cores, 8]
+    ess = host_ess(draws)
+    return {"value": n_leap / busy, "leapfrogs": n_leap, "wall_s": wall, "busy_s": busy,
+            "ess_per_sec": None if ess is None else ess / busy, "mean_accept": float(np.mean([r[3] for r in res]))}
+
+
+def cpu_c1_sample(n_transitions=1000, burn=100):
+    """configs[0] as the reference runs it: ONE chain, single-threaded (OMP_NUM_THREADS=1 in the reference's CI),
+    HMC velocity_verlet L = 10, diagonal inverse mass matrix, 100-dim iid Gaussian."""
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=1)
+    except Exception:
+        limiter = None
+    from oracle import kernels, models, streams
+    d, sigma = make_c1_problem()
+    model = models.IIDGaussian(np.zeros(d), sigma)
+    kernel = kernels.hmc_new_kernel(streams.StreamDraws(11, "hmc"), model)
+    state = kernels.new_state(np.random.default_rng(2).standard_normal(d), model)
+    L, eps, imm = 10, 0.25, sigma ** 2
+    pos, acc = [], []
+    for i in range(burn + n_transitions):
+        if i == burn:
+            t0 = time.perf_counter()
+        info, _ = kernel(state, eps, imm, L)
+        state = info.state._replace(momentum=None)
+        if i >= burn:
+            pos.append(np.asarray(info.state.position)[:8].copy())
+            acc.append(float(info.acceptance_probability))
+    dt = time.perf_counter() - t0
+    del limiter
+    ess = host_ess(np.array(pos)[:, None, :])
+    return {"value": n_transitions * L / dt, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dt,
+            "ess_per_sec": None if ess is None else ess / dt, "mean_accept": float(np.mean(acc)),
+            "sample": f"1 oracle chain, {burn} burn-in + {n_transitions} HMC transitions of L = {L}, single-threaded"}
 
 
 def run_reference_arm(args):
@@ -150,11 +209,12 @@ def run_reference_arm(args):
     n_tr = cpu_transitions(args.workload, warm + args.steps)
     vals = []
     for i in range(warm + args.steps):
-        v, n_leap, wall = cpu_reference_sample(args.workload, cores, n_tr)
+        r = cpu_reference_sample(args.workload, cores, n_tr)
         if i >= warm:
-            vals.append((v, n_leap, wall))
-    value = float(np.mean([v[0] for v in vals]))
-    ms = float(np.mean([v[2] for v in vals]) * 1e3)
+            vals.append(r)
+    value = float(np.mean([v["value"] for v in vals]))
+    ms = float(np.mean([v["wall_s"] for v in vals]) * 1e3)
+    ess = [v["ess_per_sec"] for v in vals if v["ess_per_sec"] is not None]
     sample = (f"{cores} oracle chains (one per core, 1 BLAS thread each) x {n_tr} NUTS transitions of the "
               f"{args.workload} target per step")
     line = {
@@ -163,8 +223,10 @@ def run_reference_arm(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": describe(args.workload) + " -- CPU arm: NumPy oracle restating aesara-devs/aehmc "
                                "(the real reference needs Aesara, which is not installable here)",
-                   "chains": cores, "dim": d, "step_size": EPS[kind]},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                   "chains": cores, "dim": d, "step_size": EPS[kind],
+                   "mean_accept": float(np.mean([v["mean_accept"] for v in vals]))},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "ess_per_sec": float(np.mean(ess)) if ess else None},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -242,7 +304,27 @@ def _event_ms(fn, reps, dev):
     return e0.elapsed_time(e1) / reps
 
 
-def dense_roofline(metric, Cn, d, ticks, step_ms, hbm_peak, dev):
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def measured_traffic(key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, one `ncu --set full` capture) of a kernel
+    at a workload, from the committed profile summary; None when this round holds no capture for it."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        row = table["kernels"].get(key)
+        if row is None:
+            return None, None
+        return float(row["dram_bytes_per_launch"]), f"profiles/r02_traffic.json[{key}] <- {row['from']} (commit {table.get('commit', '?')})"
+    except Exception:
+        return None, None
+
+
+def dense_roofline(metric, Cn, d, ticks, step_ms, hbm_peak, dev, name):
     """Dominant kernel of c2: the FP64 dense apply (DMMA tensor path), timed alone on the engine's stream."""
     import ctypes as C
     import torch
@@ -278,10 +360,10 @@ def dense_roofline(metric, Cn, d, ticks, step_ms, hbm_peak, dev):
     elementwise_ms = max(step_ms - ticks * 2.0 * gemm_ms, 1e-9)
     b_nuts = 11.0 * d * 8.0       # algorithmic bytes of one NUTS inner step incl. U-turn bookkeeping
     hbm_achieved = b_nuts * Cn * ticks / (elementwise_ms * 1e-3) / 1e9
+    traffic, traffic_from = measured_traffic(f"dense_apply@{name}")
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_ncu_gemm_summary.md (ncu --set full)
-        "traffic": 40.822016e6 + 6.891264e6 if (Cn, d) == (4096, 1000) else None,
+        "traffic": traffic, "traffic_from": traffic_from,
         "pipe": "FP64 tensor (DMMA.8x8x4): FP64 has no tcgen05 kind",
         "kernel": "dense_apply_dmma_async_kernel<BN> (out[C x d] = in[C x d] . M[d x d], FP64 DMMA + cp.async): "
                   "gradient and imm.g, 2 launches per tick",
@@ -292,13 +374,14 @@ def dense_roofline(metric, Cn, d, ticks, step_ms, hbm_peak, dev):
         "launches_per_tick": 2, "share_of_step": ticks * 2.0 * gemm_ms / step_ms,
         "cublas_same_shape_tflops": cublas_same_shape}
     elementwise = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
-                   "frac": hbm_achieved / hbm_peak, "traffic": None,
+                   "frac": hbm_achieved / hbm_peak, "traffic": measured_traffic(f"postpre@{name}")[0],
+                   "traffic_from": measured_traffic(f"postpre@{name}")[1],
                    "how": "derived: 11*d*8 algorithmic bytes per chain-tick over (step time - 2 dense applies per "
                           "tick); post+pre + potential kernels"}
     return roofline, elementwise
 
 
-def logistic_roofline(model, Cn, d, n, ticks, step_ms, peaks, dev, dtype):
+def logistic_roofline(model, Cn, d, n, ticks, step_ms, peaks, dev, dtype, name):
     """Dominant kernel of c3 / c5: the fused tcgen05 gradient (S product, residual, X^T R product in one kernel),
     timed through b2h_potential_and_grad on the engine's stream (includes three small side kernels)."""
     import torch
@@ -309,12 +392,12 @@ def logistic_roofline(model, Cn, d, n, ticks, step_ms, peaks, dev, dtype):
     flops = 4.0 * n * d * Cn
     achieved = flops / (ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", 1389.0))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     pieces = 2 if getattr(model, "tc_flag", 0.0) == 4.0 else 3
-    return {
+    traffic, traffic_from = measured_traffic(f"tc_logistic_fused16@{name}")
+    roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 4096 chains (ncu --set full,
-        # profiles/r01_ncu_tc_fused_summary.md): X once + the responses; everything else stays on chip
-        "traffic": 28.12e6 if (Cn, d, n) == (4096, 128, 100000) else None,
+        "traffic": traffic, "traffic_from": traffic_from,
         "kernel": ("tc_logistic_fused16_kernel" if pieces == 2 else "tc_logistic_fused_kernel") +
                   " (tcgen05.mma kind::f16 with both A operands in TMEM, TMA, one launch per tick): S = B X^T, "
                   "residual epilogue back into TMEM, G += R X",
@@ -325,25 +408,54 @@ def logistic_roofline(model, Cn, d, n, ticks, step_ms, peaks, dev, dtype):
         "issued_tflops": pieces * achieved, "issued_frac": pieces * achieved / peak,
         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
         "launches_per_tick": 1, "share_of_step": ticks * ms / step_ms}
+    esize = 4 if dtype == torch.float32 else 8
+    rest_ms = max(step_ms - ticks * ms, 1e-9)
+    hbm_achieved = 11.0 * d * esize * Cn * ticks / (rest_ms * 1e-3) / 1e9
+    tr = measured_traffic(f"postpre@{name}")
+    elementwise = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                   "frac": hbm_achieved / hbm_peak, "traffic": tr[0], "traffic_from": tr[1],
+                   "how": f"derived: 11*d*{esize} algorithmic bytes per chain-tick over (step time - gradient time): "
+                          "the post+pre tick kernel"}
+    return roofline, elementwise
 
 
-def run_gpu_arm(args):
+class Dist:
+    """torch.distributed plumbing of one bench process."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.dist = dist
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        import torch
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def reduce(self, values, op="sum"):
+        import torch
+        t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return t.tolist()
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def build_problem(name, dev):
     import torch
-    import torch.distributed as dist
-
     import aehmc_b200 as ab
-    from aehmc_b200 import _engine
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    kind, Cn, d, ticks, n_data = WORKLOADS[args.workload]
-    eps = EPS[kind]
+    kind, Cn, d, ticks, n_data = WORKLOADS[name]
     if kind == "dense":
         dtype, dtype_name = torch.float64, "f64"
         cov, prec = make_dense_problem(d)
@@ -354,168 +466,326 @@ def run_gpu_arm(args):
         X, y, imm = make_logistic_problem(n_data, d)
         model = ab.models.LogisticRegression(X, y, 1.0, dtype=dtype, device=dev, tensor_core=True)
         metric = ab.metrics.GaussianMetric(imm, dtype, dev)
-    chain_offset = rank * Cn
+    return model, metric, dtype, dtype_name
+
+
+def run_tick_workload(name, D, steps, warmup, min_timed_s=0.0, with_e2e=True):
+    """Device-resident and end-to-end throughput of one tick-engine workload.  Returns a dict (rank-reduced)."""
+    import torch
+    import aehmc_b200 as ab
+    from aehmc_b200 import _engine
+
+    kind, Cn, d, ticks, n_data = WORKLOADS[name]
+    eps = EPS[kind]
+    dev = D.dev
+    model, metric, dtype, dtype_name = build_problem(name, dev)
+    chain_offset = D.rank * Cn
     q_host = torch.from_numpy(initial_positions(kind, Cn, d, chain_offset)).to(dtype).pin_memory()
     srng = ab.RandomStream(seed=2026, chain_offset=chain_offset)
-    key = ("bench", rank)
+    key = ("bench", name, D.rank)
     esize = q_host.element_size()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
 
     # ---- device-resident arm: state lives in the engine workspace, each step continues it -----------------
     state = ab.nuts.new_state(q_host.to(dev), model)
     info, extras = _engine.run("nuts", model, metric, srng, state, eps, max_ticks=ticks, workspace_key=key,
                                return_counters=True)
     state = info.state
+    last = {}
 
     def step_resident():
         nonlocal state
         info, ex = _engine.run("nuts", model, metric, srng, state, eps, max_ticks=ticks, resume=True,
                                workspace_key=key, return_counters=True)
         state = info.state
+        last["info"] = info
         return ex["counters"]
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(warmup, 3)
+    for _ in range(warm):
         step_resident()
-    barrier()
-    sampler = ClockSampler(local_rank)
+    if min_timed_s > 0:                     # secondary workloads: enough steps for a timed region of min_timed_s
+        est = _event_ms(step_resident, 3, dev)
+        steps = int(min(max(steps, math.ceil(min_timed_s * 1e3 / max(est, 1e-3))), 2000))
+    D.barrier()
+    sampler = ClockSampler(D.local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    D.barrier()
     ev0.record()
     counters = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         counters.append(step_resident())
     ev1.record()
-    barrier()
+    D.barrier()
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
     cnt = torch.stack(counters).sum(0).cpu().numpy()      # leapfrogs, transitions, ticks(unused), chain-ticks
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    leap = torch.tensor([float(cnt[0]), float(cnt[1])], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(leap, op=dist.ReduceOp.SUM)
-    ms_total = t.item()
-    total_leapfrogs, total_transitions = leap[0].item(), leap[1].item()
+    acc = last["info"].acceptance_probability
+    ms_total = D.reduce([ms_total], "max")[0]
+    total_leapfrogs, total_transitions, acc_sum = D.reduce([cnt[0], cnt[1], float(acc.sum())])
     value = total_leapfrogs / (ms_total * 1e-3)
+    out = {"name": name, "kind": kind, "chains_per_gpu": Cn, "dim": d, "n_data": n_data, "ticks": ticks, "eps": eps,
+           "steps": steps, "warmup": warm, "value": value, "ms_per_step": ms_total / steps, "ms_total": ms_total,
+           "dtype": dtype, "dtype_name": dtype_name, "clocks": clocks, "model": model, "metric": metric,
+           "transitions_per_step": total_transitions / steps,
+           "mean_leapfrogs_per_transition": total_leapfrogs / max(total_transitions, 1.0),
+           "mean_accept": acc_sum / (Cn * D.world), "esize": esize, "q_host": q_host, "chain_offset": chain_offset}
 
     # ---- end-to-end arm: host buffers in, host buffers out, through the public API ----------------------
-    q_out = torch.empty((Cn, d), dtype=dtype).pin_memory()
-    acc_out = torch.empty(Cn, dtype=torch.float64).pin_memory()
+    if with_e2e:
+        q_out = torch.empty((Cn, d), dtype=dtype).pin_memory()
+        acc_out = torch.empty(Cn, dtype=torch.float64).pin_memory()
 
-    def step_e2e():
-        q_dev = q_host.to(dev, non_blocking=True)
-        st = ab.nuts.new_state(q_dev, model)
-        info, ex = _engine.run("nuts", model, metric, srng, st, eps, max_ticks=ticks, workspace_key=key,
-                               return_counters=True)
-        q_out.copy_(info.state.position, non_blocking=True)
-        acc_out.copy_(info.acceptance_probability, non_blocking=True)
-        return ex["counters"]
+        def step_e2e():
+            q_dev = q_host.to(dev, non_blocking=True)
+            st = ab.nuts.new_state(q_dev, model)
+            info, ex = _engine.run("nuts", model, metric, srng, st, eps, max_ticks=ticks, workspace_key=key,
+                                   return_counters=True)
+            q_out.copy_(info.state.position, non_blocking=True)
+            acc_out.copy_(info.acceptance_probability, non_blocking=True)
+            return ex["counters"]
 
-    for _ in range(3):
-        step_e2e()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    cs = [step_e2e() for _ in range(args.steps)]
-    e1.record()
-    barrier()
-    ms_e2e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    leap_e2e = torch.tensor([float(torch.stack(cs).sum(0)[0].item())], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-        dist.all_reduce(leap_e2e, op=dist.ReduceOp.SUM)
-    e2e_value = leap_e2e.item() / (ms_e2e.item() * 1e-3)
+        for _ in range(3):
+            step_e2e()
+        D.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        cs = [step_e2e() for _ in range(steps)]
+        e1.record()
+        D.barrier()
+        ms_e2e = D.reduce([e0.elapsed_time(e1)], "max")[0]
+        leap_e2e = D.reduce([float(torch.stack(cs).sum(0)[0].item())])[0]
+        out["e2e"] = {"value": leap_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(Cn * d * esize),
+                      "d2h_bytes_per_step": int(Cn * d * esize + Cn * 8), "seconds": ms_e2e * 1e-3,
+                      "what": "pinned host positions -> device, new_state, TICKS ticks, position + acceptance back to "
+                              "pinned host"}
+    _engine.release_workspace(key)
+    return out
 
-    # ---- roofline of the dominant kernel, timed alone on the same stream ---------------------------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+
+def rooflines_for(w, D, peaks):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    step_ms = ms_total / args.steps
-    roofline_elementwise = None
-    if kind == "dense":
-        roofline, roofline_elementwise = dense_roofline(metric, Cn, d, ticks, step_ms, hbm_peak, dev)
-        kernels_per_tick = 6          # post+pre, gradient apply, potential, imm.g apply, momentum rider GEMM + its reduce
-    else:
-        roofline = logistic_roofline(model, Cn, d, n_data, ticks, step_ms, peaks, dev, dtype)
-        kernels_per_tick = 5          # post+pre, beta split, response convert, fused gradient, finish
+    if w["kind"] == "dense":
+        return dense_roofline(w["metric"], w["chains_per_gpu"], w["dim"], w["ticks"], w["ms_per_step"], hbm_peak, D.dev,
+                              w["name"])
+    return logistic_roofline(w["model"], w["chains_per_gpu"], w["dim"], w["n_data"], w["ticks"], w["ms_per_step"], peaks,
+                             D.dev, w["dtype"], w["name"])
 
-    # ---- second metric of BASELINE.json: NUTS ESS/s (min over the monitored dims, all chains, all ranks) ----
-    ess_per_s = rhat_max = gathered = None
-    if not args.no_ess:
-        n_tr = args.ess_transitions
-        st0 = ab.nuts.new_state(q_host.to(dev), model)
-        barrier()
+
+def ess_leg(w, D, args):
+    """Second BASELINE metric (NUTS ESS/s) and the diagnostics exchange of configs[4], all inside timed regions:
+    pooled warm-up (adaptation statistics merged over the ranks) -> KEEP stored transitions -> rank-normalised split
+    bulk-ESS and R-hat (arviz defaults) of the monitored coordinates over all chains of all ranks."""
+    import torch
+    import aehmc_b200 as ab
+    from aehmc_b200 import _engine
+    dev, model, Cn, d = D.dev, w["model"], w["chains_per_gpu"], w["dim"]
+    keep, warm = args.ess_transitions, args.ess_warmup
+    kernel = ab.nuts.new_kernel(ab.RandomStream(seed=7, chain_offset=w["chain_offset"]), model)
+    st0 = ab.nuts.new_state(w["q_host"].to(dev), model)
+    imm0 = w["metric"].imm if w["kind"] == "logistic" else None
+    full = w["kind"] == "dense"
+
+    def timed(fn):
+        D.barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        info, ex = _engine.run("nuts", model, metric, ab.RandomStream(seed=7, chain_offset=chain_offset), st0, eps,
-                               n_transitions=n_tr, store_draws=n_tr, workspace_key=("ess", rank))
+        r = fn()
         s1.record()
-        barrier()
-        t_ess = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_ess, op=dist.ReduceOp.MAX)
-        burn = n_tr // 4
-        dims = list(range(min(8, d)))
-        # sufficient statistics per rank, summed over ranks with one all-reduce (NCCL): the diagnostics gather
-        ess = ab.diagnostics.ess(ex["draws"][burn:], dims=dims)
-        rhat = ab.diagnostics.rhat(ex["draws"][burn:], dims=dims)
-        ess_per_s = float(np.nanmin(ess)) / (t_ess.item() * 1e-3)
-        rhat_max = float(np.nanmax(rhat))
-        gathered = None
-        if world > 1:
-            # configs[4] words it as a "gather of draws": all-gather the monitored coordinates (NCCL) and recompute
-            # R-hat from the gathered tensor; it must agree with the all-reduced sufficient statistics
-            g = ab.diagnostics.gather_draws(ex["draws"][burn:], dims=dims)
-            r2 = ab.diagnostics.rhat(g, distributed=False)
-            gathered = {"shape": list(g.shape), "bytes": int(g.numel() * g.element_size()),
-                        "rhat_max": float(np.nanmax(r2))}
-            del g
-        del ex
+        D.barrier()
+        return r, D.reduce([s0.elapsed_time(s1)], "max")[0] * 1e-3
 
-    if rank == 0:
+    (state, (eps, imm), winfo), t_warm = timed(lambda: ab.window_adaptation.run(
+        kernel, st0, warm, pooled=True, is_mass_matrix_full=full, initial_inverse_mass_matrix=imm0,
+        initial_step_size=w["eps"]))
+    (info, ex), t_sample = timed(lambda: _engine.run("nuts", model, imm, kernel.spec["srng"], state, eps,
+                                                      n_transitions=keep, store_draws=keep, return_counters=True))
+    dims = list(range(min(8, d)))
+    draws = ex["draws"]
+
+    def diagnostics():
+        return ab.diagnostics.ess(draws, dims=dims), ab.diagnostics.rhat(draws, dims=dims)
+    (ess, rhat), t_diag = timed(diagnostics)
+    leap = D.reduce([float(ex["counters"][0].item())])[0]
+    acc = D.reduce([float(info.acceptance_probability.sum())])[0] / (Cn * D.world)
+    eps_med = float(eps.median())
+    del draws, ex
+    torch.cuda.empty_cache()
+    ess_min, rhat_max = float(np.nanmin(ess)), float(np.nanmax(rhat))
+    return {
+        "nuts_ess_per_sec": ess_min / t_sample, "rhat_max": rhat_max, "ess_min": ess_min,
+        "ess_how": f"pooled window adaptation ({warm} transitions, initial inverse mass matrix "
+                   f"{'4/N' if imm0 is not None else 'identity'}, statistics merged over the ranks) then {keep} kept NUTS "
+                   "transitions per chain; rank-normalised split bulk-ESS and R-hat (arviz defaults) of the first "
+                   f"{len(dims)} coordinates over all chains of all ranks, minimum ESS divided by the sampling time of the "
+                   "kept transitions",
+        "warmup_seconds": t_warm, "sampling_seconds": t_sample, "diagnostics_seconds": t_diag,
+        "mean_accept_after_warmup": acc, "step_size_median_after_warmup": eps_med,
+        "pooled_window_sizes": winfo.get("pooled_window_sizes"),
+        "e2e_with_diagnostics": {
+            "value": leap / (t_sample + t_diag), "unit": UNIT, "seconds": t_sample + t_diag,
+            "what": f"{keep} stored NUTS transitions of every chain + the diagnostics exchange (per-rank sort, all-gather "
+                    "of the sorted monitored draws for the global rank normalisation, all-reduce of the autocovariance "
+                    "sufficient statistics) + host ESS / R-hat arithmetic, timed together, max over ranks",
+            "collectives": "nccl all_gather + all_reduce" if D.world > 1 else "none at N = 1 (same code path)"}}
+
+
+def secondary_c4(D, peaks):
+    """configs[3]: window_adaptation (1000 steps) + 1000 NUTS draws, 10-dim funnel and eight schools, 65536 chains."""
+    import torch
+    import aehmc_b200 as ab
+    from aehmc_b200 import _engine, metrics
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    Cn, W, Dn = 65536, 1000, 1000
+    out = {}
+    for name, model in (("funnel", ab.models.NealFunnel(10, device=D.dev)), ("eight_schools", ab.models.EightSchools(device=D.dev))):
+        q0 = np.random.default_rng(0).standard_normal((Cn, 10))
+        kernel = ab.nuts.new_kernel(ab.RandomStream(seed=11), model)
+        state = ab.nuts.new_state(q0, model)
+        res = {}
+
+        def warm():
+            res["w"] = ab.window_adaptation.run(kernel, state, W)
+        ms_w = _event_ms(warm, 1, D.dev)
+        wstate, (eps, imm), _ = res["w"]
+
+        def draw():
+            res["d"] = _engine.run("nuts", model, metrics.per_chain(imm), kernel.spec["srng"], wstate, eps,
+                                   n_transitions=Dn, store_draws=0, return_counters=True)
+        ms_d = _event_ms(draw, 1, D.dev)
+        info, ex = res["d"]
+        leap = int(ex["counters"][0].item())
+        out[name] = {"value": leap / (ms_d * 1e-3), "unit": UNIT, "chains": Cn, "warmup_ms": ms_w, "sampling_ms": ms_d,
+                     "sampling_leapfrogs": leap, "transitions_per_sec": Cn * Dn / (ms_d * 1e-3),
+                     "roofline": {"bound": "hbm", "achieved": leap * 11 * 10 * 8 / (ms_d * 1e-3) / 1e9, "peak": hbm_peak,
+                                  "unit": "GB/s", "frac": leap * 11 * 10 * 8 / (ms_d * 1e-3) / 1e9 / hbm_peak,
+                                  "what": "11*d*s algorithmic bytes per leapfrog (SURVEY 8d); the state of a chain "
+                                          "stays on chip in the persistent kernel, HBM sees only draws out"},
+                     "step_size_median": float(eps.median()),
+                     "mean_accept": float(info.acceptance_probability.mean()),
+                     "last_transition_depth_hist": torch.bincount(info.num_doublings.long(), minlength=11).cpu().tolist(),
+                     "last_transition_divergent_frac": float(info.is_diverging.double().mean())}
+        del res
+    return {"workload": f"c4 (BASELINE.json configs[3]): window_adaptation({W}) + {Dn} NUTS draws, d = 10, {Cn} chains, "
+                        "f64, persistent fused kernel", **out}
+
+
+def secondary_c1(D, peaks):
+    """configs[0]: HMC, velocity_verlet, L = 10, diagonal imm, 100-dim iid Gaussian: 1 chain (the reference's own
+    configuration) and 65536 chains, next to the single-threaded CPU oracle."""
+    import aehmc_b200 as ab
+    from aehmc_b200 import _engine
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    d, sigma = make_c1_problem()
+    L = 10
+    model = ab.models.IIDGaussian(np.zeros(d), sigma, device=D.dev)
+    out = {"workload": "c1 (BASELINE.json configs[0]): HMC velocity_verlet L=10, d=100 iid Gaussian, diagonal imm, f64"}
+    for Cn, n_tr in ((1, 1000), (65536, 400)):
+        q0 = np.random.default_rng(2).standard_normal((Cn, d))
+        srng = ab.RandomStream(seed=1)
+        state = ab.hmc.new_state(q0, model)
+        res = {}
+
+        def run():
+            res["r"] = _engine.run("hmc", model, sigma ** 2, srng, state, 0.25, n_transitions=n_tr,
+                                   num_integration_steps=L, store_draws=n_tr if Cn == 1 else 0)
+        run()
+        ms = _event_ms(run, 1, D.dev)
+        info, ex = res["r"]
+        evals = Cn * n_tr * L
+        row = {"value": evals / (ms * 1e-3), "unit": UNIT, "transitions": n_tr, "ms": ms,
+               "mean_accept": float(info.acceptance_probability.mean()),
+               "roofline": {"bound": "hbm", "achieved": evals * 6 * d * 8 / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": evals * 6 * d * 8 / (ms * 1e-3) / 1e9 / hbm_peak,
+                            "what": "6*d*s algorithmic bytes per leapfrog (SURVEY 8d); the trajectory stays in registers"}}
+        if Cn == 1:
+            ess = host_ess(ex["draws"].double().cpu().numpy()[:, :, :8])
+            row["ess_per_sec"] = None if ess is None else ess / (ms * 1e-3)
+        out[f"chains_{Cn}"] = row
+    out["cpu_baseline"] = cpu_c1_sample()
+    return out
+
+
+def secondary_tick(name, D, args, peaks):
+    import torch
+    w = run_tick_workload(name, D, args.steps, args.warmup, min_timed_s=MIN_TIMED_S, with_e2e=True)
+    roofline, elementwise = rooflines_for(w, D, peaks)
+    out = {"workload": describe(name), "value": w["value"], "unit": UNIT, "ms_per_step": w["ms_per_step"],
+           "steps": w["steps"], "timed_seconds": w["ms_total"] * 1e-3, "ticks_per_step": w["ticks"], "dtype": w["dtype_name"],
+           "mean_accept": w["mean_accept"], "mean_leapfrogs_per_transition": w["mean_leapfrogs_per_transition"],
+           "e2e": w["e2e"], "clocks": w["clocks"], "roofline": roofline, "roofline_elementwise": elementwise}
+    del w
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_gpu_arm(args):
+    import torch
+    D = Dist()
+    peaks = load_peaks()
+    name = args.workload
+    w = run_tick_workload(name, D, args.steps, args.warmup)
+    roofline, roofline_elementwise = rooflines_for(w, D, peaks)
+    kind, Cn, d, ticks = w["kind"], w["chains_per_gpu"], w["dim"], w["ticks"]
+    kernels_per_tick = 6 if kind == "dense" else 5
+    # dense: post+pre, gradient apply, potential, imm.g apply, momentum rider GEMM + its reduce
+    # logistic: post+pre, beta split, response convert, fused gradient, finish
+
+    ess = {}
+    if not args.no_ess:
+        ess = ess_leg(w, D, args)
+
+    secondary = None
+    if D.world == 1 and not args.no_secondary:
+        model = w.pop("model"); metric = w.pop("metric")
+        del model, metric
+        torch.cuda.empty_cache()
+        secondary = {}
+        for sec in [s for s in ("c3", "c2") if s != name]:
+            try:
+                secondary[sec] = secondary_tick(sec, D, args, peaks)
+            except Exception as e:                                   # a secondary failure must not lose the headline
+                secondary[sec] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
+        for sec, fn in (("c4", secondary_c4), ("c1", secondary_c1)):
+            try:
+                secondary[sec] = fn(D, peaks)
+            except Exception as e:
+                secondary[sec] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
+
+    if D.rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": dtype_name, "data": "synthetic",
-            "config": {"workload": describe(args.workload), "chains_per_gpu": Cn, "chains_total": Cn * world, "dim": d,
-                       "step_size": eps, "max_num_expansions": 10, "ticks_per_step": ticks, "rng": "philox4x32-10",
+            "metric": METRIC, "value": w["value"], "unit": UNIT, "n_gpus": D.world, "steps": w["steps"],
+            "warmup": w["warmup"], "ms_per_step": w["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": w["dtype_name"], "data": "synthetic",
+            "config": {"workload": describe(name), "chains_per_gpu": Cn, "chains_total": Cn * D.world, "dim": d,
+                       "step_size": w["eps"], "max_num_expansions": 10, "ticks_per_step": ticks, "rng": "philox4x32-10",
                        "l2": "engine state larger than the 126 MB L2 (no flush needed)" if kind == "dense" else
-                             "the design matrix X (25.6 MB bf16) is meant to stay L2-resident; the chain state of "
-                             "c5 (131072 x 128 x ~20 arrays) exceeds L2",
-                       "transitions_per_step": total_transitions / args.steps,
-                       "mean_leapfrogs_per_transition": total_leapfrogs / max(total_transitions, 1.0)},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(Cn * d * esize),
-                    "d2h_bytes_per_step": int(Cn * d * esize + Cn * 8),
-                    "what": "pinned host positions -> device, new_state, TICKS ticks, position + acceptance back to pinned host"},
-            "gpu_launches": int(args.steps * (ticks * kernels_per_tick + 3)),
-            "clocks": clocks,
-            "nuts_ess_per_sec": ess_per_s, "rhat_max": rhat_max, "gathered_draws": gathered if not args.no_ess else None,
-            "ess_how": None if ess_per_s is None else
-            f"{args.ess_transitions} NUTS transitions per chain from the initial positions, first quarter discarded, "
-            "multi-chain ESS (Stan/arviz estimator, no rank normalisation) of the first 8 coordinates, minimum, "
-            "divided by the wall time of all transitions incl. the discarded ones; statistics all-reduced over ranks",
-            "roofline": roofline,
+                             "the design matrix X (25.6 MB fp16) is meant to stay L2-resident; the chain state "
+                             f"({Cn} x {d} x ~20 arrays) " + ("exceeds L2" if Cn * d * 80 > 126e6 else "fits L2"),
+                       "timed_seconds": w["ms_total"] * 1e-3,
+                       "mean_accept": w["mean_accept"],
+                       "transitions_per_step": w["transitions_per_step"],
+                       "mean_leapfrogs_per_transition": w["mean_leapfrogs_per_transition"]},
+            "e2e": w["e2e"],
+            "gpu_launches": int(w["steps"] * (ticks * kernels_per_tick + 3)),
+            "clocks": w["clocks"],
+            "roofline": roofline, "roofline_elementwise": roofline_elementwise,
         }
-        if roofline_elementwise is not None:
-            line["roofline_elementwise"] = roofline_elementwise
-        if world == 1 and not args.no_cpu:
+        line.update(ess)
+        if secondary is not None:
+            line["secondary"] = secondary
+        if D.world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            n_tr = cpu_transitions(args.workload)
-            v, n_leap, wall = cpu_reference_sample(args.workload, cores, n_tr)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            n_tr = cpu_transitions(name)
+            r = cpu_reference_sample(name, cores, n_tr)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port",
+                                    "ess_per_sec": r["ess_per_sec"], "mean_accept": r["mean_accept"],
                                     "sample": f"{cores} oracle chains (one per core) x {n_tr} NUTS transitions, "
-                                              f"{n_leap} leapfrogs in {wall:.1f} s wall"}
+                                              f"{r['leapfrogs']} leapfrogs in {r['wall_s']:.1f} s wall"}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
 
 
 def main():
@@ -524,10 +794,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-ess", action="store_true", help="skip the ESS/s leg")
-    ap.add_argument("--ess-transitions", type=int, default=40)
+    ap.add_argument("--no-ess", action="store_true", help="skip the ESS/s + diagnostics leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (c3, c2, c4, c1)")
+    ap.add_argument("--ess-transitions", type=int, default=200, help="kept NUTS transitions of the ESS leg")
+    ap.add_argument("--ess-warmup", type=int, default=100, help="pooled window-adaptation transitions before them")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -12,6 +12,8 @@ from typing import NamedTuple
 import numpy as np
 import scipy.linalg
 
+from . import streams
+
 
 class IntegratorState(NamedTuple):  # reference integrators.py:7-11
     position: object
@@ -90,6 +92,10 @@ def gaussian_metric(inverse_mass_matrix):
         rho = momentum_sum - (momentum_right + momentum_left) / 2
         turning_at_left = dot(velocity_left, rho) <= 0
         turning_at_right = dot(velocity_right, rho) <= 0
+        if streams.MARGIN_LOG is not None:
+            nr = np.sqrt(np.sum(np.square(rho))) + 1e-300
+            for v in (velocity_left, velocity_right):
+                streams.MARGIN_LOG.append(("uturn", abs(float(dot(v, rho))) / (np.sqrt(np.sum(np.square(v))) * nr + 1e-300)))
         return bool(turning_at_left | turning_at_right)
 
     return momentum_generator, kinetic_energy, is_turning

@@ -21,12 +21,20 @@ from __future__ import annotations
 import numpy as np
 
 
+# Optional decision log (tests only): when set to a list, every Bernoulli decision appends ("bernoulli", margin) with
+# margin = distance of the uniform from the decision threshold, and every U-turn test appends ("uturn", cosine): how
+# far each decision was from flipping.  Used to show that float32 tree mismatches are near-ties.
+MARGIN_LOG = None
+
+
 def bernoulli_from_uniform(u: float, p: float) -> bool:
     """Decision NumPy's ``Generator.binomial(1, p)`` takes given its uniform ``u``.
 
     p <= 0.5 uses the inversion branch (success iff u > 1-p); p > 0.5 uses the
     mirrored branch (success iff u <= p).  NaN p never accepts.
     """
+    if MARGIN_LOG is not None and p == p:
+        MARGIN_LOG.append(("bernoulli", abs(u - (1.0 - p)) if p <= 0.5 else abs(u - p)))
     if p <= 0.5:
         return bool(u > 1.0 - p)
     return bool(u <= p)

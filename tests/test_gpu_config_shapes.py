@@ -1,0 +1,192 @@
+"""Parity at the BASELINE.json configuration shapes themselves (not scaled-down stand-ins):
+
+c2  d = 1000, dense inverse mass matrix, CTA-per-chain layout (G = 256), wave-aware DMMA tiles
+c3  N = 100 000, D = 128 logistic regression: the fused tcgen05 gradient of EVERY chain against the oracle's model,
+    NUTS transitions against the oracle, and the measured tree-decision mismatch rate of the float32 tensor-core path
+c4  65 536 Philox chains with window adaptation, 32 randomly chosen chains replayed through the oracle
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import bench
+import parity
+from oracle import models as o_models
+from oracle import streams as o_streams
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+@pytest.fixture(scope="module")
+def ab(cuda_device):
+    import aehmc_b200
+    return aehmc_b200
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _gpu_nuts(ab, model, imm, q0, eps, draws, T, **kw):
+    from aehmc_b200 import _engine
+    srng = ab.InjectedDraws(draws["z"], draws["u_dir"], draws["u_biased"], draws["u_uniform"])
+    info, ex = _engine.run("nuts", model, imm, srng, ab.nuts.new_state(q0, model), eps, n_transitions=T,
+                           store_draws=T, **kw)
+    st = info.state
+    return dict(q=_np(st.position).astype(np.float64), p=_np(st.momentum).astype(np.float64),
+                U=_np(st.potential_energy).astype(np.float64), g=_np(st.potential_energy_grad).astype(np.float64),
+                acceptance_probability=_np(info.acceptance_probability), num_doublings=_np(info.num_doublings),
+                is_turning=_np(info.is_turning), is_diverging=_np(info.is_diverging),
+                n_leapfrog=_np(ex["n_leapfrog"]), draws=_np(ex["draws"]).astype(np.float64),
+                stats=_np(ex["draw_stats"]))
+
+
+def test_c2_shape_dense_d1000_cta_per_chain(ab):
+    """BASELINE configs[1] shape: d = 1000, dense metric, one CTA per chain, 8 chains x 2 transitions.
+    Tree depth, leapfrog count and flags bit-exact; positions / energies within 1e-10 relative (north star)."""
+    d, Cn, T = 1000, 8, 2
+    cov, prec = bench.make_dense_problem(d)
+    q0 = bench.initial_positions("dense", Cn, d, 0)
+    draws = parity.random_draws(np.random.default_rng(1000), Cn, T, d)
+    ref = parity.oracle_nuts(o_models.CorrelatedGaussian(np.zeros(d), prec), q0, 0.25, cov, draws, T)
+    model = ab.models.CorrelatedGaussian(np.zeros(d), prec)
+    got = _gpu_nuts(ab, model, cov, q0, 0.25, draws, T, group=256)
+    parity.assert_nuts_parity(got, ref, rtol=1e-10, atol=1e-10, what="c2 shape")
+    assert ref["n_leapfrog"].min() >= 3                      # real trees, not one-step transitions
+    np.testing.assert_allclose(got["draws"], ref["draws"], rtol=1e-10, atol=1e-10)
+
+
+@pytest.fixture(scope="module")
+def c3_problem():
+    X, y, imm = bench.make_logistic_problem(100000, 128)
+    return X, y, imm, o_models.LogisticRegression(X, y, 1.0)
+
+
+def test_c3_shape_gradient_of_every_chain_vs_oracle(ab, c3_problem):
+    """N = 100 000, D = 128, 1024 chains (8 chain tiles, ~7 data segments per CTA): the fused fp16 x 2 tcgen05 gradient
+    and potential of EVERY chain against oracle.models.LogisticRegression, and the FP64 FMA path at 1e-10."""
+    X, y, imm, om = c3_problem
+    Cn = 1024
+    q = bench.initial_positions("logistic", Cn, 128, 77) + np.sqrt(imm) * np.random.default_rng(5).standard_normal((Cn, 128))
+    refs = [om.potential_and_grad(q[c]) for c in range(Cn)]
+    U_ref, g_ref = np.array([r[0] for r in refs]), np.stack([r[1] for r in refs])
+    gs = np.abs(g_ref).max()
+    tc = ab.models.LogisticRegression(X, y, 1.0, dtype=torch.float32, tensor_core=True)
+    assert tc.tc_flag == 4.0
+    U, g = tc.potential_and_grad(q)
+    err = np.abs(_np(g).astype(np.float64) - g_ref).max(axis=1)
+    assert err.max() < 2e-5 * gs, (err.argmax(), err.max() / gs)
+    np.testing.assert_allclose(_np(U).astype(np.float64), U_ref, rtol=5e-6)
+    exact = ab.models.LogisticRegression(X, y, 1.0, dtype=torch.float64)
+    U64, g64 = exact.potential_and_grad(q)
+    np.testing.assert_allclose(_np(g64), g_ref, rtol=1e-10, atol=1e-10 * gs)
+    np.testing.assert_allclose(_np(U64), U_ref, rtol=1e-12)
+
+
+def _decision_margins(om, q0, eps, imm, draws, c, T):
+    """Smallest relative margin of any tree decision (U-turn cosines, Bernoulli thresholds) of chain c."""
+    log = []
+    o_streams.MARGIN_LOG = log
+    try:
+        one = {k: v[c:c + 1] for k, v in draws.items()}
+        parity.oracle_nuts(om, q0[c:c + 1], eps, imm, one, T)
+    finally:
+        o_streams.MARGIN_LOG = None
+    return min(m for _, m in log), min((m for k, m in log if k == "uturn"), default=np.inf)
+
+
+def test_c3_shape_nuts_parity_and_mismatch_rate(ab, c3_problem):
+    """NUTS at the c3 shape, 192 chains x 2 transitions under injected draws.
+    FP64 state + FP64 FMA gradient: every tree decision bit-exact, positions at 1e-9 (64 chains).
+    float32 state + tcgen05 gradient (the headline path) and float64 state + tcgen05 gradient: the per-transition
+    tree-decision mismatch rate is MEASURED, bounded, written to gpurun_out/, and every mismatch is shown to be a
+    near-tie (smallest decision margin of that chain in the oracle)."""
+    X, y, imm, om = c3_problem
+    Cn, T, d, eps = 192, 2, 128, 0.4
+    q0 = bench.initial_positions("logistic", Cn, d, 4242)
+    draws = parity.random_draws(np.random.default_rng(4242), Cn, T, d)
+    ref = parity.oracle_nuts(om, q0, eps, imm, draws, T)
+    ref_stats = np.array([[h[0] for h in hist] for hist in ref["hist"]]).T          # [T, C] num_doublings
+    ref_leap = np.array([[h[1] for h in hist] for hist in ref["hist"]]).T
+
+    n64 = 64
+    sub = {k: v[:n64] for k, v in draws.items()}
+    exact = ab.models.LogisticRegression(X, y, 1.0, dtype=torch.float64)
+    got = _gpu_nuts(ab, exact, imm, q0[:n64], eps, sub, T)
+    np.testing.assert_array_equal(got["stats"][:, :, 1], ref_stats[:, :n64])
+    np.testing.assert_array_equal(got["stats"][:, :, 2], ref_leap[:, :n64])
+    np.testing.assert_allclose(got["draws"], ref["draws"][:, :n64], rtol=1e-9, atol=1e-11)
+
+    report = {"shape": {"N": 100000, "D": d, "chains": Cn, "transitions": T, "step_size": eps}}
+    for label, dt in (("f32_state_tc_fp16x2", torch.float32), ("f64_state_tc_fp16x2", torch.float64)):
+        tc = ab.models.LogisticRegression(X, y, 1.0, dtype=dt, tensor_core=True)
+        assert tc.tc_flag == 4.0
+        got = _gpu_nuts(ab, tc, imm, q0, eps, draws, T)
+        same = (got["stats"][:, :, 1] == ref_stats) & (got["stats"][:, :, 2] == ref_leap)        # [T, C]
+        first_bad = np.where(~same.all(0))[0]
+        margins = []
+        for c in first_bad:
+            any_m, uturn_m = _decision_margins(om, q0, eps, imm, draws, int(c), T)
+            margins.append({"chain": int(c), "min_decision_margin": any_m, "min_uturn_cosine": uturn_m})
+        # per-transition rate over first transitions (a mismatch in transition 1 desynchronises transition 2)
+        rate_t1 = float((~same[0]).mean())
+        rate_chain = float((~same.all(0)).mean())
+        ok = same.all(0)
+        scale = np.abs(ref["q"]).max()
+        qerr = np.abs(got["q"][ok] - ref["q"][ok]).max() / scale
+        report[label] = {"mismatch_rate_first_transition": rate_t1, "mismatch_rate_any_of_2_transitions": rate_chain,
+                         "mismatched_chains": margins, "max_rel_position_error_matching_chains": float(qerr)}
+        assert rate_t1 <= 0.03, (label, rate_t1)
+        assert rate_chain <= 0.06, (label, rate_chain)
+        for m in margins:                                    # every mismatch is a near-tie of some decision
+            assert m["min_decision_margin"] < 2e-3, m
+        np.testing.assert_allclose(got["q"][ok], ref["q"][ok], rtol=1e-4, atol=1e-4 * scale)
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "r02_c3_mismatch_rate.json"), "w") as f:
+        json.dump(report, f, indent=1)
+    print("c3 mismatch report:", json.dumps(report))
+
+
+@pytest.mark.parametrize("target", ["funnel", "eight_schools"])
+def test_c4_shape_65536_chains_adaptation_replay(ab, target):
+    """BASELINE configs[3] shape: 65 536 native-RNG chains, window adaptation fused into the persistent kernel, then
+    plain transitions; 32 randomly chosen chains are replayed through the oracle with the Philox draws exported by
+    b2h_philox_fill.  (Adaptation is a feedback loop: 25 warm-up steps + 3 draws at 1e-6 / tree shapes exact.)"""
+    from aehmc_b200 import _engine, _lib, backend
+    from oracle import adaptation as o_adapt
+    Cn, W, T, d, maxd = 65536, 25, 3, 10, 10
+    model = ab.models.NealFunnel(d) if target == "funnel" else ab.models.EightSchools()
+    om = o_models.NealFunnel(d) if target == "funnel" else o_models.EightSchools()
+    q0 = np.random.default_rng(0).standard_normal((Cn, d))
+    seed = 99
+    srng = ab.RandomStream(seed=seed)
+    kernel = ab.nuts.new_kernel(srng, model)
+    state, (eps, imm), _ = ab.window_adaptation.run(kernel, ab.nuts.new_state(q0, model), W)
+    info, draws_out, stats, _ = ab.sampling.sample(kernel, state, eps, ab.metrics.per_chain(imm), T)
+    assert draws_out.shape == (T, Cn, d)
+    pick = np.sort(np.random.default_rng(1).choice(Cn, 32, replace=False))
+    dev = model.device
+    lib = _lib.load()
+    for c in pick:
+        n = W + T
+        z = torch.empty((1, n, d), dtype=torch.float64, device=dev)
+        ud = torch.empty((1, n, maxd), dtype=torch.float64, device=dev); ub = torch.empty_like(ud)
+        uu = torch.empty((1, n, (1 << maxd) - 1), dtype=torch.float64, device=dev)
+        _lib.check(lib.b2h_philox_fill(backend.context(dev), C.c_uint64(seed), C.c_uint64(int(c)), C.c_uint64(0), C.c_int64(1),
+                                       C.c_int64(n), C.c_int64(d), C.c_int32(maxd), backend.ptr(z), backend.ptr(ud),
+                                       backend.ptr(ub), backend.ptr(uu), None))
+        one = {"z": _np(z), "u_dir": _np(ud), "u_biased": _np(ub), "u_uniform": _np(uu), "u_accept": np.zeros((1, n))}
+        ref = parity.oracle_nuts(om, q0[c:c + 1], 1.0, np.ones(d), one, n, schedule_steps=W)
+        np.testing.assert_allclose(float(eps[c]), ref["eps"][0], rtol=1e-6, err_msg=f"chain {c} step size")
+        np.testing.assert_allclose(_np(imm[c]), ref["imm"][0], rtol=1e-6, err_msg=f"chain {c} imm")
+        hist = ref["hist"][0][W:]
+        np.testing.assert_array_equal(_np(stats[:, c, 1]), [h[0] for h in hist], err_msg=f"chain {c} depth")
+        np.testing.assert_array_equal(_np(stats[:, c, 2]), [h[1] for h in hist], err_msg=f"chain {c} leapfrogs")
+        np.testing.assert_allclose(_np(draws_out[:, c]), ref["draws"][W:, 0], rtol=1e-6, atol=1e-8,
+                                   err_msg=f"chain {c} draws")

@@ -330,7 +330,7 @@ def test_device_autocov_and_ess_match_host(ab):
         host_stats = ab.diagnostics.sufficient_statistics_numpy(x, 60)
         for k in ("sum_mean", "sum_mean_sq", "sum_acov"):
             np.testing.assert_allclose(dev_stats[k], host_stats[k], rtol=tol, atol=tol)
-    e_dev = ab.diagnostics.ess(torch.tensor(x, device="cuda"), 60)
+    e_dev = ab.diagnostics.ess(torch.tensor(x, device="cuda"), 60, method="mean")
     e_host = ab.diagnostics.ess_from_statistics(host_stats)
     np.testing.assert_allclose(e_dev, e_host, rtol=1e-8)
     r = ab.diagnostics.rhat(torch.tensor(x, device="cuda"))
