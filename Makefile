@@ -1,7 +1,9 @@
 # Builds libb200hmc.so (sm_100a only) in-tree, plus the CPU-side test tooling.
 NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr
+# EXTRA: experiment switches (e.g. make OBJDIR=build/obj/m3 LIBDIR=build/lib_m3 EXTRA=-DB2H_TICK_MINB=3; load with B2H_LIB=...)
+EXTRA     ?=
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr $(EXTRA)
 CSRC      := aehmc_b200/csrc
 LIBDIR    := aehmc_b200/lib
 OBJDIR    := build/obj

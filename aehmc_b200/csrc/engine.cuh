@@ -231,10 +231,14 @@ struct RegFront {
 };
 
 // Split engine (one launch per tick part): the front of the tick lives in registers between the second half
-// kick of one leapfrog (post) and the first half kick + drift of the next (pre), so each of q, p, g (and V, W
-// for a dense metric) is read once and written once per tick.  bind_post loads what the post part needs (g and
-// W arrive from the gradient / metric contractions); bind loads the whole front after a sub-tree or transition
-// switch.  DENSE selects whether V / W exist.
+// kick of one leapfrog (post) and the first half kick + drift of the next (pre), so each of p (and V for a dense
+// metric) is read once and written once per tick.  Inside a sub-tree the edge arrays are NOT kept current:
+//   q   the drifted position is written once, to xa (the gradient's input), and read back from there;
+//   g,W arrive from the gradient / metric contractions (xb, xc) every tick and are consumed by the next half
+//       kick in registers; nothing reads the edge's copy before the sub-tree ends.
+// flush() (sub-tree end, or the last tick of a call) writes the whole front back to the edge arrays.
+// bind_post loads what the post part needs; bind loads the whole front from the edge after a sub-tree or
+// transition switch.  DENSE selects whether V / W exist.
 template <typename T, int E, bool DENSE>
 struct TickFront {
     static constexpr int kE = E;
@@ -247,12 +251,13 @@ struct TickFront {
         const T* Gd = rt ? ch.v.gr : ch.v.gl;
         const T* V = rt ? ch.v.vr : ch.v.vl;
         const T* W = rt ? ch.v.wr : ch.v.wl;
+        const T* XA = ch.v.xa + (i64)ch.c * ch.v.d;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int j = ch.lane + e * G;
             const bool in = j < ch.v.d;
             const i64 a = in ? ch.at(j) : ch.at(0);
-            fq[e] = in ? Q[a] : (T)0;
+            fq[e] = in ? (all ? Q[a] : XA[in ? j : 0]) : (T)0;
             fp[e] = in ? P[a] : (T)0;
             if (DENSE) fv[e] = in ? V[a] : (T)0;
             fg[e] = (all && in) ? Gd[a] : (T)0;
@@ -273,9 +278,9 @@ struct TickFront {
             const int j = ch.lane + e * G;
             if (j < ch.v.d) {
                 const i64 a = ch.at(j);
-                Q[a] = fq[e]; P[a] = fp[e];
+                P[a] = fp[e];
                 if (DENSE) V[a] = fv[e];
-                if (all) { Gd[a] = fg[e]; if (DENSE) W[a] = fw[e]; }
+                if (all) { Q[a] = fq[e]; Gd[a] = fg[e]; if (DENSE) W[a] = fw[e]; }
             }
         }
     }

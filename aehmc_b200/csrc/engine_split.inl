@@ -46,9 +46,11 @@ __global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksSplit) spl
     }
 }
 
-// post of tick t and pre of tick t+1 in one pass with the front in registers (TickFront): q, p, g (V, W) of the
-// edge are read once and written once per tick instead of twice.
-template <typename T, int G, bool DENSE, bool HMC, int E>
+// post of tick t and pre of tick t+1 in one pass with the front in registers (TickFront): p (V) of the edge are
+// read once and written once per tick, q goes through xa only, g (W) are not written at all inside a sub-tree.
+// PRE = false is the last tick of a call: the post part only, then the whole front goes back to the edge arrays so
+// that the state in memory is complete (the next call starts with split_pre_kernel).
+template <typename T, int G, bool DENSE, bool HMC, int E, bool PRE>
 __global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksTick)
 split_postpre_kernel(EngineView<T> v, int* not_done) {
     __shared__ double red_s[128];
@@ -70,8 +72,14 @@ split_postpre_kernel(EngineView<T> v, int* not_done) {
             if (ch.r.phase != PH_DONE && not_done) atomicAdd(not_done, 1);
             if (v.counters) atomicAdd((unsigned long long*)&v.counters[3], 1ull);
         }
+        if (!PRE) {
+            if (!ended) f.flush(ch);
+            ch.store();
+            return;
+        }
         if (ch.r.phase == PH_DONE) { ch.store(); return; }
     }
+    if (!PRE) return;
     if (ch.r.phase == PH_START) {
         if (HMC) hmc_begin<T, G, DENSE>(ch);
         else begin_transition<T, G, DENSE>(ch);
@@ -79,7 +87,7 @@ split_postpre_kernel(EngineView<T> v, int* not_done) {
     }
     if (rebind) f.bind(ch);
     half_kick_drift<T, G, DENSE, true>(ch, f);
-    f.store(ch, !rebind);                      // after a re-bind g (and W) in memory are already current
+    f.store(ch, false);                        // p (V) only: q is in xa, g (W) stay in the edge / come from xb (xc)
     ch.store();
 }
 
@@ -194,19 +202,32 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
         split_pre_kernel<T, G, false, HMC><<<grid, thr, 0, st>>>(v);
         return 0;
     };
+#define B2H_POSTPRE(D_, E_, P_) split_postpre_kernel<T, G, D_, HMC, E_, P_><<<grid, thr, 0, st>>>(v, nd)
     auto launch_postpre = [&](i64 t, int* nd) -> int {                       // post of tick t - 1, pre of tick t
         if (pl.dense) {
             if (int e = pre_prologue(t)) return e;
-            if (epl <= 1) split_postpre_kernel<T, G, true, HMC, 1><<<grid, thr, 0, st>>>(v, nd);
-            else if (epl <= 2) split_postpre_kernel<T, G, true, HMC, 2><<<grid, thr, 0, st>>>(v, nd);
-            else split_postpre_kernel<T, G, true, HMC, 4><<<grid, thr, 0, st>>>(v, nd);
+            if (epl <= 1) B2H_POSTPRE(true, 1, true);
+            else if (epl <= 2) B2H_POSTPRE(true, 2, true);
+            else B2H_POSTPRE(true, 4, true);
             return pre_epilogue(t);
         }
-        if (epl <= 1) split_postpre_kernel<T, G, false, HMC, 1><<<grid, thr, 0, st>>>(v, nd);
-        else if (epl <= 2) split_postpre_kernel<T, G, false, HMC, 2><<<grid, thr, 0, st>>>(v, nd);
-        else split_postpre_kernel<T, G, false, HMC, 4><<<grid, thr, 0, st>>>(v, nd);
+        if (epl <= 1) B2H_POSTPRE(false, 1, true);
+        else if (epl <= 2) B2H_POSTPRE(false, 2, true);
+        else B2H_POSTPRE(false, 4, true);
         return 0;
     };
+    auto launch_post_last = [&](int* nd) {                                   // post of the call's last tick
+        if (pl.dense) {
+            if (epl <= 1) B2H_POSTPRE(true, 1, false);
+            else if (epl <= 2) B2H_POSTPRE(true, 2, false);
+            else B2H_POSTPRE(true, 4, false);
+        } else {
+            if (epl <= 1) B2H_POSTPRE(false, 1, false);
+            else if (epl <= 2) B2H_POSTPRE(false, 2, false);
+            else B2H_POSTPRE(false, 4, false);
+        }
+    };
+#undef B2H_POSTPRE
 
     rc = launch_pre(0);
     for (i64 tick = 0; tick < bound && rc == 0; ++tick) {
@@ -221,6 +242,8 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
         if (fuse && !last) {
             rc = launch_postpre(tick + 1, nd);
             if (rc) break;
+        } else if (fuse) {
+            launch_post_last(nd);
         } else {
             if (pl.dense) split_post_kernel<T, G, true, HMC><<<grid, thr, 0, st>>>(v, nd);
             else split_post_kernel<T, G, false, HMC><<<grid, thr, 0, st>>>(v, nd);

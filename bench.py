@@ -598,6 +598,9 @@ def ess_leg(w, D, args):
     (state, (eps, imm), winfo), t_warm = timed(lambda: ab.window_adaptation.run(
         kernel, st0, warm, pooled=True, is_mass_matrix_full=full, initial_inverse_mass_matrix=imm0,
         initial_step_size=w["eps"]))
+    # one step size for all chains (the median of the per-chain dual-averaging results): with per-chain step sizes the
+    # chains with the smallest ones build the deepest trees and the whole batch waits for them
+    eps = torch.full_like(eps, float(eps.median()))
     (info, ex), t_sample = timed(lambda: _engine.run("nuts", model, imm, kernel.spec["srng"], state, eps,
                                                       n_transitions=keep, store_draws=keep, return_counters=True))
     dims = list(range(min(8, d)))
@@ -616,7 +619,7 @@ def ess_leg(w, D, args):
         "nuts_ess_per_sec": ess_min / t_sample, "rhat_max": rhat_max, "ess_min": ess_min,
         "ess_how": f"pooled window adaptation ({warm} transitions, initial inverse mass matrix "
                    f"{'4/N' if imm0 is not None else 'identity'}, statistics merged over the ranks) then {keep} kept NUTS "
-                   "transitions per chain; rank-normalised split bulk-ESS and R-hat (arviz defaults) of the first "
+                   "transitions per chain at the median adapted step size; rank-normalised split bulk-ESS and R-hat (arviz defaults) of the first "
                    f"{len(dims)} coordinates over all chains of all ranks, minimum ESS divided by the sampling time of the "
                    "kept transitions",
         "warmup_seconds": t_warm, "sampling_seconds": t_sample, "diagnostics_seconds": t_diag,
