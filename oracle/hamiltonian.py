@@ -93,8 +93,8 @@ def gaussian_metric(inverse_mass_matrix):
         turning_at_left = dot(velocity_left, rho) <= 0
         turning_at_right = dot(velocity_right, rho) <= 0
         if streams.MARGIN_LOG is not None:
-            nr = np.sqrt(np.sum(np.square(rho))) + 1e-300
-            for v in (velocity_left, velocity_right):
+            nr = np.sqrt(np.sum(np.square(rho)))
+            for v in (velocity_left, velocity_right) if nr > 0 else ():      # rho == 0: a one-state trajectory, no tie
                 streams.MARGIN_LOG.append(("uturn", abs(float(dot(v, rho))) / (np.sqrt(np.sum(np.square(v))) * nr + 1e-300)))
         return bool(turning_at_left | turning_at_right)
 

@@ -11,7 +11,7 @@ def test_readme_quick_start(cuda_device):
 
     model = ab.models.IIDGaussian([0.0], [1.0])
     srng = ab.RandomStream(seed=0)
-    kernel = ab.nuts.new_kernel(srng, model)
+    kernel = ab.nuts.new_kernel(srng, model, exact_doubling=True)
     state = ab.nuts.new_state(np.zeros((2048, 1)), model)
     info, updates = kernel(state, 1e-2, 1.0)
     assert info.state.position.shape == (2048, 1) and "n_leapfrog" in updates
@@ -21,6 +21,14 @@ def test_readme_quick_start(cuda_device):
     assert draws.shape == (10, 2048, 1)
     rhat, ess = ab.diagnostics.rhat(draws), ab.diagnostics.ess(draws)
     assert abs(float(rhat[0]) - 1.0) < 0.05 and float(ess[0]) > 2000
+    assert abs(float(draws.double().std()) - 1.0) < 0.05
+
+    # the reference's own sub-tree length (the default: decision-for-decision parity) is NOT invariant on this
+    # target: the rank-normalised R-hat (arviz's default) shows it, the plain one does not
+    ref_kernel = ab.nuts.new_kernel(ab.RandomStream(seed=0), model)
+    st, (eps, imm_r), _ = ab.window_adaptation.run(ref_kernel, ab.nuts.new_state(np.zeros((2048, 1)), model), num_steps=200)
+    _, dr, _, _ = ab.sampling.sample(ref_kernel, st, eps, ab.metrics.per_chain(imm_r), 100, thin=10)
+    assert float(ab.diagnostics.rhat(dr)[0]) > 1.2 and float(ab.diagnostics.rhat(dr, method="identity")[0]) < 1.05
 
     funnel = ab.models.UserModel(r'''
 template <typename S, typename T>
