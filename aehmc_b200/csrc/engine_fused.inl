@@ -6,8 +6,10 @@
 
 namespace b2h {
 
+// E > 8 only exists for thread-per-chain (G = 1): the chain's whole front is the thread's registers, so the launch
+// bound leaves the thread its 255 registers instead of trading them for resident warps.
 template <typename T, int G, int MODEL, bool HMC, int E>
-__global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksFused)
+__global__ void __launch_bounds__(Geo<G>::kThreads, (E > 8 ? 2 : Geo<G>::kMinBlocksFused))
 fused_run_kernel(EngineView<T> v, ModelDev m, i64 max_ticks) {
     typedef typename FrontOf<T, E>::type Front;
     __shared__ double red_s[128];
@@ -76,6 +78,11 @@ static void launch_fused_model(cudaStream_t st, const EngineView<T>& v, const Mo
         if (use_regs && epl <= 2) return launch_fused_e<T, G, HMC, MODEL, 2>(st, v, m, max_ticks);
         if (use_regs && epl <= 4) return launch_fused_e<T, G, HMC, MODEL, 4>(st, v, m, max_ticks);
         if (use_regs && epl <= 8) return launch_fused_e<T, G, HMC, MODEL, 8>(st, v, m, max_ticks);
+        if constexpr (G == 1) {
+            // thread per chain, tiny targets (funnel, eight schools: d = 10): the whole front in the thread's registers
+            if (use_regs && epl <= 10) return launch_fused_e<T, G, HMC, MODEL, 10>(st, v, m, max_ticks);
+            if (use_regs && epl <= 16) return launch_fused_e<T, G, HMC, MODEL, 16>(st, v, m, max_ticks);
+        }
     }
     (void)epl;
     launch_fused_e<T, G, HMC, MODEL, 0>(st, v, m, max_ticks);

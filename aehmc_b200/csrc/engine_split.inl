@@ -50,15 +50,6 @@ __global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksSplit) spl
 // read once and written once per tick, q goes through xa only, g (W) are not written at all inside a sub-tree.
 // PRE = false is the last tick of a call: the post part only, then the whole front goes back to the edge arrays so
 // that the state in memory is complete (the next call starts with split_pre_kernel).
-// L2 prefetch of one chain row (32-byte sectors spread over the group's lanes)
-template <typename T, int G>
-B2H_DEVINL void prefetch_row(const T* row, int d) {
-    const char* p = reinterpret_cast<const char*>(row);
-    const int bytes = d * (int)sizeof(T);
-    for (int off = Group<G>::lane() * 32; off < bytes; off += G * 32)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
-}
-
 template <typename T, int G, bool DENSE, bool HMC, int E, bool PRE>
 __global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksTick)
 split_postpre_kernel(EngineView<T> v, int* not_done) {
@@ -66,25 +57,6 @@ split_postpre_kernel(EngineView<T> v, int* not_done) {
     const int c = Geo<G>::chain();
     if (c >= v.C) return;
     Chain<T, G> ch(v, c, red_s);
-#ifndef B2H_NO_TICK_PREFETCH
-    {
-        // Which edge is the front, and which checkpoint level the step touches, is only known once the chain record
-        // has arrived: start every row the tick can need on its way to L2 now (the direction-independent ones and
-        // the momentum (velocity) rows of BOTH edges), so that the loads issued after the record find them there
-        // instead of paying a second DRAM round trip.
-        const i64 ro = (i64)c * v.d;               // split engine: row-major [C][d]
-        prefetch_row<T, G>(v.xa + ro, v.d);
-        prefetch_row<T, G>(v.xb + ro, v.d);
-        prefetch_row<T, G>(v.sms + ro, v.d);
-        prefetch_row<T, G>(v.pl + ro, v.d);
-        prefetch_row<T, G>(v.pr + ro, v.d);
-        if (DENSE) {
-            prefetch_row<T, G>(v.xc + ro, v.d);
-            prefetch_row<T, G>(v.vl + ro, v.d);
-            prefetch_row<T, G>(v.vr + ro, v.d);
-        }
-    }
-#endif
     ch.load();
     if (ch.r.phase == PH_DONE) return;
     TickFront<T, E, DENSE> f;
