@@ -13,11 +13,13 @@ from .trajectory import Diagnostics
 
 _workspaces = {}
 _resume_offsets = {}
+_resume_groups = {}
 
 
 def _evict(key):
     _workspaces.pop(key, None)
     _resume_offsets.pop(key, None)
+    _resume_groups.pop(key, None)
 
 
 def _workspace(key, nbytes, dev, owner=None):
@@ -113,8 +115,11 @@ def run(kind, model, metric, srng, state, step_size, *, n_transitions=1, max_num
     # (seed, chain, transition) however the run is chunked
     if resume and key in _resume_offsets:
         rng.transition_offset = _resume_offsets[key]
+        cfg.group = _resume_groups[key]          # the workspace layout is the one of the call that started the run
     else:
         _resume_offsets[key] = int(rng.transition_offset)
+        _resume_groups[key] = int(lib.b2h_nuts_plan_group(C.byref(m), C.byref(mt), C.byref(cfg), C.c_int64(Cn),
+                                                          C.c_int32(1 if max_ticks > 0 else 0)))
     ad = adapt.struct() if adapt is not None else None
     ctx = backend.context(dev)
     if kind == "nuts":

@@ -108,6 +108,12 @@ int64_t b2h_nuts_workspace_bytes(const b2h_model* model, const b2h_metric* metri
     return engine_workspace_bytes(model, metric, cfg, C);
 }
 
+int32_t b2h_nuts_plan_group(const b2h_model* model, const b2h_metric* metric, const b2h_cfg* cfg, int64_t C,
+                            int32_t free_running) {
+    if (!model || !metric || !cfg) return -1;
+    return engine_plan_group(model, metric, cfg, C, free_running != 0);
+}
+
 int64_t b2h_hmc_workspace_bytes(const b2h_model* model, const b2h_metric* metric, const b2h_cfg* cfg, int64_t C) {
     if (!model || !metric || !cfg) return -1;
     return engine_workspace_bytes(model, metric, cfg, C);

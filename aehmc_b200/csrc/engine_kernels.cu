@@ -31,10 +31,18 @@ struct Carver {
     }
 };
 
-static int auto_group(int d, long long C) {
-    // tiny targets: thread-per-chain only when there are enough chains to fill the machine with threads
-    // (measured on config 4, 65536 chains: 8 lanes per chain is 20-35 % faster than 1)
-    if (d <= 16) return C >= 262144 ? 1 : 8;
+static int auto_group(int d, long long C, int model_kind, bool free_running) {
+    // Tiny targets: thread per chain (the whole front in the thread's registers, fused_run_kernel E = 10 / 16) once there
+    // are enough chains to fill the machine with threads.  Measured on config 4 (65536 chains, d = 10,
+    // benchmarks/c4_tail_probe.py): eight schools 1.01 vs 0.64 G evals/s free-running and 0.70 vs 0.54 for a fixed
+    // number of transitions; the funnel ties free-running (0.74 vs 0.79) but its per-chain work is so heavy-tailed
+    // (max / mean = 24) that a fixed number of transitions is bound by the slowest chains, and a lone chain steps
+    // faster on 8 lanes (7 vs 11 us per leapfrog).
+    if (d <= 16) {
+        if (C >= 262144) return 1;
+        if (C >= 32768 && (free_running || model_kind != B2H_MODEL_FUNNEL)) return 1;
+        return 8;
+    }
     if (d <= 64) return 8;
     if (d <= 512) return 32;
     return 256;
@@ -45,12 +53,12 @@ static bool model_is_fused(int kind) {
 }
 
 static int make_plan(const b2h_model* model, const b2h_metric* metric, const b2h_cfg* cfg, EnginePlan& pl,
-                     long long C = 0) {
+                     long long C = 0, bool free_running = false) {
     pl.dense = metric->kind == B2H_IMM_DENSE;
     pl.per_chain_imm = metric->kind == B2H_IMM_DIAG_PER_CHAIN;
     pl.scalar_imm = metric->kind == B2H_IMM_SCALAR;
     pl.split = pl.dense || !model_is_fused(model->kind);
-    int G = cfg->group > 0 ? cfg->group : auto_group(model->dim, C);
+    int G = cfg->group > 0 ? cfg->group : auto_group(model->dim, C, model->kind, free_running);
     if (pl.split && G < 8) G = 8;          // split scratch is row-major: needs the row-major layout
     if (G != 1 && G != 8 && G != 32 && G != 256) {
         set_error("group must be one of 0 (auto), 1, 8, 32, 256");
@@ -180,7 +188,7 @@ static int run_typed(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* met
                      void* draws, double* draw_stats, int n_store, int64_t* counters, void* ws, i64 ws_bytes,
                      bool hmc) {
     EnginePlan pl;
-    int rc = make_plan(model, metric, cfg, pl, C64);
+    int rc = make_plan(model, metric, cfg, pl, C64, max_ticks > 0);
     if (rc) return rc;
     const int C = (int)C64, d = model->dim;
     const int maxd = hmc ? 1 : cfg->max_num_expansions;
@@ -550,6 +558,12 @@ int nuts_run_impl(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric
                                 max_ticks, resume, diag, draws, draw_stats, n_store, counters, ws, ws_bytes, hmc);
     set_error("dtype must be B2H_F32 or B2H_F64");
     return B2H_ERR_ARG;
+}
+
+int engine_plan_group(const b2h_model* model, const b2h_metric* metric, const b2h_cfg* cfg, i64 C, bool free_running) {
+    EnginePlan pl;
+    if (make_plan(model, metric, cfg, pl, C, free_running)) return -1;
+    return pl.G;
 }
 
 i64 engine_workspace_bytes(const b2h_model* model, const b2h_metric* metric, const b2h_cfg* cfg, i64 C) {

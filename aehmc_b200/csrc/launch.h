@@ -98,6 +98,7 @@ int nuts_expand_impl(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* met
 int nuts_subtree_impl(b2h_ctx* ctx, const b2h_model* model, const b2h_metric* metric, const b2h_rng* rng,
                       const b2h_cfg* cfg, b2h_subtree* sub, const double* eps, i64 C, void* ws, i64 ws_bytes);
 i64 engine_workspace_bytes(const b2h_model* model, const b2h_metric* metric, const b2h_cfg* cfg, i64 C);
+int engine_plan_group(const b2h_model* model, const b2h_metric* metric, const b2h_cfg* cfg, i64 C, bool free_running);
 
 static inline size_t dtype_size(int dtype) { return dtype == B2H_F64 ? 8 : 4; }
 

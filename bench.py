@@ -654,16 +654,37 @@ def secondary_c4(D, peaks):
 
         def draw():
             res["d"] = _engine.run("nuts", model, metrics.per_chain(imm), kernel.spec["srng"], wstate, eps,
-                                   n_transitions=Dn, store_draws=0, return_counters=True)
+                                   n_transitions=Dn, store_draws=Dn, return_counters=True)
         ms_d = _event_ms(draw, 1, D.dev)
         info, ex = res["d"]
         leap = int(ex["counters"][0].item())
+        per_chain = ex["draw_stats"][:, :, 2].sum(0)
+        tail = {"mean": float(per_chain.mean()), "p99": float(torch.quantile(per_chain, 0.99)),
+                "max": float(per_chain.max())}
+        ex = None
+        res["d"] = (info, None)
+        torch.cuda.empty_cache()
+        # the same chains free-running for the mean number of leapfrogs: every lane busy all the time (throughput of the
+        # kernel), against the fixed-number-of-transitions run above, which ends with its slowest chains
+        ticks = max(int(tail["mean"]), 1)
+
+        def free():
+            res["f"] = _engine.run("nuts", model, metrics.per_chain(imm), kernel.spec["srng"], wstate, eps,
+                                   max_ticks=ticks, return_counters=True)
+        ms_f = _event_ms(free, 1, D.dev)
+        leap_f = int(res["f"][1]["counters"][0].item())
         out[name] = {"value": leap / (ms_d * 1e-3), "unit": UNIT, "chains": Cn, "warmup_ms": ms_w, "sampling_ms": ms_d,
                      "sampling_leapfrogs": leap, "transitions_per_sec": Cn * Dn / (ms_d * 1e-3),
+                     "per_chain_leapfrogs": tail,
+                     "free_running": {"value": leap_f / (ms_f * 1e-3), "unit": UNIT, "ticks": ticks, "ms": ms_f,
+                                      "what": "every chain takes `ticks` leapfrogs (transitions restart independently): "
+                                              "the kernel's throughput without the tail of the slowest chains"},
                      "roofline": {"bound": "hbm", "achieved": leap * 11 * 10 * 8 / (ms_d * 1e-3) / 1e9, "peak": hbm_peak,
                                   "unit": "GB/s", "frac": leap * 11 * 10 * 8 / (ms_d * 1e-3) / 1e9 / hbm_peak,
+                                  "frac_free_running": leap_f * 11 * 10 * 8 / (ms_f * 1e-3) / 1e9 / hbm_peak,
                                   "what": "11*d*s algorithmic bytes per leapfrog (SURVEY 8d); the state of a chain "
-                                          "stays on chip in the persistent kernel, HBM sees only draws out"},
+                                          "stays on chip in the persistent kernel (latency / divergence bound, SURVEY 8d), "
+                                          "HBM sees only draws out"},
                      "step_size_median": float(eps.median()),
                      "mean_accept": float(info.acceptance_probability.mean()),
                      "last_transition_depth_hist": torch.bincount(info.num_doublings.long(), minlength=11).cpu().tolist(),

@@ -241,6 +241,10 @@ int b2h_nuts_run(b2h_ctx*, const b2h_model*, const b2h_metric*, const b2h_rng*, 
                  int32_t n_transitions, int64_t max_ticks, int32_t resume, b2h_diag* diag, void* draws,
                  double* draw_stats, int32_t n_store, int64_t* counters, void* workspace, int64_t workspace_bytes);
 int64_t b2h_nuts_workspace_bytes(const b2h_model*, const b2h_metric*, const b2h_cfg*, int64_t C);
+/* Threads per chain (1, 8, 32 or 256) a run with cfg->group == 0 will use; free_running != 0: a max_ticks run.  The
+ * workspace layout depends on it: a resumed call must run with the group of the call that started the run (pass it
+ * as cfg->group). */
+int32_t b2h_nuts_plan_group(const b2h_model*, const b2h_metric*, const b2h_cfg*, int64_t C, int32_t free_running);
 int64_t b2h_hmc_workspace_bytes(const b2h_model*, const b2h_metric*, const b2h_cfg*, int64_t C);
 
 /* ---- stand-alone trajectory builders with caller-supplied tree state (every model; scalar / diagonal metrics: the
