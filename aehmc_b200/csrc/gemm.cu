@@ -330,6 +330,9 @@ dense_apply_dmma_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGroup<do
 // Requires 16-byte aligned rows (even K, N, leading dimensions); otherwise the register-staged kernel runs.
 // ---------------------------------------------------------------------------------------------
 constexpr int STAGES = 3, ALD = BK + 4;
+#ifndef B2H_GEMM_WARPS_DEFAULT
+#define B2H_GEMM_WARPS_DEFAULT 8
+#endif
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -338,12 +341,17 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N_)); }
 
-template <int BN_>
-__global__ void __launch_bounds__(GT, 1)
+// MI: 16-row MMA tiles per warp along M.  MI = 2: 8 warps (4 x 2), warp tile 32 x BN_/2.  MI = 1: 16 warps (8 x 2), warp
+// tile 16 x BN_/2 -- half the accumulators per thread, twice the warps to cover the per-k-tile barrier.
+template <int BN_, int MI>
+__global__ void __launch_bounds__((128 / (16 * MI)) * 2 * 32, 1)
 dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGroup<double> g2, int N, int K, int tiles_n,
                               int tiles_m0, int tiles_m1, int k_chunk, i64 split_stride) {
     typedef double T;
-    constexpr int NJ = BN_ / 16;               // 8-wide MMA tiles per warp along N (warp tile 32 x BN_/2)
+    constexpr int NJ = BN_ / 16;               // 8-wide MMA tiles per warp along N (warp tile 16 MI x BN_/2)
+    constexpr int WROWS = 128 / (16 * MI);     // warps along M
+    constexpr int NT = WROWS * 2 * 32;         // threads of the CTA
+    constexpr int A_ITERS = (BM * 8) / NT;     // 16-byte chunks of the A tile per thread
     constexpr int BLD = BN_ + 8;
     constexpr int A_STAGE = BM * ALD, B_STAGE = BK * BLD;
     int tile_m = blockIdx.x / tiles_n;
@@ -371,33 +379,33 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
     T* Ss = Bs + STAGES * B_STAGE;                                // [STAGES][BK]   (sub vector slices)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp & 3) * 32, wn = (warp >> 2) * (BN_ / 2);
+    const int wm = (warp % WROWS) * (16 * MI), wn = (warp / WROWS) * (BN_ / 2);
     const int gq = lane >> 2, tq = lane & 3;
 
     // copy assignment: A tile = 128 rows x 8 chunks (16 B = 2 k); 8 consecutive threads take one row
-    i64 a_src[4];
+    i64 a_src[A_ITERS];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int row = (tid + GT * i) >> 3, gr = m0 + row;
+    for (int i = 0; i < A_ITERS; ++i) {
+        const int row = (tid + NT * i) >> 3, gr = m0 + row;
         a_src[i] = gr < M ? (i64)(g.in_rows ? g.in_rows[gr] : gr) * lda : -1;
     }
     constexpr int B_CHUNKS = BK * (BN_ / 2);
-    constexpr int B_ITERS = (B_CHUNKS + GT - 1) / GT;
+    constexpr int B_ITERS = (B_CHUNKS + NT - 1) / NT;
 
     auto issue = [&](int kt, int stage) {
         const int k0 = k_begin + kt * BK;
         T* as = As + stage * A_STAGE;
         T* bs = Bs + stage * B_STAGE;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int c = tid + GT * i, row = c >> 3, kc = (c & 7) * 2;
+        for (int i = 0; i < A_ITERS; ++i) {
+            const int c = tid + NT * i, row = c >> 3, kc = (c & 7) * 2;
             const int gk = k0 + kc;
             const bool ok = a_src[i] >= 0 && gk < k_end;
             cp_async16(as + row * ALD + kc, ok ? (const void*)(A + a_src[i] + gk) : (const void*)A, ok ? 16 : 0);
         }
 #pragma unroll
         for (int i = 0; i < B_ITERS; ++i) {
-            const int c = tid + GT * i;
+            const int c = tid + NT * i;
             if (c < B_CHUNKS) {
                 const int kr = c / (BN_ / 2), nc = (c % (BN_ / 2)) * 2;
                 const int gk = k0 + kr, gn = n0 + nc;
@@ -411,9 +419,9 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
         }
     };
 
-    T acc[2][NJ][4];
+    T acc[MI][NJ][4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
 #pragma unroll
@@ -439,13 +447,13 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
         const T* ss = Ss + stage * BK;
 #pragma unroll
         for (int k0 = 0; k0 < BK; k0 += 8) {
-            T fa[2][4], fb[NJ][2];
+            T fa[MI][4], fb[NJ][2];
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const int kk = k0 + tq + 4 * q;
                 const T sv = sub ? ss[kk] : 0.0;
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
+                for (int i = 0; i < MI; ++i) {
                     fa[i][2 * q] = as[(i * 16) * ALD + kk] - sv;
                     fa[i][2 * q + 1] = as[(i * 16 + 8) * ALD + kk] - sv;
                 }
@@ -453,7 +461,7 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
                 for (int j = 0; j < NJ; ++j) fb[j][q] = bs[kk * BLD + j * 8];
             }
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < MI; ++i)
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) Dmma<8>::run(acc[i][j], fa[i], fb[j]);
         }
@@ -461,7 +469,7 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
     cp_async_wait<0>();
 
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int gr = m0 + wm + i * 16 + h * 8 + gq;
@@ -481,10 +489,18 @@ static void launch_async(cudaStream_t st, const GemmGroup<double>& g0, const Gem
     constexpr int smem = (STAGES * (BM * ALD + BK * (BN_ + 8)) + STAGES * BK) * (int)sizeof(double);
     int tiles_m0 = (g0.M + BM - 1) / BM, tiles_m1 = (g1.M + BM - 1) / BM, tiles_m2 = (g2.M + BM - 1) / BM;
     int tiles_n = (N + BN_ - 1) / BN_;
-    cudaFuncSetAttribute(dense_apply_dmma_async_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     dim3 grid((tiles_m0 + tiles_m1 + tiles_m2) * tiles_n, nsplit);
-    dense_apply_dmma_async_kernel<BN_><<<grid, GT, smem, st>>>(g0, g1, g2, N, K, tiles_n, tiles_m0, tiles_m1, k_chunk,
-                                                               split_stride);
+    static int warps = -1;
+    if (warps < 0) { const char* e = getenv("B2H_GEMM_WARPS"); warps = e ? atoi(e) : B2H_GEMM_WARPS_DEFAULT; }
+    if (warps == 16) {
+        cudaFuncSetAttribute(dense_apply_dmma_async_kernel<BN_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        dense_apply_dmma_async_kernel<BN_, 1><<<grid, 512, smem, st>>>(g0, g1, g2, N, K, tiles_n, tiles_m0, tiles_m1, k_chunk,
+                                                                       split_stride);
+    } else {
+        cudaFuncSetAttribute(dense_apply_dmma_async_kernel<BN_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        dense_apply_dmma_async_kernel<BN_, 2><<<grid, 256, smem, st>>>(g0, g1, g2, N, K, tiles_n, tiles_m0, tiles_m1, k_chunk,
+                                                                       split_stride);
+    }
 }
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
