@@ -15,6 +15,17 @@
 #ifndef B2H_DEVINL
 #define B2H_DEVINL __device__ __forceinline__
 #endif
+// Scalar helpers whose double-precision exp / log / Philox bodies are hundreds of instructions each: kept OUT of line
+// so that the engine kernels, which call them at a dozen sites, stay small enough for the instruction cache (ncu:
+// `no_instruction` was the top stall of the tick kernel and of the persistent kernel with everything inlined).  They
+// take and return scalars only, so the chain record stays in registers across the calls.
+#ifndef B2H_DEVCALL
+#ifdef B2H_HOST_SIM
+#define B2H_DEVCALL static inline
+#else
+#define B2H_DEVCALL static __device__ __noinline__
+#endif
+#endif
 
 namespace b2h {
 
@@ -27,7 +38,7 @@ typedef long long i64;
 // log(exp(a)+exp(b)) exactly as oracle/tree.py:logaddexp (max + log(sum exp(x-max)),
 // -inf,-inf -> -inf).  Always double: weights are float64 in the reference
 // whatever floatX is (nuts.py:123-124).
-B2H_DEVINL double lae(double a, double b) {
+B2H_DEVCALL double lae(double a, double b) {
     if (isnan(a) || isnan(b)) return nan("");
     double m = a > b ? a : b;
     if (isinf(m)) {
@@ -37,7 +48,7 @@ B2H_DEVINL double lae(double a, double b) {
     return m + log(exp(a - m) + exp(b - m));
 }
 
-B2H_DEVINL double expit(double x) {
+B2H_DEVCALL double expit(double x) {
     if (isnan(x)) return x;
     if (x < -709.0) return 0.0;
     return 1.0 / (1.0 + exp(-x));
@@ -88,14 +99,14 @@ B2H_DEVINL double u53(uint32_t lo, uint32_t hi) {          // [0, 1)
 
 struct PhiloxKey { uint32_t k0, k1; };
 
-B2H_DEVINL double philox_uniform(PhiloxKey key, uint64_t chain, uint32_t transition, uint32_t kind, uint32_t slot) {
+B2H_DEVCALL double philox_uniform(PhiloxKey key, uint64_t chain, uint32_t transition, uint32_t kind, uint32_t slot) {
     uint32_t o[4];
     philox4x32_10(slot, kind, transition, (uint32_t)chain, key.k0 ^ (uint32_t)(chain >> 32), key.k1, o);
     return u53(o[0], o[1]);
 }
 
 // element j of the standard-normal momentum vector (Box-Muller on one Philox block per pair)
-B2H_DEVINL double philox_normal(PhiloxKey key, uint64_t chain, uint32_t transition, uint32_t j) {
+B2H_DEVCALL double philox_normal(PhiloxKey key, uint64_t chain, uint32_t transition, uint32_t j) {
     uint32_t o[4];
     philox4x32_10(j >> 1, DRAW_Z, transition, (uint32_t)chain, key.k0 ^ (uint32_t)(chain >> 32), key.k1, o);
     double u1 = 1.0 - u53(o[0], o[1]);                      // (0, 1]
