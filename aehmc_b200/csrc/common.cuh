@@ -38,7 +38,7 @@ typedef long long i64;
 // log(exp(a)+exp(b)) exactly as oracle/tree.py:logaddexp (max + log(sum exp(x-max)),
 // -inf,-inf -> -inf).  Always double: weights are float64 in the reference
 // whatever floatX is (nuts.py:123-124).
-B2H_DEVCALL double lae(double a, double b) {
+B2H_DEVINL double lae_inl(double a, double b) {
     if (isnan(a) || isnan(b)) return nan("");
     double m = a > b ? a : b;
     if (isinf(m)) {
@@ -48,11 +48,18 @@ B2H_DEVCALL double lae(double a, double b) {
     return m + log(exp(a - m) + exp(b - m));
 }
 
-B2H_DEVCALL double expit(double x) {
+B2H_DEVINL double expit_inl(double x) {
     if (isnan(x)) return x;
     if (x < -709.0) return 0.0;
     return 1.0 / (1.0 + exp(-x));
 }
+
+B2H_DEVCALL double lae(double a, double b) { return lae_inl(a, b); }
+B2H_DEVCALL double expit(double x) { return expit_inl(x); }
+// Thread-per-chain kernels (G == 1) reach these under divergence, where a call costs more than it saves (measured:
+// eight schools 0.91 -> 0.79 G evals/s with calls); the group-per-chain kernels call the out-of-line copies.
+template <int G> B2H_DEVINL double lae_g(double a, double b) { return G == 1 ? lae_inl(a, b) : lae(a, b); }
+template <int G> B2H_DEVINL double expit_g(double x) { return G == 1 ? expit_inl(x) : expit(x); }
 
 // Decision numpy's Generator.binomial(1, p) takes from its single uniform u
 // (oracle/streams.py:bernoulli_from_uniform).  NaN p never accepts.
@@ -115,6 +122,21 @@ B2H_DEVCALL double philox_normal(PhiloxKey key, uint64_t chain, uint32_t transit
     double s, c;
     sincospi(2.0 * u2, &s, &c);
     return (j & 1) ? r * s : r * c;
+}
+
+// both normals of Box-Muller pair `pair` (elements 2 pair and 2 pair + 1 of the momentum vector): the same values
+// philox_normal returns for them, from ONE Philox block
+B2H_DEVCALL void philox_normal_pair(PhiloxKey key, uint64_t chain, uint32_t transition, uint32_t pair, double* z0,
+                                    double* z1) {
+    uint32_t o[4];
+    philox4x32_10(pair, DRAW_Z, transition, (uint32_t)chain, key.k0 ^ (uint32_t)(chain >> 32), key.k1, o);
+    double u1 = 1.0 - u53(o[0], o[1]);                      // (0, 1]
+    double u2 = u53(o[2], o[3]);
+    double r = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    *z0 = r * c;
+    *z1 = r * s;
 }
 
 // ---------------------------------------------------------------------------

@@ -317,8 +317,11 @@ B2H_DEVINL void begin_subtree(Chain<T, G>& ch) {
 // Diagonal metric family: p = sqrt(1/imm) z (metrics.py:46,50,67).
 // Dense: (p0, v0) were produced by the momentum GEMMs into compact row mom_slot.
 // ---------------------------------------------------------------------------
+// zs / zready (thread-per-chain persistent kernel): standard normals of THIS transition that were drawn ahead of time,
+// one Box-Muller pair per tick, while all lanes of the warp were converged (see fused_run_kernel): element j < zready
+// is zs[j * zstride], the others are drawn here.
 template <typename T, int G, bool DENSE, bool NUTS = true>
-B2H_DEVINL void begin_transition(Chain<T, G>& ch) {
+B2H_DEVINL void begin_transition(Chain<T, G>& ch, const double* zs = nullptr, int zready = 0, int zstride = 0) {
     const EngineView<T>& v = ch.v;
     constexpr int CH = DENSE ? kBatch : 1;             // dense metric == split engine
     T kacc = 0;
@@ -337,7 +340,7 @@ B2H_DEVINL void begin_transition(Chain<T, G>& ch) {
                     w0[i] = v.wp[a];
                 } else {
                     const T im = ch.imm(j);
-                    const T z = (T)draw_z(v.rng, ch.c, ch.r.t, j, v.d);
+                    const T z = (j < zready) ? (T)zs[j * zstride] : (T)draw_z(v.rng, ch.c, ch.r.t, j, v.d);
                     p0[i] = sqrt((T)1 / im) * z;
                     vel[i] = im * p0[i];
                 }
@@ -712,12 +715,12 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
         take = true;                                   // trajectory.py:276-277: proposal = first state
         r.w_sub = w_new; r.slpa_sub = lpa;
     } else {
-        double pa = expit(w_new - r.w_sub);
+        double pa = expit_g<G>(w_new - r.w_sub);
         if (isnan(pa)) pa = 0.0;
         double u = draw_u(v.rng, DRAW_UNIFORM, ch.c, r.t, uniform_slot(k, s), v.maxd);
         take = bern(u, pa);
-        r.w_sub = lae(r.w_sub, w_new);                 // proposals.py:141-144
-        r.slpa_sub = lae(r.slpa_sub, lpa);
+        r.w_sub = lae_g<G>(r.w_sub, w_new);                 // proposals.py:141-144
+        r.slpa_sub = lae_g<G>(r.slpa_sub, lpa);
     }
     if (take) {
         r.E_sub = (double)E; r.U_sub = (double)U_new;
@@ -786,7 +789,7 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
     double ub = draw_u(v.rng, DRAW_BIASED, ch.c, r.t, k, v.maxd);
     bool accb = bern(ub, pb);
     if (div || term) {
-        r.slpa_prop = lae(r.slpa_sub, r.slpa_prop);             // trajectory.py:560-564
+        r.slpa_prop = lae_g<G>(r.slpa_sub, r.slpa_prop);             // trajectory.py:560-564
     } else {
         if (accb) {
             for (int jb = ch.lane; jb < d; jb += CH * G) {
@@ -813,8 +816,8 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
             }
             r.E_prop = r.E_sub; r.U_prop = r.U_sub;
         }
-        r.w_prop = lae(r.w_prop, r.w_sub);
-        r.slpa_prop = lae(r.slpa_prop, r.slpa_sub);
+        r.w_prop = lae_g<G>(r.w_prop, r.w_sub);
+        r.slpa_prop = lae_g<G>(r.slpa_prop, r.slpa_sub);
     }
     const int nd = k + 1;
     if (div || top_turn || term || nd >= v.maxd) {              // trajectory.py:577 / scan length
@@ -831,8 +834,8 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
 // edge, flip, Metropolis accept (Q15: divergent transitions are not force-rejected).
 // ---------------------------------------------------------------------------
 template <typename T, int G, bool DENSE>
-B2H_DEVINL void hmc_begin(Chain<T, G>& ch) {
-    begin_transition<T, G, DENSE, false>(ch);   // edges = state + fresh momentum, E0
+B2H_DEVINL void hmc_begin(Chain<T, G>& ch, const double* zs = nullptr, int zready = 0, int zstride = 0) {
+    begin_transition<T, G, DENSE, false>(ch, zs, zready, zstride);   // edges = state + fresh momentum, E0
     ch.r.go_right = 1;
     ch.r.hmc_step = 0;
 }

@@ -13,6 +13,13 @@ __global__ void __launch_bounds__(Geo<G>::kThreads, (E > 8 ? 2 : Geo<G>::kMinBlo
 fused_run_kernel(EngineView<T> v, ModelDev m, i64 max_ticks) {
     typedef typename FrontOf<T, E>::type Front;
     __shared__ double red_s[128];
+    // Thread per chain: drawing the d normals of a new momentum inside begin_transition runs with the few lanes of the
+    // warp that start a transition on that tick (ncu: 45 % of the kernel's warp-instructions at 5 of 32 lanes).  The
+    // normals of the NEXT transition are drawn ahead instead, one Box-Muller pair per tick at the point of the loop
+    // where all lanes are converged, into this per-thread column of shared memory.
+    constexpr bool kAhead = (G == 1 && E > 0);
+    constexpr int ZE = kAhead ? ((E + 1) & ~1) : 1;
+    __shared__ double zsm[ZE][kAhead ? Geo<G>::kThreads : 1];
     const int c = Geo<G>::chain();
     if (c >= v.C) return;
     Chain<T, G> ch(v, c, red_s);
@@ -20,13 +27,19 @@ fused_run_kernel(EngineView<T> v, ModelDev m, i64 max_ticks) {
     Front f;
     bool bound = false;
     i64 tick = 0;
+    int zfill = 0, ztrans = -1;                 // normals drawn ahead, and the transition they belong to
+    const bool ahead = kAhead && v.rng.mode == 0;
+    const double* zs = kAhead ? &zsm[0][threadIdx.x] : nullptr;
     while (max_ticks <= 0 || tick < max_ticks) {
         if (ch.r.phase == PH_DONE) break;
         if (ch.r.phase == PH_START) {
-            if (HMC) hmc_begin<T, G, false>(ch);
-            else begin_transition<T, G, false>(ch);
+            const int zready = (ahead && ztrans == ch.r.t) ? zfill : 0;
+            if (HMC) hmc_begin<T, G, false>(ch, zs, zready, Geo<G>::kThreads);
+            else begin_transition<T, G, false>(ch, zs, zready, Geo<G>::kThreads);
             Group<G>::sync();
             bound = false;
+            zfill = 0;
+            ztrans = ch.r.t + 1;
         }
         if (!bound) { f.bind(ch); bound = Front::kRegs; }
         half_kick_drift<T, G, false, false>(ch, f);
@@ -37,6 +50,16 @@ fused_run_kernel(EngineView<T> v, ModelDev m, i64 max_ticks) {
             Group<G>::sync();
             U = model_grad<T, G, MODEL>(m, f.Q + ch.base, f.Gd + ch.base, v.sj, ch.lane, ch.red);
             Group<G>::sync();
+        }
+        if constexpr (kAhead) {
+            if (ahead && zfill < v.d) {
+                double z0, z1;
+                philox_normal_pair(v.rng.key, v.rng.chain_offset + (uint64_t)c,
+                                   (uint32_t)(v.rng.transition_offset + (uint64_t)ztrans), (uint32_t)(zfill >> 1), &z0, &z1);
+                zsm[zfill][threadIdx.x] = z0;
+                zsm[zfill + 1][threadIdx.x] = z1;
+                zfill += 2;
+            }
         }
         bool ended;
         if (HMC) ended = hmc_post<T, G, false, false>(ch, U, f);
