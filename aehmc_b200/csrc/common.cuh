@@ -56,10 +56,14 @@ B2H_DEVINL double expit_inl(double x) {
 
 B2H_DEVCALL double lae(double a, double b) { return lae_inl(a, b); }
 B2H_DEVCALL double expit(double x) { return expit_inl(x); }
-// Thread-per-chain kernels (G == 1) reach these under divergence, where a call costs more than it saves (measured:
-// eight schools 0.91 -> 0.79 G evals/s with calls); the group-per-chain kernels call the out-of-line copies.
-template <int G> B2H_DEVINL double lae_g(double a, double b) { return G == 1 ? lae_inl(a, b) : lae(a, b); }
-template <int G> B2H_DEVINL double expit_g(double x) { return G == 1 ? expit_inl(x) : expit(x); }
+// Who calls and who inlines (measured, config 4 / config 1 / config 5): the sub-warp layouts (several chains of one
+// warp in different tree phases: instruction-cache bound) gain from the out-of-line copies (eight schools, 8 lanes per
+// chain: 0.63 -> 0.74 G evals/s); thread-per-chain kernels reach the helpers under divergence, where a call costs more
+// than it saves (0.91 -> 0.79); warp- and CTA-per-chain kernels lose the instruction-level parallelism between the
+// independent draws of one lane (HMC d = 100: 1.50 -> 1.35).
+template <int G> struct Helpers { static constexpr bool kCall = (G > 1 && G < 32); };
+template <int G> B2H_DEVINL double lae_g(double a, double b) { return Helpers<G>::kCall ? lae(a, b) : lae_inl(a, b); }
+template <int G> B2H_DEVINL double expit_g(double x) { return Helpers<G>::kCall ? expit(x) : expit_inl(x); }
 
 // Decision numpy's Generator.binomial(1, p) takes from its single uniform u
 // (oracle/streams.py:bernoulli_from_uniform).  NaN p never accepts.
@@ -106,14 +110,14 @@ B2H_DEVINL double u53(uint32_t lo, uint32_t hi) {          // [0, 1)
 
 struct PhiloxKey { uint32_t k0, k1; };
 
-B2H_DEVCALL double philox_uniform(PhiloxKey key, uint64_t chain, uint32_t transition, uint32_t kind, uint32_t slot) {
+B2H_DEVINL double philox_uniform_inl(PhiloxKey key, uint64_t chain, uint32_t transition, uint32_t kind, uint32_t slot) {
     uint32_t o[4];
     philox4x32_10(slot, kind, transition, (uint32_t)chain, key.k0 ^ (uint32_t)(chain >> 32), key.k1, o);
     return u53(o[0], o[1]);
 }
 
 // element j of the standard-normal momentum vector (Box-Muller on one Philox block per pair)
-B2H_DEVCALL double philox_normal(PhiloxKey key, uint64_t chain, uint32_t transition, uint32_t j) {
+B2H_DEVINL double philox_normal_inl(PhiloxKey key, uint64_t chain, uint32_t transition, uint32_t j) {
     uint32_t o[4];
     philox4x32_10(j >> 1, DRAW_Z, transition, (uint32_t)chain, key.k0 ^ (uint32_t)(chain >> 32), key.k1, o);
     double u1 = 1.0 - u53(o[0], o[1]);                      // (0, 1]
@@ -122,6 +126,13 @@ B2H_DEVCALL double philox_normal(PhiloxKey key, uint64_t chain, uint32_t transit
     double s, c;
     sincospi(2.0 * u2, &s, &c);
     return (j & 1) ? r * s : r * c;
+}
+
+B2H_DEVCALL double philox_uniform(PhiloxKey key, uint64_t chain, uint32_t transition, uint32_t kind, uint32_t slot) {
+    return philox_uniform_inl(key, chain, transition, kind, slot);
+}
+B2H_DEVCALL double philox_normal(PhiloxKey key, uint64_t chain, uint32_t transition, uint32_t j) {
+    return philox_normal_inl(key, chain, transition, j);
 }
 
 // both normals of Box-Muller pair `pair` (elements 2 pair and 2 pair + 1 of the momentum vector): the same values

@@ -119,6 +119,7 @@ struct EngineView {
 // ---------------------------------------------------------------------------
 // draws
 // ---------------------------------------------------------------------------
+template <int G = 32>
 B2H_DEVINL double draw_u(const RngView& r, int kind, int c, int t, int idx, int maxd) {
     if (r.mode == 1) {
         i64 row = (i64)c * r.n_injected + t + (i64)r.transition_offset;
@@ -127,14 +128,21 @@ B2H_DEVINL double draw_u(const RngView& r, int kind, int c, int t, int idx, int 
         if (kind == DRAW_UNIFORM) return r.u_uniform[row * (((i64)1 << maxd) - 1) + idx];
         return r.u_accept[row];
     }
-    return philox_uniform(r.key, r.chain_offset + (uint64_t)c, (uint32_t)(r.transition_offset + (uint64_t)t),
-                          (uint32_t)kind, (uint32_t)idx);
+    if (Helpers<G>::kCall)
+        return philox_uniform(r.key, r.chain_offset + (uint64_t)c, (uint32_t)(r.transition_offset + (uint64_t)t),
+                              (uint32_t)kind, (uint32_t)idx);
+    return philox_uniform_inl(r.key, r.chain_offset + (uint64_t)c, (uint32_t)(r.transition_offset + (uint64_t)t),
+                              (uint32_t)kind, (uint32_t)idx);
 }
 
+template <int G = 32>
 B2H_DEVINL double draw_z(const RngView& r, int c, int t, int j, int d) {
     if (r.mode == 1) return r.z[((i64)c * r.n_injected + t + (i64)r.transition_offset) * d + j];
-    return philox_normal(r.key, r.chain_offset + (uint64_t)c, (uint32_t)(r.transition_offset + (uint64_t)t),
-                         (uint32_t)j);
+    if (Helpers<G>::kCall)
+        return philox_normal(r.key, r.chain_offset + (uint64_t)c, (uint32_t)(r.transition_offset + (uint64_t)t),
+                             (uint32_t)j);
+    return philox_normal_inl(r.key, r.chain_offset + (uint64_t)c, (uint32_t)(r.transition_offset + (uint64_t)t),
+                             (uint32_t)j);
 }
 
 // ---------------------------------------------------------------------------
@@ -306,7 +314,7 @@ struct TickFront {
 // ---------------------------------------------------------------------------
 template <typename T, int G>
 B2H_DEVINL void begin_subtree(Chain<T, G>& ch) {
-    double u = draw_u(ch.v.rng, DRAW_DIR, ch.c, ch.r.t, ch.r.k, ch.v.maxd);
+    double u = draw_u<G>(ch.v.rng, DRAW_DIR, ch.c, ch.r.t, ch.r.k, ch.v.maxd);
     ch.r.go_right = bern(u, 0.5) ? 1 : 0;
     ch.r.s = 0;
 }
@@ -340,7 +348,7 @@ B2H_DEVINL void begin_transition(Chain<T, G>& ch, const double* zs = nullptr, in
                     w0[i] = v.wp[a];
                 } else {
                     const T im = ch.imm(j);
-                    const T z = (j < zready) ? (T)zs[j * zstride] : (T)draw_z(v.rng, ch.c, ch.r.t, j, v.d);
+                    const T z = (j < zready) ? (T)zs[j * zstride] : (T)draw_z<G>(v.rng, ch.c, ch.r.t, j, v.d);
                     p0[i] = sqrt((T)1 / im) * z;
                     vel[i] = im * p0[i];
                 }
@@ -388,7 +396,7 @@ B2H_DEVINL void begin_transition(Chain<T, G>& ch, const double* zs = nullptr, in
         const int tn = ch.r.t + 1;
         const bool have = (v.rng.mode == 0) || (tn + (i64)v.rng.transition_offset < v.rng.n_injected);
         T* zrow = v.mom_z + ((i64)v.mom_parity * v.C + slot) * v.d;
-        for (int j = ch.lane; j < v.d; j += G) zrow[j] = have ? (T)draw_z(v.rng, ch.c, tn, j, v.d) : (T)0;
+        for (int j = ch.lane; j < v.d; j += G) zrow[j] = have ? (T)draw_z<G>(v.rng, ch.c, tn, j, v.d) : (T)0;
     }
     if (NUTS) begin_subtree(ch);
 }
@@ -717,7 +725,7 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
     } else {
         double pa = expit_g<G>(w_new - r.w_sub);
         if (isnan(pa)) pa = 0.0;
-        double u = draw_u(v.rng, DRAW_UNIFORM, ch.c, r.t, uniform_slot(k, s), v.maxd);
+        double u = draw_u<G>(v.rng, DRAW_UNIFORM, ch.c, r.t, uniform_slot(k, s), v.maxd);
         take = bern(u, pa);
         r.w_sub = lae_g<G>(r.w_sub, w_new);                 // proposals.py:141-144
         r.slpa_sub = lae_g<G>(r.slpa_sub, lpa);
@@ -786,7 +794,7 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
     // biased progressive sampling is always drawn (Q8, proposals.py:130-131)
     double diff = r.w_sub - r.w_prop;
     double pb = fmin(fmax(exp(diff), 0.0), 1.0);
-    double ub = draw_u(v.rng, DRAW_BIASED, ch.c, r.t, k, v.maxd);
+    double ub = draw_u<G>(v.rng, DRAW_BIASED, ch.c, r.t, k, v.maxd);
     bool accb = bern(ub, pb);
     if (div || term) {
         r.slpa_prop = lae_g<G>(r.slpa_sub, r.slpa_prop);             // trajectory.py:560-564
@@ -877,7 +885,7 @@ B2H_DEVINL bool hmc_post(Chain<T, G>& ch, T U_new, Front& f) {
     if (isnan(delta)) delta = -INFINITY;
     const bool div = fabs(delta) > v.div_thr;
     double p_accept = fmin(fmax(exp(delta), 0.0), 1.0);
-    double u = draw_u(v.rng, DRAW_ACCEPT, ch.c, r.t, 0, v.maxd);
+    double u = draw_u<G>(v.rng, DRAW_ACCEPT, ch.c, r.t, 0, v.maxd);
     bool acc = bern(u, p_accept);
     B2H_ELEMS(Front, ee, j, ch.lane, d, G) {
         i64 a = ch.at(j);

@@ -35,13 +35,12 @@ static int auto_group(int d, long long C, int model_kind, bool free_running) {
     // Tiny targets: thread per chain (the whole front in the thread's registers, fused_run_kernel E = 10 / 16) once there
     // are enough chains to fill the machine with threads.  Measured on config 4 (65536 chains, d = 10,
     // benchmarks/c4_tail_probe.py): eight schools 1.01 vs 0.64 G evals/s free-running and 0.70 vs 0.54 for a fixed
-    // number of transitions; the funnel ties free-running (0.74 vs 0.79) but its per-chain work is so heavy-tailed
-    // (max / mean = 24) that a fixed number of transitions is bound by the slowest chains, and a lone chain steps
-    // faster on 8 lanes (7 vs 11 us per leapfrog).
+    // number of transitions; the funnel's deep trees run better on 8 lanes (free-running 0.79 vs 0.59-0.74), and its
+    // per-chain work is so heavy-tailed (max / mean = 16-24) that a fixed number of transitions is bound by the slowest
+    // chains, where a lone chain steps faster on 8 lanes (7 vs 11 us per leapfrog).
     if (d <= 16) {
-        if (C >= 262144) return 1;
-        if (C >= 32768 && (free_running || model_kind != B2H_MODEL_FUNNEL)) return 1;
-        return 8;
+        if (model_kind == B2H_MODEL_FUNNEL) return C >= 262144 ? 1 : 8;
+        return C >= 32768 ? 1 : 8;
     }
     if (d <= 64) return 8;
     if (d <= 512) return 32;
