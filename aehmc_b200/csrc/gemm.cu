@@ -329,9 +329,12 @@ dense_apply_dmma_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGroup<do
 // reads per fragment are 32 distinct 8-byte words = 2 wavefronts); B is [k][n] with rows padded by 8.
 // Requires 16-byte aligned rows (even K, N, leading dimensions); otherwise the register-staged kernel runs.
 // ---------------------------------------------------------------------------------------------
-constexpr int STAGES = 3, ALD = BK + 4;
+constexpr int STAGES = 3;
 #ifndef B2H_GEMM_WARPS_DEFAULT
 #define B2H_GEMM_WARPS_DEFAULT 8
+#endif
+#ifndef B2H_GEMM_BK_DEFAULT
+#define B2H_GEMM_BK_DEFAULT 32
 #endif
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
@@ -343,7 +346,8 @@ template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile
 
 // MI: 16-row MMA tiles per warp along M.  MI = 2: 8 warps (4 x 2), warp tile 32 x BN_/2.  MI = 1: 16 warps (8 x 2), warp
 // tile 16 x BN_/2 -- half the accumulators per thread, twice the warps to cover the per-k-tile barrier.
-template <int BN_, int MI>
+// BK_: k-tile depth (16, or 32: half the barriers and commit groups per flop, 203 KB of shared memory for 3 stages).
+template <int BN_, int MI, int BK_>
 __global__ void __launch_bounds__((128 / (16 * MI)) * 2 * 32, 1)
 dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGroup<double> g2, int N, int K, int tiles_n,
                               int tiles_m0, int tiles_m1, int k_chunk, i64 split_stride) {
@@ -351,9 +355,11 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
     constexpr int NJ = BN_ / 16;               // 8-wide MMA tiles per warp along N (warp tile 16 MI x BN_/2)
     constexpr int WROWS = 128 / (16 * MI);     // warps along M
     constexpr int NT = WROWS * 2 * 32;         // threads of the CTA
-    constexpr int A_ITERS = (BM * 8) / NT;     // 16-byte chunks of the A tile per thread
+    constexpr int ALD_ = BK_ + 4;              // padded A row (doubles)
+    constexpr int CPR = BK_ / 2;               // 16-byte chunks per A row
+    constexpr int A_ITERS = (BM * CPR) / NT;   // 16-byte chunks of the A tile per thread
     constexpr int BLD = BN_ + 8;
-    constexpr int A_STAGE = BM * ALD, B_STAGE = BK * BLD;
+    constexpr int A_STAGE = BM * ALD_, B_STAGE = BK_ * BLD;
     int tile_m = blockIdx.x / tiles_n;
     const int tile_n = blockIdx.x % tiles_n;
     const int which = tile_m < tiles_m0 ? 0 : (tile_m < tiles_m0 + tiles_m1 ? 1 : 2);
@@ -376,7 +382,7 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* As = reinterpret_cast<T*>(smem_raw);                       // [STAGES][BM][ALD]
     T* Bs = As + STAGES * A_STAGE;                                // [STAGES][BK][BLD]
-    T* Ss = Bs + STAGES * B_STAGE;                                // [STAGES][BK]   (sub vector slices)
+    T* Ss = Bs + STAGES * B_STAGE;                                // [STAGES][BK_]  (sub vector slices)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp % WROWS) * (16 * MI), wn = (warp / WROWS) * (BN_ / 2);
@@ -386,22 +392,22 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
     i64 a_src[A_ITERS];
 #pragma unroll
     for (int i = 0; i < A_ITERS; ++i) {
-        const int row = (tid + NT * i) >> 3, gr = m0 + row;
+        const int row = (tid + NT * i) / CPR, gr = m0 + row;
         a_src[i] = gr < M ? (i64)(g.in_rows ? g.in_rows[gr] : gr) * lda : -1;
     }
-    constexpr int B_CHUNKS = BK * (BN_ / 2);
+    constexpr int B_CHUNKS = BK_ * (BN_ / 2);
     constexpr int B_ITERS = (B_CHUNKS + NT - 1) / NT;
 
     auto issue = [&](int kt, int stage) {
-        const int k0 = k_begin + kt * BK;
+        const int k0 = k_begin + kt * BK_;
         T* as = As + stage * A_STAGE;
         T* bs = Bs + stage * B_STAGE;
 #pragma unroll
         for (int i = 0; i < A_ITERS; ++i) {
-            const int c = tid + NT * i, row = c >> 3, kc = (c & 7) * 2;
+            const int c = tid + NT * i, row = c / CPR, kc = (c % CPR) * 2;
             const int gk = k0 + kc;
             const bool ok = a_src[i] >= 0 && gk < k_end;
-            cp_async16(as + row * ALD + kc, ok ? (const void*)(A + a_src[i] + gk) : (const void*)A, ok ? 16 : 0);
+            cp_async16(as + row * ALD_ + kc, ok ? (const void*)(A + a_src[i] + gk) : (const void*)A, ok ? 16 : 0);
         }
 #pragma unroll
         for (int i = 0; i < B_ITERS; ++i) {
@@ -413,9 +419,9 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
                 cp_async16(bs + kr * BLD + nc, ok ? (const void*)(B + (i64)gk * ldb + gn) : (const void*)B, ok ? 16 : 0);
             }
         }
-        if (sub && tid < BK / 2) {
+        if (sub && tid < BK_ / 2) {
             const int gk = k0 + tid * 2;
-            cp_async16(Ss + stage * BK + tid * 2, gk < k_end ? (const void*)(sub + gk) : (const void*)sub, gk < k_end ? 16 : 0);
+            cp_async16(Ss + stage * BK_ + tid * 2, gk < k_end ? (const void*)(sub + gk) : (const void*)sub, gk < k_end ? 16 : 0);
         }
     };
 
@@ -427,7 +433,7 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.0;
 
-    const int nk = max((k_end - k_begin + BK - 1) / BK, 0);
+    const int nk = max((k_end - k_begin + BK_ - 1) / BK_, 0);
 #pragma unroll
     for (int st = 0; st < STAGES - 1; ++st) {
         if (st < nk) issue(st, st);
@@ -442,11 +448,11 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
             cp_async_commit();
         }
         const int stage = kt % STAGES;
-        const T* as = As + stage * A_STAGE + (wm + gq) * ALD;
+        const T* as = As + stage * A_STAGE + (wm + gq) * ALD_;
         const T* bs = Bs + stage * B_STAGE + wn + gq;
-        const T* ss = Ss + stage * BK;
+        const T* ss = Ss + stage * BK_;
 #pragma unroll
-        for (int k0 = 0; k0 < BK; k0 += 8) {
+        for (int k0 = 0; k0 < BK_; k0 += 8) {
             T fa[MI][4], fb[NJ][2];
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
@@ -454,8 +460,8 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
                 const T sv = sub ? ss[kk] : 0.0;
 #pragma unroll
                 for (int i = 0; i < MI; ++i) {
-                    fa[i][2 * q] = as[(i * 16) * ALD + kk] - sv;
-                    fa[i][2 * q + 1] = as[(i * 16 + 8) * ALD + kk] - sv;
+                    fa[i][2 * q] = as[(i * 16) * ALD_ + kk] - sv;
+                    fa[i][2 * q + 1] = as[(i * 16 + 8) * ALD_ + kk] - sv;
                 }
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) fb[j][q] = bs[kk * BLD + j * 8];
@@ -483,24 +489,31 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
         }
 }
 
+template <int BN_, int MI, int BK_>
+static void launch_async_v(cudaStream_t st, dim3 grid, int threads, const GemmGroup<double>& g0, const GemmGroup<double>& g1,
+                           const GemmGroup<double>& g2, int N, int K, int tiles_n, int tiles_m0, int tiles_m1, int k_chunk,
+                           i64 split_stride) {
+    constexpr int smem = (STAGES * (BM * (BK_ + 4) + BK_ * (BN_ + 8)) + STAGES * BK_) * (int)sizeof(double);
+    cudaFuncSetAttribute(dense_apply_dmma_async_kernel<BN_, MI, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    dense_apply_dmma_async_kernel<BN_, MI, BK_><<<grid, threads, smem, st>>>(g0, g1, g2, N, K, tiles_n, tiles_m0, tiles_m1,
+                                                                             k_chunk, split_stride);
+}
+
 template <int BN_>
 static void launch_async(cudaStream_t st, const GemmGroup<double>& g0, const GemmGroup<double>& g1,
                          const GemmGroup<double>& g2, int N, int K, int nsplit, int k_chunk, i64 split_stride) {
-    constexpr int smem = (STAGES * (BM * ALD + BK * (BN_ + 8)) + STAGES * BK) * (int)sizeof(double);
     int tiles_m0 = (g0.M + BM - 1) / BM, tiles_m1 = (g1.M + BM - 1) / BM, tiles_m2 = (g2.M + BM - 1) / BM;
     int tiles_n = (N + BN_ - 1) / BN_;
     dim3 grid((tiles_m0 + tiles_m1 + tiles_m2) * tiles_n, nsplit);
-    static int warps = -1;
+    static int warps = -1, bk = -1;
     if (warps < 0) { const char* e = getenv("B2H_GEMM_WARPS"); warps = e ? atoi(e) : B2H_GEMM_WARPS_DEFAULT; }
-    if (warps == 16) {
-        cudaFuncSetAttribute(dense_apply_dmma_async_kernel<BN_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        dense_apply_dmma_async_kernel<BN_, 1><<<grid, 512, smem, st>>>(g0, g1, g2, N, K, tiles_n, tiles_m0, tiles_m1, k_chunk,
-                                                                       split_stride);
-    } else {
-        cudaFuncSetAttribute(dense_apply_dmma_async_kernel<BN_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        dense_apply_dmma_async_kernel<BN_, 2><<<grid, 256, smem, st>>>(g0, g1, g2, N, K, tiles_n, tiles_m0, tiles_m1, k_chunk,
-                                                                       split_stride);
-    }
+    if (bk < 0) { const char* e = getenv("B2H_GEMM_BK"); bk = e ? atoi(e) : B2H_GEMM_BK_DEFAULT; }
+    if (warps == 16)
+        launch_async_v<BN_, 1, 16>(st, grid, 512, g0, g1, g2, N, K, tiles_n, tiles_m0, tiles_m1, k_chunk, split_stride);
+    else if (bk == 32)
+        launch_async_v<BN_, 2, 32>(st, grid, 256, g0, g1, g2, N, K, tiles_n, tiles_m0, tiles_m1, k_chunk, split_stride);
+    else
+        launch_async_v<BN_, 2, 16>(st, grid, 256, g0, g1, g2, N, K, tiles_n, tiles_m0, tiles_m1, k_chunk, split_stride);
 }
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
