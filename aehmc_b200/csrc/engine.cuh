@@ -155,13 +155,41 @@ struct Chain {
     i64 base;        // c*sc
     i64 ckbase;      // c*sck
     double* red;     // smem scratch for block groups
+    // U-turn checkpoints of this chain (termination.py:63-131): rows in the workspace, or -- persistent kernel, when they
+    // fit -- a shared-memory copy staged for the whole launch (stage_checkpoints); element (level, j) is at ck(level, j)
+    T *mck, *sckp, *vck;
+    i64 ck_ls, ck_sj;
     ChainRec r;      // register copy
 
     B2H_DEVINL Chain(const EngineView<T>& v_, int c_, double* red_)
-        : v(v_), c(c_), lane(Group<G>::lane()), base((i64)c_ * v_.sc), ckbase((i64)c_ * v_.sck), red(red_) {}
+        : v(v_), c(c_), lane(Group<G>::lane()), base((i64)c_ * v_.sc), ckbase((i64)c_ * v_.sck), red(red_),
+          mck(v_.mck + (i64)c_ * v_.sck), sckp(v_.sckp + (i64)c_ * v_.sck),
+          vck(v_.vck ? v_.vck + (i64)c_ * v_.sck : nullptr), ck_ls((i64)v_.d * v_.sj), ck_sj(v_.sj) {}
 
     B2H_DEVINL i64 at(int j) const { return base + (i64)j * v.sj; }
-    B2H_DEVINL i64 ck(int level, int j) const { return ckbase + ((i64)level * v.d + j) * v.sj; }
+    B2H_DEVINL i64 ck(int level, int j) const { return (i64)level * ck_ls + (i64)j * ck_sj; }
+    // checkpoints [2][maxd][d] of this chain into / out of shared memory (diagonal-family metrics: no vck)
+    B2H_DEVINL void stage_checkpoints(T* smem) {
+        const int n = v.maxd * v.d;
+        for (int k = lane; k < n; k += G) {
+            const i64 src = (i64)(k / v.d) * ck_ls + (i64)(k % v.d) * ck_sj;
+            smem[k] = mck[src];
+            smem[n + k] = sckp[src];
+        }
+        mck = smem; sckp = smem + n; ck_ls = v.d; ck_sj = 1;
+        Group<G>::sync();
+    }
+    B2H_DEVINL void unstage_checkpoints() {
+        Group<G>::sync();
+        const int n = v.maxd * v.d;
+        T* gm = v.mck + ckbase;
+        T* gs = v.sckp + ckbase;
+        for (int k = lane; k < n; k += G) {
+            const i64 dst = ((i64)(k / v.d) * v.d + (k % v.d)) * v.sj;
+            gm[dst] = mck[k];
+            gs[dst] = sckp[k];
+        }
+    }
     B2H_DEVINL T imm(int j) const { return v.imm[(i64)c * v.imm_sc + (i64)j * v.imm_sj]; }
     B2H_DEVINL void load() { r = v.rec[c]; }
     B2H_DEVINL void store() {
@@ -602,8 +630,8 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
                 if (s != 0) so[i] = v.sms[a];
                 if (lev0) {
                     const i64 b = ch.ck(imax, j);
-                    cm[i] = v.mck[b]; cs[i] = v.sckp[b];
-                    if (DENSE) cv[i] = v.vck[b];
+                    cm[i] = ch.mck[b]; cs[i] = ch.sckp[b];
+                    if (DENSE) cv[i] = ch.vck[b];
                 }
             }
         }
@@ -632,9 +660,9 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
                 if (Front::kRegs) smreg[Front::kRegs ? ee : 0] = sm;
                 if (even) {
                     const i64 b = ch.ck(imax, j);
-                    v.mck[b] = p;
-                    v.sckp[b] = sm;
-                    if (DENSE) v.vck[b] = vel;
+                    ch.mck[b] = p;
+                    ch.sckp[b] = sm;
+                    if (DENSE) ch.vck[b] = vel;
                 }
                 if (lev0) {
                     const T subsum = sm - cs[i] + cm[i];
@@ -661,8 +689,8 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
                         const i64 a = ch.at(j), b = ch.ck(imax - l, j);
                         pv[i] = f.p(ee, a);
                         sv[i] = Front::kRegs ? smreg[Front::kRegs ? ee : 0] : v.sms[a];
-                        cm[i] = v.mck[b]; cs[i] = v.sckp[b];
-                        if (DENSE) { cv[i] = v.vck[b]; vv[i] = f.vel(ee, a); }
+                        cm[i] = ch.mck[b]; cs[i] = ch.sckp[b];
+                        if (DENSE) { cv[i] = ch.vck[b]; vv[i] = f.vel(ee, a); }
                         else { const T im = ch.imm(j); cv[i] = im * cm[i]; vv[i] = im * pv[i]; }
                     }
                 }
@@ -694,11 +722,11 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
             T xl = 0, xr = 0;
             B2H_ELEMS(Front, ee, j, ch.lane, d, G) {
                 i64 a = ch.at(j), b = ch.ck(i, j);
-                T m = v.mck[b], sc = v.sckp[b], p = f.p(ee, a), sm = v.sms[a];
+                T m = ch.mck[b], sc = ch.sckp[b], p = f.p(ee, a), sm = v.sms[a];
                 T subsum = sm - sc + m;
                 T rho = subsum - (p + m) / (T)2;
                 T vleft, vright;
-                if (DENSE) { vleft = v.vck[b]; vright = f.vel(ee, a); }
+                if (DENSE) { vleft = ch.vck[b]; vright = f.vel(ee, a); }
                 else { T im = ch.imm(j); vleft = im * m; vright = im * p; }
                 xl += vleft * rho;
                 xr += vright * rho;

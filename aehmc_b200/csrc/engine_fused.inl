@@ -10,9 +10,10 @@ namespace b2h {
 // bound leaves the thread its 255 registers instead of trading them for resident warps.
 template <typename T, int G, int MODEL, bool HMC, int E>
 __global__ void __launch_bounds__(Geo<G>::kThreads, (E > 8 ? 2 : Geo<G>::kMinBlocksFused))
-fused_run_kernel(EngineView<T> v, ModelDev m, i64 max_ticks) {
+fused_run_kernel(EngineView<T> v, ModelDev m, i64 max_ticks, int stage_ck) {
     typedef typename FrontOf<T, E>::type Front;
     __shared__ double red_s[128];
+    extern __shared__ __align__(16) unsigned char ck_smem[];    // stage_ck: [chains of the CTA][2][maxd][d] checkpoints
     // Thread per chain: drawing the d normals of a new momentum inside begin_transition runs with the few lanes of the
     // warp that start a transition on that tick (ncu: 45 % of the kernel's warp-instructions at 5 of 32 lanes).  The
     // normals of the NEXT transition are drawn ahead instead, one Box-Muller pair per tick at the point of the loop
@@ -24,6 +25,10 @@ fused_run_kernel(EngineView<T> v, ModelDev m, i64 max_ticks) {
     if (c >= v.C) return;
     Chain<T, G> ch(v, c, red_s);
     ch.load();
+    // U-turn checkpoints staged in shared memory for the whole launch when the CTA's chains fit (termination.py:63-131:
+    // written on even steps, read on odd ones, 2 x max_num_expansions x d values per chain)
+    if (stage_ck)
+        ch.stage_checkpoints(reinterpret_cast<T*>(ck_smem) + (size_t)(G > 32 ? 0 : threadIdx.x / G) * 2 * v.maxd * v.d);
     Front f;
     bool bound = false;
     i64 tick = 0;
@@ -69,6 +74,7 @@ fused_run_kernel(EngineView<T> v, ModelDev m, i64 max_ticks) {
         ++tick;
     }
     if (bound) f.flush(ch);                // max_ticks ran out in the middle of a sub-tree
+    if (stage_ck) ch.unstage_checkpoints();
     ch.store();
     if (v.counters && ch.lane == 0) atomicAdd((unsigned long long*)&v.counters[3], (unsigned long long)tick);
 }
@@ -83,9 +89,18 @@ static ModelDev to_dev(const b2h_model* m) {
     return d;
 }
 
+// shared-memory staging of the checkpoints: when the chains of one CTA need at most this many bytes (all resident CTAs
+// of an SM then still fit its 227 KB)
+constexpr size_t kStageCkMaxBytes = 40 * 1024;
+
 template <typename T, int G, bool HMC, int MODEL, int E>
 static void launch_fused_e(cudaStream_t st, const EngineView<T>& v, const ModelDev& m, i64 max_ticks) {
-    fused_run_kernel<T, G, MODEL, HMC, E><<<Geo<G>::grid(v.C), Geo<G>::kThreads, 0, st>>>(v, m, max_ticks);
+    static int use_stage = -1;
+    if (use_stage < 0) { const char* e = getenv("B2H_STAGE_CKPT"); use_stage = e ? atoi(e) : 1; }
+    const size_t bytes = (size_t)Geo<G>::kChainsPerBlock * 2 * v.maxd * v.d * sizeof(T);
+    const bool stage = use_stage && !HMC && v.sj == 1 && bytes <= kStageCkMaxBytes;
+    fused_run_kernel<T, G, MODEL, HMC, E><<<Geo<G>::grid(v.C), Geo<G>::kThreads, stage ? bytes : 0, st>>>(v, m, max_ticks,
+                                                                                                          stage ? 1 : 0);
 }
 
 // Register front when the chain's row fits 2, 4 or 8 elements per lane (B2H_REG_FRONT=0 disables it).
