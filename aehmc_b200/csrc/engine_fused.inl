@@ -95,10 +95,16 @@ constexpr size_t kStageCkMaxBytes = 40 * 1024;
 
 template <typename T, int G, bool HMC, int MODEL, int E>
 static void launch_fused_e(cudaStream_t st, const EngineView<T>& v, const ModelDev& m, i64 max_ticks) {
-    static int use_stage = -1;
-    if (use_stage < 0) { const char* e = getenv("B2H_STAGE_CKPT"); use_stage = e ? atoi(e) : 1; }
+    // Measured (config 4, 8 lanes per chain, benchmarks/c4_tail_probe.py): free-running, where every lane is busy and
+    // the checkpoint traffic competes for L2, staging gives the funnel 0.74 -> 0.89 G evals/s; a run of a fixed number
+    // of transitions ends with a few lone chains whose step latency is what counts, and there the staged kernel's
+    // generic-address loads make a leapfrog 9 % slower (1338 -> 1473 ms for 200 transitions).  B2H_STAGE_CKPT=0 / 1
+    // forces it off / on.
+    static int use_stage = -2;
+    if (use_stage == -2) { const char* e = getenv("B2H_STAGE_CKPT"); use_stage = e ? atoi(e) : -1; }
     const size_t bytes = (size_t)Geo<G>::kChainsPerBlock * 2 * v.maxd * v.d * sizeof(T);
-    const bool stage = use_stage && !HMC && v.sj == 1 && bytes <= kStageCkMaxBytes;
+    const bool want = use_stage < 0 ? max_ticks > 0 : use_stage != 0;
+    const bool stage = want && !HMC && v.sj == 1 && bytes <= kStageCkMaxBytes;
     fused_run_kernel<T, G, MODEL, HMC, E><<<Geo<G>::grid(v.C), Geo<G>::kThreads, stage ? bytes : 0, st>>>(v, m, max_ticks,
                                                                                                           stage ? 1 : 0);
 }
