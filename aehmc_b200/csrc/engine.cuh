@@ -207,6 +207,9 @@ template <typename T>
 struct MemFront {
     static constexpr int kE = 1 << 30;
     static constexpr bool kRegs = false;
+    static constexpr bool kSumRegs = false;     // the sub-tree momentum sum goes through v.sms every tick
+    B2H_DEVINL T sum(int) const { return 0; }
+    B2H_DEVINL void set_sum(int, T) {}
     T *Q, *P, *Gd, *V, *W;              // V = imm p, W = imm g: dense metric only
     template <int G> B2H_DEVINL void bind(const Chain<T, G>& ch) {
         Q = ch.r.go_right ? ch.v.qr : ch.v.ql;
@@ -232,7 +235,8 @@ template <typename T, int E>
 struct RegFront {
     static constexpr int kE = E;
     static constexpr bool kRegs = true;
-    T fq[E], fp[E], fg[E];
+    static constexpr bool kSumRegs = true;      // the sub-tree momentum sum stays in registers too; v.sms is written by flush
+    T fq[E], fp[E], fg[E], fs[E];
     template <int G> B2H_DEVINL void bind(const Chain<T, G>& ch) {
         const T* Q = ch.r.go_right ? ch.v.qr : ch.v.ql;
         const T* P = ch.r.go_right ? ch.v.pr : ch.v.pl;
@@ -240,8 +244,8 @@ struct RegFront {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int j = ch.lane + e * G;
-            if (j < ch.v.d) { i64 a = ch.at(j); fq[e] = Q[a]; fp[e] = P[a]; fg[e] = Gd[a]; }
-            else { fq[e] = 0; fp[e] = 0; fg[e] = 0; }
+            if (j < ch.v.d) { i64 a = ch.at(j); fq[e] = Q[a]; fp[e] = P[a]; fg[e] = Gd[a]; fs[e] = ch.v.sms[a]; }
+            else { fq[e] = 0; fp[e] = 0; fg[e] = 0; fs[e] = 0; }
         }
     }
     template <int G> B2H_DEVINL void flush(const Chain<T, G>& ch) {
@@ -251,9 +255,11 @@ struct RegFront {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int j = ch.lane + e * G;
-            if (j < ch.v.d) { i64 a = ch.at(j); Q[a] = fq[e]; P[a] = fp[e]; Gd[a] = fg[e]; }
+            if (j < ch.v.d) { i64 a = ch.at(j); Q[a] = fq[e]; P[a] = fp[e]; Gd[a] = fg[e]; ch.v.sms[a] = fs[e]; }
         }
     }
+    B2H_DEVINL T sum(int e) const { return fs[e]; }
+    B2H_DEVINL void set_sum(int e, T x) { fs[e] = x; }
     B2H_DEVINL T q(int e, i64) const { return fq[e]; }
     B2H_DEVINL T p(int e, i64) const { return fp[e]; }
     B2H_DEVINL T g(int e, i64) const { return fg[e]; }
@@ -279,6 +285,9 @@ template <typename T, int E, bool DENSE>
 struct TickFront {
     static constexpr int kE = E;
     static constexpr bool kRegs = true;
+    static constexpr bool kSumRegs = false;
+    B2H_DEVINL T sum(int) const { return 0; }
+    B2H_DEVINL void set_sum(int, T) {}
     T fq[E], fp[E], fg[E], fv[DENSE ? E : 1], fw[DENSE ? E : 1];
     template <int G> B2H_DEVINL void load(const Chain<T, G>& ch, bool all) {
         const bool rt = ch.r.go_right != 0;
@@ -598,6 +607,9 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
     //  checkpoint levels (termination.py:164-187 with metrics.py:95-102).  Which levels are read depends
     //  only on the step number, so nothing here waits for the energy.
     const int s = r.s, k = r.k;
+    // the step's progressive-sampling uniform does not depend on the energies: drawn first, so that its Philox rounds
+    // overlap the row loads below instead of extending the scalar chain after the reduction
+    const double u_step = (s != 0) ? draw_u<G>(v.rng, DRAW_UNIFORM, ch.c, r.t, uniform_slot(k, s), v.maxd) : 0.0;
     int imin, imax;
     if (s == 0) { imin = r.imin; imax = r.imax; }
     else storage_indices(s, imin, imax);
@@ -627,7 +639,7 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
                 pv[i] = f.p(ee, a);
                 if (DENSE) { gx[i] = v.xb[m]; wx[i] = v.xc[m]; vv[i] = f.vel(ee, a); }
                 else { gx[i] = SPLIT ? v.xb[m] : f.g(ee, a); imv[i] = ch.imm(j); }
-                if (s != 0) so[i] = v.sms[a];
+                if (s != 0) so[i] = Front::kSumRegs ? f.sum(ee) : v.sms[a];
                 if (lev0) {
                     const i64 b = ch.ck(imax, j);
                     cm[i] = ch.mck[b]; cs[i] = ch.sckp[b];
@@ -656,7 +668,7 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
                 }
                 kacc += vel * p;
                 const T sm = (s == 0) ? p : so[i] + p;
-                v.sms[a] = sm;
+                if (Front::kSumRegs) f.set_sum(ee, sm); else v.sms[a] = sm;
                 if (Front::kRegs) smreg[Front::kRegs ? ee : 0] = sm;
                 if (even) {
                     const i64 b = ch.ck(imax, j);
@@ -722,7 +734,7 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
             T xl = 0, xr = 0;
             B2H_ELEMS(Front, ee, j, ch.lane, d, G) {
                 i64 a = ch.at(j), b = ch.ck(i, j);
-                T m = ch.mck[b], sc = ch.sckp[b], p = f.p(ee, a), sm = v.sms[a];
+                T m = ch.mck[b], sc = ch.sckp[b], p = f.p(ee, a), sm = Front::kSumRegs ? f.sum(ee) : v.sms[a];
                 T subsum = sm - sc + m;
                 T rho = subsum - (p + m) / (T)2;
                 T vleft, vright;
@@ -753,8 +765,7 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
     } else {
         double pa = expit_g<G>(w_new - r.w_sub);
         if (isnan(pa)) pa = 0.0;
-        double u = draw_u<G>(v.rng, DRAW_UNIFORM, ch.c, r.t, uniform_slot(k, s), v.maxd);
-        take = bern(u, pa);
+        take = bern(u_step, pa);
         r.w_sub = lae_g<G>(r.w_sub, w_new);                 // proposals.py:141-144
         r.slpa_sub = lae_g<G>(r.slpa_sub, lpa);
     }
