@@ -235,8 +235,10 @@ template <typename T, int E>
 struct RegFront {
     static constexpr int kE = E;
     static constexpr bool kRegs = true;
-    static constexpr bool kSumRegs = true;      // the sub-tree momentum sum stays in registers too; v.sms is written by flush
-    T fq[E], fp[E], fg[E], fs[E];
+    // the sub-tree momentum sum stays in registers too (v.sms is written by flush) unless the front already fills the
+    // register file (thread per chain, E >= 10: measured 6 % slower with the extra spills)
+    static constexpr bool kSumRegs = (E <= 8);
+    T fq[E], fp[E], fg[E], fs[kSumRegs ? E : 1];
     template <int G> B2H_DEVINL void bind(const Chain<T, G>& ch) {
         const T* Q = ch.r.go_right ? ch.v.qr : ch.v.ql;
         const T* P = ch.r.go_right ? ch.v.pr : ch.v.pl;
@@ -244,8 +246,8 @@ struct RegFront {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int j = ch.lane + e * G;
-            if (j < ch.v.d) { i64 a = ch.at(j); fq[e] = Q[a]; fp[e] = P[a]; fg[e] = Gd[a]; fs[e] = ch.v.sms[a]; }
-            else { fq[e] = 0; fp[e] = 0; fg[e] = 0; fs[e] = 0; }
+            if (j < ch.v.d) { i64 a = ch.at(j); fq[e] = Q[a]; fp[e] = P[a]; fg[e] = Gd[a]; if (kSumRegs) fs[e] = ch.v.sms[a]; }
+            else { fq[e] = 0; fp[e] = 0; fg[e] = 0; if (kSumRegs) fs[e] = 0; }
         }
     }
     template <int G> B2H_DEVINL void flush(const Chain<T, G>& ch) {
@@ -255,11 +257,11 @@ struct RegFront {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int j = ch.lane + e * G;
-            if (j < ch.v.d) { i64 a = ch.at(j); Q[a] = fq[e]; P[a] = fp[e]; Gd[a] = fg[e]; ch.v.sms[a] = fs[e]; }
+            if (j < ch.v.d) { i64 a = ch.at(j); Q[a] = fq[e]; P[a] = fp[e]; Gd[a] = fg[e]; if (kSumRegs) ch.v.sms[a] = fs[e]; }
         }
     }
-    B2H_DEVINL T sum(int e) const { return fs[e]; }
-    B2H_DEVINL void set_sum(int e, T x) { fs[e] = x; }
+    B2H_DEVINL T sum(int e) const { return fs[kSumRegs ? e : 0]; }
+    B2H_DEVINL void set_sum(int e, T x) { fs[kSumRegs ? e : 0] = x; }
     B2H_DEVINL T q(int e, i64) const { return fq[e]; }
     B2H_DEVINL T p(int e, i64) const { return fp[e]; }
     B2H_DEVINL T g(int e, i64) const { return fg[e]; }
