@@ -46,61 +46,24 @@ __global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksSplit) spl
     }
 }
 
-// L2 prefetch of one chain row (32-byte sectors spread over the group's lanes)
-template <typename T, int G>
-B2H_DEVINL void prefetch_row(const T* row, int bytes) {
-    const char* p = reinterpret_cast<const char*>(row) + Group<G>::lane() * 32;
-    for (int off = Group<G>::lane() * 32; off < bytes; off += G * 32, p += G * 32)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
-// Rows the NEXT chain of a persistent CTA will read in its post part, requested from L2 while the current chain is
-// being processed (the chain's own dependent chain record -> rows round trips are what the tick kernel waits on: ncu,
-// 44 % of the stall samples).  Only hot scalars of the next chain's record are read here (one 32-byte sector).
-template <typename T, int G, bool DENSE>
-B2H_DEVINL void prefetch_chain_rows(const EngineView<T>& v, int cn) {
-    const ChainRec* rn = v.rec + cn;
-    const int phase = rn->phase, go_right = rn->go_right, s = rn->s, imax_old = rn->imax;
-    if (phase != PH_RUN) return;
-    const int bytes = v.d * (int)sizeof(T);
-    const i64 ro = (i64)cn * v.d;
-    prefetch_row<T, G>(v.xa + ro, bytes);
-    prefetch_row<T, G>(v.xb + ro, bytes);
-    prefetch_row<T, G>((go_right ? v.pr : v.pl) + ro, bytes);
-    if (s != 0) prefetch_row<T, G>(v.sms + ro, bytes);
-    if (DENSE) {
-        prefetch_row<T, G>(v.xc + ro, bytes);
-        prefetch_row<T, G>((go_right ? v.vr : v.vl) + ro, bytes);
-    }
-    int imin, imax;
-    if (s == 0) { imin = 0; imax = imax_old; } else storage_indices(s, imin, imax);
-    if (s >= 1 && imax >= imin) {                       // the first checkpoint level the step's U-turn test reads
-        const i64 co = (i64)cn * v.sck + (i64)imax * v.d;
-        prefetch_row<T, G>(v.mck + co, bytes);
-        prefetch_row<T, G>(v.sckp + co, bytes);
-        if (DENSE) prefetch_row<T, G>(v.vck + co, bytes);
-    }
-}
-
-// One chain's post of tick t and pre of tick t+1 in one pass with the front in registers (TickFront): p (V) of the edge
-// are read once and written once per tick, q goes through xa only, g (W) are not written at all inside a sub-tree.
+// post of tick t and pre of tick t+1 in one pass with the front in registers (TickFront): p (V) of the edge are
+// read once and written once per tick, q goes through xa only, g (W) are not written at all inside a sub-tree.
 // PRE = false is the last tick of a call: the post part only, then the whole front goes back to the edge arrays so
 // that the state in memory is complete (the next call starts with split_pre_kernel).
 template <typename T, int G, bool DENSE, bool HMC, int E, bool PRE>
-B2H_DEVINL void postpre_chain(const EngineView<T>& v, int c, int c_next, int* not_done, double* red_s) {
+__global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksTick)
+split_postpre_kernel(EngineView<T> v, int* not_done) {
+    __shared__ double red_s[128];
+    const int c = Geo<G>::chain();
+    if (c >= v.C) return;
     Chain<T, G> ch(v, c, red_s);
     ch.load();
-    if (ch.r.phase == PH_DONE) {
-        if (c_next >= 0) prefetch_chain_rows<T, G, DENSE>(v, c_next);
-        return;
-    }
+    if (ch.r.phase == PH_DONE) return;
     TickFront<T, E, DENSE> f;
     bool rebind = true;
     if (ch.r.phase == PH_RUN) {
         f.bind_post(ch);
         const T U = v.Unew[c];
-        // this chain's own rows are on their way: ask for the next chain's
-        if (c_next >= 0) prefetch_chain_rows<T, G, DENSE>(v, c_next);
         bool ended;
         if (HMC) ended = hmc_post<T, G, DENSE, true>(ch, U, f);
         else ended = post_gradient<T, G, DENSE, true>(ch, U, f);
@@ -115,8 +78,6 @@ B2H_DEVINL void postpre_chain(const EngineView<T>& v, int c, int c_next, int* no
             return;
         }
         if (ch.r.phase == PH_DONE) { ch.store(); return; }
-    } else if (c_next >= 0) {
-        prefetch_chain_rows<T, G, DENSE>(v, c_next);
     }
     if (!PRE) return;
     if (ch.r.phase == PH_START) {
@@ -128,21 +89,6 @@ B2H_DEVINL void postpre_chain(const EngineView<T>& v, int c, int c_next, int* no
     half_kick_drift<T, G, DENSE, true>(ch, f);
     f.store(ch, false);                        // p (V) only: q is in xa, g (W) stay in the edge / come from xb (xc)
     ch.store();
-}
-
-// Persistent form: the grid holds as many CTAs as stay resident; every CTA walks its chains with a grid stride and
-// requests the next chain's rows from L2 while it works on the current one.
-template <typename T, int G, bool DENSE, bool HMC, int E, bool PRE>
-__global__ void __launch_bounds__(Geo<G>::kThreads, Geo<G>::kMinBlocksTick)
-split_postpre_kernel(EngineView<T> v, int* not_done, int prefetch) {
-    __shared__ double red_s[128];
-    constexpr int CPB = Geo<G>::kChainsPerBlock;
-    const int stride = (int)gridDim.x * CPB;
-    for (int c = Geo<G>::chain(); c < v.C; c += stride) {
-        const int cn = c + stride;
-        postpre_chain<T, G, DENSE, HMC, E, PRE>(v, c, (prefetch && cn < v.C) ? cn : -1, not_done, red_s);
-        if (Group<G>::kBlock) __syncthreads();
-    }
 }
 
 // sum the split-K planes of a rider contraction and scatter the rows to their chains:
@@ -207,13 +153,6 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
     cudaStream_t rider_stream = use_side ? ctx->side : st;
     const int epl = (d + G - 1) / G;                 // front elements per lane
     const bool fuse = use_fuse && epl <= 4;
-    // fused tick kernel: persistent CTAs (as many as stay resident) with next-chain prefetch when there is more than one
-    // wave of chains; B2H_TICK_PERSIST=0 launches one CTA per chain group as before
-    static int use_persist = -1;
-    if (use_persist < 0) { const char* e = getenv("B2H_TICK_PERSIST"); use_persist = e ? atoi(e) : 1; }
-    const int resident = ctx->sm_count * Geo<G>::kMinBlocksTick;
-    const int tick_grid = (use_persist && grid > resident) ? resident : grid;
-    const int tick_prefetch = (use_persist && grid > resident) ? 1 : 0;
 
     // Dense metric, before the kernel that holds the pre part of tick t: all momentum contractions launched so far
     // must have landed (a chain that started a transition one tick ago -- HMC with L = 1, a first-step divergence --
@@ -263,7 +202,7 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
         split_pre_kernel<T, G, false, HMC><<<grid, thr, 0, st>>>(v);
         return 0;
     };
-#define B2H_POSTPRE(D_, E_, P_) split_postpre_kernel<T, G, D_, HMC, E_, P_><<<tick_grid, thr, 0, st>>>(v, nd, tick_prefetch)
+#define B2H_POSTPRE(D_, E_, P_) split_postpre_kernel<T, G, D_, HMC, E_, P_><<<grid, thr, 0, st>>>(v, nd)
     auto launch_postpre = [&](i64 t, int* nd) -> int {                       // post of tick t - 1, pre of tick t
         if (pl.dense) {
             if (int e = pre_prologue(t)) return e;
