@@ -169,7 +169,7 @@ struct Group {
     }
     // all-reduce sum of N doubles across the group
     template <int N>
-    B2H_DEVINL static void sum(double (&v)[N], double* smem /* >= N*(G/32) doubles when kBlock */) {
+    B2H_DEVINL static void sum(double (&v)[N], double* smem /* >= N*(G/32 + 1) doubles when kBlock */) {
         if (G == 1) return;
         constexpr int W = G >= 32 ? 32 : G;
         const unsigned m = mask();
@@ -187,13 +187,16 @@ struct Group {
                 for (int i = 0; i < N; ++i) smem[i * NW + w] = v[i];
             }
             __syncthreads();
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
+            // N threads add the NW partials of one value each (same order as before); everybody reads the N totals
+            if (threadIdx.x < N) {
                 double s = 0.0;
 #pragma unroll
-                for (int k = 0; k < NW; ++k) s += smem[i * NW + k];
-                v[i] = s;
+                for (int k = 0; k < NW; ++k) s += smem[threadIdx.x * NW + k];
+                smem[N * NW + threadIdx.x] = s;
             }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i] = smem[N * NW + i];
         }
     }
     B2H_DEVINL static double sum1(double x, double* smem) {

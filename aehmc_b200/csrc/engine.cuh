@@ -166,8 +166,15 @@ struct Chain {
           mck(v_.mck + (i64)c_ * v_.sck), sckp(v_.sckp + (i64)c_ * v_.sck),
           vck(v_.vck ? v_.vck + (i64)c_ * v_.sck : nullptr), ck_ls((i64)v_.d * v_.sj), ck_sj(v_.sj) {}
 
-    B2H_DEVINL i64 at(int j) const { return base + (i64)j * v.sj; }
-    B2H_DEVINL i64 ck(int level, int j) const { return (i64)level * ck_ls + (i64)j * ck_sj; }
+    // groups of several threads always work on the row-major layout (element stride 1): no stride multiplies there
+    B2H_DEVINL i64 at(int j) const {
+        if constexpr (G > 1) return base + j;
+        else return base + (i64)j * v.sj;
+    }
+    B2H_DEVINL i64 ck(int level, int j) const {
+        if constexpr (G > 1) return (i64)(level * v.d + j);
+        else return (i64)level * ck_ls + (i64)j * ck_sj;
+    }
     // checkpoints [2][maxd][d] of this chain into / out of shared memory (diagonal-family metrics: no vck)
     B2H_DEVINL void stage_checkpoints(T* smem) {
         const int n = v.maxd * v.d;
@@ -725,7 +732,15 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
     red[0] = (double)kacc;
 #pragma unroll
     for (int l = 0; l < LV; ++l) { red[1 + 2 * l] = (double)dl[l]; red[2 + 2 * l] = (double)dr[l]; }
-    Group<G>::template sum<1 + 2 * LV>(red, ch.red);
+    // 7 of 8 steps check at most one checkpoint level (the count depends on the step number only, so the whole group
+    // agrees): reduce the kinetic energy and that level's two dot products, not all 1 + 2 LV values
+    if (nlev <= 1) {
+        double r3[3] = {red[0], red[1], red[2]};
+        Group<G>::template sum<3>(r3, ch.red);
+        red[0] = r3[0]; red[1] = r3[1]; red[2] = r3[2];
+    } else {
+        Group<G>::template sum<1 + 2 * LV>(red, ch.red);
+    }
     const T K = (T)0.5 * (T)red[0];
     bool term = false;
 #pragma unroll
