@@ -26,8 +26,9 @@ enum Phase : int { PH_START = 0, PH_RUN = 1, PH_DONE = 2 };
 // elements per lane whose loads are issued together before the first store of the batch
 constexpr int kBatch = 4;
 
-// Per-chain scalar record (one 256-byte line per chain).
-struct __align__(16) ChainRec {
+// Per-chain scalar record (one 256-byte line per chain).  ChainRecLive is the part that carries state (192 bytes:
+// what the tile kernel loads and stores); the rest of the line is padding.
+struct __align__(16) ChainRecLive {
     double w_sub, slpa_sub, w_prop, slpa_prop;  // Q13: always float64
     double E0, E_sub, E_prop, U_sub, U_prop;
     double eps;
@@ -40,6 +41,9 @@ struct __align__(16) ChainRec {
     i64 total_leap;
     int t_base, sub_term;                        // t at the start of the current call (resume); sub-tree U-turn flag
     double U_left, U_right, U_front;             // potential energy at the edges / at the front (explicit-state API)
+};
+static_assert(sizeof(ChainRecLive) == 192, "ChainRecLive is the first 192 bytes of the record");
+struct __align__(16) ChainRec : ChainRecLive {
     double pad[8];
 };
 static_assert(sizeof(ChainRec) == 256, "ChainRec must be one 256-byte record");
@@ -215,8 +219,10 @@ struct MemFront {
     static constexpr int kE = 1 << 30;
     static constexpr bool kRegs = false;
     static constexpr bool kSumRegs = false;     // the sub-tree momentum sum goes through v.sms every tick
+    static constexpr bool kImmRegs = false;     // the diagonal metric is read from memory at every use
     B2H_DEVINL T sum(int) const { return 0; }
     B2H_DEVINL void set_sum(int, T) {}
+    B2H_DEVINL T im(int) const { return 0; }
     T *Q, *P, *Gd, *V, *W;              // V = imm p, W = imm g: dense metric only
     template <int G> B2H_DEVINL void bind(const Chain<T, G>& ch) {
         Q = ch.r.go_right ? ch.v.qr : ch.v.ql;
@@ -245,7 +251,9 @@ struct RegFront {
     // the sub-tree momentum sum stays in registers too (v.sms is written by flush) unless the front already fills the
     // register file (thread per chain, E >= 10: measured 6 % slower with the extra spills)
     static constexpr bool kSumRegs = (E <= 8);
-    T fq[E], fp[E], fg[E], fs[kSumRegs ? E : 1];
+    // ... and so does this chain's diagonal inverse mass matrix (constant within a transition; re-read by bind)
+    static constexpr bool kImmRegs = (E <= 8);
+    T fq[E], fp[E], fg[E], fs[kSumRegs ? E : 1], fim[kImmRegs ? E : 1];
     template <int G> B2H_DEVINL void bind(const Chain<T, G>& ch) {
         const T* Q = ch.r.go_right ? ch.v.qr : ch.v.ql;
         const T* P = ch.r.go_right ? ch.v.pr : ch.v.pl;
@@ -253,8 +261,8 @@ struct RegFront {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int j = ch.lane + e * G;
-            if (j < ch.v.d) { i64 a = ch.at(j); fq[e] = Q[a]; fp[e] = P[a]; fg[e] = Gd[a]; if (kSumRegs) fs[e] = ch.v.sms[a]; }
-            else { fq[e] = 0; fp[e] = 0; fg[e] = 0; if (kSumRegs) fs[e] = 0; }
+            if (j < ch.v.d) { i64 a = ch.at(j); fq[e] = Q[a]; fp[e] = P[a]; fg[e] = Gd[a]; if (kSumRegs) fs[e] = ch.v.sms[a]; if (kImmRegs) fim[e] = ch.imm(j); }
+            else { fq[e] = 0; fp[e] = 0; fg[e] = 0; if (kSumRegs) fs[e] = 0; if (kImmRegs) fim[e] = 0; }
         }
     }
     template <int G> B2H_DEVINL void flush(const Chain<T, G>& ch) {
@@ -267,6 +275,7 @@ struct RegFront {
             if (j < ch.v.d) { i64 a = ch.at(j); Q[a] = fq[e]; P[a] = fp[e]; Gd[a] = fg[e]; if (kSumRegs) ch.v.sms[a] = fs[e]; }
         }
     }
+    B2H_DEVINL T im(int e) const { return fim[kImmRegs ? e : 0]; }
     B2H_DEVINL T sum(int e) const { return fs[kSumRegs ? e : 0]; }
     B2H_DEVINL void set_sum(int e, T x) { fs[kSumRegs ? e : 0] = x; }
     B2H_DEVINL T q(int e, i64) const { return fq[e]; }
@@ -295,8 +304,10 @@ struct TickFront {
     static constexpr int kE = E;
     static constexpr bool kRegs = true;
     static constexpr bool kSumRegs = false;
+    static constexpr bool kImmRegs = false;
     B2H_DEVINL T sum(int) const { return 0; }
     B2H_DEVINL void set_sum(int, T) {}
+    B2H_DEVINL T im(int) const { return 0; }
     T fq[E], fp[E], fg[E], fv[DENSE ? E : 1], fw[DENSE ? E : 1];
     template <int G> B2H_DEVINL void load(const Chain<T, G>& ch, bool all) {
         const bool rt = ch.r.go_right != 0;
@@ -465,12 +476,11 @@ B2H_DEVINL void half_kick_drift(Chain<T, G>& ch, Front& f) {
 #pragma unroll
         for (int i = 0; i < CH; ++i) {                     // loads of the batch first (see post_gradient)
             const int ee = cix * CH + i, j = jb + i * G;
-            pv[i] = 0; gv[i] = 0; vv[i] = 0; wv[i] = 0; qv[i] = 0;
             if (ee < Front::kE && j < v.d) {
                 const i64 a = ch.at(j);
                 pv[i] = f.p(ee, a); gv[i] = f.g(ee, a); qv[i] = f.q(ee, a);
                 if (DENSE) { vv[i] = f.vel(ee, a); wv[i] = f.w(ee, a); }
-                else vv[i] = ch.imm(j);
+                else vv[i] = Front::kImmRegs ? f.im(ee) : ch.imm(j);
             }
         }
 #pragma unroll
@@ -642,12 +652,11 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
             const int ee = cix * CH + i, j = jb + i * G;
-            gx[i] = 0; wx[i] = 0; so[i] = 0; pv[i] = 0; vv[i] = 0; imv[i] = 0; cm[i] = 0; cs[i] = 0; cv[i] = 0;
             if (ee < Front::kE && j < d) {
                 const i64 a = ch.at(j), m = (i64)ch.c * d + j;
                 pv[i] = f.p(ee, a);
                 if (DENSE) { gx[i] = v.xb[m]; wx[i] = v.xc[m]; vv[i] = f.vel(ee, a); }
-                else { gx[i] = SPLIT ? v.xb[m] : f.g(ee, a); imv[i] = ch.imm(j); }
+                else { gx[i] = SPLIT ? v.xb[m] : f.g(ee, a); imv[i] = Front::kImmRegs ? f.im(ee) : ch.imm(j); }
                 if (s != 0) so[i] = Front::kSumRegs ? f.sum(ee) : v.sms[a];
                 if (lev0) {
                     const i64 b = ch.ck(imax, j);
@@ -705,14 +714,13 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
 #pragma unroll
                 for (int i = 0; i < CH; ++i) {
                     const int ee = cix * CH + i, j = jb + i * G;
-                    pv[i] = 0; vv[i] = 0; sv[i] = 0; cm[i] = 0; cs[i] = 0; cv[i] = 0;
                     if (ee < Front::kE && j < d) {
                         const i64 a = ch.at(j), b = ch.ck(imax - l, j);
                         pv[i] = f.p(ee, a);
                         sv[i] = Front::kRegs ? smreg[Front::kRegs ? ee : 0] : v.sms[a];
                         cm[i] = ch.mck[b]; cs[i] = ch.sckp[b];
                         if (DENSE) { cv[i] = ch.vck[b]; vv[i] = f.vel(ee, a); }
-                        else { const T im = ch.imm(j); cv[i] = im * cm[i]; vv[i] = im * pv[i]; }
+                        else { const T im = Front::kImmRegs ? f.im(ee) : ch.imm(j); cv[i] = im * cm[i]; vv[i] = im * pv[i]; }
                     }
                 }
 #pragma unroll
@@ -756,7 +764,7 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
                 T rho = subsum - (p + m) / (T)2;
                 T vleft, vright;
                 if (DENSE) { vleft = ch.vck[b]; vright = f.vel(ee, a); }
-                else { T im = ch.imm(j); vleft = im * m; vright = im * p; }
+                else { T im = Front::kImmRegs ? f.im(ee) : ch.imm(j); vleft = im * m; vright = im * p; }
                 xl += vleft * rho;
                 xr += vright * rho;
             }

@@ -2,6 +2,7 @@
 #include <stdlib.h>
 
 #include "engine_host.cuh"
+#include "engine_tile.inl"
 
 namespace b2h {
 
@@ -147,12 +148,16 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
         }
     }
     bool side_pending[2] = {false, false};
-    static int use_side = -1, use_fuse = -1;
+    static int use_side = -1, use_fuse = -1, use_tile = -1;
     if (use_side < 0) { const char* e = getenv("B2H_SIDE_STREAM"); use_side = e ? atoi(e) : 1; }
     if (use_fuse < 0) { const char* e = getenv("B2H_FUSE_TICK"); use_fuse = e ? atoi(e) : 1; }
+    if (use_tile < 0) { const char* e = getenv("B2H_TILE_TICK"); use_tile = e ? atoi(e) : 1; }
     cudaStream_t rider_stream = use_side ? ctx->side : st;
     const int epl = (d + G - 1) / G;                 // front elements per lane
-    const bool fuse = use_fuse && epl <= 4;
+    // NUTS: the tile kernel (engine_tile.inl) is the tick for every row length; HMC (and B2H_TILE_TICK=0) keep the
+    // register-front kernel, which needs the chain's row to fit its group's registers
+    const bool tile_tick = use_fuse && use_tile && !HMC;
+    const bool fuse = use_fuse && (tile_tick || epl <= 4);
 
     // Dense metric, before the kernel that holds the pre part of tick t: all momentum contractions launched so far
     // must have landed (a chain that started a transition one tick ago -- HMC with L = 1, a first-step divergence --
@@ -204,6 +209,15 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
     };
 #define B2H_POSTPRE(D_, E_, P_) split_postpre_kernel<T, G, D_, HMC, E_, P_><<<grid, thr, 0, st>>>(v, nd)
     auto launch_postpre = [&](i64 t, int* nd) -> int {                       // post of tick t - 1, pre of tick t
+        if (tile_tick) {
+            if (pl.dense) {
+                if (int e = pre_prologue(t)) return e;
+                launch_tile_tick<T, true>(st, v, nd, true, ctx->sm_count);
+                return pre_epilogue(t);
+            }
+            launch_tile_tick<T, false>(st, v, nd, true, ctx->sm_count);
+            return 0;
+        }
         if (pl.dense) {
             if (int e = pre_prologue(t)) return e;
             if (epl <= 1) B2H_POSTPRE(true, 1, true);
@@ -217,6 +231,11 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
         return 0;
     };
     auto launch_post_last = [&](int* nd) {                                   // post of the call's last tick
+        if (tile_tick) {
+            if (pl.dense) launch_tile_tick<T, true>(st, v, nd, false, ctx->sm_count);
+            else launch_tile_tick<T, false>(st, v, nd, false, ctx->sm_count);
+            return;
+        }
         if (pl.dense) {
             if (epl <= 1) B2H_POSTPRE(true, 1, false);
             else if (epl <= 2) B2H_POSTPRE(true, 2, false);

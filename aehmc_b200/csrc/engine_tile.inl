@@ -1,0 +1,816 @@
+// The tile tick kernel of the split engine (NUTS): post of tick t fused with pre of tick t + 1, like
+// split_postpre_kernel, but organised so that the work per chain-tick is a few hundred instructions instead of ~2000:
+//
+//  * a warp owns a TILE of TC consecutive chains (TC = 32 / 8 / 1, chosen from the number of chains);
+//  * the SCALAR part of the state machine (energies, log-sum-exp weights, progressive / biased sampling, Philox
+//    uniforms, U-turn and divergence decisions, dual averaging: trajectory.py:195-273,537-608, proposals.py:41-144,
+//    algorithms.py:104-115) runs ONE LANE PER CHAIN: the double-precision exp / log chains and the Philox rounds are
+//    issued once per 32 chains instead of once per chain, and divergence between chains costs predicated scalar
+//    code only;
+//  * the VECTOR part (kick, kinetic energy, momentum sums, checkpoint rows, U-turn dot products, proposal copies,
+//    half kick + drift: integrators.py:58-73, termination.py:109-187, metrics.py:70-102) runs WARP PER CHAIN in a loop
+//    over the tile with warp-uniform control flow (the chain's flags are broadcast from its lane), 128-bit row
+//    accesses and one butterfly reduction per chain.  No register front: the passes stream the rows, the few rows a
+//    later pass needs again (p_half, q', g') are re-read from L1 / L2.
+//
+// Passes:  S0 (scalars of the step)  ->  A (kick, K, sums, checkpoints, U-turn dots)  ->  S1 (energy, sampling, end
+// of sub-tree?)  ->  B (sub-tree ends: front back to the edge, proposal, trajectory sum, top-level U-turn)  ->  S2
+// (expand_once decisions, end of transition, adaptation scalars)  ->  C (proposal copy, draw, Welford, next
+// transition's momentum and edges)  ->  S3 (initial energy, direction)  ->  D (half kick + drift of the next tick,
+// fused with the sub-tree proposal of chains that continue).
+//
+// The arithmetic per element and the decisions are those of engine.cuh's post_gradient / begin_transition /
+// half_kick_drift / end_transition / adapt_update (same expressions, same rounding: this file is compiled with
+// -fmad=false like the rest of the engine); only the order of the partial sums inside a reduction differs, as it
+// already does between the thread-, warp- and CTA-per-chain layouts.
+#pragma once
+
+#include "engine_host.cuh"
+
+namespace b2h {
+namespace tile {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+template <typename T, int VEC>
+B2H_DEVINL void ldv(T (&x)[VEC], const T* __restrict__ p) {
+    if constexpr (VEC == 1) {
+        x[0] = *p;
+    } else if constexpr (sizeof(T) == 4) {
+        static_assert(VEC == 4, "float rows move as float4");
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+    } else {
+        static_assert(VEC == 2, "double rows move as double2");
+        const double2 t = *reinterpret_cast<const double2*>(p);
+        x[0] = t.x; x[1] = t.y;
+    }
+}
+
+template <typename T, int VEC>
+B2H_DEVINL void stv(T* __restrict__ p, const T (&x)[VEC]) {
+    if constexpr (VEC == 1) {
+        *p = x[0];
+    } else if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+    } else {
+        *reinterpret_cast<double2*>(p) = make_double2(x[0], x[1]);
+    }
+}
+
+// diagonal-family inverse mass matrix of one chain: row (stride 1) or a single scalar (stride 0)
+template <typename T, int VEC>
+B2H_DEVINL void ld_imm(T (&x)[VEC], const T* __restrict__ row, int j, i64 sj) {
+    if (sj == 0) {
+        const T s = row[0];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) x[i] = s;
+    } else {
+        ldv<T, VEC>(x, row + j);
+    }
+}
+
+// standard normals j .. j + VEC - 1 of transition t: the values draw_z returns, one Philox block per Box-Muller pair
+template <typename T, int VEC>
+B2H_DEVINL void draw_z_vec(const RngView& rg, int c, int t, int j, int d, T (&z)[VEC]) {
+    if (rg.mode == 1 || VEC == 1) {
+#pragma unroll
+        for (int x = 0; x < VEC; ++x) z[x] = (T)draw_z<8>(rg, c, t, j + x, d);
+    } else {
+#pragma unroll
+        for (int x = 0; x + 1 < VEC; x += 2) {
+            double z0, z1;
+            philox_normal_pair(rg.key, rg.chain_offset + (uint64_t)c, (uint32_t)(rg.transition_offset + (uint64_t)t),
+                               (uint32_t)((j + x) >> 1), &z0, &z1);
+            z[x] = (T)z0;
+            z[x + 1] = (T)z1;
+        }
+    }
+}
+
+
+// L2 prefetch of the part of a row this thread will load (rows of a chain a few iterations ahead: the passes are
+// bound by the latency of their row loads, not by bandwidth)
+template <typename T>
+B2H_DEVINL void pf_row(const T* row, int j0, int d, int step) {
+    for (int j = j0; j < d; j += step) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + j));
+}
+
+// Who works on a chain.  WPC == 1: a warp owns a tile of TC chains, chain slot i is owned by lane i, values travel
+// by shuffle.  WPC > 1 (TC == 1, long rows): the CTA's WPC warps share ONE chain, thread 0 owns it, values travel
+// through shared memory (each broadcast has its own slot: nothing is reused within a launch).
+template <int TC, int WPC>
+struct Coop {
+    static_assert(WPC == 1 || TC == 1, "several warps per chain: one chain per CTA");
+    static constexpr int kThreads = WPC > 1 ? 32 * WPC : 128;
+    B2H_DEVINL static int tid() { return WPC > 1 ? (int)threadIdx.x : (int)(threadIdx.x & 31); }
+    B2H_DEVINL static bool owner(int i) { return tid() == i; }
+    template <typename V>
+    B2H_DEVINL static V get(V x, int i, double* slots, int slot) {
+        if constexpr (WPC == 1) {
+            return __shfl_sync(kFull, x, i);
+        } else {
+            V* s = reinterpret_cast<V*>(slots + slot);
+            if (threadIdx.x == 0) *s = x;
+            __syncthreads();
+            return *s;
+        }
+    }
+    // bit i set: chain slot i has the flag
+    B2H_DEVINL static unsigned mask(bool flag, double* slots, int slot) {
+        if constexpr (WPC == 1) return __ballot_sync(kFull, flag);
+        else return get<int>(flag ? 1 : 0, 0, slots, slot) ? 1u : 0u;
+    }
+    template <int N>
+    B2H_DEVINL static void sum(double (&v)[N], double* red) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(kFull, v[i], off);
+        }
+        if constexpr (WPC > 1) {
+            const int w = threadIdx.x >> 5;
+            __syncthreads();                       // the previous reduction's partials have been read
+            if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) red[i * WPC + w] = v[i];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < WPC; ++k) s += red[i * WPC + k];
+                v[i] = s;
+            }
+        }
+    }
+};
+
+#ifndef B2H_TILE_MINB
+#define B2H_TILE_MINB 4
+#endif
+#ifndef B2H_TILE_PD
+#define B2H_TILE_PD 3
+#endif
+
+template <typename T, int TC, int WPC, int VEC, bool DENSE>
+__global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? 16 / WPC : B2H_TILE_MINB)) tile_tick_kernel(EngineView<T> v, int* not_done, int pre) {
+    typedef Coop<TC, WPC> Co;
+    __shared__ double slots[32];                         // WPC > 1: one slot per broadcast value
+    __shared__ double red_s[3 * WPC];                    // WPC > 1: per-warp partials of a reduction
+    const int lane = Co::tid();                          // index of this thread in the group that shares a chain's rows
+    const int c0 = WPC > 1 ? (int)blockIdx.x : (int)(((i64)blockIdx.x * 128 + threadIdx.x) >> 5) * TC;
+    if (c0 >= v.C) return;
+    const int d = v.d;
+    const int c = c0 + lane;
+    const bool own = lane < TC && c < v.C;
+    ChainRecLive r{};
+    r.phase = PH_DONE;
+    if (own) r = *static_cast<const ChainRecLive*>(v.rec + c);
+    const int ph0 = r.phase;
+    if (Co::mask(ph0 != PH_DONE, slots, 0) == 0) return;
+    const bool run = ph0 == PH_RUN;
+    constexpr int STEP = 32 * WPC * VEC;
+    const int j0 = lane * VEC;
+
+    // ---- S0: what the step needs before its rows arrive -------------------------------------------------------------
+    int s = 0, k = 0, imax = 0, nlev = 0;
+    double u_step = 0.0;
+    T U_new = 0, e = 0, he = 0;
+    if (run) {
+        s = r.s; k = r.k;
+        // progressive-sampling uniform of the step (proposals.py:96-100): independent of the energies
+        if (s != 0) u_step = draw_u<8>(v.rng, DRAW_UNIFORM, c, r.t, uniform_slot(k, s), v.maxd);
+        int imin;
+        if (s == 0) { imin = r.imin; imax = r.imax; }            // Q2 / Q3: stale indices at step 0
+        else storage_indices(s, imin, imax);
+        r.imin = imin; r.imax = imax;
+        nlev = (s >= 1 && imax >= imin) ? (imax - imin + 1) : 0;
+        e = (T)(r.go_right ? r.eps : -r.eps);
+        he = (T)0.5 * e;
+        U_new = v.Unew[c];
+    }
+
+    // ---- A: p' = p_half - (0.5 e) g', K(p'), sub-tree momentum sum, checkpoint write (even steps), U-turn dot products
+    //         (odd steps: the levels imin .. imax of termination.py:164-187) ---------------------------------------
+    T myK = 0;
+    bool term = false;
+    {
+        const int fa = run ? (1 | (r.go_right ? 2 : 0) | (s == 0 ? 4 : 0) | ((s & 1) == 0 ? 8 : 0) | (imax << 8) | (nlev << 16)) : 0;
+        // rows of the chain B2H_TILE_PD iterations ahead into L2 (tiles of several chains: rows are short)
+        auto prefetch = [&](unsigned nx) {
+            if (nx >= 32u) return;
+            const int f = __shfl_sync(kFull, fa, nx);
+            const bool gr = f & 2, s0 = f & 4;
+            const int imx = (f >> 8) & 0xff, nl = (f >> 16) & 0xff;
+            const i64 rb = (i64)(c0 + (int)nx) * d;
+            pf_row((gr ? v.pr : v.pl) + rb, j0, d, STEP);
+            pf_row(v.xb + rb, j0, d, STEP);
+            if (DENSE) { pf_row((gr ? v.vr : v.vl) + rb, j0, d, STEP); pf_row(v.xc + rb, j0, d, STEP); }
+            if (!s0) pf_row(v.sms + rb, j0, d, STEP);
+            if (nl > 0) {
+                const i64 cb = (i64)(c0 + (int)nx) * v.sck + (i64)imx * d;
+                pf_row(v.mck + cb, j0, d, STEP); pf_row(v.sckp + cb, j0, d, STEP);
+                if (DENSE) pf_row(v.vck + cb, j0, d, STEP);
+            }
+        };
+        unsigned act = Co::mask((fa & 1) != 0, slots, 1);
+        if constexpr (TC > 1) {
+#pragma unroll
+            for (int kk = 2; kk <= B2H_TILE_PD; ++kk) prefetch(__fns(act, 0, kk));
+        }
+#pragma unroll 1
+        while (act) {
+            const int i = __ffs(act) - 1;
+            act &= act - 1;
+            if constexpr (TC > 1) prefetch(__fns(act, 0, B2H_TILE_PD));
+            const int f = Co::get(fa, i, slots, 2);
+            const T hei = Co::get(he, i, slots, 3);
+            const bool gr = f & 2, s0 = f & 4, even = f & 8;
+            const int imx = (f >> 8) & 0xff, nl = (f >> 16) & 0xff;
+            const int ci = c0 + i;
+            const i64 rb = (i64)ci * d;
+            const T* __restrict__ P = (gr ? v.pr : v.pl) + rb;
+            const T* __restrict__ XB = v.xb + rb;
+            const T* __restrict__ V = DENSE ? (gr ? v.vr : v.vl) + rb : nullptr;
+            const T* __restrict__ XC = DENSE ? v.xc + rb : nullptr;
+            const T* __restrict__ IM = DENSE ? nullptr : v.imm + (i64)ci * v.imm_sc;
+            T* __restrict__ SMS = v.sms + rb;
+            const i64 cb = (i64)ci * v.sck + (i64)imx * d;
+            T* __restrict__ MCK = v.mck + cb;
+            T* __restrict__ SCK = v.sckp + cb;
+            T* __restrict__ VCK = DENSE ? v.vck + cb : nullptr;
+            T kacc = 0, dl = 0, dr = 0;
+            for (int j = j0; j < d; j += STEP) {
+                T pv[VEC], gx[VEC], so[VEC], cm[VEC], cs[VEC], cv[VEC], im[VEC], vv[VEC], wx[VEC];
+                ldv<T, VEC>(pv, P + j);
+                ldv<T, VEC>(gx, XB + j);
+                if (DENSE) { ldv<T, VEC>(vv, V + j); ldv<T, VEC>(wx, XC + j); }
+                else ld_imm<T, VEC>(im, IM, j, v.imm_sj);
+                if (!s0) ldv<T, VEC>(so, SMS + j);
+                if (nl > 0) {
+                    ldv<T, VEC>(cm, MCK + j); ldv<T, VEC>(cs, SCK + j);
+                    if (DENSE) ldv<T, VEC>(cv, VCK + j);
+                }
+                T p[VEC], vel[VEC], sm[VEC];
+#pragma unroll
+                for (int x = 0; x < VEC; ++x) {
+                    p[x] = pv[x] - hei * gx[x];                          // integrators.py:66
+                    if (DENSE) vel[x] = vv[x] - hei * wx[x];             // imm p' = imm p_half - (0.5 e) imm g'
+                    else vel[x] = im[x] * p[x];
+                    kacc += vel[x] * p[x];                               // metrics.py:70-73
+                    sm[x] = s0 ? p[x] : so[x] + p[x];                    // trajectory.py:243,278
+                    if (nl > 0) {
+                        const T subsum = sm[x] - cs[x] + cm[x];
+                        const T rho = subsum - (p[x] + cm[x]) / (T)2;
+                        const T vleft = DENSE ? cv[x] : im[x] * cm[x];
+                        dl += vleft * rho;
+                        dr += vel[x] * rho;
+                    }
+                }
+                stv<T, VEC>(SMS + j, sm);
+                if (even) {                                              // termination.py:109-124
+                    stv<T, VEC>(MCK + j, p);
+                    stv<T, VEC>(SCK + j, sm);
+                    if (DENSE) stv<T, VEC>(VCK + j, vel);
+                }
+            }
+            double red[3] = {(double)kacc, (double)dl, (double)dr};
+            if (nl > 0) Co::template sum<3>(red, red_s);
+            else { double r1[1] = {red[0]}; Co::template sum<1>(r1, red_s); red[0] = r1[0]; }
+            bool tm = nl > 0 && ((T)red[1] <= (T)0 || (T)red[2] <= (T)0);
+            // deeper levels (steps with two or more trailing one-bits); the outcome is an OR over the levels
+            for (int l = 1; l < nl && !tm; ++l) {
+                const T* __restrict__ MC = MCK - (i64)l * d;
+                const T* __restrict__ SC = SCK - (i64)l * d;
+                const T* __restrict__ VC = DENSE ? VCK - (i64)l * d : nullptr;
+                T xl = 0, xr = 0;
+                for (int j = j0; j < d; j += STEP) {
+                    T pv[VEC], gx[VEC], sm[VEC], cm[VEC], cs[VEC], cv[VEC], im[VEC], vv[VEC], wx[VEC];
+                    ldv<T, VEC>(pv, P + j);
+                    ldv<T, VEC>(gx, XB + j);
+                    if (DENSE) { ldv<T, VEC>(vv, V + j); ldv<T, VEC>(wx, XC + j); ldv<T, VEC>(cv, VC + j); }
+                    else ld_imm<T, VEC>(im, IM, j, v.imm_sj);
+                    ldv<T, VEC>(sm, SMS + j);
+                    ldv<T, VEC>(cm, MC + j); ldv<T, VEC>(cs, SC + j);
+#pragma unroll
+                    for (int x = 0; x < VEC; ++x) {
+                        const T p = pv[x] - hei * gx[x];
+                        const T vright = DENSE ? vv[x] - hei * wx[x] : im[x] * p;
+                        const T vleft = DENSE ? cv[x] : im[x] * cm[x];
+                        const T subsum = sm[x] - cs[x] + cm[x];
+                        const T rho = subsum - (p + cm[x]) / (T)2;
+                        xl += vleft * rho;
+                        xr += vright * rho;
+                    }
+                }
+                double r2[2] = {(double)xl, (double)xr};
+                Co::template sum<2>(r2, red_s);
+                if ((T)r2[0] <= (T)0 || (T)r2[1] <= (T)0) tm = true;
+            }
+            if (Co::owner(i)) { myK = (T)0.5 * (T)red[0]; term = tm; }
+        }
+    }
+
+    // ---- S1: energy, divergence, progressive sampling inside the sub-tree, end of the sub-tree? ---------------------
+    bool take = false, end_sub = false, div = false, expand = false;
+    if (run) {
+        const T E = U_new + myK;
+        double delta = (double)((T)r.E0 - E);
+        if (isnan(delta)) delta = -INFINITY;
+        div = fabs(delta) > v.div_thr;
+        const double w_new = delta;                                  // proposals.py:41-52, Q10
+        const double lpa = delta > 0 ? 0.0 : delta;
+        if (s == 0) {
+            take = true;                                             // trajectory.py:276-277
+            r.w_sub = w_new; r.slpa_sub = lpa;
+        } else {
+            double pa = expit(w_new - r.w_sub);                      // proposals.py:96-100, Q7
+            if (isnan(pa)) pa = 0.0;
+            take = bern(u_step, pa);
+            r.w_sub = lae(r.w_sub, w_new);                           // proposals.py:141-144
+            r.slpa_sub = lae(r.slpa_sub, lpa);
+        }
+        if (take) { r.E_sub = (double)E; r.U_sub = (double)U_new; }
+        r.sub_len = (s == 0) ? 1 : r.sub_len + 1;
+        r.nleap += 1;
+        r.total_leap += 1;
+        r.U_front = (double)U_new;
+        const int sub_limit = v.sub_max_steps > 0 ? v.sub_max_steps : (1 << k) - (v.exact_doubling ? 1 : 0);
+        end_sub = div || term || (s == sub_limit);                   // Q1
+        if (!end_sub) {
+            r.s = s + 1;
+        } else {
+            if (r.go_right) r.U_right = r.U_front; else r.U_left = r.U_front;
+            r.sub_term = term ? 1 : 0;
+            if (v.stop_at_subtree_end) {                             // trajectory.dynamic_integration.integrate on its own
+                r.last_flags = (div ? 2 : 0) | (term ? 4 : 0);
+                r.last_nleap = r.sub_len;
+                r.phase = PH_DONE;
+            } else {
+                expand = true;
+            }
+        }
+    }
+
+    // ---- B: sub-tree ends (and every running chain on the last tick of a call): the front goes back to the edge
+    //         arrays, sub-tree proposal if taken, trajectory momentum sum and the top-level U-turn (trajectory.py:537-553)
+    bool top_turn = false;
+    {
+        const bool flush = run && (end_sub || !pre);
+        const int fb = flush ? (1 | (take ? 2 : 0) | (expand ? 4 : 0) | (r.go_right ? 8 : 0)) : 0;
+        auto prefetch = [&](unsigned nx) {
+            if (nx >= 32u) return;
+            const int f = __shfl_sync(kFull, fb, nx);
+            const bool ex = f & 4, gr = f & 8;
+            const i64 rb = (i64)(c0 + (int)nx) * d;
+            pf_row((gr ? v.pr : v.pl) + rb, j0, d, STEP);
+            pf_row(v.xb + rb, j0, d, STEP);
+            pf_row(v.xa + rb, j0, d, STEP);
+            if (DENSE) { pf_row((gr ? v.vr : v.vl) + rb, j0, d, STEP); pf_row(v.xc + rb, j0, d, STEP); }
+            if (ex) {
+                pf_row(v.msum + rb, j0, d, STEP); pf_row(v.sms + rb, j0, d, STEP);
+                pf_row((gr ? v.pl : v.pr) + rb, j0, d, STEP);
+                if (DENSE) pf_row((gr ? v.vl : v.vr) + rb, j0, d, STEP);
+            }
+        };
+        unsigned act = Co::mask((fb & 1) != 0, slots, 4);
+        {
+            if constexpr (TC > 1) {
+#pragma unroll
+                for (int kk = 2; kk <= B2H_TILE_PD; ++kk) prefetch(__fns(act, 0, kk));
+            }
+#pragma unroll 1
+            while (act) {
+                const int i = __ffs(act) - 1;
+                act &= act - 1;
+                if constexpr (TC > 1) prefetch(__fns(act, 0, B2H_TILE_PD));
+                const int f = Co::get(fb, i, slots, 5);
+                const T hei = Co::get(he, i, slots, 6);
+                const bool tk = f & 2, ex = f & 4, gr = f & 8;
+                const int ci = c0 + i;
+                const i64 rb = (i64)ci * d;
+                T* __restrict__ P = (gr ? v.pr : v.pl) + rb;
+                T* __restrict__ Q = (gr ? v.qr : v.ql) + rb;
+                T* __restrict__ Gd = (gr ? v.gr : v.gl) + rb;
+                T* __restrict__ V = DENSE ? (gr ? v.vr : v.vl) + rb : nullptr;
+                T* __restrict__ W = DENSE ? (gr ? v.wr : v.wl) + rb : nullptr;
+                const T* __restrict__ PO = (gr ? v.pl : v.pr) + rb;
+                const T* __restrict__ VO = DENSE ? (gr ? v.vl : v.vr) + rb : nullptr;
+                const T* __restrict__ XA = v.xa + rb;
+                const T* __restrict__ XB = v.xb + rb;
+                const T* __restrict__ XC = DENSE ? v.xc + rb : nullptr;
+                const T* __restrict__ IM = DENSE ? nullptr : v.imm + (i64)ci * v.imm_sc;
+                T tl = 0, tr = 0;
+                for (int j = j0; j < d; j += STEP) {
+                    T pv[VEC], gx[VEC], qx[VEC], vv[VEC], wx[VEC];
+                    ldv<T, VEC>(pv, P + j);
+                    ldv<T, VEC>(gx, XB + j);
+                    ldv<T, VEC>(qx, XA + j);
+                    if (DENSE) { ldv<T, VEC>(vv, V + j); ldv<T, VEC>(wx, XC + j); }
+                    T m0[VEC], m1[VEC], po[VEC], vo[VEC], im[VEC];
+                    if (ex) {
+                        ldv<T, VEC>(m0, v.msum + rb + j);
+                        ldv<T, VEC>(m1, v.sms + rb + j);
+                        ldv<T, VEC>(po, PO + j);
+                        if (DENSE) ldv<T, VEC>(vo, VO + j);
+                        else ld_imm<T, VEC>(im, IM, j, v.imm_sj);
+                    }
+                    T p[VEC], vel[VEC];
+#pragma unroll
+                    for (int x = 0; x < VEC; ++x) {
+                        p[x] = pv[x] - hei * gx[x];
+                        vel[x] = DENSE ? vv[x] - hei * wx[x] : (T)0;
+                    }
+                    if (tk) {
+                        stv<T, VEC>(v.qs + rb + j, qx); stv<T, VEC>(v.ps + rb + j, p); stv<T, VEC>(v.gs + rb + j, gx);
+                        if (DENSE) stv<T, VEC>(v.ws + rb + j, wx);
+                    }
+                    stv<T, VEC>(Q + j, qx); stv<T, VEC>(P + j, p); stv<T, VEC>(Gd + j, gx);
+                    if (DENSE) { stv<T, VEC>(V + j, vel); stv<T, VEC>(W + j, wx); }
+                    if (ex) {
+                        T ms[VEC];
+#pragma unroll
+                        for (int x = 0; x < VEC; ++x) {
+                            const T plv = gr ? po[x] : p[x], prv = gr ? p[x] : po[x];
+                            T xl, xr;
+                            if (DENSE) { xl = gr ? vo[x] : vel[x]; xr = gr ? vel[x] : vo[x]; }
+                            else { xl = im[x] * plv; xr = im[x] * prv; }
+                            ms[x] = m0[x] + m1[x];
+                            const T rho = ms[x] - (prv + plv) / (T)2;
+                            tl += xl * rho;
+                            tr += xr * rho;
+                        }
+                        stv<T, VEC>(v.msum + rb + j, ms);
+                    }
+                }
+                if (ex) {
+                    double r2[2] = {(double)tl, (double)tr};
+                    Co::template sum<2>(r2, red_s);
+                    if (Co::owner(i)) top_turn = ((T)r2[0] <= (T)0) || ((T)r2[1] <= (T)0);
+                }
+            }
+        }
+    }
+
+    // ---- S2: expand_once (trajectory.py:551-608): acceptance statistic, biased progressive sampling, end of the
+    //          transition (nuts.py:138-151) with the dual-averaging update, or the next sub-tree's direction ----------
+    bool copy_prop = false, store_draw = false, slow = false, wendv = false;
+    int draw_slot = 0, wc_n = 0;
+    if (expand) {
+        r.accept_prob = exp(r.slpa_sub) / (double)r.sub_len;        // Q9
+        const double diff = r.w_sub - r.w_prop;
+        const double pb = fmin(fmax(exp(diff), 0.0), 1.0);
+        const double ub = draw_u<8>(v.rng, DRAW_BIASED, c, r.t, k, v.maxd);   // Q8: always drawn
+        const bool accb = bern(ub, pb);
+        if (div || term) {
+            r.slpa_prop = lae(r.slpa_sub, r.slpa_prop);             // trajectory.py:560-564
+        } else {
+            if (accb) { copy_prop = true; r.E_prop = r.E_sub; r.U_prop = r.U_sub; }
+            r.w_prop = lae(r.w_prop, r.w_sub);
+            r.slpa_prop = lae(r.slpa_prop, r.slpa_sub);
+        }
+        const int nd = k + 1;
+        if (div || top_turn || term || nd >= v.maxd) {              // trajectory.py:577 / scan length
+            // end_transition
+            const int t = r.t;
+            const int tl = t - r.t_base;
+            r.last_nd = nd;
+            r.last_flags = (top_turn ? 1 : 0) | (div ? 2 : 0) | (r.sub_term ? 4 : 0);
+            r.last_nleap = r.nleap;
+            const int thin = v.out.thin > 1 ? v.out.thin : 1;
+            const int slot = tl / thin;
+            if (slot < v.out.n_store && slot * thin == tl) {
+                store_draw = v.out.draws != nullptr;
+                draw_slot = slot;
+                if (v.out.draw_stats) {
+                    double* ds = v.out.draw_stats + ((i64)slot * v.C + c) * 4;
+                    ds[0] = r.accept_prob; ds[1] = (double)nd; ds[2] = (double)r.nleap; ds[3] = (double)r.last_flags;
+                }
+            }
+            if (v.adapt.enabled && t + v.adapt.step_offset < v.adapt.num_steps) {
+                // adapt_update, scalar part (window_adaptation.py:194-215, algorithms.py:104-115, step_size.py:97)
+                const AdaptView& ad = v.adapt;
+                const int step = t + ad.step_offset;
+                i64 dstep = ad.da_step[c];
+                const double x_old = ad.da_x[c], xavg = ad.da_x_avg[c], gavg = ad.da_g_avg[c];
+                double mu = ad.da_mu[c];
+                const double grad = ad.target - r.accept_prob;
+                const double eta = 1.0 / ((double)dstep + ad.t0);
+                double new_gavg = (1.0 - eta) * gavg + eta * grad;
+                double new_x = mu - (sqrt((double)dstep) / ad.gamma) * new_gavg;
+                const double x_eta = pow((double)dstep, -ad.kappa);
+                double new_xavg = x_eta * x_old + (1.0 - x_eta) * xavg;     // Q16: OLD iterate
+                dstep += 1;
+                double eps = exp(new_x);
+                slow = ad.stage[step] != 0 && !ad.pooled;
+                const bool wend = ad.window_end[step] != 0;
+                i64 n = ad.pooled ? 0 : ad.wc_n[c];
+                if (slow) n += 1;
+                wc_n = (int)n;
+                if (wend) {
+                    wendv = !ad.pooled;
+                    n = 0;
+                    mu = eps;
+                    dstep = 1; new_x = 0.0; new_xavg = 0.0; new_gavg = 0.0;
+                }
+                if (step == ad.num_steps - 1) eps = exp(new_xavg);
+                ad.da_step[c] = dstep; ad.da_x[c] = new_x; ad.da_x_avg[c] = new_xavg; ad.da_g_avg[c] = new_gavg;
+                ad.da_mu[c] = mu;
+                if (!ad.pooled) ad.wc_n[c] = n;
+                r.eps = eps;
+            }
+            r.t = t + 1;
+            r.phase = (v.n_transitions > 0 && (r.t - r.t_base) >= v.n_transitions) ? PH_DONE : PH_START;
+        } else {
+            r.k = nd;
+            const double u = draw_u<8>(v.rng, DRAW_DIR, c, r.t, r.k, v.maxd);   // trajectory.py:516-518
+            r.go_right = bern(u, 0.5) ? 1 : 0;
+            r.s = 0;
+        }
+    }
+
+    // ---- C: proposal <- sub-tree proposal, stored draw, Welford / window end (algorithms.py:187-197,
+    //         mass_matrix.py:103-116), and the start of the next transition (nuts.py:113-135) ------------------------
+    const bool begin = pre && own && r.phase == PH_START;
+    T K0 = 0;
+    {
+        int mslot = 0;
+        bool have = false;
+        if (DENSE && begin) {
+            // queue the momentum of the transition AFTER the one that starts now (see begin_transition)
+            mslot = atomicAdd(v.mom_count + v.mom_parity, 1);
+            v.mom_list[(i64)v.mom_parity * v.C + mslot] = c;
+            const int tn = r.t + 1;
+            have = (v.rng.mode == 0) || (tn + (i64)v.rng.transition_offset < v.rng.n_injected);
+        }
+        const int fc = (copy_prop ? 1 : 0) | (store_draw ? 2 : 0) | (slow ? 4 : 0) | (wendv ? 8 : 0) | (begin ? 16 : 0) |
+                       (have ? 32 : 0);
+        unsigned act = Co::mask((fc & 31) != 0, slots, 7);
+        {
+#pragma unroll 1
+            while (act) {
+                const int i = __ffs(act) - 1;
+                act &= act - 1;
+                const int f = Co::get(fc, i, slots, 8);
+                const bool cp = f & 1, sd = f & 2, sl = f & 4, we = f & 8, bg = f & 16, hv = f & 32;
+                const int ci = c0 + i;
+                const i64 rb = (i64)ci * d;
+                const int ti = Co::get(r.t, i, slots, 9);
+                const int dsl = Co::get(draw_slot, i, slots, 10);
+                const int ni = Co::get(wc_n, i, slots, 11);
+                const int msl = Co::get(mslot, i, slots, 12);
+                T* __restrict__ DR = sd ? (T*)v.out.draws + ((i64)dsl * v.C + ci) * d : nullptr;
+                T* __restrict__ MEAN = (T*)v.adapt.wc_mean + rb;
+                T* __restrict__ M2 = (T*)v.adapt.wc_m2 + rb;
+                T* __restrict__ IMW = v.imm + (i64)ci * v.imm_sc;
+                T* __restrict__ ZROW = DENSE ? v.mom_z + ((i64)v.mom_parity * v.C + msl) * d : nullptr;
+                const T scale = (T)((double)ni / ((double)ni + 5.0));
+                const T shrink = (T)(1e-3 * (5.0 / ((double)ni + 5.0)));
+                T kacc = 0;
+                for (int j = j0; j < d; j += STEP) {
+                    T qv[VEC], gv[VEC], wv[VEC];
+                    if (cp) {
+                        T pv[VEC];
+                        ldv<T, VEC>(qv, v.qs + rb + j); ldv<T, VEC>(pv, v.ps + rb + j); ldv<T, VEC>(gv, v.gs + rb + j);
+                        if (DENSE) ldv<T, VEC>(wv, v.ws + rb + j);
+                        stv<T, VEC>(v.qp + rb + j, qv); stv<T, VEC>(v.pp + rb + j, pv); stv<T, VEC>(v.gp + rb + j, gv);
+                        if (DENSE) stv<T, VEC>(v.wp + rb + j, wv);
+                    } else {
+                        ldv<T, VEC>(qv, v.qp + rb + j);
+                        if (bg) {
+                            ldv<T, VEC>(gv, v.gp + rb + j);
+                            if (DENSE) ldv<T, VEC>(wv, v.wp + rb + j);
+                        }
+                    }
+                    if (sd) stv<T, VEC>(DR + j, qv);
+                    T im[VEC];
+                    bool have_im = false;
+                    if (sl || we) {
+                        T mean[VEC], m2[VEC];
+                        ldv<T, VEC>(mean, MEAN + j); ldv<T, VEC>(m2, M2 + j);
+#pragma unroll
+                        for (int x = 0; x < VEC; ++x) {
+                            if (sl) {
+                                const T delta = qv[x] - mean[x];
+                                const T mn = mean[x] + delta / (T)ni;
+                                const T ud = qv[x] - mn;
+                                mean[x] = mn;
+                                m2[x] = m2[x] + ud * delta;
+                            }
+                            if (we) {
+                                const T cov = m2[x] / (T)(ni - 1);
+                                im[x] = scale * cov + shrink;
+                                mean[x] = 0;
+                                m2[x] = 0;
+                            }
+                        }
+                        stv<T, VEC>(MEAN + j, mean); stv<T, VEC>(M2 + j, m2);
+                        if (we) { stv<T, VEC>(IMW + j, im); have_im = true; }
+                    }
+                    if (bg) {
+                        T p0[VEC], vel[VEC];
+                        if (DENSE) {
+                            ldv<T, VEC>(p0, v.mom_p + rb + j);
+                            ldv<T, VEC>(vel, v.mom_v + rb + j);
+                        } else {
+                            if (!have_im) ld_imm<T, VEC>(im, IMW, j, v.imm_sj);
+                            T z[VEC];
+                            draw_z_vec<T, VEC>(v.rng, ci, ti, j, d, z);
+#pragma unroll
+                            for (int x = 0; x < VEC; ++x) {
+                                p0[x] = sqrt((T)1 / im[x]) * z[x];       // metrics.py:46,50,67
+                                vel[x] = im[x] * p0[x];
+                            }
+                        }
+                        if (DENSE) {
+                            stv<T, VEC>(v.vl + rb + j, vel); stv<T, VEC>(v.vr + rb + j, vel);
+                            stv<T, VEC>(v.wl + rb + j, wv); stv<T, VEC>(v.wr + rb + j, wv);
+                        }
+                        stv<T, VEC>(v.ql + rb + j, qv); stv<T, VEC>(v.qr + rb + j, qv);
+                        stv<T, VEC>(v.pl + rb + j, p0); stv<T, VEC>(v.pr + rb + j, p0);
+                        stv<T, VEC>(v.gl + rb + j, gv); stv<T, VEC>(v.gr + rb + j, gv);
+                        stv<T, VEC>(v.pp + rb + j, p0);
+                        stv<T, VEC>(v.msum + rb + j, p0);
+#pragma unroll
+                        for (int x = 0; x < VEC; ++x) kacc += vel[x] * p0[x];
+                        if (DENSE) {
+                            T z[VEC];
+                            if (hv) draw_z_vec<T, VEC>(v.rng, ci, ti + 1, j, d, z);
+                            else {
+#pragma unroll
+                                for (int x = 0; x < VEC; ++x) z[x] = 0;
+                            }
+                            stv<T, VEC>(ZROW + j, z);
+                        }
+                    }
+                }
+                if (bg) {
+                    double r1[1] = {(double)kacc};
+                    Co::template sum<1>(r1, red_s);
+                    if (Co::owner(i)) K0 = (T)0.5 * (T)r1[0];
+                }
+            }
+        }
+    }
+
+    // ---- S3: initial energy and the first sub-tree's direction (nuts.py:117-124, trajectory.py:516-518) -------------
+    if (begin) {
+        const T E0 = (T)r.U_prop + K0;
+        r.E0 = (double)E0;
+        r.U_left = r.U_prop; r.U_right = r.U_prop;
+        r.E_prop = (double)E0;
+        r.w_prop = 0.0;
+        r.slpa_prop = -INFINITY;
+        r.imin = 0; r.imax = 0;
+        r.k = 0;
+        r.nleap = 0;
+        r.phase = PH_RUN;
+        const double u = draw_u<8>(v.rng, DRAW_DIR, c, r.t, 0, v.maxd);
+        r.go_right = bern(u, 0.5) ? 1 : 0;
+        r.s = 0;
+    }
+
+    // ---- D: first half of the next leapfrog (integrators.py:59-62): p_half = p - (0.5 e) g, q' = q + e imm p_half.
+    //         A chain that continues its sub-tree has its front in (P = p_half, xa = q', xb = g'[, V, xc]): p' is
+    //         recomputed, and its sub-tree proposal (if taken) is stored from the same registers; the others take
+    //         the front from the edge arrays of their (new) direction. -----------------------------------------------
+    if (pre) {
+        const bool go = own && r.phase == PH_RUN;
+        const bool cont = run && !end_sub;
+        const T en = go ? (T)(r.go_right ? r.eps : -r.eps) : (T)0;
+        const T hen = (T)0.5 * en;
+        const int fd = go ? (1 | (cont ? 2 : 0) | ((cont && take) ? 4 : 0) | (r.go_right ? 8 : 0)) : 0;
+        auto prefetch = [&](unsigned nx) {
+            if (nx >= 32u) return;
+            const int f = __shfl_sync(kFull, fd, nx);
+            const bool ct = f & 2, gr = f & 8;
+            const i64 rb = (i64)(c0 + (int)nx) * d;
+            pf_row((gr ? v.pr : v.pl) + rb, j0, d, STEP);
+            if (DENSE) pf_row((gr ? v.vr : v.vl) + rb, j0, d, STEP);
+            if (ct) {
+                pf_row(v.xb + rb, j0, d, STEP); pf_row(v.xa + rb, j0, d, STEP);
+                if (DENSE) pf_row(v.xc + rb, j0, d, STEP);
+            } else {
+                pf_row((gr ? v.qr : v.ql) + rb, j0, d, STEP); pf_row((gr ? v.gr : v.gl) + rb, j0, d, STEP);
+                if (DENSE) pf_row((gr ? v.wr : v.wl) + rb, j0, d, STEP);
+            }
+        };
+        unsigned act = Co::mask((fd & 1) != 0, slots, 13);
+        if constexpr (TC > 1) {
+#pragma unroll
+            for (int kk = 2; kk <= B2H_TILE_PD; ++kk) prefetch(__fns(act, 0, kk));
+        }
+#pragma unroll 1
+        while (act) {
+            const int i = __ffs(act) - 1;
+            act &= act - 1;
+            if constexpr (TC > 1) prefetch(__fns(act, 0, B2H_TILE_PD));
+            const int f = Co::get(fd, i, slots, 14);
+            const T ei = Co::get(en, i, slots, 15);
+            const T hei = Co::get(hen, i, slots, 16);
+            const bool ct = f & 2, tk = f & 4, gr = f & 8;
+            const int ci = c0 + i;
+            const i64 rb = (i64)ci * d;
+            T* __restrict__ P = (gr ? v.pr : v.pl) + rb;
+            T* __restrict__ V = DENSE ? (gr ? v.vr : v.vl) + rb : nullptr;
+            const T* __restrict__ Q = (gr ? v.qr : v.ql) + rb;
+            const T* __restrict__ Gd = (gr ? v.gr : v.gl) + rb;
+            const T* __restrict__ W = DENSE ? (gr ? v.wr : v.wl) + rb : nullptr;
+            T* __restrict__ XA = v.xa + rb;
+            const T* __restrict__ XB = v.xb + rb;
+            const T* __restrict__ XC = DENSE ? v.xc + rb : nullptr;
+            const T* __restrict__ IM = DENSE ? nullptr : v.imm + (i64)ci * v.imm_sc;
+            for (int j = j0; j < d; j += STEP) {
+                T q[VEC], p[VEC], g[VEC], vel[VEC], w[VEC], im[VEC];
+                if (ct) {
+                    T pv[VEC], vv[VEC];
+                    ldv<T, VEC>(pv, P + j);
+                    ldv<T, VEC>(g, XB + j);
+                    ldv<T, VEC>(q, XA + j);
+                    if (DENSE) { ldv<T, VEC>(vv, V + j); ldv<T, VEC>(w, XC + j); }
+#pragma unroll
+                    for (int x = 0; x < VEC; ++x) {
+                        p[x] = pv[x] - hei * g[x];                   // the kick pass A applied (same e: same sub-tree)
+                        if (DENSE) vel[x] = vv[x] - hei * w[x];
+                    }
+                    if (tk) {
+                        stv<T, VEC>(v.qs + rb + j, q); stv<T, VEC>(v.ps + rb + j, p); stv<T, VEC>(v.gs + rb + j, g);
+                        if (DENSE) stv<T, VEC>(v.ws + rb + j, w);
+                    }
+                } else {
+                    ldv<T, VEC>(q, Q + j); ldv<T, VEC>(p, P + j); ldv<T, VEC>(g, Gd + j);
+                    if (DENSE) { ldv<T, VEC>(vel, V + j); ldv<T, VEC>(w, W + j); }
+                }
+                if (!DENSE) ld_imm<T, VEC>(im, IM, j, v.imm_sj);
+                T ph[VEC], vh[VEC], qn[VEC];
+#pragma unroll
+                for (int x = 0; x < VEC; ++x) {
+                    ph[x] = p[x] - hei * g[x];
+                    if (DENSE) vh[x] = vel[x] - hei * w[x];          // imm.(p - h g) by linearity
+                    else vh[x] = im[x] * ph[x];
+                    qn[x] = q[x] + ei * vh[x];
+                }
+                stv<T, VEC>(P + j, ph);
+                if (DENSE) stv<T, VEC>(V + j, vh);
+                stv<T, VEC>(XA + j, qn);
+            }
+        }
+    }
+
+    // ---- epilogue -------------------------------------------------------------------------------------------------
+    if (own && ph0 != PH_DONE) *static_cast<ChainRecLive*>(v.rec + c) = r;
+    if constexpr (WPC == 1) {
+        const unsigned ran = __ballot_sync(kFull, run);
+        const unsigned alive = __ballot_sync(kFull, run && r.phase != PH_DONE);
+        if (lane == 0) {
+            if (not_done && alive) atomicAdd(not_done, __popc(alive));
+            if (v.counters && ran) atomicAdd((unsigned long long*)&v.counters[3], (unsigned long long)__popc(ran));
+        }
+    } else if (own && run) {
+        if (not_done && r.phase != PH_DONE) atomicAdd(not_done, 1);
+        if (v.counters) atomicAdd((unsigned long long*)&v.counters[3], 1ull);
+    }
+}
+
+}  // namespace tile
+
+// chains per warp: enough warps to fill the machine first (16 per SM), then as many chains per warp as possible so
+// that the scalar passes run with all lanes busy
+static inline int tile_chains_per_warp(int C, int sm_count) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("B2H_TILE_TC"); forced = e ? atoi(e) : 0; }
+    if (forced == 1 || forced == 8 || forced == 32) return forced;
+    const i64 want = (i64)sm_count * 16;
+    if ((i64)C >= 32 * want) return 32;
+    if ((i64)C >= 8 * want) return 8;
+    return 1;
+}
+
+template <typename T, bool DENSE>
+static void launch_tile_tick(cudaStream_t st, const EngineView<T>& v, int* nd, bool pre, int sm_count) {
+    constexpr int NV = 16 / (int)sizeof(T);
+    const bool aligned = ((size_t)v.d * sizeof(T)) % 16 == 0 && ((uintptr_t)v.imm % 16 == 0 || DENSE) &&
+                         (uintptr_t)v.out.draws % 16 == 0;
+    const int tc = aligned ? tile_chains_per_warp(v.C, sm_count) : 1;
+    const int p = pre ? 1 : 0;
+    if (tc == 1 && aligned) {
+        // one chain per warp, or -- long rows -- per CTA of 4 / 8 warps (at most two 128-bit pieces per thread and row)
+        static int forced = -1;
+        if (forced < 0) { const char* e = getenv("B2H_TILE_WPC"); forced = e ? atoi(e) : 0; }
+        const int pieces = v.d / NV;
+        int wpc = pieces > 256 ? 8 : (pieces > 64 ? 4 : 1);
+        if (forced == 1 || forced == 4 || forced == 8) wpc = forced;
+        if (wpc == 8) { tile::tile_tick_kernel<T, 1, 8, NV, DENSE><<<v.C, 256, 0, st>>>(v, nd, p); return; }
+        if (wpc == 4) { tile::tile_tick_kernel<T, 1, 4, NV, DENSE><<<v.C, 128, 0, st>>>(v, nd, p); return; }
+    }
+    const i64 warps = ((i64)v.C + tc - 1) / tc;
+    const int grid = (int)((warps + 3) / 4);
+    if (!aligned) tile::tile_tick_kernel<T, 1, 1, 1, DENSE><<<grid, 128, 0, st>>>(v, nd, p);
+    else if (tc == 32) tile::tile_tick_kernel<T, 32, 1, NV, DENSE><<<grid, 128, 0, st>>>(v, nd, p);
+    else if (tc == 8) tile::tile_tick_kernel<T, 8, 1, NV, DENSE><<<grid, 128, 0, st>>>(v, nd, p);
+    else tile::tile_tick_kernel<T, 1, 1, NV, DENSE><<<grid, 128, 0, st>>>(v, nd, p);
+}
+
+}  // namespace b2h
