@@ -64,6 +64,7 @@ int b2h_ctx_destroy(b2h_ctx* ctx) {
         cudaStreamDestroy(ctx->side);
         cudaFreeHost(ctx->host_flag);
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_pre[i]); cudaEventDestroy(ctx->ev_side[i]); }
+        for (cudaEvent_t e : ctx->tick_events) cudaEventDestroy(e);
     }
     delete ctx;
     return 0;
@@ -72,6 +73,36 @@ int b2h_ctx_destroy(b2h_ctx* ctx) {
 int b2h_ctx_sync(b2h_ctx* ctx) {
     if (!ctx) { set_error("null context"); return B2H_ERR_ARG; }
     B2H_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// fold the recorded event pairs into the totals (synchronises the stream)
+static int tick_timer_collect(b2h_ctx* ctx) {
+    B2H_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i + 1 < ctx->tick_events_used; i += 2) {
+        float ms = 0.f;
+        B2H_CUDA(cudaEventElapsedTime(&ms, ctx->tick_events[i], ctx->tick_events[i + 1]));
+        ctx->tick_ms += ms;
+        ctx->tick_launches += 1;
+    }
+    ctx->tick_events_used = 0;
+    return 0;
+}
+
+int b2h_tick_timer(b2h_ctx* ctx, int32_t enable) {
+    if (!ctx) { set_error("null context"); return B2H_ERR_ARG; }
+    if (int rc = tick_timer_collect(ctx)) return rc;
+    ctx->tick_timer = enable != 0;
+    ctx->tick_ms = 0.0;
+    ctx->tick_launches = 0;
+    return 0;
+}
+
+int b2h_tick_timer_read(b2h_ctx* ctx, double* total_ms, int64_t* launches) {
+    if (!ctx || !total_ms || !launches) { set_error("null argument"); return B2H_ERR_ARG; }
+    if (int rc = tick_timer_collect(ctx)) return rc;
+    *total_ms = ctx->tick_ms;
+    *launches = ctx->tick_launches;
     return 0;
 }
 

@@ -208,26 +208,44 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
         return 0;
     };
 #define B2H_POSTPRE(D_, E_, P_) split_postpre_kernel<T, G, D_, HMC, E_, P_><<<grid, thr, 0, st>>>(v, nd)
+    // b2h_tick_timer: an event before and after the tick kernel on the engine's stream
+    auto tick_mark = [&]() {
+        if (!ctx->tick_timer) return;
+        if (ctx->tick_events_used == ctx->tick_events.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return;
+            ctx->tick_events.push_back(e);
+        }
+        cudaEventRecord(ctx->tick_events[ctx->tick_events_used++], st);
+    };
     auto launch_postpre = [&](i64 t, int* nd) -> int {                       // post of tick t - 1, pre of tick t
         if (tile_tick) {
             if (pl.dense) {
                 if (int e = pre_prologue(t)) return e;
+                tick_mark();
                 launch_tile_tick<T, true>(st, v, nd, true, ctx->sm_count);
+                tick_mark();
                 return pre_epilogue(t);
             }
+            tick_mark();
             launch_tile_tick<T, false>(st, v, nd, true, ctx->sm_count);
+            tick_mark();
             return 0;
         }
         if (pl.dense) {
             if (int e = pre_prologue(t)) return e;
+            tick_mark();
             if (epl <= 1) B2H_POSTPRE(true, 1, true);
             else if (epl <= 2) B2H_POSTPRE(true, 2, true);
             else B2H_POSTPRE(true, 4, true);
+            tick_mark();
             return pre_epilogue(t);
         }
+        tick_mark();
         if (epl <= 1) B2H_POSTPRE(false, 1, true);
         else if (epl <= 2) B2H_POSTPRE(false, 2, true);
         else B2H_POSTPRE(false, 4, true);
+        tick_mark();
         return 0;
     };
     auto launch_post_last = [&](int* nd) {                                   // post of the call's last tick

@@ -89,12 +89,23 @@ B2H_DEVINL void draw_z_vec(const RngView& rg, int c, int t, int j, int d, T (&z)
 }
 
 
-// L2 prefetch of the part of a row this thread will load (rows of a chain a few iterations ahead: the passes are
-// bound by the latency of their row loads, not by bandwidth)
-template <typename T>
-B2H_DEVINL void pf_row(const T* row, int j0, int d, int step) {
-    for (int j = j0; j < d; j += step) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + j));
+// Asynchronous 16-byte copy global -> shared (LDGSTS) and its group bookkeeping.  Tiles of several chains (short
+// rows: one 16-byte piece per lane and row) are bound by the latency of their row loads, not by bandwidth: every lane
+// copies ITS pieces of the rows of the next kRing - 1 chains into its own slots of a shared-memory ring while the
+// current chain is processed, and later reads back exactly the bytes it copied (no cross-lane synchronisation).
+B2H_DEVINL void cp16(unsigned sdst /* shared-space address */, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(gsrc) : "memory");
 }
+B2H_DEVINL void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+B2H_DEVINL void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+#ifndef B2H_TILE_RING
+#define B2H_TILE_RING 4
+#endif
+constexpr int kRing = B2H_TILE_RING;                         // stages of the ring (chains in flight per warp: kRing - 1)
+constexpr int kRowBytes = 512;                   // one row of a stage: 32 lanes x 16 bytes
+template <bool DENSE> struct RingRows { static constexpr int value = DENSE ? 9 : 6; };
 
 // Who works on a chain.  WPC == 1: a warp owns a tile of TC chains, chain slot i is owned by lane i, values travel
 // by shuffle.  WPC > 1 (TC == 1, long rows): the CTA's WPC warps share ONE chain, thread 0 owns it, values travel
@@ -150,9 +161,6 @@ struct Coop {
 #ifndef B2H_TILE_MINB
 #define B2H_TILE_MINB 4
 #endif
-#ifndef B2H_TILE_PD
-#define B2H_TILE_PD 3
-#endif
 
 template <typename T, int TC, int WPC, int VEC, bool DENSE>
 __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? 16 / WPC : B2H_TILE_MINB)) tile_tick_kernel(EngineView<T> v, int* not_done, int pre) {
@@ -173,6 +181,20 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? 16 / WPC
     const bool run = ph0 == PH_RUN;
     constexpr int STEP = 32 * WPC * VEC;
     const int j0 = lane * VEC;
+    // tiles of several chains: this warp's ring of row stages (dynamic shared memory; see cp16)
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    constexpr int NROW = RingRows<DENSE>::value;
+    [[maybe_unused]] unsigned char* const ring = dyn_smem + (size_t)(threadIdx.x >> 5) * (kRing * NROW * kRowBytes);
+    // this lane's 16-byte slot of (stage 0, row 0), as a shared-space address for the asynchronous copies
+    [[maybe_unused]] const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + (threadIdx.x & 31) * 16;
+    // an inverse mass matrix shared by all chains (scalar or one diagonal): this lane's piece is loaded once
+    [[maybe_unused]] const bool imm_shared = !DENSE && v.imm_sc == 0;
+    [[maybe_unused]] T im_sh[VEC];
+    if constexpr (TC > 1 && !DENSE) {
+#pragma unroll
+        for (int x = 0; x < VEC; ++x) im_sh[x] = 0;
+        if (imm_shared && j0 < d) ld_imm<T, VEC>(im_sh, v.imm, j0, v.imm_sj);
+    }
 
     // ---- S0: what the step needs before its rows arrive -------------------------------------------------------------
     int s = 0, k = 0, imax = 0, nlev = 0;
@@ -198,33 +220,49 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? 16 / WPC
     bool term = false;
     {
         const int fa = run ? (1 | (r.go_right ? 2 : 0) | (s == 0 ? 4 : 0) | ((s & 1) == 0 ? 8 : 0) | (imax << 8) | (nlev << 16)) : 0;
-        // rows of the chain B2H_TILE_PD iterations ahead into L2 (tiles of several chains: rows are short)
-        auto prefetch = [&](unsigned nx) {
-            if (nx >= 32u) return;
-            const int f = __shfl_sync(kFull, fa, nx);
-            const bool gr = f & 2, s0 = f & 4;
-            const int imx = (f >> 8) & 0xff, nl = (f >> 16) & 0xff;
-            const i64 rb = (i64)(c0 + (int)nx) * d;
-            pf_row((gr ? v.pr : v.pl) + rb, j0, d, STEP);
-            pf_row(v.xb + rb, j0, d, STEP);
-            if (DENSE) { pf_row((gr ? v.vr : v.vl) + rb, j0, d, STEP); pf_row(v.xc + rb, j0, d, STEP); }
-            if (!s0) pf_row(v.sms + rb, j0, d, STEP);
-            if (nl > 0) {
-                const i64 cb = (i64)(c0 + (int)nx) * v.sck + (i64)imx * d;
-                pf_row(v.mck + cb, j0, d, STEP); pf_row(v.sckp + cb, j0, d, STEP);
-                if (DENSE) pf_row(v.vck + cb, j0, d, STEP);
-            }
-        };
+        // tiles of several chains: ring slot of (stage st, row r) for this lane; rows 0 P, 1 xb, 2 sms, 3 mck, 4 sckp,
+        // 5 imm, 6 V, 7 xc, 8 vck
+        [[maybe_unused]] auto slot = [&](int st, int row) -> unsigned { return ring_s + (unsigned)((st * NROW + row) * kRowBytes); };
         unsigned act = Co::mask((fa & 1) != 0, slots, 1);
+        [[maybe_unused]] unsigned iss = act;
+        [[maybe_unused]] auto issue = [&](int st) {
+            if (iss) {
+                const int i = __ffs(iss) - 1;
+                iss &= iss - 1;
+                const int f = __shfl_sync(kFull, fa, i);
+                if (j0 < d) {
+                    const bool gr = f & 2, s0 = f & 4;
+                    const int imx = (f >> 8) & 0xff, nl = (f >> 16) & 0xff;
+                    const int ci = c0 + i;
+                    const i64 rb = (i64)ci * d + j0;
+                    cp16(slot(st, 0), (gr ? v.pr : v.pl) + rb);
+                    cp16(slot(st, 1), v.xb + rb);
+                    if (!s0) cp16(slot(st, 2), v.sms + rb);
+                    if (nl > 0) {
+                        const i64 cb = (i64)ci * v.sck + (i64)imx * d + j0;
+                        cp16(slot(st, 3), v.mck + cb);
+                        cp16(slot(st, 4), v.sckp + cb);
+                        if (DENSE) cp16(slot(st, 8), v.vck + cb);
+                    }
+                    if (DENSE) { cp16(slot(st, 6), (gr ? v.vr : v.vl) + rb); cp16(slot(st, 7), v.xc + rb); }
+                    else if (!imm_shared) cp16(slot(st, 5), v.imm + (i64)ci * v.imm_sc + j0);
+                }
+            }
+            cp_commit();
+        };
+        [[maybe_unused]] int stg = 0;
         if constexpr (TC > 1) {
 #pragma unroll
-            for (int kk = 2; kk <= B2H_TILE_PD; ++kk) prefetch(__fns(act, 0, kk));
+            for (int st = 0; st < kRing - 1; ++st) issue(st);
         }
 #pragma unroll 1
         while (act) {
+            if constexpr (TC > 1) {
+                issue(stg == 0 ? kRing - 1 : stg - 1);      // the stage the previous iteration consumed
+                cp_wait<kRing - 1>();                       // this iteration's rows have landed
+            }
             const int i = __ffs(act) - 1;
             act &= act - 1;
-            if constexpr (TC > 1) prefetch(__fns(act, 0, B2H_TILE_PD));
             const int f = Co::get(fa, i, slots, 2);
             const T hei = Co::get(he, i, slots, 3);
             const bool gr = f & 2, s0 = f & 4, even = f & 8;
@@ -242,16 +280,45 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? 16 / WPC
             T* __restrict__ SCK = v.sckp + cb;
             T* __restrict__ VCK = DENSE ? v.vck + cb : nullptr;
             T kacc = 0, dl = 0, dr = 0;
+            // where the rows are read from: global memory, or (tiles of several chains) this stage of the ring, whose
+            // row r starts at slot(stg, r) - 16 lane, so that "+ j" with j = j0 lands on this lane's piece
+            const T* Pl = P;
+            const T* XBl = XB;
+            const T* Vl = V;
+            const T* XCl = XC;
+            const T* IMl = IM;
+            const T* SMSl = SMS;
+            const T* MCKl = MCK;
+            const T* SCKl = SCK;
+            const T* VCKl = VCK;
+            if constexpr (TC > 1) {
+                const unsigned char* sb = ring + (size_t)(stg * NROW) * kRowBytes;
+                Pl = reinterpret_cast<const T*>(sb);
+                XBl = reinterpret_cast<const T*>(sb + 1 * kRowBytes);
+                SMSl = reinterpret_cast<const T*>(sb + 2 * kRowBytes);
+                MCKl = reinterpret_cast<const T*>(sb + 3 * kRowBytes);
+                SCKl = reinterpret_cast<const T*>(sb + 4 * kRowBytes);
+                if (!DENSE && !imm_shared) IMl = reinterpret_cast<const T*>(sb + 5 * kRowBytes);
+                if (DENSE) {
+                    Vl = reinterpret_cast<const T*>(sb + 6 * kRowBytes);
+                    XCl = reinterpret_cast<const T*>(sb + 7 * kRowBytes);
+                    VCKl = reinterpret_cast<const T*>(sb + 8 * kRowBytes);
+                }
+                stg = stg + 1 == kRing ? 0 : stg + 1;
+            }
             for (int j = j0; j < d; j += STEP) {
                 T pv[VEC], gx[VEC], so[VEC], cm[VEC], cs[VEC], cv[VEC], im[VEC], vv[VEC], wx[VEC];
-                ldv<T, VEC>(pv, P + j);
-                ldv<T, VEC>(gx, XB + j);
-                if (DENSE) { ldv<T, VEC>(vv, V + j); ldv<T, VEC>(wx, XC + j); }
-                else ld_imm<T, VEC>(im, IM, j, v.imm_sj);
-                if (!s0) ldv<T, VEC>(so, SMS + j);
+                ldv<T, VEC>(pv, Pl + j);
+                ldv<T, VEC>(gx, XBl + j);
+                if (DENSE) { ldv<T, VEC>(vv, Vl + j); ldv<T, VEC>(wx, XCl + j); }
+                else if (TC > 1 && imm_shared) {
+#pragma unroll
+                    for (int x = 0; x < VEC; ++x) im[x] = im_sh[x];
+                } else ld_imm<T, VEC>(im, IMl, j, v.imm_sj);
+                if (!s0) ldv<T, VEC>(so, SMSl + j);
                 if (nl > 0) {
-                    ldv<T, VEC>(cm, MCK + j); ldv<T, VEC>(cs, SCK + j);
-                    if (DENSE) ldv<T, VEC>(cv, VCK + j);
+                    ldv<T, VEC>(cm, MCKl + j); ldv<T, VEC>(cs, SCKl + j);
+                    if (DENSE) ldv<T, VEC>(cv, VCKl + j);
                 }
                 T p[VEC], vel[VEC], sm[VEC];
 #pragma unroll
@@ -360,32 +427,12 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? 16 / WPC
     {
         const bool flush = run && (end_sub || !pre);
         const int fb = flush ? (1 | (take ? 2 : 0) | (expand ? 4 : 0) | (r.go_right ? 8 : 0)) : 0;
-        auto prefetch = [&](unsigned nx) {
-            if (nx >= 32u) return;
-            const int f = __shfl_sync(kFull, fb, nx);
-            const bool ex = f & 4, gr = f & 8;
-            const i64 rb = (i64)(c0 + (int)nx) * d;
-            pf_row((gr ? v.pr : v.pl) + rb, j0, d, STEP);
-            pf_row(v.xb + rb, j0, d, STEP);
-            pf_row(v.xa + rb, j0, d, STEP);
-            if (DENSE) { pf_row((gr ? v.vr : v.vl) + rb, j0, d, STEP); pf_row(v.xc + rb, j0, d, STEP); }
-            if (ex) {
-                pf_row(v.msum + rb, j0, d, STEP); pf_row(v.sms + rb, j0, d, STEP);
-                pf_row((gr ? v.pl : v.pr) + rb, j0, d, STEP);
-                if (DENSE) pf_row((gr ? v.vl : v.vr) + rb, j0, d, STEP);
-            }
-        };
         unsigned act = Co::mask((fb & 1) != 0, slots, 4);
         {
-            if constexpr (TC > 1) {
-#pragma unroll
-                for (int kk = 2; kk <= B2H_TILE_PD; ++kk) prefetch(__fns(act, 0, kk));
-            }
 #pragma unroll 1
             while (act) {
                 const int i = __ffs(act) - 1;
                 act &= act - 1;
-                if constexpr (TC > 1) prefetch(__fns(act, 0, B2H_TILE_PD));
                 const int f = Co::get(fb, i, slots, 5);
                 const T hei = Co::get(he, i, slots, 6);
                 const bool tk = f & 2, ex = f & 4, gr = f & 8;
@@ -682,31 +729,45 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? 16 / WPC
         const T en = go ? (T)(r.go_right ? r.eps : -r.eps) : (T)0;
         const T hen = (T)0.5 * en;
         const int fd = go ? (1 | (cont ? 2 : 0) | ((cont && take) ? 4 : 0) | (r.go_right ? 8 : 0)) : 0;
-        auto prefetch = [&](unsigned nx) {
-            if (nx >= 32u) return;
-            const int f = __shfl_sync(kFull, fd, nx);
-            const bool ct = f & 2, gr = f & 8;
-            const i64 rb = (i64)(c0 + (int)nx) * d;
-            pf_row((gr ? v.pr : v.pl) + rb, j0, d, STEP);
-            if (DENSE) pf_row((gr ? v.vr : v.vl) + rb, j0, d, STEP);
-            if (ct) {
-                pf_row(v.xb + rb, j0, d, STEP); pf_row(v.xa + rb, j0, d, STEP);
-                if (DENSE) pf_row(v.xc + rb, j0, d, STEP);
-            } else {
-                pf_row((gr ? v.qr : v.ql) + rb, j0, d, STEP); pf_row((gr ? v.gr : v.gl) + rb, j0, d, STEP);
-                if (DENSE) pf_row((gr ? v.wr : v.wl) + rb, j0, d, STEP);
-            }
-        };
+        // ring rows: 0 P, 1 g source (xb / edge g), 2 q source (xa / edge q), 5 imm, 6 V, 7 w source (xc / edge w)
+        [[maybe_unused]] auto slot = [&](int st, int row) -> unsigned { return ring_s + (unsigned)((st * NROW + row) * kRowBytes); };
         unsigned act = Co::mask((fd & 1) != 0, slots, 13);
+        [[maybe_unused]] unsigned iss = act;
+        [[maybe_unused]] auto issue = [&](int st) {
+            if (iss) {
+                const int i = __ffs(iss) - 1;
+                iss &= iss - 1;
+                const int f = __shfl_sync(kFull, fd, i);
+                if (j0 < d) {
+                    const bool ct = f & 2, gr = f & 8;
+                    const int ci = c0 + i;
+                    const i64 rb = (i64)ci * d + j0;
+                    cp16(slot(st, 0), (gr ? v.pr : v.pl) + rb);
+                    cp16(slot(st, 1), (ct ? v.xb : (gr ? v.gr : v.gl)) + rb);
+                    cp16(slot(st, 2), (ct ? v.xa : (gr ? v.qr : v.ql)) + rb);
+                    if (DENSE) {
+                        cp16(slot(st, 6), (gr ? v.vr : v.vl) + rb);
+                        cp16(slot(st, 7), (ct ? v.xc : (gr ? v.wr : v.wl)) + rb);
+                    } else if (!imm_shared) {
+                        cp16(slot(st, 5), v.imm + (i64)ci * v.imm_sc + j0);
+                    }
+                }
+            }
+            cp_commit();
+        };
+        [[maybe_unused]] int stg = 0;
         if constexpr (TC > 1) {
 #pragma unroll
-            for (int kk = 2; kk <= B2H_TILE_PD; ++kk) prefetch(__fns(act, 0, kk));
+            for (int st = 0; st < kRing - 1; ++st) issue(st);
         }
 #pragma unroll 1
         while (act) {
+            if constexpr (TC > 1) {
+                issue(stg == 0 ? kRing - 1 : stg - 1);
+                cp_wait<kRing - 1>();
+            }
             const int i = __ffs(act) - 1;
             act &= act - 1;
-            if constexpr (TC > 1) prefetch(__fns(act, 0, B2H_TILE_PD));
             const int f = Co::get(fd, i, slots, 14);
             const T ei = Co::get(en, i, slots, 15);
             const T hei = Co::get(hen, i, slots, 16);
@@ -722,28 +783,47 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? 16 / WPC
             const T* __restrict__ XB = v.xb + rb;
             const T* __restrict__ XC = DENSE ? v.xc + rb : nullptr;
             const T* __restrict__ IM = DENSE ? nullptr : v.imm + (i64)ci * v.imm_sc;
+            // where the front is read from: continuing chains (q, g[, w]) = (xa, xb[, xc]), the others the edge arrays;
+            // tiles of several chains: this stage of the ring
+            const T* Pl = P;
+            const T* Gl = ct ? XB : Gd;
+            const T* Ql = ct ? (const T*)XA : Q;
+            const T* Vl = V;
+            const T* Wl = ct ? XC : W;
+            const T* IMl = IM;
+            if constexpr (TC > 1) {
+                const unsigned char* sb = ring + (size_t)(stg * NROW) * kRowBytes;
+                Pl = reinterpret_cast<const T*>(sb);
+                Gl = reinterpret_cast<const T*>(sb + 1 * kRowBytes);
+                Ql = reinterpret_cast<const T*>(sb + 2 * kRowBytes);
+                if (!DENSE && !imm_shared) IMl = reinterpret_cast<const T*>(sb + 5 * kRowBytes);
+                if (DENSE) {
+                    Vl = reinterpret_cast<const T*>(sb + 6 * kRowBytes);
+                    Wl = reinterpret_cast<const T*>(sb + 7 * kRowBytes);
+                }
+                stg = stg + 1 == kRing ? 0 : stg + 1;
+            }
             for (int j = j0; j < d; j += STEP) {
                 T q[VEC], p[VEC], g[VEC], vel[VEC], w[VEC], im[VEC];
+                ldv<T, VEC>(p, Pl + j);
+                ldv<T, VEC>(g, Gl + j);
+                ldv<T, VEC>(q, Ql + j);
+                if (DENSE) { ldv<T, VEC>(vel, Vl + j); ldv<T, VEC>(w, Wl + j); }
+                else if (TC > 1 && imm_shared) {
+#pragma unroll
+                    for (int x = 0; x < VEC; ++x) im[x] = im_sh[x];
+                } else ld_imm<T, VEC>(im, IMl, j, v.imm_sj);
                 if (ct) {
-                    T pv[VEC], vv[VEC];
-                    ldv<T, VEC>(pv, P + j);
-                    ldv<T, VEC>(g, XB + j);
-                    ldv<T, VEC>(q, XA + j);
-                    if (DENSE) { ldv<T, VEC>(vv, V + j); ldv<T, VEC>(w, XC + j); }
 #pragma unroll
                     for (int x = 0; x < VEC; ++x) {
-                        p[x] = pv[x] - hei * g[x];                   // the kick pass A applied (same e: same sub-tree)
-                        if (DENSE) vel[x] = vv[x] - hei * w[x];
+                        p[x] = p[x] - hei * g[x];                    // the kick pass A applied (same e: same sub-tree)
+                        if (DENSE) vel[x] = vel[x] - hei * w[x];
                     }
                     if (tk) {
                         stv<T, VEC>(v.qs + rb + j, q); stv<T, VEC>(v.ps + rb + j, p); stv<T, VEC>(v.gs + rb + j, g);
                         if (DENSE) stv<T, VEC>(v.ws + rb + j, w);
                     }
-                } else {
-                    ldv<T, VEC>(q, Q + j); ldv<T, VEC>(p, P + j); ldv<T, VEC>(g, Gd + j);
-                    if (DENSE) { ldv<T, VEC>(vel, V + j); ldv<T, VEC>(w, W + j); }
                 }
-                if (!DENSE) ld_imm<T, VEC>(im, IM, j, v.imm_sj);
                 T ph[VEC], vh[VEC], qn[VEC];
 #pragma unroll
                 for (int x = 0; x < VEC; ++x) {
@@ -788,19 +868,33 @@ static inline int tile_chains_per_warp(int C, int sm_count) {
     return 1;
 }
 
+template <typename T, int TC, int VEC, bool DENSE>
+static void launch_tile_ring(cudaStream_t st, const EngineView<T>& v, int* nd, int p, int grid) {
+    // tiles of several chains: 4 warps x kRing stages x rows x 512 bytes of dynamic shared memory
+    constexpr int bytes = 4 * tile::kRing * tile::RingRows<DENSE>::value * tile::kRowBytes;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(tile::tile_tick_kernel<T, TC, 1, VEC, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        configured = true;
+    }
+    tile::tile_tick_kernel<T, TC, 1, VEC, DENSE><<<grid, 128, bytes, st>>>(v, nd, p);
+}
+
 template <typename T, bool DENSE>
 static void launch_tile_tick(cudaStream_t st, const EngineView<T>& v, int* nd, bool pre, int sm_count) {
     constexpr int NV = 16 / (int)sizeof(T);
     const bool aligned = ((size_t)v.d * sizeof(T)) % 16 == 0 && ((uintptr_t)v.imm % 16 == 0 || DENSE) &&
                          (uintptr_t)v.out.draws % 16 == 0;
-    const int tc = aligned ? tile_chains_per_warp(v.C, sm_count) : 1;
+    // several chains per warp: rows of one 16-byte piece per lane (they travel through the shared-memory ring)
+    const bool short_rows = (size_t)v.d * sizeof(T) <= (size_t)tile::kRowBytes;
+    const int tc = aligned && short_rows ? tile_chains_per_warp(v.C, sm_count) : 1;
     const int p = pre ? 1 : 0;
     if (tc == 1 && aligned) {
         // one chain per warp, or -- long rows -- per CTA of 4 / 8 warps (at most two 128-bit pieces per thread and row)
         static int forced = -1;
         if (forced < 0) { const char* e = getenv("B2H_TILE_WPC"); forced = e ? atoi(e) : 0; }
         const int pieces = v.d / NV;
-        int wpc = pieces > 256 ? 8 : (pieces > 64 ? 4 : 1);
+        int wpc = pieces > 64 ? 4 : 1;
         if (forced == 1 || forced == 4 || forced == 8) wpc = forced;
         if (wpc == 8) { tile::tile_tick_kernel<T, 1, 8, NV, DENSE><<<v.C, 256, 0, st>>>(v, nd, p); return; }
         if (wpc == 4) { tile::tile_tick_kernel<T, 1, 4, NV, DENSE><<<v.C, 128, 0, st>>>(v, nd, p); return; }
@@ -808,8 +902,8 @@ static void launch_tile_tick(cudaStream_t st, const EngineView<T>& v, int* nd, b
     const i64 warps = ((i64)v.C + tc - 1) / tc;
     const int grid = (int)((warps + 3) / 4);
     if (!aligned) tile::tile_tick_kernel<T, 1, 1, 1, DENSE><<<grid, 128, 0, st>>>(v, nd, p);
-    else if (tc == 32) tile::tile_tick_kernel<T, 32, 1, NV, DENSE><<<grid, 128, 0, st>>>(v, nd, p);
-    else if (tc == 8) tile::tile_tick_kernel<T, 8, 1, NV, DENSE><<<grid, 128, 0, st>>>(v, nd, p);
+    else if (tc == 32) launch_tile_ring<T, 32, NV, DENSE>(st, v, nd, p, grid);
+    else if (tc == 8) launch_tile_ring<T, 8, NV, DENSE>(st, v, nd, p, grid);
     else tile::tile_tick_kernel<T, 1, 1, NV, DENSE><<<grid, 128, 0, st>>>(v, nd, p);
 }
 

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 #include "../../include/b200hmc.h"
 
@@ -16,6 +17,12 @@ struct b2h_ctx {
     cudaStream_t side;
     cudaEvent_t ev_pre[2], ev_side[2];
     int* host_flag;   // pinned, for the split engine's completion poll
+    // b2h_tick_timer: event pairs around the tick-kernel launches of the split engine (measurement aid, off by default)
+    bool tick_timer = false;
+    std::vector<cudaEvent_t> tick_events;
+    size_t tick_events_used = 0;
+    double tick_ms = 0.0;
+    long long tick_launches = 0;
 };
 
 namespace b2h {

@@ -324,7 +324,7 @@ def measured_traffic(key):
         return None, None
 
 
-def dense_roofline(metric, Cn, d, ticks, step_ms, hbm_peak, dev, name):
+def dense_roofline(metric, Cn, d, ticks, step_ms, hbm_peak, dev, name, tick=None):
     """Dominant kernel of c2: the FP64 dense apply (DMMA tensor path), timed alone on the engine's stream."""
     import ctypes as C
     import torch
@@ -358,8 +358,6 @@ def dense_roofline(metric, Cn, d, ticks, step_ms, hbm_peak, dev, name):
     best = min(_event_ms(lambda: torch.matmul(a, mm), 1, dev) for _ in range(5))
     cublas_same_shape = flops / (best * 1e-3) / 1e12
     elementwise_ms = max(step_ms - ticks * 2.0 * gemm_ms, 1e-9)
-    b_nuts = 11.0 * d * 8.0       # algorithmic bytes of one NUTS inner step incl. U-turn bookkeeping
-    hbm_achieved = b_nuts * Cn * ticks / (elementwise_ms * 1e-3) / 1e9
     traffic, traffic_from = measured_traffic(f"dense_apply@{name}")
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
@@ -373,15 +371,11 @@ def dense_roofline(metric, Cn, d, ticks, step_ms, hbm_peak, dev, name):
         "peak_sustained": fp64_sustained, "frac_of_sustained": achieved / fp64_sustained,
         "launches_per_tick": 2, "share_of_step": ticks * 2.0 * gemm_ms / step_ms,
         "cublas_same_shape_tflops": cublas_same_shape}
-    elementwise = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
-                   "frac": hbm_achieved / hbm_peak, "traffic": measured_traffic(f"postpre@{name}")[0],
-                   "traffic_from": measured_traffic(f"postpre@{name}")[1],
-                   "how": "derived: 11*d*8 algorithmic bytes per chain-tick over (step time - 2 dense applies per "
-                          "tick); post+pre + potential kernels"}
+    elementwise = elementwise_roofline(tick, name, Cn, d, 8, ticks, elementwise_ms, hbm_peak)
     return roofline, elementwise
 
 
-def logistic_roofline(model, Cn, d, n, ticks, step_ms, peaks, dev, dtype, name):
+def logistic_roofline(model, Cn, d, n, ticks, step_ms, peaks, dev, dtype, name, tick=None):
     """Dominant kernel of c3 / c5: the fused tcgen05 gradient (S product, residual, X^T R product in one kernel),
     timed through b2h_potential_and_grad on the engine's stream (includes three small side kernels)."""
     import torch
@@ -410,12 +404,7 @@ def logistic_roofline(model, Cn, d, n, ticks, step_ms, peaks, dev, dtype, name):
         "launches_per_tick": 1, "share_of_step": ticks * ms / step_ms}
     esize = 4 if dtype == torch.float32 else 8
     rest_ms = max(step_ms - ticks * ms, 1e-9)
-    hbm_achieved = 11.0 * d * esize * Cn * ticks / (rest_ms * 1e-3) / 1e9
-    tr = measured_traffic(f"postpre@{name}")
-    elementwise = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
-                   "frac": hbm_achieved / hbm_peak, "traffic": tr[0], "traffic_from": tr[1],
-                   "how": f"derived: 11*d*{esize} algorithmic bytes per chain-tick over (step time - gradient time): "
-                          "the post+pre tick kernel"}
+    elementwise = elementwise_roofline(tick, name, Cn, d, esize, ticks, rest_ms, hbm_peak)
     return roofline, elementwise
 
 
@@ -531,6 +520,11 @@ def run_tick_workload(name, D, steps, warmup, min_timed_s=0.0, with_e2e=True):
            "mean_leapfrogs_per_transition": total_leapfrogs / max(total_transitions, 1.0),
            "mean_accept": acc_sum / (Cn * D.world), "esize": esize, "q_host": q_host, "chain_offset": chain_offset}
 
+    # ---- the tick kernel (integrator + U-turn + proposal bookkeeping of one leapfrog of every chain) timed on its own:
+    #      b2h_tick_timer brackets each of its launches with CUDA events on the engine's stream (outside the headline
+    #      region above: the events would serialise nothing, but they are not part of the product path)
+    out["tick_kernel"] = time_tick_kernel(step_resident, dev)
+
     # ---- end-to-end arm: host buffers in, host buffers out, through the public API ----------------------
     if with_e2e:
         q_out = torch.empty((Cn, d), dtype=dtype).pin_memory()
@@ -563,13 +557,57 @@ def run_tick_workload(name, D, steps, warmup, min_timed_s=0.0, with_e2e=True):
     return out
 
 
+def time_tick_kernel(step, dev, steps=2):
+    """Average duration of the split engine's tick kernel over `steps` engine calls (CUDA events around every launch)."""
+    import ctypes as C
+    from aehmc_b200 import _lib, backend
+    lib = _lib.load()
+    ctx = backend.context(dev)
+    _lib.check(lib.b2h_tick_timer(ctx, 1))
+    for _ in range(steps):
+        step()
+    ms, n = C.c_double(0.0), C.c_int64(0)
+    _lib.check(lib.b2h_tick_timer_read(ctx, C.byref(ms), C.byref(n)))
+    _lib.check(lib.b2h_tick_timer(ctx, 0))
+    if n.value == 0:
+        return None
+    return {"avg_launch_us": ms.value * 1e3 / n.value, "launches": int(n.value)}
+
+
+def elementwise_roofline(tick, name, Cn, d, esize, ticks, rest_ms, hbm_peak):
+    """HBM roofline of the tick kernel.  `achieved` = ALGORITHMIC bytes (11*d*s per chain-tick, NUTS
+    inner step with U-turn bookkeeping) over the kernel's measured launch time; `traffic` = the DRAM bytes one launch
+    really moves (ncu), with the bandwidth that corresponds to it."""
+    alg = 11.0 * d * esize * Cn
+    tr = measured_traffic(f"tile_tick@{name}")
+    if tick is not None:
+        sec = tick["avg_launch_us"] * 1e-6
+        how = (f"11*d*{esize} algorithmic bytes per chain-tick x {Cn} chains over the tick kernel's average launch time, "
+               f"CUDA events around each of {tick['launches']} launches (b2h_tick_timer)")
+    else:                                   # register-front kernels (B2H_TILE_TICK=0) or no split engine: by subtraction
+        sec = rest_ms * 1e-3 / ticks
+        how = f"derived: 11*d*{esize} algorithmic bytes per chain-tick over (step time - contraction time) / ticks"
+    achieved = alg / sec / 1e9
+    row = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+           "traffic": tr[0], "traffic_from": tr[1], "how": how,
+           "kernel": "tile_tick_kernel (engine_tile.inl): kick, kinetic energy, momentum sums, U-turn checkpoints and dot "
+                     "products, progressive / biased sampling, sub-tree and transition ends, half kick + drift of the "
+                     "next leapfrog -- one launch per tick",
+           "algorithmic_bytes_per_launch": alg, "avg_launch_us": sec * 1e6,
+           "everything_but_contractions_ms_per_tick": rest_ms / ticks}
+    if tr[0] is not None:
+        row["traffic_gbs"] = tr[0] / sec / 1e9
+        row["traffic_frac"] = tr[0] / sec / 1e9 / hbm_peak
+    return row
+
+
 def rooflines_for(w, D, peaks):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     if w["kind"] == "dense":
         return dense_roofline(w["metric"], w["chains_per_gpu"], w["dim"], w["ticks"], w["ms_per_step"], hbm_peak, D.dev,
-                              w["name"])
+                              w["name"], w.get("tick_kernel"))
     return logistic_roofline(w["model"], w["chains_per_gpu"], w["dim"], w["n_data"], w["ticks"], w["ms_per_step"], peaks,
-                             D.dev, w["dtype"], w["name"])
+                             D.dev, w["dtype"], w["name"], w.get("tick_kernel"))
 
 
 def ess_leg(w, D, args):

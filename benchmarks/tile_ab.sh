@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of the tile tick kernel (engine_tile.inl): value, ms per step of c5 / c2 / c3 for environment / library variants
+# A/B of the tile tick kernel (engine_tile.inl) for environment / library variants: bench value + ncu kernel durations
 out=${1:-gpurun_out/tile_ab.jsonl}
 : > $out
 run() {  # label, workload, env...
@@ -7,15 +7,6 @@ run() {  # label, workload, env...
   env "$@" python bench.py --workload $wl --no-ess --no-cpu --no-secondary --steps 6 --warmup 3 2>/dev/null | tail -1 | \
     python -c "import sys,json; d=json.loads(sys.stdin.read()); print(json.dumps({'label':'$label','wl':'$wl','value':d['value'],'ms_per_step':d['ms_per_step'],'grad_ms':d['roofline']['avg_launch_ms'],'elem_frac':d['roofline_elementwise']['frac'],'accept':d['config'].get('mean_accept'),'mhz':d['clocks']['sm_mhz']}))" | tee -a $out
 }
-run tile c5 B2H_TILE_TICK=1
-run tile_m6 c5 B2H_LIB=build/lib_m6/libb200hmc.so
-run tile_tc8 c5 B2H_TILE_TC=8
-run tile_m6_tc8 c5 B2H_TILE_TC=8 B2H_LIB=build/lib_m6/libb200hmc.so
-run tile_wpc8 c2 B2H_TILE_TICK=1
-run tile_wpc4 c2 B2H_TILE_WPC=4
-run tile_wpc1 c2 B2H_TILE_WPC=1
-run regfront c2 B2H_TILE_TICK=0
-run tile c3 B2H_TILE_TICK=1
 # kernel durations (ncu, serialised, cold cache): avg us of the tile kernel per variant
 nk() {  # label, workload, env...
   label=$1; shift; wl=$1; shift
@@ -26,10 +17,7 @@ rows=[r for r in csv.reader(sys.stdin) if len(r)>5 and r[0].isdigit()]
 v=[float(r[-1]) for r in rows]
 import json; print(json.dumps({'label':'$label','wl':'$wl','ncu_avg_us':(sum(v)/len(v)/1000 if v else None),'n':len(v),'kernel':rows[0][4][:60] if rows else None}))" | tee -a $out
 }
-nk tile c5 B2H_TILE_TICK=1
-nk tile_m6 c5 B2H_LIB=build/lib_m6/libb200hmc.so
-nk tile_tc8 c5 B2H_TILE_TC=8
-nk tile_m6_tc8 c5 B2H_TILE_TC=8 B2H_LIB=build/lib_m6/libb200hmc.so
-nk tile_wpc8 c2 B2H_TILE_TICK=1
-nk tile_wpc4 c2 B2H_TILE_WPC=4
-nk tile_wpc1 c2 B2H_TILE_WPC=1
+if [ "$2" = "tests" ]; then python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee -a $out; fi
+nk ring4 c5 B2H_TILE_TICK=1
+nk m6r3 c5 B2H_LIB=build/lib_m6r3/libb200hmc.so
+nk m5r3 c5 B2H_LIB=build/lib_m5r3/libb200hmc.so
