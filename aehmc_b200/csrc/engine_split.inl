@@ -148,10 +148,11 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
         }
     }
     bool side_pending[2] = {false, false};
-    static int use_side = -1, use_fuse = -1, use_tile = -1;
+    static int use_side = -1, use_fuse = -1;
     if (use_side < 0) { const char* e = getenv("B2H_SIDE_STREAM"); use_side = e ? atoi(e) : 1; }
     if (use_fuse < 0) { const char* e = getenv("B2H_FUSE_TICK"); use_fuse = e ? atoi(e) : 1; }
-    if (use_tile < 0) { const char* e = getenv("B2H_TILE_TICK"); use_tile = e ? atoi(e) : 1; }
+    int use_tile = 1;                                 // read at every call: the parity tests compare both tick kernels
+    { const char* e = getenv("B2H_TILE_TICK"); if (e) use_tile = atoi(e); }
     cudaStream_t rider_stream = use_side ? ctx->side : st;
     const int epl = (d + G - 1) / G;                 // front elements per lane
     // NUTS: the tile kernel (engine_tile.inl) is the tick for every row length; HMC (and B2H_TILE_TICK=0) keep the

@@ -158,12 +158,15 @@ struct Coop {
     }
 };
 
+#ifndef B2H_TILE_WPC_WARPS
+#define B2H_TILE_WPC_WARPS 16        // resident warps per SM the several-warps-per-chain kernels are compiled for
+#endif
 #ifndef B2H_TILE_MINB
 #define B2H_TILE_MINB 4
 #endif
 
 template <typename T, int TC, int WPC, int VEC, bool DENSE>
-__global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? 16 / WPC : B2H_TILE_MINB)) tile_tick_kernel(EngineView<T> v, int* not_done, int pre) {
+__global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? B2H_TILE_WPC_WARPS / WPC : B2H_TILE_MINB)) tile_tick_kernel(EngineView<T> v, int* not_done, int pre) {
     typedef Coop<TC, WPC> Co;
     __shared__ double slots[32];                         // WPC > 1: one slot per broadcast value
     __shared__ double red_s[3 * WPC];                    // WPC > 1: per-warp partials of a reduction
@@ -184,6 +187,13 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? 16 / WPC
     // tiles of several chains: this warp's ring of row stages (dynamic shared memory; see cp16)
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     constexpr int NROW = RingRows<DENSE>::value;
+    // one chain per warp / CTA: the ring can pipeline the PIECES of the long rows instead (B2H_TILE_RING1=1).  Measured at c2
+    // (d = 1000, dense, 4 warps per chain): 156 us with it, 154 us without -- its 72 KB of shared memory cost one of the four
+    // CTAs per SM -- so it is off.
+#ifndef B2H_TILE_RING1
+#define B2H_TILE_RING1 0
+#endif
+    constexpr bool RING1 = B2H_TILE_RING1 && TC == 1 && VEC > 1;
     [[maybe_unused]] unsigned char* const ring = dyn_smem + (size_t)(threadIdx.x >> 5) * (kRing * NROW * kRowBytes);
     // this lane's 16-byte slot of (stage 0, row 0), as a shared-space address for the asynchronous copies
     [[maybe_unused]] const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + (threadIdx.x & 31) * 16;
@@ -291,8 +301,9 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? 16 / WPC
             const T* MCKl = MCK;
             const T* SCKl = SCK;
             const T* VCKl = VCK;
-            if constexpr (TC > 1) {
-                const unsigned char* sb = ring + (size_t)(stg * NROW) * kRowBytes;
+            // this stage of the ring as the source of the loads
+            [[maybe_unused]] auto from_stage = [&](int st) {
+                const unsigned char* sb = ring + (size_t)(st * NROW) * kRowBytes;
                 Pl = reinterpret_cast<const T*>(sb);
                 XBl = reinterpret_cast<const T*>(sb + 1 * kRowBytes);
                 SMSl = reinterpret_cast<const T*>(sb + 2 * kRowBytes);
@@ -304,21 +315,53 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? 16 / WPC
                     XCl = reinterpret_cast<const T*>(sb + 7 * kRowBytes);
                     VCKl = reinterpret_cast<const T*>(sb + 8 * kRowBytes);
                 }
+            };
+            if constexpr (TC > 1) {
+                from_stage(stg);
                 stg = stg + 1 == kRing ? 0 : stg + 1;
             }
+            // one chain per warp / CTA (long rows): the ring pipelines the PIECES of the rows instead of the chains
+            [[maybe_unused]] auto issue_piece = [&](int jn, int st) {
+                if (jn < d) {
+                    cp16(slot(st, 0), P + jn);
+                    cp16(slot(st, 1), XB + jn);
+                    if (!s0) cp16(slot(st, 2), SMS + jn);
+                    if (nl > 0) {
+                        cp16(slot(st, 3), MCK + jn);
+                        cp16(slot(st, 4), SCK + jn);
+                        if (DENSE) cp16(slot(st, 8), VCK + jn);
+                    }
+                    if (DENSE) { cp16(slot(st, 6), V + jn); cp16(slot(st, 7), XC + jn); }
+                    else if (!imm_shared) cp16(slot(st, 5), IM + jn);
+                }
+                cp_commit();
+            };
+            [[maybe_unused]] int pq = 0;
+            if constexpr (RING1) {
+#pragma unroll
+                for (int st = 0; st < kRing - 1; ++st) issue_piece(j0 + st * STEP, st);
+            }
             for (int j = j0; j < d; j += STEP) {
+                if constexpr (RING1) {
+                    issue_piece(j + (kRing - 1) * STEP, (pq + kRing - 1) % kRing);
+                    cp_wait<kRing - 1>();
+                    from_stage(pq);
+                    pq = pq + 1 == kRing ? 0 : pq + 1;
+                }
+                // ring rows hold this lane's piece at the lane's own slot
+                const int jl = (TC > 1 || RING1) ? (int)(threadIdx.x & 31) * VEC : j;
                 T pv[VEC], gx[VEC], so[VEC], cm[VEC], cs[VEC], cv[VEC], im[VEC], vv[VEC], wx[VEC];
-                ldv<T, VEC>(pv, Pl + j);
-                ldv<T, VEC>(gx, XBl + j);
-                if (DENSE) { ldv<T, VEC>(vv, Vl + j); ldv<T, VEC>(wx, XCl + j); }
+                ldv<T, VEC>(pv, Pl + jl);
+                ldv<T, VEC>(gx, XBl + jl);
+                if (DENSE) { ldv<T, VEC>(vv, Vl + jl); ldv<T, VEC>(wx, XCl + jl); }
                 else if (TC > 1 && imm_shared) {
 #pragma unroll
                     for (int x = 0; x < VEC; ++x) im[x] = im_sh[x];
-                } else ld_imm<T, VEC>(im, IMl, j, v.imm_sj);
-                if (!s0) ldv<T, VEC>(so, SMSl + j);
+                } else ld_imm<T, VEC>(im, IMl, imm_shared ? j : jl, v.imm_sj);
+                if (!s0) ldv<T, VEC>(so, SMSl + jl);
                 if (nl > 0) {
-                    ldv<T, VEC>(cm, MCKl + j); ldv<T, VEC>(cs, SCKl + j);
-                    if (DENSE) ldv<T, VEC>(cv, VCKl + j);
+                    ldv<T, VEC>(cm, MCKl + jl); ldv<T, VEC>(cs, SCKl + jl);
+                    if (DENSE) ldv<T, VEC>(cv, VCKl + jl);
                 }
                 T p[VEC], vel[VEC], sm[VEC];
 #pragma unroll
@@ -791,8 +834,8 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? 16 / WPC
             const T* Vl = V;
             const T* Wl = ct ? XC : W;
             const T* IMl = IM;
-            if constexpr (TC > 1) {
-                const unsigned char* sb = ring + (size_t)(stg * NROW) * kRowBytes;
+            [[maybe_unused]] auto from_stage = [&](int st) {
+                const unsigned char* sb = ring + (size_t)(st * NROW) * kRowBytes;
                 Pl = reinterpret_cast<const T*>(sb);
                 Gl = reinterpret_cast<const T*>(sb + 1 * kRowBytes);
                 Ql = reinterpret_cast<const T*>(sb + 2 * kRowBytes);
@@ -801,18 +844,49 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? 16 / WPC
                     Vl = reinterpret_cast<const T*>(sb + 6 * kRowBytes);
                     Wl = reinterpret_cast<const T*>(sb + 7 * kRowBytes);
                 }
+            };
+            if constexpr (TC > 1) {
+                from_stage(stg);
                 stg = stg + 1 == kRing ? 0 : stg + 1;
             }
+            // one chain per warp / CTA: the pieces of the rows travel through the ring (see pass A)
+            const T* const Pg = P;
+            const T* const Gg = Gl;
+            const T* const Qg = Ql;
+            const T* const Vg = V;
+            const T* const Wg = Wl;
+            [[maybe_unused]] auto issue_piece = [&](int jn, int st) {
+                if (jn < d) {
+                    cp16(slot(st, 0), Pg + jn);
+                    cp16(slot(st, 1), Gg + jn);
+                    cp16(slot(st, 2), Qg + jn);
+                    if (DENSE) { cp16(slot(st, 6), Vg + jn); cp16(slot(st, 7), Wg + jn); }
+                    else if (!imm_shared) cp16(slot(st, 5), IM + jn);
+                }
+                cp_commit();
+            };
+            [[maybe_unused]] int pq = 0;
+            if constexpr (RING1) {
+#pragma unroll
+                for (int st = 0; st < kRing - 1; ++st) issue_piece(j0 + st * STEP, st);
+            }
             for (int j = j0; j < d; j += STEP) {
+                if constexpr (RING1) {
+                    issue_piece(j + (kRing - 1) * STEP, (pq + kRing - 1) % kRing);
+                    cp_wait<kRing - 1>();
+                    from_stage(pq);
+                    pq = pq + 1 == kRing ? 0 : pq + 1;
+                }
+                const int jl = (TC > 1 || RING1) ? (int)(threadIdx.x & 31) * VEC : j;
                 T q[VEC], p[VEC], g[VEC], vel[VEC], w[VEC], im[VEC];
-                ldv<T, VEC>(p, Pl + j);
-                ldv<T, VEC>(g, Gl + j);
-                ldv<T, VEC>(q, Ql + j);
-                if (DENSE) { ldv<T, VEC>(vel, Vl + j); ldv<T, VEC>(w, Wl + j); }
+                ldv<T, VEC>(p, Pl + jl);
+                ldv<T, VEC>(g, Gl + jl);
+                ldv<T, VEC>(q, Ql + jl);
+                if (DENSE) { ldv<T, VEC>(vel, Vl + jl); ldv<T, VEC>(w, Wl + jl); }
                 else if (TC > 1 && imm_shared) {
 #pragma unroll
                     for (int x = 0; x < VEC; ++x) im[x] = im_sh[x];
-                } else ld_imm<T, VEC>(im, IMl, j, v.imm_sj);
+                } else ld_imm<T, VEC>(im, IMl, imm_shared ? j : jl, v.imm_sj);
                 if (ct) {
 #pragma unroll
                     for (int x = 0; x < VEC; ++x) {
@@ -859,8 +933,9 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? 16 / WPC
 // chains per warp: enough warps to fill the machine first (16 per SM), then as many chains per warp as possible so
 // that the scalar passes run with all lanes busy
 static inline int tile_chains_per_warp(int C, int sm_count) {
-    static int forced = -1;
-    if (forced < 0) { const char* e = getenv("B2H_TILE_TC"); forced = e ? atoi(e) : 0; }
+    // B2H_TILE_TC / B2H_TILE_WPC (read at every call): force a layout, for the parity tests and A/B measurements
+    const char* e = getenv("B2H_TILE_TC");
+    const int forced = e ? atoi(e) : 0;
     if (forced == 1 || forced == 8 || forced == 32) return forced;
     const i64 want = (i64)sm_count * 16;
     if ((i64)C >= 32 * want) return 32;
@@ -868,16 +943,17 @@ static inline int tile_chains_per_warp(int C, int sm_count) {
     return 1;
 }
 
-template <typename T, int TC, int VEC, bool DENSE>
+// kernels that read their rows through the ring: kRing stages x rows x 512 bytes of dynamic shared memory per warp
+template <typename T, int TC, int WPC, int VEC, bool DENSE>
 static void launch_tile_ring(cudaStream_t st, const EngineView<T>& v, int* nd, int p, int grid) {
-    // tiles of several chains: 4 warps x kRing stages x rows x 512 bytes of dynamic shared memory
-    constexpr int bytes = 4 * tile::kRing * tile::RingRows<DENSE>::value * tile::kRowBytes;
+    constexpr int threads = tile::Coop<TC, WPC>::kThreads;
+    constexpr int bytes = (TC > 1 || B2H_TILE_RING1) ? (threads / 32) * tile::kRing * tile::RingRows<DENSE>::value * tile::kRowBytes : 0;
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(tile::tile_tick_kernel<T, TC, 1, VEC, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cudaFuncSetAttribute(tile::tile_tick_kernel<T, TC, WPC, VEC, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         configured = true;
     }
-    tile::tile_tick_kernel<T, TC, 1, VEC, DENSE><<<grid, 128, bytes, st>>>(v, nd, p);
+    tile::tile_tick_kernel<T, TC, WPC, VEC, DENSE><<<grid, threads, bytes, st>>>(v, nd, p);
 }
 
 template <typename T, bool DENSE>
@@ -885,26 +961,24 @@ static void launch_tile_tick(cudaStream_t st, const EngineView<T>& v, int* nd, b
     constexpr int NV = 16 / (int)sizeof(T);
     const bool aligned = ((size_t)v.d * sizeof(T)) % 16 == 0 && ((uintptr_t)v.imm % 16 == 0 || DENSE) &&
                          (uintptr_t)v.out.draws % 16 == 0;
-    // several chains per warp: rows of one 16-byte piece per lane (they travel through the shared-memory ring)
+    // several chains per warp: rows of one 16-byte piece per lane (the ring pipelines the chains)
     const bool short_rows = (size_t)v.d * sizeof(T) <= (size_t)tile::kRowBytes;
     const int tc = aligned && short_rows ? tile_chains_per_warp(v.C, sm_count) : 1;
     const int p = pre ? 1 : 0;
-    if (tc == 1 && aligned) {
-        // one chain per warp, or -- long rows -- per CTA of 4 / 8 warps (at most two 128-bit pieces per thread and row)
-        static int forced = -1;
-        if (forced < 0) { const char* e = getenv("B2H_TILE_WPC"); forced = e ? atoi(e) : 0; }
-        const int pieces = v.d / NV;
-        int wpc = pieces > 64 ? 4 : 1;
-        if (forced == 1 || forced == 4 || forced == 8) wpc = forced;
-        if (wpc == 8) { tile::tile_tick_kernel<T, 1, 8, NV, DENSE><<<v.C, 256, 0, st>>>(v, nd, p); return; }
-        if (wpc == 4) { tile::tile_tick_kernel<T, 1, 4, NV, DENSE><<<v.C, 128, 0, st>>>(v, nd, p); return; }
-    }
     const i64 warps = ((i64)v.C + tc - 1) / tc;
     const int grid = (int)((warps + 3) / 4);
-    if (!aligned) tile::tile_tick_kernel<T, 1, 1, 1, DENSE><<<grid, 128, 0, st>>>(v, nd, p);
-    else if (tc == 32) launch_tile_ring<T, 32, NV, DENSE>(st, v, nd, p, grid);
-    else if (tc == 8) launch_tile_ring<T, 8, NV, DENSE>(st, v, nd, p, grid);
-    else tile::tile_tick_kernel<T, 1, 1, NV, DENSE><<<grid, 128, 0, st>>>(v, nd, p);
+    if (!aligned) { tile::tile_tick_kernel<T, 1, 1, 1, DENSE><<<grid, 128, 0, st>>>(v, nd, p); return; }
+    if (tc == 32) { launch_tile_ring<T, 32, 1, NV, DENSE>(st, v, nd, p, grid); return; }
+    if (tc == 8) { launch_tile_ring<T, 8, 1, NV, DENSE>(st, v, nd, p, grid); return; }
+    // one chain per warp, or -- long rows -- per CTA of 4 (8) warps; the ring pipelines the pieces of the rows
+    const char* e = getenv("B2H_TILE_WPC");
+    const int forced = e ? atoi(e) : 0;
+    const int pieces = v.d / NV;
+    int wpc = pieces > 64 ? 4 : 1;
+    if (forced == 1 || forced == 4 || forced == 8) wpc = forced;
+    if (wpc == 8) launch_tile_ring<T, 1, 8, NV, DENSE>(st, v, nd, p, v.C);
+    else if (wpc == 4) launch_tile_ring<T, 1, 4, NV, DENSE>(st, v, nd, p, v.C);
+    else launch_tile_ring<T, 1, 1, NV, DENSE>(st, v, nd, p, grid);
 }
 
 }  // namespace b2h
