@@ -611,8 +611,15 @@ B2H_DEVINL void end_transition(Chain<T, G>& ch, int num_doublings, bool is_turni
 // V = imm p_half.
 // ---------------------------------------------------------------------------
 // Returns true when the tick ended a sub-tree (the front was written back and must be re-bound).
+// DEFER (thread-per-chain persistent kernel): a step that ends a sub-tree returns kSubtreeEnd | flags WITHOUT running the
+// sub-tree end; the caller runs subtree_end() later, when enough lanes of its warp wait for that path (the outcome does
+// not depend on when it runs: nothing else touches the chain in between).
+enum : int { kSubtreeEnd = 4, kEndDiv = 1, kEndTerm = 2 };
 template <typename T, int G, bool DENSE, bool SPLIT, class Front>
-B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
+B2H_DEVINL bool subtree_end(Chain<T, G>& ch, Front& f, bool div, bool term);
+
+template <typename T, int G, bool DENSE, bool SPLIT, class Front, bool DEFER = false>
+B2H_DEVINL int post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
     const EngineView<T>& v = ch.v;
     ChainRec& r = ch.r;
     const int d = v.d;
@@ -809,7 +816,20 @@ B2H_DEVINL bool post_gradient(Chain<T, G>& ch, T U_new, Front& f) {
 
     const int sub_limit = v.sub_max_steps > 0 ? v.sub_max_steps : (1 << k) - (v.exact_doubling ? 1 : 0);
     const bool end_sub = div || term || (s == sub_limit);      // Q1: 2**k more steps after step 0
-    if (!end_sub) { r.s = s + 1; return false; }
+    if (!end_sub) { r.s = s + 1; return 0; }
+    if (DEFER) return kSubtreeEnd | (div ? kEndDiv : 0) | (term ? kEndTerm : 0);
+    return subtree_end<T, G, DENSE, SPLIT, Front>(ch, f, div, term) ? 1 : 0;
+}
+
+// End of a sub-tree: the front goes back to the edge arrays, then expand_once (trajectory.py:537-608) or, for the
+// stand-alone dynamic_integration, the stop.  Always returns true (the front must be re-bound).
+template <typename T, int G, bool DENSE, bool SPLIT, class Front>
+B2H_DEVINL bool subtree_end(Chain<T, G>& ch, Front& f, bool div, bool term) {
+    const EngineView<T>& v = ch.v;
+    ChainRec& r = ch.r;
+    const int d = v.d;
+    const int k = r.k;
+    constexpr int CH = SPLIT ? kBatch : 1;
     f.flush(ch);                                                // the edge arrays must be current from here on
     Group<G>::sync();
     if (r.go_right) r.U_right = r.U_front; else r.U_left = r.U_front;

@@ -6,6 +6,21 @@
 
 namespace b2h {
 
+#ifndef B2H_DEFER_PATHS
+#define B2H_DEFER_PATHS 1
+#endif
+// Lanes of a warp that must wait for a deferred path before it runs (it also runs when no lane of the warp can step).
+// Measured on config 4 (65536 chains, thread per chain, 200 transitions / free-running, ms; benchmarks/defer_ab.sh):
+//   eight schools  no deferral 128 / 94   8 lanes 107 / 85   16 lanes 90 / 68   24 lanes + 3-tick limit 95 / 73   32 + 4: 106 / 95
+//   funnel         no deferral 1982 / 740 8 lanes 1520 / 741 16 lanes 1444 / 1040
+// A limit on the ticks a lane may wait did not pay (16 lanes + 2 ticks: 107 / 77 and 1977 / 828).
+#ifndef B2H_DEFER_LANES
+#define B2H_DEFER_LANES 16
+#endif
+#ifndef B2H_DEFER_LANES_FUNNEL
+#define B2H_DEFER_LANES_FUNNEL 8     // deep, uneven trees: the path is rare, waiting for half a warp idles the parked lanes
+#endif
+
 // E > 8 only exists for thread-per-chain (G = 1): the chain's whole front is the thread's registers, so the launch
 // bound leaves the thread its 255 registers instead of trading them for resident warps.
 template <typename T, int G, int MODEL, bool HMC, int E>
@@ -21,10 +36,14 @@ fused_run_kernel(EngineView<T> v, ModelDev m, i64 max_ticks, int stage_ck) {
     constexpr bool kAhead = (G == 1 && E > 0);
     constexpr int ZE = kAhead ? ((E + 1) & ~1) : 1;
     __shared__ double zsm[ZE][kAhead ? Geo<G>::kThreads : 1];
-    const int c = Geo<G>::chain();
-    if (c >= v.C) return;
+    // deferred paths (below) vote with the whole warp: a lane without a chain stays, as a finished one
+    constexpr bool kDefer = (G == 1 && E > 0 && !HMC) && B2H_DEFER_PATHS;
+    const bool has_chain = Geo<G>::chain() < v.C;
+    if (!has_chain && !kDefer) return;
+    const int c = has_chain ? Geo<G>::chain() : 0;
     Chain<T, G> ch(v, c, red_s);
-    ch.load();
+    if (has_chain) ch.load();
+    else ch.r.phase = PH_DONE;
     // U-turn checkpoints staged in shared memory for the whole launch when the CTA's chains fit (termination.py:63-131:
     // written on even steps, read on odd ones, 2 x max_num_expansions x d values per chain)
     if (stage_ck)
@@ -35,6 +54,62 @@ fused_run_kernel(EngineView<T> v, ModelDev m, i64 max_ticks, int stage_ck) {
     int zfill = 0, ztrans = -1;                 // normals drawn ahead, and the transition they belong to
     const bool ahead = kAhead && v.rng.mode == 0;
     const double* zs = kAhead ? &zsm[0][threadIdx.x] : nullptr;
+    // Thread per chain, NUTS: the paths only SOME lanes of a warp need on a given tick -- the end of a sub-tree
+    // (expand_once: a third of the ticks of a chain with short trees) and the start of a transition -- used to run
+    // with those few lanes while the others waited (ncu: 11.5 of 32 lanes active).  Here a lane that reaches such a path
+    // parks until kDeferLanes lanes of its warp wait for the same path (or no lane of the warp can step), and the path
+    // then runs once for all of them.  A chain's result does not depend on when its own steps run.
+    if constexpr (kDefer) {
+        constexpr unsigned kAll = 0xffffffffu;
+        int pend = 0;                               // kSubtreeEnd | flags: this lane's sub-tree end waits to be run
+        constexpr int kLanes = MODEL == MODEL_FUNNEL ? B2H_DEFER_LANES_FUNNEL : B2H_DEFER_LANES;
+        while (true) {
+            const bool live = ch.r.phase != PH_DONE && (max_ticks <= 0 || tick < max_ticks);
+            if (!__any_sync(kAll, live)) break;
+            const bool can_step = live && ch.r.phase == PH_RUN && pend == 0;
+            const bool none_steps = !__any_sync(kAll, can_step);
+            // (1) sub-tree ends
+            const bool want_end = live && pend != 0;
+            if (__popc(__ballot_sync(kAll, want_end)) >= kLanes || none_steps) {
+                if (want_end) {
+                    subtree_end<T, G, false, false, Front>(ch, f, (pend & kEndDiv) != 0, (pend & kEndTerm) != 0);
+                    pend = 0;
+                    bound = false;
+                }
+            }
+            // (2) transition starts (a sub-tree end above may have produced some)
+            const bool want_begin = live && pend == 0 && ch.r.phase == PH_START;
+            const bool none_steps2 = !__any_sync(kAll, live && ch.r.phase == PH_RUN && pend == 0);
+            if (__popc(__ballot_sync(kAll, want_begin)) >= kLanes || none_steps2) {
+                if (want_begin) {
+                    const int zready = (ahead && ztrans == ch.r.t) ? zfill : 0;
+                    begin_transition<T, G, false>(ch, zs, zready, Geo<G>::kThreads);
+                    bound = false;
+                    zfill = 0;
+                    ztrans = ch.r.t + 1;
+                }
+            }
+            // (3) one leapfrog of every lane that can step
+            if (live && ch.r.phase == PH_RUN && pend == 0) {
+                if (!bound) { f.bind(ch); bound = true; }
+                half_kick_drift<T, G, false, false>(ch, f);
+                const T U = model_grad_front<T, G, MODEL>(m, f, ch.lane, ch.red);
+                if (ahead && zfill < v.d) {
+                    double z0, z1;
+                    philox_normal_pair(v.rng.key, v.rng.chain_offset + (uint64_t)c,
+                                       (uint32_t)(v.rng.transition_offset + (uint64_t)ztrans), (uint32_t)(zfill >> 1), &z0, &z1);
+                    zsm[zfill][threadIdx.x] = z0;
+                    zsm[zfill + 1][threadIdx.x] = z1;
+                    zfill += 2;
+                }
+                pend = post_gradient<T, G, false, false, Front, true>(ch, U, f);
+                if (!(pend & kSubtreeEnd)) pend = 0;
+                ++tick;
+            }
+        }
+        // a sub-tree end still parked when the tick budget ran out belongs to the last tick
+        if (pend != 0) { subtree_end<T, G, false, false, Front>(ch, f, (pend & kEndDiv) != 0, (pend & kEndTerm) != 0); bound = false; }
+    } else
     while (max_ticks <= 0 || tick < max_ticks) {
         if (ch.r.phase == PH_DONE) break;
         if (ch.r.phase == PH_START) {
@@ -73,6 +148,7 @@ fused_run_kernel(EngineView<T> v, ModelDev m, i64 max_ticks, int stage_ck) {
         Group<G>::sync();
         ++tick;
     }
+    if (!has_chain) return;
     if (bound) f.flush(ch);                // max_ticks ran out in the middle of a sub-tree
     if (stage_ck) ch.unstage_checkpoints();
     ch.store();
