@@ -948,11 +948,9 @@ template <typename T, int TC, int WPC, int VEC, bool DENSE>
 static void launch_tile_ring(cudaStream_t st, const EngineView<T>& v, int* nd, int p, int grid) {
     constexpr int threads = tile::Coop<TC, WPC>::kThreads;
     constexpr int bytes = (TC > 1 || B2H_TILE_RING1) ? (threads / 32) * tile::kRing * tile::RingRows<DENSE>::value * tile::kRowBytes : 0;
-    static bool configured = false;
-    if (!configured) {
+    // set at every launch (cheap): the attribute belongs to the function in the CURRENT device's context
+    if (bytes > 0)
         cudaFuncSetAttribute(tile::tile_tick_kernel<T, TC, WPC, VEC, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        configured = true;
-    }
     tile::tile_tick_kernel<T, TC, WPC, VEC, DENSE><<<grid, threads, bytes, st>>>(v, nd, p);
 }
 
