@@ -92,7 +92,7 @@ static int tick_timer_collect(b2h_ctx* ctx) {
 int b2h_tick_timer(b2h_ctx* ctx, int32_t enable) {
     if (!ctx) { set_error("null context"); return B2H_ERR_ARG; }
     if (int rc = tick_timer_collect(ctx)) return rc;
-    ctx->tick_timer = enable != 0;
+    ctx->tick_timer = (enable == 1 || enable == 2) ? enable : 0;
     ctx->tick_ms = 0.0;
     ctx->tick_launches = 0;
     return 0;

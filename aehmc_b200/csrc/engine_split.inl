@@ -210,8 +210,7 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
     };
 #define B2H_POSTPRE(D_, E_, P_) split_postpre_kernel<T, G, D_, HMC, E_, P_><<<grid, thr, 0, st>>>(v, nd)
     // b2h_tick_timer: an event before and after the tick kernel on the engine's stream
-    auto tick_mark = [&]() {
-        if (!ctx->tick_timer) return;
+    auto mark_event = [&]() {
         if (ctx->tick_events_used == ctx->tick_events.size()) {
             cudaEvent_t e;
             if (cudaEventCreate(&e) != cudaSuccess) return;
@@ -219,6 +218,8 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
         }
         cudaEventRecord(ctx->tick_events[ctx->tick_events_used++], st);
     };
+    auto grad_mark = [&]() { if (ctx->tick_timer == 2) mark_event(); };
+    auto tick_mark = [&]() { if (ctx->tick_timer == 1) mark_event(); };
     auto launch_postpre = [&](i64 t, int* nd) -> int {                       // post of tick t - 1, pre of tick t
         if (tile_tick) {
             if (pl.dense) {
@@ -269,7 +270,9 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
 
     rc = launch_pre(0);
     for (i64 tick = 0; tick < bound && rc == 0; ++tick) {
+        grad_mark();
         rc = potential_and_grad_impl<T>(ctx, model, v.xa, v.Unew, v.xb, C, model_ws, model_ws_bytes);
+        grad_mark();
         if (rc) break;
         const bool last = tick + 1 == bound;
         const bool check = (max_ticks <= 0) && ((tick & 3) == 3 || last);

@@ -18,7 +18,7 @@ struct b2h_ctx {
     cudaEvent_t ev_pre[2], ev_side[2];
     int* host_flag;   // pinned, for the split engine's completion poll
     // b2h_tick_timer: event pairs around the tick-kernel launches of the split engine (measurement aid, off by default)
-    bool tick_timer = false;
+    int tick_timer = 0;               // 0 off, 1 the tick kernel, 2 the gradient call (potential_and_grad) of every tick
     std::vector<cudaEvent_t> tick_events;
     size_t tick_events_used = 0;
     double tick_ms = 0.0;

@@ -174,8 +174,10 @@ int b2h_ctx_sync(b2h_ctx* ctx); /* cudaStreamSynchronize */
 /* Measurement aid (bench.py's roofline of the integrator / U-turn kernel): with the timer enabled, every launch of the
  * tick kernel of b2h_nuts_run's per-tick engine (the kernel that fuses integrators.py:58-73, termination.py:109-187,
  * trajectory.py:195-273,537-608 for one leapfrog of every chain) is bracketed by a pair of CUDA events on the
- * context's stream.  b2h_tick_timer(ctx, enable) resets the totals; b2h_tick_timer_read synchronises the stream and
- * returns the summed kernel time and the number of launches since the last reset.  Off by default. */
+ * context's stream.  enable = 2 brackets the model-gradient call of every tick instead (hmc.py:33-34 for all chains: the
+ * contraction kernels of logistic regression / the correlated Gaussian, timed inside the step).  b2h_tick_timer(ctx,
+ * enable) resets the totals; b2h_tick_timer_read synchronises the stream and returns the summed time and the number
+ * of bracketed launches since the last reset.  Off (0) by default. */
 int b2h_tick_timer(b2h_ctx* ctx, int32_t enable);
 int b2h_tick_timer_read(b2h_ctx* ctx, double* total_ms, int64_t* launches);
 
