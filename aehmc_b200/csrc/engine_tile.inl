@@ -187,13 +187,6 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? B2H_TILE
     // tiles of several chains: this warp's ring of row stages (dynamic shared memory; see cp16)
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     constexpr int NROW = RingRows<DENSE>::value;
-    // one chain per warp / CTA: the ring can pipeline the PIECES of the long rows instead (B2H_TILE_RING1=1).  Measured at c2
-    // (d = 1000, dense, 4 warps per chain): 156 us with it, 154 us without -- its 72 KB of shared memory cost one of the four
-    // CTAs per SM -- so it is off.
-#ifndef B2H_TILE_RING1
-#define B2H_TILE_RING1 0
-#endif
-    constexpr bool RING1 = B2H_TILE_RING1 && TC == 1 && VEC > 1;
     [[maybe_unused]] unsigned char* const ring = dyn_smem + (size_t)(threadIdx.x >> 5) * (kRing * NROW * kRowBytes);
     // this lane's 16-byte slot of (stage 0, row 0), as a shared-space address for the asynchronous copies
     [[maybe_unused]] const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + (threadIdx.x & 31) * 16;
@@ -320,36 +313,8 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? B2H_TILE
                 from_stage(stg);
                 stg = stg + 1 == kRing ? 0 : stg + 1;
             }
-            // one chain per warp / CTA (long rows): the ring pipelines the PIECES of the rows instead of the chains
-            [[maybe_unused]] auto issue_piece = [&](int jn, int st) {
-                if (jn < d) {
-                    cp16(slot(st, 0), P + jn);
-                    cp16(slot(st, 1), XB + jn);
-                    if (!s0) cp16(slot(st, 2), SMS + jn);
-                    if (nl > 0) {
-                        cp16(slot(st, 3), MCK + jn);
-                        cp16(slot(st, 4), SCK + jn);
-                        if (DENSE) cp16(slot(st, 8), VCK + jn);
-                    }
-                    if (DENSE) { cp16(slot(st, 6), V + jn); cp16(slot(st, 7), XC + jn); }
-                    else if (!imm_shared) cp16(slot(st, 5), IM + jn);
-                }
-                cp_commit();
-            };
-            [[maybe_unused]] int pq = 0;
-            if constexpr (RING1) {
-#pragma unroll
-                for (int st = 0; st < kRing - 1; ++st) issue_piece(j0 + st * STEP, st);
-            }
             for (int j = j0; j < d; j += STEP) {
-                if constexpr (RING1) {
-                    issue_piece(j + (kRing - 1) * STEP, (pq + kRing - 1) % kRing);
-                    cp_wait<kRing - 1>();
-                    from_stage(pq);
-                    pq = pq + 1 == kRing ? 0 : pq + 1;
-                }
-                // ring rows hold this lane's piece at the lane's own slot
-                const int jl = (TC > 1 || RING1) ? (int)(threadIdx.x & 31) * VEC : j;
+                const int jl = TC > 1 ? j0 : j;                  // ring rows hold this lane's piece at the lane's own slot
                 T pv[VEC], gx[VEC], so[VEC], cm[VEC], cs[VEC], cv[VEC], im[VEC], vv[VEC], wx[VEC];
                 ldv<T, VEC>(pv, Pl + jl);
                 ldv<T, VEC>(gx, XBl + jl);
@@ -849,35 +814,8 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? B2H_TILE
                 from_stage(stg);
                 stg = stg + 1 == kRing ? 0 : stg + 1;
             }
-            // one chain per warp / CTA: the pieces of the rows travel through the ring (see pass A)
-            const T* const Pg = P;
-            const T* const Gg = Gl;
-            const T* const Qg = Ql;
-            const T* const Vg = V;
-            const T* const Wg = Wl;
-            [[maybe_unused]] auto issue_piece = [&](int jn, int st) {
-                if (jn < d) {
-                    cp16(slot(st, 0), Pg + jn);
-                    cp16(slot(st, 1), Gg + jn);
-                    cp16(slot(st, 2), Qg + jn);
-                    if (DENSE) { cp16(slot(st, 6), Vg + jn); cp16(slot(st, 7), Wg + jn); }
-                    else if (!imm_shared) cp16(slot(st, 5), IM + jn);
-                }
-                cp_commit();
-            };
-            [[maybe_unused]] int pq = 0;
-            if constexpr (RING1) {
-#pragma unroll
-                for (int st = 0; st < kRing - 1; ++st) issue_piece(j0 + st * STEP, st);
-            }
             for (int j = j0; j < d; j += STEP) {
-                if constexpr (RING1) {
-                    issue_piece(j + (kRing - 1) * STEP, (pq + kRing - 1) % kRing);
-                    cp_wait<kRing - 1>();
-                    from_stage(pq);
-                    pq = pq + 1 == kRing ? 0 : pq + 1;
-                }
-                const int jl = (TC > 1 || RING1) ? (int)(threadIdx.x & 31) * VEC : j;
+                const int jl = TC > 1 ? j0 : j;
                 T q[VEC], p[VEC], g[VEC], vel[VEC], w[VEC], im[VEC];
                 ldv<T, VEC>(p, Pl + jl);
                 ldv<T, VEC>(g, Gl + jl);
@@ -943,11 +881,11 @@ static inline int tile_chains_per_warp(int C, int sm_count) {
     return 1;
 }
 
-// kernels that read their rows through the ring: kRing stages x rows x 512 bytes of dynamic shared memory per warp
+// tiles of several chains read their rows through the ring: kRing stages x rows x 512 bytes of dynamic shared memory per warp
 template <typename T, int TC, int WPC, int VEC, bool DENSE>
 static void launch_tile_ring(cudaStream_t st, const EngineView<T>& v, int* nd, int p, int grid) {
     constexpr int threads = tile::Coop<TC, WPC>::kThreads;
-    constexpr int bytes = (TC > 1 || B2H_TILE_RING1) ? (threads / 32) * tile::kRing * tile::RingRows<DENSE>::value * tile::kRowBytes : 0;
+    constexpr int bytes = TC > 1 ? (threads / 32) * tile::kRing * tile::RingRows<DENSE>::value * tile::kRowBytes : 0;
     // set at every launch (cheap): the attribute belongs to the function in the CURRENT device's context
     if (bytes > 0)
         cudaFuncSetAttribute(tile::tile_tick_kernel<T, TC, WPC, VEC, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -968,7 +906,8 @@ static void launch_tile_tick(cudaStream_t st, const EngineView<T>& v, int* nd, b
     if (!aligned) { tile::tile_tick_kernel<T, 1, 1, 1, DENSE><<<grid, 128, 0, st>>>(v, nd, p); return; }
     if (tc == 32) { launch_tile_ring<T, 32, 1, NV, DENSE>(st, v, nd, p, grid); return; }
     if (tc == 8) { launch_tile_ring<T, 8, 1, NV, DENSE>(st, v, nd, p, grid); return; }
-    // one chain per warp, or -- long rows -- per CTA of 4 (8) warps; the ring pipelines the pieces of the rows
+    // one chain per warp, or -- long rows -- per CTA of 4 (8) warps, direct loads (pipelining the PIECES of a long row through
+    // the ring was measured at c2: 156 us against 154 us, its shared memory costs one of the four CTAs per SM)
     const char* e = getenv("B2H_TILE_WPC");
     const int forced = e ? atoi(e) : 0;
     const int pieces = v.d / NV;
