@@ -64,7 +64,13 @@ B2H_DEVCALL double expit(double x) { return expit_inl(x); }
 // chain: 0.63 -> 0.74 G evals/s); thread-per-chain kernels reach the helpers under divergence, where a call costs more
 // than it saves (0.91 -> 0.79); warp- and CTA-per-chain kernels lose the instruction-level parallelism between the
 // independent draws of one lane (HMC d = 100: 1.50 -> 1.35).
-template <int G> struct Helpers { static constexpr bool kCall = (G > 1 && G < 32); };
+// Thread per chain: with the rare paths of the persistent kernel deferred (engine_fused.inl) most lanes reach the helpers
+// together, and the smaller loop body wins (eight schools c4: 89.5 -> 86.9 ms for 200 transitions, free-running 69.4 -> 66.1;
+// before the deferral the calls under divergence cost more than they saved: 0.91 -> 0.79 G evals/s).
+#ifndef B2H_CALL_G1
+#define B2H_CALL_G1 1
+#endif
+template <int G> struct Helpers { static constexpr bool kCall = (G > 1 && G < 32) || (B2H_CALL_G1 && G == 1); };
 template <int G> B2H_DEVINL double lae_g(double a, double b) { return Helpers<G>::kCall ? lae(a, b) : lae_inl(a, b); }
 template <int G> B2H_DEVINL double expit_g(double x) { return Helpers<G>::kCall ? expit(x) : expit_inl(x); }
 

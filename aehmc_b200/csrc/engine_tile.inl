@@ -166,8 +166,9 @@ struct Coop {
 #endif
 
 template <typename T, int TC, int WPC, int VEC, bool DENSE>
-__global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? B2H_TILE_WPC_WARPS / WPC : B2H_TILE_MINB)) tile_tick_kernel(EngineView<T> v, int* not_done, int pre) {
+__global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? B2H_TILE_WPC_WARPS / WPC : B2H_TILE_MINB)) tile_tick_kernel(EngineView<T> v, int* not_done, int flags) {
     typedef Coop<TC, WPC> Co;
+    const bool pre = (flags & 1) != 0;                   // the half kick + drift of the next tick follows (not the last tick of a call)
     __shared__ double slots[32];                         // WPC > 1: one slot per broadcast value
     __shared__ double red_s[3 * WPC];                    // WPC > 1: per-warp partials of a reduction
     const int lane = Co::tid();                          // index of this thread in the group that shares a chain's rows
@@ -190,6 +191,12 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? B2H_TILE
     [[maybe_unused]] unsigned char* const ring = dyn_smem + (size_t)(threadIdx.x >> 5) * (kRing * NROW * kRowBytes);
     // this lane's 16-byte slot of (stage 0, row 0), as a shared-space address for the asynchronous copies
     [[maybe_unused]] const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + (threadIdx.x & 31) * 16;
+    // one chain per warp / CTA: what pass A computes or reads and pass D needs again -- p', g', q'[, imm p', imm g'] of a
+    // chain that continues its sub-tree -- waits in shared memory instead of being re-read (same thread, same pieces: no
+    // synchronisation); flags bit 1, set by the launcher when the rows fit
+    constexpr int SROWS = DENSE ? 5 : 3;
+    [[maybe_unused]] const bool stash = TC == 1 && VEC > 1 && (flags & 2) != 0;
+    [[maybe_unused]] T* const stash_rows = reinterpret_cast<T*>(dyn_smem) + (size_t)(WPC > 1 ? 0 : (threadIdx.x >> 5)) * SROWS * d;
     // an inverse mass matrix shared by all chains (scalar or one diagonal): this lane's piece is loaded once
     [[maybe_unused]] const bool imm_shared = !DENSE && v.imm_sc == 0;
     [[maybe_unused]] T im_sh[VEC];
@@ -328,6 +335,10 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? B2H_TILE
                     ldv<T, VEC>(cm, MCKl + jl); ldv<T, VEC>(cs, SCKl + jl);
                     if (DENSE) ldv<T, VEC>(cv, VCKl + jl);
                 }
+                [[maybe_unused]] T qx[VEC];
+                if constexpr (TC == 1 && VEC > 1) {
+                    if (stash) ldv<T, VEC>(qx, v.xa + rb + j);       // for pass D (it would read it anyway)
+                }
                 T p[VEC], vel[VEC], sm[VEC];
 #pragma unroll
                 for (int x = 0; x < VEC; ++x) {
@@ -349,6 +360,14 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? B2H_TILE
                     stv<T, VEC>(MCK + j, p);
                     stv<T, VEC>(SCK + j, sm);
                     if (DENSE) stv<T, VEC>(VCK + j, vel);
+                }
+                if constexpr (TC == 1 && VEC > 1) {
+                    if (stash) {
+                        stv<T, VEC>(stash_rows + j, p);
+                        stv<T, VEC>(stash_rows + d + j, gx);
+                        stv<T, VEC>(stash_rows + 2 * d + j, qx);
+                        if (DENSE) { stv<T, VEC>(stash_rows + 3 * d + j, vel); stv<T, VEC>(stash_rows + 4 * d + j, wx); }
+                    }
                 }
             }
             double red[3] = {(double)kacc, (double)dl, (double)dr};
@@ -814,6 +833,12 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? B2H_TILE
                 from_stage(stg);
                 stg = stg + 1 == kRing ? 0 : stg + 1;
             }
+            // a continuing chain whose pass A left (p', g', q'[, imm p', imm g']) in shared memory: already kicked
+            const bool stashed = TC == 1 && VEC > 1 && stash && ct;
+            if (stashed) {
+                Pl = stash_rows; Gl = stash_rows + d; Ql = stash_rows + 2 * d;
+                if (DENSE) { Vl = stash_rows + 3 * d; Wl = stash_rows + 4 * d; }
+            }
             for (int j = j0; j < d; j += STEP) {
                 const int jl = TC > 1 ? j0 : j;
                 T q[VEC], p[VEC], g[VEC], vel[VEC], w[VEC], im[VEC];
@@ -826,10 +851,12 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? B2H_TILE
                     for (int x = 0; x < VEC; ++x) im[x] = im_sh[x];
                 } else ld_imm<T, VEC>(im, IMl, imm_shared ? j : jl, v.imm_sj);
                 if (ct) {
+                    if (!stashed) {
 #pragma unroll
-                    for (int x = 0; x < VEC; ++x) {
-                        p[x] = p[x] - hei * g[x];                    // the kick pass A applied (same e: same sub-tree)
-                        if (DENSE) vel[x] = vel[x] - hei * w[x];
+                        for (int x = 0; x < VEC; ++x) {
+                            p[x] = p[x] - hei * g[x];                // the kick pass A applied (same e: same sub-tree)
+                            if (DENSE) vel[x] = vel[x] - hei * w[x];
+                        }
                     }
                     if (tk) {
                         stv<T, VEC>(v.qs + rb + j, q); stv<T, VEC>(v.ps + rb + j, p); stv<T, VEC>(v.gs + rb + j, g);
@@ -881,15 +908,23 @@ static inline int tile_chains_per_warp(int C, int sm_count) {
     return 1;
 }
 
-// tiles of several chains read their rows through the ring: kRing stages x rows x 512 bytes of dynamic shared memory per warp
+// Dynamic shared memory: tiles of several chains read their rows through the ring (kRing stages x rows x 512 bytes per
+// warp); one chain per warp / CTA stashes the rows pass D needs again (3 or 5 rows per chain) when they fit `stash_bytes`.
 template <typename T, int TC, int WPC, int VEC, bool DENSE>
-static void launch_tile_ring(cudaStream_t st, const EngineView<T>& v, int* nd, int p, int grid) {
+static void launch_tile_smem(cudaStream_t st, const EngineView<T>& v, int* nd, int p, int grid) {
     constexpr int threads = tile::Coop<TC, WPC>::kThreads;
-    constexpr int bytes = TC > 1 ? (threads / 32) * tile::kRing * tile::RingRows<DENSE>::value * tile::kRowBytes : 0;
+    int bytes = 0, flags = p;
+    if (TC > 1) {
+        bytes = (threads / 32) * tile::kRing * tile::RingRows<DENSE>::value * tile::kRowBytes;
+    } else if (VEC > 1) {
+        const char* e = getenv("B2H_TILE_STASH");                 // 0: re-read the rows instead (A/B measurements)
+        const size_t need = (size_t)(WPC > 1 ? 1 : 4) * (DENSE ? 5 : 3) * v.d * sizeof(T);
+        if (need <= 56 * 1024 && !(e && atoi(e) == 0)) { bytes = (int)need; flags |= 2; }
+    }
     // set at every launch (cheap): the attribute belongs to the function in the CURRENT device's context
-    if (bytes > 0)
+    if (bytes > 48 * 1024)
         cudaFuncSetAttribute(tile::tile_tick_kernel<T, TC, WPC, VEC, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    tile::tile_tick_kernel<T, TC, WPC, VEC, DENSE><<<grid, threads, bytes, st>>>(v, nd, p);
+    tile::tile_tick_kernel<T, TC, WPC, VEC, DENSE><<<grid, threads, bytes, st>>>(v, nd, flags);
 }
 
 template <typename T, bool DENSE>
@@ -904,8 +939,8 @@ static void launch_tile_tick(cudaStream_t st, const EngineView<T>& v, int* nd, b
     const i64 warps = ((i64)v.C + tc - 1) / tc;
     const int grid = (int)((warps + 3) / 4);
     if (!aligned) { tile::tile_tick_kernel<T, 1, 1, 1, DENSE><<<grid, 128, 0, st>>>(v, nd, p); return; }
-    if (tc == 32) { launch_tile_ring<T, 32, 1, NV, DENSE>(st, v, nd, p, grid); return; }
-    if (tc == 8) { launch_tile_ring<T, 8, 1, NV, DENSE>(st, v, nd, p, grid); return; }
+    if (tc == 32) { launch_tile_smem<T, 32, 1, NV, DENSE>(st, v, nd, p, grid); return; }
+    if (tc == 8) { launch_tile_smem<T, 8, 1, NV, DENSE>(st, v, nd, p, grid); return; }
     // one chain per warp, or -- long rows -- per CTA of 4 (8) warps, direct loads (pipelining the PIECES of a long row through
     // the ring was measured at c2: 156 us against 154 us, its shared memory costs one of the four CTAs per SM)
     const char* e = getenv("B2H_TILE_WPC");
@@ -913,9 +948,9 @@ static void launch_tile_tick(cudaStream_t st, const EngineView<T>& v, int* nd, b
     const int pieces = v.d / NV;
     int wpc = pieces > 64 ? 4 : 1;
     if (forced == 1 || forced == 4 || forced == 8) wpc = forced;
-    if (wpc == 8) launch_tile_ring<T, 1, 8, NV, DENSE>(st, v, nd, p, v.C);
-    else if (wpc == 4) launch_tile_ring<T, 1, 4, NV, DENSE>(st, v, nd, p, v.C);
-    else launch_tile_ring<T, 1, 1, NV, DENSE>(st, v, nd, p, grid);
+    if (wpc == 8) launch_tile_smem<T, 1, 8, NV, DENSE>(st, v, nd, p, v.C);
+    else if (wpc == 4) launch_tile_smem<T, 1, 4, NV, DENSE>(st, v, nd, p, v.C);
+    else launch_tile_smem<T, 1, 1, NV, DENSE>(st, v, nd, p, grid);
 }
 
 }  // namespace b2h
