@@ -800,9 +800,9 @@ def run_gpu_arm(args):
     w = run_tick_workload(name, D, args.steps, args.warmup)
     roofline, roofline_elementwise = rooflines_for(w, D, peaks)
     kind, Cn, d, ticks = w["kind"], w["chains_per_gpu"], w["dim"], w["ticks"]
-    kernels_per_tick = 6 if kind == "dense" else 5
-    # dense: post+pre, gradient apply, potential, imm.g apply, momentum rider GEMM + its reduce
-    # logistic: post+pre, beta split, response convert, fused gradient, finish
+    kernels_per_tick = 6 if kind == "dense" else 4
+    # dense: tick kernel, gradient apply, potential, imm.g apply, momentum rider GEMM + its reduce
+    # logistic: tick kernel, beta split, fused gradient, finish (profiles/r02_launches_c5.md)
 
     ess = {}
     if not args.no_ess:
