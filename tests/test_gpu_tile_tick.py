@@ -139,3 +139,31 @@ def test_layouts_agree_bit_for_bit_with_the_native_rng(ab, monkeypatch, dtype_na
     assert same.mean() >= (0.97 if dtype_name == "float64" else 0.5)
     if dtype_name == "float64":            # float32 trajectories decorrelate within a few transitions
         np.testing.assert_allclose(q_old[same], res[1][0][same], rtol=1e-6, atol=1e-8)
+
+
+def test_tick_timer_brackets_the_tick_kernel_and_the_gradient_call(ab):
+    """b2h_tick_timer (include/b200hmc.h): mode 1 times every launch of the tick kernel, mode 2 every gradient call, of the
+    per-tick engine; a max_ticks run of T ticks has T gradient calls and T - 1 full (post + pre) tick kernels -- the
+    post-only launch that closes the call is not counted."""
+    import ctypes as C
+    from aehmc_b200 import _engine, _lib, backend
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    N, d, Cn, ticks = 128, 8, 64, 6
+    X = rng.standard_normal((N, d))
+    y = (rng.random(N) < 0.5).astype(np.float64)
+    model = ab.models.LogisticRegression(X, y, 1.0)
+    state = ab.nuts.new_state(0.1 * rng.standard_normal((Cn, d)), model)
+    ctx = backend.context(model.device)
+    for mode in (1, 2):
+        _lib.check(lib.b2h_tick_timer(ctx, mode))
+        _engine.run("nuts", model, np.full(d, 4.0 / N), ab.RandomStream(seed=1), state, 0.3, max_ticks=ticks)
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        _lib.check(lib.b2h_tick_timer_read(ctx, C.byref(ms), C.byref(n)))
+        _lib.check(lib.b2h_tick_timer(ctx, 0))
+        assert n.value == (ticks - 1 if mode == 1 else ticks) and ms.value > 0.0
+    # off: nothing is recorded
+    _engine.run("nuts", model, np.full(d, 4.0 / N), ab.RandomStream(seed=1), state, 0.3, max_ticks=ticks)
+    ms, n = C.c_double(0.0), C.c_int64(0)
+    _lib.check(lib.b2h_tick_timer_read(ctx, C.byref(ms), C.byref(n)))
+    assert n.value == 0
