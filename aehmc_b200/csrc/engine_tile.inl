@@ -10,8 +10,11 @@
 //  * the VECTOR part (kick, kinetic energy, momentum sums, checkpoint rows, U-turn dot products, proposal copies,
 //    half kick + drift: integrators.py:58-73, termination.py:109-187, metrics.py:70-102) runs WARP PER CHAIN in a loop
 //    over the tile with warp-uniform control flow (the chain's flags are broadcast from its lane), 128-bit row
-//    accesses and one butterfly reduction per chain.  No register front: the passes stream the rows, the few rows a
-//    later pass needs again (p_half, q', g') are re-read from L1 / L2.
+//    accesses and one butterfly reduction per chain.  No register front: the passes stream the rows.
+//  * Tiles of several chains (short rows) are bound by the latency of their row loads: the rows of the next three chains
+//    are copied asynchronously (cp.async) into a shared-memory ring while the current chain is processed.  Layouts with
+//    one chain per warp / per CTA of 4 or 8 warps (long rows; thread 0 owns the scalars, values travel through shared
+//    memory) keep what pass D needs again in shared memory between the passes.
 //
 // Passes:  S0 (scalars of the step)  ->  A (kick, K, sums, checkpoints, U-turn dots)  ->  S1 (energy, sampling, end
 // of sub-tree?)  ->  B (sub-tree ends: front back to the edge, proposal, trajectory sum, top-level U-turn)  ->  S2
