@@ -180,10 +180,13 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? B2H_TILE
     const int d = v.d;
     const int c = c0 + lane;
     const bool own = lane < TC && c < v.C;
-    ChainRecLive r{};
-    r.phase = PH_DONE;
+    // the chain's record: registers of its lane; several warps per chain: shared memory (only thread 0 uses it, and the
+    // other 127 threads do not pay 48 registers for a copy they never read)
+    ChainRecLive r_lane{};
+    __shared__ ChainRecLive r_cta;
+    ChainRecLive& r = WPC > 1 ? r_cta : r_lane;
     if (own) r = *static_cast<const ChainRecLive*>(v.rec + c);
-    const int ph0 = r.phase;
+    const int ph0 = own ? r.phase : (int)PH_DONE;
     if (Co::mask(ph0 != PH_DONE, slots, 0) == 0) return;
     const bool run = ph0 == PH_RUN;
     constexpr int STEP = 32 * WPC * VEC;

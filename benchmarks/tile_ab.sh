@@ -18,9 +18,7 @@ v=[float(r[-1]) for r in rows]
 import json; print(json.dumps({'label':'$label','wl':'$wl','ncu_avg_us':(sum(v)/len(v)/1000 if v else None),'n':len(v),'kernel':rows[0][4][:60] if rows else None}))" | tee -a $out
 }
 if [ "$2" = "tests" ]; then python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee -a $out; fi
-nk stash c2 B2H_TILE_TICK=1
-nk nostash c2 B2H_TILE_STASH=0
-nk stash c3 B2H_TILE_TICK=1
-nk nostash c3 B2H_TILE_STASH=0
-run stash c2 B2H_TILE_TICK=1
-run nostash c2 B2H_TILE_STASH=0
+nk w16 c2 B2H_TILE_TICK=1
+nk w12 c2 B2H_LIB=build/lib_w12/libb200hmc.so
+nk w8 c2 B2H_LIB=build/lib_w8/libb200hmc.so
+nk w16_wpc8 c2 B2H_TILE_WPC=8
