@@ -324,7 +324,7 @@ def measured_traffic(key):
         return None, None
 
 
-def dense_roofline(metric, Cn, d, ticks, step_ms, hbm_peak, dev, name, tick=None):
+def dense_roofline(metric, Cn, d, ticks, step_ms, hbm_peak, dev, name, tick=None, grad=None):
     """Dominant kernel of c2: the FP64 dense apply (DMMA tensor path), timed alone on the engine's stream."""
     import ctypes as C
     import torch
@@ -370,7 +370,10 @@ def dense_roofline(metric, Cn, d, ticks, step_ms, hbm_peak, dev, name, tick=None
                        "has no FP64 figure; SURVEY.md 8d names FP64 compute as the bound of config 2)",
         "peak_sustained": fp64_sustained, "frac_of_sustained": achieved / fp64_sustained,
         "launches_per_tick": 2, "share_of_step": ticks * 2.0 * gemm_ms / step_ms,
-        "cublas_same_shape_tflops": cublas_same_shape}
+        "cublas_same_shape_tflops": cublas_same_shape,
+        # the model's gradient call (this dense apply + the potential kernel) timed inside the step, where the momentum
+        # contractions of restarting chains run beside it on the side stream
+        "gradient_call_in_step_ms": grad["avg_launch_us"] * 1e-3 if grad else None}
     elementwise = elementwise_roofline(tick, name, Cn, d, 8, ticks, elementwise_ms, hbm_peak)
     return roofline, elementwise
 
@@ -612,7 +615,7 @@ def rooflines_for(w, D, peaks):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     if w["kind"] == "dense":
         return dense_roofline(w["metric"], w["chains_per_gpu"], w["dim"], w["ticks"], w["ms_per_step"], hbm_peak, D.dev,
-                              w["name"], w.get("tick_kernel"))
+                              w["name"], w.get("tick_kernel"), w.get("gradient_in_step"))
     return logistic_roofline(w["model"], w["chains_per_gpu"], w["dim"], w["n_data"], w["ticks"], w["ms_per_step"], peaks,
                              D.dev, w["dtype"], w["name"], w.get("tick_kernel"), w.get("gradient_in_step"))
 
