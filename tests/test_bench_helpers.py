@@ -33,3 +33,18 @@ def test_reference_arm_sample_is_bounded():
         assert 3 <= many <= full
         assert name in bench.describe(name)
     assert "configs[1]" in bench.describe("c2") and "configs[2]" in bench.describe("c3") and "configs[4]" in bench.describe("c5")
+
+
+def test_elementwise_roofline_arithmetic():
+    """The HBM roofline of the tick kernel: algorithmic bytes 11 d s C over the measured launch time; the traffic figures
+    come from the committed profile table (profiles/r02_traffic.json), never from a constant in bench.py."""
+    tick = {"avg_launch_us": 300.0, "launches": 62}
+    row = bench.elementwise_roofline(tick, "c5", 131072, 128, 4, 32, rest_ms=10.0, hbm_peak=6547.8)
+    alg = 11.0 * 128 * 4 * 131072
+    assert row["algorithmic_bytes_per_launch"] == alg
+    assert abs(row["achieved"] - alg / 300e-6 / 1e9) < 1e-6 and abs(row["frac"] - row["achieved"] / 6547.8) < 1e-12
+    assert row["traffic"] is not None and "r02_traffic.json" in row["traffic_from"]
+    assert abs(row["traffic_frac"] - row["traffic"] / 300e-6 / 1e9 / 6547.8) < 1e-12
+    # without a measured tick kernel (register-front kernels): derived from the step time, and said so
+    row2 = bench.elementwise_roofline(None, "c5", 131072, 128, 4, 32, rest_ms=16.0, hbm_peak=6547.8)
+    assert row2["how"].startswith("derived") and abs(row2["avg_launch_us"] - 500.0) < 1e-9
