@@ -15,6 +15,7 @@
 // transition (p0 = z . sqrt^T, v0 = p0 . imm), whose row count is only known on
 // the device and which would otherwise cost a full launch latency each.  Rows
 // can be gathered (in_rows) and scattered (out_rows) through index lists.
+#include <type_traits>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -337,9 +338,28 @@ constexpr int STAGES = 3;
 #define B2H_GEMM_BK_DEFAULT 32
 #endif
 
+// Fragment loads.  B2H_GEMM_FRAG128 = 1 (default): every lane fetches TWO fragment values per shared-memory load
+// (LDS.128) -- the k-slots tq / tq + 4 of the m16n8k8 shape are bound to the adjacent reduction indices 2 tq / 2 tq + 1
+// (the same binding for A and B, so the product is unchanged up to the order of the partial sums) and the n8 tiles 2 p /
+// 2 p + 1 of a warp take the even / odd columns of a 16-column group -- and the fragments of the next k8 step are in
+// flight while the current one is multiplied.  12 loads per 14 MMAs instead of 22; the paddings make the quarter-warp
+// accesses conflict free (A rows shift by 16 banks, B row pairs by 8).
+#ifndef B2H_GEMM_FRAG128
+#define B2H_GEMM_FRAG128 1
+#endif
+constexpr int kApad = B2H_GEMM_FRAG128 ? 8 : 4;
+constexpr int kBpad = B2H_GEMM_FRAG128 ? 2 : 8;
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async16s(unsigned sdst, const void* gsrc, int src_bytes) {   // shared-space address
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(sdst), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async16p(unsigned sdst, const void* gsrc, int src_bytes, bool active) {   // predicated
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}"
+                 :: "r"(sdst), "l"(gsrc), "r"(src_bytes), "r"((int)active));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N_)); }
@@ -355,10 +375,10 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
     constexpr int NJ = BN_ / 16;               // 8-wide MMA tiles per warp along N (warp tile 16 MI x BN_/2)
     constexpr int WROWS = 128 / (16 * MI);     // warps along M
     constexpr int NT = WROWS * 2 * 32;         // threads of the CTA
-    constexpr int ALD_ = BK_ + 4;              // padded A row (doubles)
+    constexpr int ALD_ = BK_ + kApad;          // padded A row (doubles)
     constexpr int CPR = BK_ / 2;               // 16-byte chunks per A row
     constexpr int A_ITERS = (BM * CPR) / NT;   // 16-byte chunks of the A tile per thread
-    constexpr int BLD = BN_ + 8;
+    constexpr int BLD = BN_ + kBpad;
     constexpr int A_STAGE = BM * ALD_, B_STAGE = BK_ * BLD;
     int tile_m = blockIdx.x / tiles_n;
     const int tile_n = blockIdx.x % tiles_n;
@@ -387,36 +407,55 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp % WROWS) * (16 * MI), wn = (warp / WROWS) * (BN_ / 2);
     const int gq = lane >> 2, tq = lane & 3;
+#ifdef B2H_GEMM_NO_STAGGER
+    const bool early = true;
+#else
+    const bool early = warp < NT / 64;
+#endif
 
-    // copy assignment: A tile = 128 rows x 8 chunks (16 B = 2 k); 8 consecutive threads take one row
-    i64 a_src[A_ITERS];
+    // Copy assignment, everything that does not depend on the k-tile computed once (the per-tile issue is ~6
+    // instructions per 16-byte copy; the generic index arithmetic it replaces took 300 per k-tile and warp, executed by
+    // every warp right after the barrier, i.e. with the tensor pipe idle).
+    // A tile: BM rows x CPR chunks (16 B = 2 k); CPR consecutive threads take one row, NT / CPR rows per pass.
+    constexpr int A_RPP = NT / CPR;
+    const int a_kc = (tid % CPR) * 2;
+    const T* a_ptr[A_ITERS];
+    unsigned a_valid = 0;
 #pragma unroll
     for (int i = 0; i < A_ITERS; ++i) {
-        const int row = (tid + NT * i) / CPR, gr = m0 + row;
-        a_src[i] = gr < M ? (i64)(g.in_rows ? g.in_rows[gr] : gr) * lda : -1;
+        const int gr = m0 + tid / CPR + A_RPP * i;
+        const bool ok = gr < M;
+        a_ptr[i] = A + (ok ? (i64)(g.in_rows ? g.in_rows[gr] : gr) * lda : (i64)0);
+        a_valid |= ok ? (1u << i) : 0u;
     }
-    constexpr int B_CHUNKS = BK_ * (BN_ / 2);
-    constexpr int B_ITERS = (B_CHUNKS + NT - 1) / NT;
+    const unsigned a_dst = (unsigned)__cvta_generic_to_shared(As) + (unsigned)(((tid / CPR) * ALD_ + a_kc) * sizeof(T));
+    // B tile: BK_ rows x BN_/2 chunks; 64 threads per row (those beyond the tile width idle), NT / 64 rows per pass.
+    static_assert(BN_ / 2 <= 64, "B copy: one row per 64 threads");
+    constexpr int B_RPP = NT / 64, B_ITERS = BK_ / B_RPP;
+    const int b_col = (tid & 63) * 2, b_row = tid >> 6;
+    const bool b_ok = b_col < BN_ && n0 + b_col < N;
+    const T* b_ptr = B + (b_ok ? n0 + b_col : 0);
+    const int ldb_i = (int)ldb;
+    const unsigned b_dst = (unsigned)__cvta_generic_to_shared(Bs) + (unsigned)((b_row * BLD + b_col) * sizeof(T));
 
     auto issue = [&](int kt, int stage) {
         const int k0 = k_begin + kt * BK_;
-        T* as = As + stage * A_STAGE;
-        T* bs = Bs + stage * B_STAGE;
+        {
+            const bool okk = k0 + a_kc < k_end;
+            const int kofs = okk ? k0 + a_kc : 0;
+            const unsigned dst = a_dst + (unsigned)(stage * A_STAGE * sizeof(T));
 #pragma unroll
-        for (int i = 0; i < A_ITERS; ++i) {
-            const int c = tid + NT * i, row = c / CPR, kc = (c % CPR) * 2;
-            const int gk = k0 + kc;
-            const bool ok = a_src[i] >= 0 && gk < k_end;
-            cp_async16(as + row * ALD_ + kc, ok ? (const void*)(A + a_src[i] + gk) : (const void*)A, ok ? 16 : 0);
+            for (int i = 0; i < A_ITERS; ++i)
+                cp_async16s(dst + (unsigned)(i * A_RPP * ALD_ * sizeof(T)), a_ptr[i] + kofs,
+                            (okk && ((a_valid >> i) & 1u)) ? 16 : 0);
         }
+        {
+            const unsigned dst = b_dst + (unsigned)(stage * B_STAGE * sizeof(T));
 #pragma unroll
-        for (int i = 0; i < B_ITERS; ++i) {
-            const int c = tid + NT * i;
-            if (c < B_CHUNKS) {
-                const int kr = c / (BN_ / 2), nc = (c % (BN_ / 2)) * 2;
-                const int gk = k0 + kr, gn = n0 + nc;
-                const bool ok = gk < k_end && gn < N;
-                cp_async16(bs + kr * BLD + nc, ok ? (const void*)(B + (i64)gk * ldb + gn) : (const void*)B, ok ? 16 : 0);
+            for (int i = 0; i < B_ITERS; ++i) {
+                const int gk = k0 + b_row + i * B_RPP;             // rows past the end of K: zero fill, address clamped
+                cp_async16p(dst + (unsigned)(i * B_RPP * BLD * sizeof(T)), b_ptr + (i64)min(gk, k_end - 1) * ldb_i,
+                            (b_ok && gk < k_end) ? 16 : 0, b_col < BN_);
             }
         }
         if (sub && tid < BK_ / 2) {
@@ -442,12 +481,62 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();                                          // tile kt landed; buffer (kt-1)%STAGES is free
-        {
+        auto refill = [&]() {
             const int nx = kt + STAGES - 1;
             if (nx < nk) issue(nx, nx % STAGES);
             cp_async_commit();
-        }
+        };
         const int stage = kt % STAGES;
+#if B2H_GEMM_FRAG128
+        const T* as = As + stage * A_STAGE + (wm + gq) * ALD_ + 2 * tq;
+        const T* bs = Bs + stage * B_STAGE + (2 * tq) * BLD + wn;
+        const T* ss = Ss + stage * BK_ + 2 * tq;
+        constexpr int NP = NJ / 2;                                // column pairs of n8 tiles; NJ odd: one single tile
+        // SUB: the launch subtracts a vector from the rows of A (the model's q - mu).  The subtraction runs on the
+        // same FP64 pipe as the MMAs (ncu: a DADD waits for the pipe twice as long as a DMMA), so launches without a
+        // vector -- two of the three contractions of a tick -- take a loop body without it.
+        auto ktile = [&](auto sub_tag) {
+            constexpr bool SUB = decltype(sub_tag)::value;
+            T fa[MI][4], fb[NJ][2];
+            // The two warps of a scheduler (w and w + NT / 64) refill the freed stage at different times: one right
+            // after the barrier while the other already multiplies, the other in the middle of the k-tile -- the
+            // copy-issue instructions of either run beside the other's MMAs instead of leaving the tensor pipe idle.
+            if (early) refill();
+#pragma unroll
+            for (int s8 = 0; s8 < BK_ / 8; ++s8) {
+                const int k0 = s8 * 8;
+                double2 sv = make_double2(0.0, 0.0);
+                if constexpr (SUB) sv = *reinterpret_cast<const double2*>(ss + k0);
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const double2 t = *reinterpret_cast<const double2*>(as + (i * 16 + h * 8) * ALD_ + k0);
+                        fa[i][h] = SUB ? t.x - sv.x : t.x;        // k-slot tq     <- k0 + 2 tq
+                        fa[i][2 + h] = SUB ? t.y - sv.y : t.y;    // k-slot tq + 4 <- k0 + 2 tq + 1
+                    }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const T* br = bs + (k0 + q) * BLD;
+#pragma unroll
+                    for (int pp = 0; pp < NP; ++pp) {
+                        const double2 t = *reinterpret_cast<const double2*>(br + 16 * pp + 2 * gq);
+                        fb[2 * pp][q] = t.x;
+                        fb[2 * pp + 1][q] = t.y;
+                    }
+                    if constexpr (NJ & 1) fb[NJ - 1][q] = br[16 * NP + gq];
+                }
+                if (s8 == BK_ / 16 && !early) refill();
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) Dmma<8>::run(acc[i][j], fa[i], fb[j]);
+            }
+        };
+        if (sub) ktile(std::true_type{});
+        else ktile(std::false_type{});
+#else
+        refill();
         const T* as = As + stage * A_STAGE + (wm + gq) * ALD_;
         const T* bs = Bs + stage * B_STAGE + wn + gq;
         const T* ss = Ss + stage * BK_;
@@ -471,6 +560,7 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) Dmma<8>::run(acc[i][j], fa[i], fb[j]);
         }
+#endif
     }
     cp_async_wait<0>();
 
@@ -481,11 +571,29 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
             const int gr = m0 + wm + i * 16 + h * 8 + gq;
             if (gr >= M) continue;
             const i64 orow = (i64)((g.out_rows && !split) ? g.out_rows[gr] : gr) * ldo;
+#if B2H_GEMM_FRAG128
+            // tiles 2 p / 2 p + 1 hold the even / odd columns of group p: a lane owns 4 consecutive columns of it
+#pragma unroll
+            for (int pp = 0; pp < NJ / 2; ++pp) {
+                const int gn = n0 + wn + 16 * pp + 4 * tq;
+                if (gn < N)
+                    *reinterpret_cast<double2*>(out + orow + gn) = make_double2(acc[i][2 * pp][2 * h], acc[i][2 * pp + 1][2 * h]);
+                if (gn + 2 < N)
+                    *reinterpret_cast<double2*>(out + orow + gn + 2) =
+                        make_double2(acc[i][2 * pp][2 * h + 1], acc[i][2 * pp + 1][2 * h + 1]);
+            }
+            if constexpr (NJ & 1) {
+                const int gn = n0 + wn + 16 * (NJ / 2) + tq * 2;
+                if (gn < N)
+                    *reinterpret_cast<double2*>(out + orow + gn) = make_double2(acc[i][NJ - 1][2 * h], acc[i][NJ - 1][2 * h + 1]);
+            }
+#else
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 const int gn = n0 + wn + j * 8 + tq * 2;
                 if (gn < N) *reinterpret_cast<double2*>(out + orow + gn) = make_double2(acc[i][j][2 * h], acc[i][j][2 * h + 1]);
             }
+#endif
         }
 }
 
@@ -493,7 +601,7 @@ template <int BN_, int MI, int BK_>
 static void launch_async_v(cudaStream_t st, dim3 grid, int threads, const GemmGroup<double>& g0, const GemmGroup<double>& g1,
                            const GemmGroup<double>& g2, int N, int K, int tiles_n, int tiles_m0, int tiles_m1, int k_chunk,
                            i64 split_stride) {
-    constexpr int smem = (STAGES * (BM * (BK_ + 4) + BK_ * (BN_ + 8)) + STAGES * BK_) * (int)sizeof(double);
+    constexpr int smem = (STAGES * (BM * (BK_ + kApad) + BK_ * (BN_ + kBpad)) + STAGES * BK_) * (int)sizeof(double);
     cudaFuncSetAttribute(dense_apply_dmma_async_kernel<BN_, MI, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     dense_apply_dmma_async_kernel<BN_, MI, BK_><<<grid, threads, smem, st>>>(g0, g1, g2, N, K, tiles_n, tiles_m0, tiles_m1,
                                                                              k_chunk, split_stride);
