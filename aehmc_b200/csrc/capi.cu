@@ -1,4 +1,5 @@
 // Context management, error reporting and the sampler entry points of the C-ABI.
+#include <stdlib.h>
 #include <string.h>
 
 #include "launch.h"
@@ -45,11 +46,17 @@ int b2h_ctx_create(int device, void* stream, b2h_ctx** out) {
     ctx->device = device;
     ctx->stream = (cudaStream_t)stream;
     ctx->sm_count = prop.multiProcessorCount;
-    // highest priority: the few momentum tiles must be picked up as soon as SMs free up, not after the main
-    // stream's full-size launches (the next tick waits for them)
+    // the momentum tiles of restarting chains run at the LOWEST priority beside the full-size launches of a dense-metric
+    // run, which hop onto the high-priority stream (engine_split.inl); B2H_HI_STREAM=0: the former arrangement (side
+    // stream at the highest priority, everything else on the caller's stream)
     int prio_least = 0, prio_greatest = 0;
     B2H_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
-    B2H_CUDA(cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_greatest));
+    const char* hop = getenv("B2H_HI_STREAM");
+    const bool use_hi = !(hop && atoi(hop) == 0);
+    B2H_CUDA(cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, use_hi ? prio_least : prio_greatest));
+    ctx->hi = nullptr;
+    if (use_hi) B2H_CUDA(cudaStreamCreateWithPriority(&ctx->hi, cudaStreamNonBlocking, prio_greatest));
+    B2H_CUDA(cudaEventCreateWithFlags(&ctx->ev_hop, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         B2H_CUDA(cudaEventCreateWithFlags(&ctx->ev_pre[i], cudaEventDisableTiming));
         B2H_CUDA(cudaEventCreateWithFlags(&ctx->ev_side[i], cudaEventDisableTiming));
@@ -62,6 +69,8 @@ int b2h_ctx_create(int device, void* stream, b2h_ctx** out) {
 int b2h_ctx_destroy(b2h_ctx* ctx) {
     if (ctx) {
         cudaStreamDestroy(ctx->side);
+        if (ctx->hi) cudaStreamDestroy(ctx->hi);
+        cudaEventDestroy(ctx->ev_hop);
         cudaFreeHost(ctx->host_flag);
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_pre[i]); cudaEventDestroy(ctx->ev_side[i]); }
         for (cudaEvent_t e : ctx->tick_events) cudaEventDestroy(e);

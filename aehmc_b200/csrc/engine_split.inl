@@ -185,10 +185,13 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
         const i64 plane = (i64)C * d;
         T* part1 = v.mom_part;
         T* part2 = v.mom_part + (size_t)kRiderSplit * plane;
+        // metric->reserved bit 0: the factors are the reference's triangular ones (sqrt_t = L^-1 lower, chol_t = L^T
+        // upper: metrics.py:56-58), so half of each contraction is skipped
+        const int tri = (metric->reserved & 1) ? 1 : 0;
         GemmGroup<T> g1{v.mom_z + (size_t)b * C * d, (i64)d, sqrt_t, (i64)d, part1, (i64)d, C, v.mom_count + b,
-                        nullptr, nullptr, nullptr};
+                        nullptr, nullptr, nullptr, tri ? 2 : 0};
         GemmGroup<T> g2{v.mom_z + (size_t)b * C * d, (i64)d, chol_t, (i64)d, part2, (i64)d, C, v.mom_count + b,
-                        nullptr, nullptr, nullptr};
+                        nullptr, nullptr, nullptr, tri ? 1 : 0};
         launch_gemm_grouped<T>(rider_stream, g1, g2, none, d, d, kRiderSplit, plane, 0);
         rider_reduce_kernel<T><<<dim3(C, 2), 128, 0, rider_stream>>>(
             part1, v.mom_count + b, v.mom_list + (size_t)b * C, v.mom_p, part2, v.mom_count + b,
@@ -314,6 +317,25 @@ int run_split_g(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const b2h_
                 int* not_done_dev, int resume, bool hmc) {
 #define B2H_RUN_SPLIT(G, H) \
     run_split<T, G, H>(ctx, v, pl, model, metric, cfg, max_ticks, n_transitions, model_ws, model_ws_bytes, not_done_dev, resume)
+    // Dense metric: the whole call runs on the context's high-priority stream, ordered after the caller's stream at
+    // entry and before it at exit (launch.h: the momentum tiles of the side stream then only fill idle SMs).
+    struct Hop {
+        b2h_ctx* c;
+        cudaStream_t user;
+        bool on;
+        ~Hop() {
+            if (!on) return;
+            cudaEventRecord(c->ev_hop, c->stream);
+            cudaStreamWaitEvent(user, c->ev_hop, 0);
+            c->stream = user;
+        }
+    } hop{ctx, ctx->stream, false};
+    if (pl.dense && ctx->hi) {
+        B2H_CUDA(cudaEventRecord(ctx->ev_hop, ctx->stream));
+        B2H_CUDA(cudaStreamWaitEvent(ctx->hi, ctx->ev_hop, 0));
+        ctx->stream = ctx->hi;
+        hop.on = true;
+    }
     if (hmc) {
         switch (pl.G) {
             case 8: return B2H_RUN_SPLIT(8, true);

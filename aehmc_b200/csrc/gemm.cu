@@ -393,9 +393,14 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
     const T* __restrict__ B = g.B;
     const T* __restrict__ sub = g.sub;
     const i64 lda = g.lda, ldb = g.ldb, ldo = g.ldo;
-    // split-K: slice blockIdx.y reduces k in [k_begin, k_end) into its own partial plane (rows not scattered)
-    const int k_begin = blockIdx.y * k_chunk;
-    const int k_end = min(K, k_begin + k_chunk);
+    // split-K: slice blockIdx.y reduces k in [k_begin, k_end) into its own partial plane (rows not scattered).
+    // Triangular B: only the k-range [k_lo, k_hi) of this column tile can hold non-zeros; it is what the slices share.
+    int k_lo = 0, k_hi = K;
+    if (g.tri == 1) k_hi = min(K, n0 + BN_);
+    else if (g.tri == 2) k_lo = min(K, (n0 / BK_) * BK_);
+    if (g.tri) k_chunk = (((k_hi - k_lo + (int)gridDim.y - 1) / (int)gridDim.y + BK_ - 1) / BK_) * BK_;
+    const int k_begin = k_lo + blockIdx.y * k_chunk;
+    const int k_end = min(k_hi, k_begin + k_chunk);
     const bool split = gridDim.y > 1;
     T* __restrict__ out = g.out + (i64)blockIdx.y * split_stride;
 

@@ -16,6 +16,11 @@ struct b2h_ctx {
     // stream's kernels they share SMs fluidly instead of adding a mostly empty wave to a full launch
     cudaStream_t side;
     cudaEvent_t ev_pre[2], ev_side[2];
+    // dense-metric runs of the split engine hop from the caller's stream onto this high-priority stream (and back at
+    // the end of the call), so that the side stream's momentum tiles -- lowest priority -- only take SMs no full-size
+    // launch is waiting for (the 8 of 148 a 288-tile contraction leaves idle in its second wave)
+    cudaStream_t hi;
+    cudaEvent_t ev_hop;
     int* host_flag;   // pinned, for the split engine's completion poll
     // b2h_tick_timer: event pairs around the tick-kernel launches of the split engine (measurement aid, off by default)
     int tick_timer = 0;               // 0 off, 1 the tick kernel, 2 the gradient call (potential_and_grad) of every tick
@@ -51,6 +56,8 @@ struct GemmGroup {
     const T* sub;          // optional [K] vector subtracted from every A row on load
     const int* in_rows;    // optional gather list: A row of logical row r is in_rows[r]
     const int* out_rows;   // optional scatter list for the output rows
+    int tri;               // B known to be 1: upper-triangular (B[k][n] = 0 for k > n), 2: lower-triangular, 0: general.
+                           // The DMMA tile kernel then skips the k-range of a column tile that only holds zeros.
 };
 template <typename T>
 void launch_gemm_grouped(cudaStream_t st, const GemmGroup<T>& g0, const GemmGroup<T>& g1, const GemmGroup<T>& g2, int N,

@@ -71,7 +71,9 @@ class GaussianMetric:
 
     def struct(self):
         p = lambda t: None if t is None else t.data_ptr()
-        return _lib.Metric(self.kind, 0, self.scalar, p(self.imm), p(self.sqrt_t), p(self.chol_t))
+        # flags bit 0: sqrt_t / chol_t are the triangular Cholesky factors built above (b200hmc.h)
+        return _lib.Metric(self.kind, 1 if self.kind == _lib.IMM_DENSE else 0, self.scalar, p(self.imm), p(self.sqrt_t),
+                           p(self.chol_t))
 
     def _ws_for(self, n_elems):
         nbytes = n_elems * (8 if self.dtype == torch.float64 else 4) + 512

@@ -83,7 +83,9 @@ enum {
 
 typedef struct {
     int32_t kind;
-    int32_t reserved;
+    int32_t reserved;   /* flags.  bit 0 (dense only): sqrt_t and chol_t are the TRIANGULAR factors described below (sqrt_t
+                           lower-, chol_t upper-triangular), so the momentum contractions may skip their zero halves; 0: any
+                           factors with sqrt_t^T sqrt_t = imm^-1 and chol_t = (imm sqrt_t^T)^T are read in full            */
     double scalar;
     const void* imm;    /* device; dense: symmetric [d x d] */
     const void* sqrt_t; /* device, dense only: TRANSPOSE of mass_matrix_sqrt = solve_triangular(chol(imm), I,
