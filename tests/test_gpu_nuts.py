@@ -307,6 +307,42 @@ def test_nuts_dense_metric_first_step_divergence(ab):
     np.testing.assert_allclose(_np(info.state.momentum), ref["p"], rtol=1e-9, atol=1e-11)
 
 
+def test_nuts_dense_metric_triangular_flag(ab, monkeypatch):
+    """b2h_metric.reserved bit 0 (the factors are triangular: the momentum contractions of restarting chains skip the
+    zero k-range of every column tile, gemm.cu) against the same run reading the factors in full; d = 300 spans three
+    column tiles, so both triangles really skip."""
+    from aehmc_b200 import _engine, _lib
+    rng = np.random.default_rng(43)
+    C, T, d = 6, 3, 300
+    mu, cov, prec = _corr_case(rng, d)
+    q0 = mu + rng.standard_normal((C, d))
+    draws = parity.random_draws(rng, C, T, d)
+    model = ab.models.CorrelatedGaussian(mu, prec)
+
+    def run():
+        srng = ab.InjectedDraws(draws["z"], draws["u_dir"], draws["u_biased"], draws["u_uniform"])
+        return _engine.run("nuts", model, cov, srng, ab.nuts.new_state(q0, model), 0.15, n_transitions=T, store_draws=T)
+
+    info1, ex1 = run()
+    flags = []
+    full = ab.metrics.GaussianMetric.struct
+
+    def struct_no_flag(self):
+        m = full(self)
+        flags.append(int(m.reserved))
+        m.reserved = 0
+        return m
+
+    monkeypatch.setattr(ab.metrics.GaussianMetric, "struct", struct_no_flag)
+    info0, ex0 = run()
+    assert flags and all(f == 1 for f in flags)
+    np.testing.assert_array_equal(_np(info1.num_doublings), _np(info0.num_doublings))
+    np.testing.assert_array_equal(_np(ex1["n_leapfrog"]), _np(ex0["n_leapfrog"]))
+    assert _np(ex1["n_leapfrog"]).sum() > 2 * C * T
+    np.testing.assert_allclose(_np(ex1["draws"]), _np(ex0["draws"]), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(_np(info1.state.momentum), _np(info0.state.momentum), rtol=1e-10, atol=1e-12)
+
+
 @pytest.mark.parametrize("metric_kind", ["diag", "dense"])
 def test_hmc_proposal_closure_matches_oracle(ab, metric_kind):
     """hmc.hmc_proposal(integrator, kinetic_energy, L, threshold) -> propose(srng, state, step_size)
