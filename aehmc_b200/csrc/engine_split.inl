@@ -101,13 +101,14 @@ __global__ void rider_reduce_kernel(const T* part0, const int* count0, const int
     const int* count = blockIdx.y ? count1 : count0;
     const int* list = blockIdx.y ? list1 : list0;
     T* out = blockIdx.y ? out1 : out0;
-    const int r = blockIdx.x;
-    if (r >= *count) return;
-    const i64 dst = (i64)list[r] * d;
-    for (int j = threadIdx.x; j < d; j += blockDim.x) {
-        T s = 0;
-        for (int k = 0; k < nsplit; ++k) s += part[(i64)k * plane + (i64)r * d + j];
-        out[dst + j] = s;
+    const int n = *count;
+    for (int r = blockIdx.x; r < n; r += gridDim.x) {             // a few hundred of the C rows restart on a tick
+        const i64 dst = (i64)list[r] * d;
+        for (int j = threadIdx.x; j < d; j += blockDim.x) {
+            T s = 0;
+            for (int k = 0; k < nsplit; ++k) s += part[(i64)k * plane + (i64)r * d + j];
+            out[dst + j] = s;
+        }
     }
 }
 
@@ -193,7 +194,7 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
         GemmGroup<T> g2{v.mom_z + (size_t)b * C * d, (i64)d, chol_t, (i64)d, part2, (i64)d, C, v.mom_count + b,
                         nullptr, nullptr, nullptr, tri ? 1 : 0};
         launch_gemm_grouped<T>(rider_stream, g1, g2, none, d, d, kRiderSplit, plane, 0);
-        rider_reduce_kernel<T><<<dim3(C, 2), 128, 0, rider_stream>>>(
+        rider_reduce_kernel<T><<<dim3(C < 592 ? C : 592, 2), 128, 0, rider_stream>>>(
             part1, v.mom_count + b, v.mom_list + (size_t)b * C, v.mom_p, part2, v.mom_count + b,
             v.mom_list + (size_t)b * C, v.mom_v, kRiderSplit, plane, d);
         if (use_side) {

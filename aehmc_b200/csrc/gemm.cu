@@ -15,6 +15,7 @@
 // transition (p0 = z . sqrt^T, v0 = p0 . imm), whose row count is only known on
 // the device and which would otherwise cost a full launch latency each.  Rows
 // can be gathered (in_rows) and scattered (out_rows) through index lists.
+#include <algorithm>
 #include <type_traits>
 #include <stdlib.h>
 
@@ -367,10 +368,10 @@ template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile
 // MI: 16-row MMA tiles per warp along M.  MI = 2: 8 warps (4 x 2), warp tile 32 x BN_/2.  MI = 1: 16 warps (8 x 2), warp
 // tile 16 x BN_/2 -- half the accumulators per thread, twice the warps to cover the per-k-tile barrier.
 // BK_: k-tile depth (16, or 32: half the barriers and commit groups per flop, 203 KB of shared memory for 3 stages).
-template <int BN_, int MI, int BK_>
+template <int BN_, int MI, int BK_, bool LOOP>
 __global__ void __launch_bounds__((128 / (16 * MI)) * 2 * 32, 1)
 dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGroup<double> g2, int N, int K, int tiles_n,
-                              int tiles_m0, int tiles_m1, int k_chunk, i64 split_stride) {
+                              int tiles_m0, int tiles_m1, int k_chunk_in, i64 split_stride, int total_tiles) {
     typedef double T;
     constexpr int NJ = BN_ / 16;               // 8-wide MMA tiles per warp along N (warp tile 16 MI x BN_/2)
     constexpr int WROWS = 128 / (16 * MI);     // warps along M
@@ -380,15 +381,22 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
     constexpr int A_ITERS = (BM * CPR) / NT;   // 16-byte chunks of the A tile per thread
     constexpr int BLD = BN_ + kBpad;
     constexpr int A_STAGE = BM * ALD_, B_STAGE = BK_ * BLD;
-    int tile_m = blockIdx.x / tiles_n;
-    const int tile_n = blockIdx.x % tiles_n;
+    // One tile per CTA (gridDim.x == total_tiles), except for launches whose row count only the device knows (the
+    // momentum contractions of restarting chains: the grid would cover all C rows and 9 of 10 CTAs -- each needing a
+    // whole SM's shared memory -- would exit at once): a small grid walks the tiles and skips the empty ones.
+    int tile = blockIdx.x;
+    do {
+    if (LOOP && tile != (int)blockIdx.x) __syncthreads();         // every warp is done with the previous tile's stages
+    int k_chunk = k_chunk_in;
+    int tile_m = tile / tiles_n;
+    const int tile_n = tile % tiles_n;
     const int which = tile_m < tiles_m0 ? 0 : (tile_m < tiles_m0 + tiles_m1 ? 1 : 2);
     const GemmGroup<T>& g = which == 0 ? g0 : (which == 1 ? g1 : g2);
     tile_m -= which == 0 ? 0 : (which == 1 ? tiles_m0 : tiles_m0 + tiles_m1);
     int M = g.M;
     if (g.m_dev) M = min(M, *g.m_dev);
     const int m0 = tile_m * BM, n0 = tile_n * BN_;
-    if (m0 >= M) return;
+    if (m0 >= M) continue;
     const T* __restrict__ A = g.A;
     const T* __restrict__ B = g.B;
     const T* __restrict__ sub = g.sub;
@@ -600,6 +608,7 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
             }
 #endif
         }
+    } while (LOOP && (tile += gridDim.x) < total_tiles);          // tiles of this CTA
 }
 
 template <int BN_, int MI, int BK_>
@@ -607,9 +616,23 @@ static void launch_async_v(cudaStream_t st, dim3 grid, int threads, const GemmGr
                            const GemmGroup<double>& g2, int N, int K, int tiles_n, int tiles_m0, int tiles_m1, int k_chunk,
                            i64 split_stride) {
     constexpr int smem = (STAGES * (BM * (BK_ + kApad) + BK_ * (BN_ + kBpad)) + STAGES * BK_) * (int)sizeof(double);
-    cudaFuncSetAttribute(dense_apply_dmma_async_kernel<BN_, MI, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    dense_apply_dmma_async_kernel<BN_, MI, BK_><<<grid, threads, smem, st>>>(g0, g1, g2, N, K, tiles_n, tiles_m0, tiles_m1,
-                                                                             k_chunk, split_stride);
+    const int total = (int)grid.x;
+    if ((g0.M > 0 && g0.m_dev) || (g1.M > 0 && g1.m_dev) || (g2.M > 0 && g2.m_dev)) {
+        static int sms = 0;
+        if (sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        }
+        grid.x = (unsigned)std::max(1, std::min(total, (2 * sms + (int)grid.y - 1) / (int)grid.y));
+        cudaFuncSetAttribute(dense_apply_dmma_async_kernel<BN_, MI, BK_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        dense_apply_dmma_async_kernel<BN_, MI, BK_, true><<<grid, threads, smem, st>>>(g0, g1, g2, N, K, tiles_n, tiles_m0,
+                                                                                       tiles_m1, k_chunk, split_stride, total);
+        return;
+    }
+    cudaFuncSetAttribute(dense_apply_dmma_async_kernel<BN_, MI, BK_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    dense_apply_dmma_async_kernel<BN_, MI, BK_, false><<<grid, threads, smem, st>>>(g0, g1, g2, N, K, tiles_n, tiles_m0,
+                                                                                    tiles_m1, k_chunk, split_stride, total);
 }
 
 template <int BN_>
