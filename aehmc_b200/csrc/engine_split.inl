@@ -193,10 +193,12 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
                         nullptr, nullptr, nullptr, tri ? 2 : 0};
         GemmGroup<T> g2{v.mom_z + (size_t)b * C * d, (i64)d, chol_t, (i64)d, part2, (i64)d, C, v.mom_count + b,
                         nullptr, nullptr, nullptr, tri ? 1 : 0};
-        launch_gemm_grouped<T>(rider_stream, g1, g2, none, d, d, kRiderSplit, plane, 0);
+        static int rsplit = 0;
+        if (rsplit == 0) { const char* e = getenv("B2H_RIDER_SPLIT"); rsplit = e ? atoi(e) : kRiderSplit; if (rsplit < 1 || rsplit > kRiderSplit) rsplit = kRiderSplit; }
+        launch_gemm_grouped<T>(rider_stream, g1, g2, none, d, d, rsplit, plane, 0);
         rider_reduce_kernel<T><<<dim3(C < 592 ? C : 592, 2), 128, 0, rider_stream>>>(
             part1, v.mom_count + b, v.mom_list + (size_t)b * C, v.mom_p, part2, v.mom_count + b,
-            v.mom_list + (size_t)b * C, v.mom_v, kRiderSplit, plane, d);
+            v.mom_list + (size_t)b * C, v.mom_v, rsplit, plane, d);
         if (use_side) {
             B2H_CUDA(cudaEventRecord(ctx->ev_side[b], ctx->side));
             side_pending[b] = true;
