@@ -99,6 +99,9 @@ struct EngineView {
     i64 imm_sc, imm_sj;
     // split-mode scratch (row-major [C][d]) and dense-momentum compaction
     T *xa, *xb, *xc, *Unew;              // xa = q' (gradient input), xb = g' (gradient output), xc = imm.g' (dense)
+    // Gaussian targets: U = 0.5 (q' - u_center) . g', which the tile tick kernel's pass A forms from the rows it reads
+    // anyway instead of a separate kernel over q' and g' (nullptr: U comes from Unew)
+    const T* u_center;
     // dense-metric momentum, one transition of lookahead: mom_p/mom_v [C][d] hold p0 = sqrt z and v0 = imm p0 of
     // each chain's NEXT transition; a chain that starts a transition consumes them and queues a request
     // (list/count of parity mom_parity, normals in mom_z) that rides along the following dense applies.

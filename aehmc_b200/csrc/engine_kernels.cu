@@ -93,6 +93,7 @@ static size_t carve(EngineView<T>& v, char* base, const EnginePlan& pl, const b2
     v.adapt.wc_mean = v.adapt.wc_m2 = nullptr;
     if (adapt) { v.adapt.wc_mean = cv.take<T>(n); v.adapt.wc_m2 = cv.take<T>(n); }
     v.xa = v.xb = v.xc = v.Unew = nullptr;
+    v.u_center = nullptr;
     v.mom_p = v.mom_v = v.mom_z = nullptr; v.mom_count = nullptr; v.mom_list = nullptr;
     if (pl.split) {
         v.xa = cv.take<T>(n); v.xb = cv.take<T>(n); v.Unew = cv.take<T>(C);

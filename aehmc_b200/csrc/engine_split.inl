@@ -274,10 +274,21 @@ static int run_split(b2h_ctx* ctx, EngineView<T>& v, const EnginePlan& pl, const
     };
 #undef B2H_POSTPRE
 
+    // Correlated Gaussian target under the tile tick kernel's one-chain layouts: U = 0.5 (q' - mu) . g' is formed by the
+    // tick kernel's pass A (it holds q' and g' already); the gradient call is the contraction alone.
+    // B2H_TICK_POTENTIAL=0: the separate potential kernel (A/B measurements, parity tests)
+    bool grad_only = false;
+    v.u_center = nullptr;
+    if (tile_tick && model->kind == B2H_MODEL_CORR_GAUSSIAN && ((uintptr_t)model->a % 16) == 0) {
+        const char* e = getenv("B2H_TICK_POTENTIAL");
+        const bool layout = pl.dense ? tile_tick_unit_chain_layout<T, true>(v, ctx->sm_count)
+                                     : tile_tick_unit_chain_layout<T, false>(v, ctx->sm_count);
+        if (layout && !(e && atoi(e) == 0)) { grad_only = true; v.u_center = (const T*)model->a; }
+    }
     rc = launch_pre(0);
     for (i64 tick = 0; tick < bound && rc == 0; ++tick) {
         grad_mark();
-        rc = potential_and_grad_impl<T>(ctx, model, v.xa, v.Unew, v.xb, C, model_ws, model_ws_bytes);
+        rc = potential_and_grad_impl<T>(ctx, model, v.xa, v.Unew, v.xb, C, model_ws, model_ws_bytes, grad_only);
         grad_mark();
         if (rc) break;
         const bool last = tick + 1 == bound;

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? B2H_TILE
     typedef Coop<TC, WPC> Co;
     const bool pre = (flags & 1) != 0;                   // the half kick + drift of the next tick follows (not the last tick of a call)
     __shared__ double slots[32];                         // WPC > 1: one slot per broadcast value
-    __shared__ double red_s[3 * WPC];                    // WPC > 1: per-warp partials of a reduction
+    __shared__ double red_s[4 * WPC];                    // WPC > 1: per-warp partials of a reduction
     const int lane = Co::tid();                          // index of this thread in the group that shares a chain's rows
     const int c0 = WPC > 1 ? (int)blockIdx.x : (int)(((i64)blockIdx.x * 128 + threadIdx.x) >> 5) * TC;
     if (c0 >= v.C) return;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? B2H_TILE
         nlev = (s >= 1 && imax >= imin) ? (imax - imin + 1) : 0;
         e = (T)(r.go_right ? r.eps : -r.eps);
         he = (T)0.5 * e;
-        U_new = v.Unew[c];
+        if (!(TC == 1 && VEC > 1 && v.u_center)) U_new = v.Unew[c];   // else pass A forms it from q' and g'
     }
 
     // ---- A: p' = p_half - (0.5 e) g', K(p'), sub-tree momentum sum, checkpoint write (even steps), U-turn dot products
@@ -296,6 +296,8 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? B2H_TILE
             T* __restrict__ SCK = v.sckp + cb;
             T* __restrict__ VCK = DENSE ? v.vck + cb : nullptr;
             T kacc = 0, dl = 0, dr = 0;
+            [[maybe_unused]] T uacc = 0;
+            [[maybe_unused]] const bool ucen = TC == 1 && VEC > 1 && v.u_center != nullptr;
             // where the rows are read from: global memory, or (tiles of several chains) this stage of the ring, whose
             // row r starts at slot(stg, r) - 16 lane, so that "+ j" with j = j0 lands on this lane's piece
             const T* Pl = P;
@@ -343,7 +345,13 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? B2H_TILE
                 }
                 [[maybe_unused]] T qx[VEC];
                 if constexpr (TC == 1 && VEC > 1) {
-                    if (stash) ldv<T, VEC>(qx, v.xa + rb + j);       // for pass D (it would read it anyway)
+                    if (stash || ucen) ldv<T, VEC>(qx, v.xa + rb + j);   // for pass D (it would read it anyway) / for U
+                    if (ucen) {                                          // U = 0.5 (q' - centre) . g' (Gaussian targets)
+                        T mu[VEC];
+                        ldv<T, VEC>(mu, v.u_center + j);
+#pragma unroll
+                        for (int x = 0; x < VEC; ++x) uacc += (qx[x] - mu[x]) * gx[x];
+                    }
                 }
                 T p[VEC], vel[VEC], sm[VEC];
 #pragma unroll
@@ -377,8 +385,18 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? B2H_TILE
                 }
             }
             double red[3] = {(double)kacc, (double)dl, (double)dr};
-            if (nl > 0) Co::template sum<3>(red, red_s);
-            else { double r1[1] = {red[0]}; Co::template sum<1>(r1, red_s); red[0] = r1[0]; }
+            [[maybe_unused]] double usum = 0.0;
+            if constexpr (TC == 1 && VEC > 1) {
+                if (ucen) {                                              // warp-uniform: the potential rides along
+                    double r4[4] = {red[0], red[1], red[2], (double)uacc};
+                    Co::template sum<4>(r4, red_s);
+                    red[0] = r4[0]; red[1] = r4[1]; red[2] = r4[2]; usum = r4[3];
+                } else if (nl > 0) Co::template sum<3>(red, red_s);
+                else { double r1[1] = {red[0]}; Co::template sum<1>(r1, red_s); red[0] = r1[0]; }
+            } else {
+                if (nl > 0) Co::template sum<3>(red, red_s);
+                else { double r1[1] = {red[0]}; Co::template sum<1>(r1, red_s); red[0] = r1[0]; }
+            }
             bool tm = nl > 0 && ((T)red[1] <= (T)0 || (T)red[2] <= (T)0);
             // deeper levels (steps with two or more trailing one-bits); the outcome is an OR over the levels
             for (int l = 1; l < nl && !tm; ++l) {
@@ -409,7 +427,11 @@ __global__ void __launch_bounds__((Coop<TC, WPC>::kThreads), (WPC > 1 ? B2H_TILE
                 Co::template sum<2>(r2, red_s);
                 if ((T)r2[0] <= (T)0 || (T)r2[1] <= (T)0) tm = true;
             }
-            if (Co::owner(i)) { myK = (T)0.5 * (T)red[0]; term = tm; }
+            if (Co::owner(i)) {
+                myK = (T)0.5 * (T)red[0];
+                term = tm;
+                if constexpr (TC == 1 && VEC > 1) { if (ucen) U_new = (T)0.5 * (T)usum; }
+            }
         }
     }
 
@@ -931,6 +953,16 @@ static void launch_tile_smem(cudaStream_t st, const EngineView<T>& v, int* nd, i
     if (bytes > 48 * 1024)
         cudaFuncSetAttribute(tile::tile_tick_kernel<T, TC, WPC, VEC, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     tile::tile_tick_kernel<T, TC, WPC, VEC, DENSE><<<grid, threads, bytes, st>>>(v, nd, flags);
+}
+
+// true when launch_tile_tick will run a one-chain layout with vector rows (TC == 1, VEC > 1): the layouts whose pass A
+// can form the potential of a Gaussian target itself (EngineView::u_center)
+template <typename T, bool DENSE>
+static bool tile_tick_unit_chain_layout(const EngineView<T>& v, int sm_count) {
+    const bool aligned = ((size_t)v.d * sizeof(T)) % 16 == 0 && ((uintptr_t)v.imm % 16 == 0 || DENSE) &&
+                         (uintptr_t)v.out.draws % 16 == 0;
+    const bool short_rows = (size_t)v.d * sizeof(T) <= (size_t)tile::kRowBytes;
+    return aligned && (short_rows ? tile_chains_per_warp(v.C, sm_count) : 1) == 1;
 }
 
 template <typename T, bool DENSE>

@@ -73,7 +73,8 @@ void launch_gemm(cudaStream_t st, const T* A, i64 lda, const T* B, i64 ldb, T* o
 
 // primitives.cu
 template <typename T>
-int potential_and_grad_impl(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U, T* g, i64 C, void* ws, i64 ws_bytes);
+int potential_and_grad_impl(b2h_ctx* ctx, const b2h_model* m, const T* q, T* U, T* g, i64 C, void* ws, i64 ws_bytes,
+                            bool gradient_only = false);   // gradient_only: the caller forms U itself (EngineView::u_center)
 i64 potential_workspace_bytes_impl(const b2h_model* m, int dtype, i64 C);
 
 // logreg.cu

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128) corr_potential_kernel(const T* q, const T
 
 template <typename T>
 int potential_and_grad_impl(b2h_ctx* ctx, const b2h_model* model, const T* q, T* U, T* g, i64 C, void* ws,
-                            i64 ws_bytes) {
+                            i64 ws_bytes, bool gradient_only) {
     cudaStream_t st = ctx->stream;
     ModelDev m = to_dev(model);
     const int d = model->dim;
@@ -69,7 +69,7 @@ int potential_and_grad_impl(b2h_ctx* ctx, const b2h_model* model, const T* q, T*
             break;
         case B2H_MODEL_CORR_GAUSSIAN:
             launch_dense_apply<T>(st, q, (const T*)model->b, g, (int)C, d, d, nullptr, (const T*)model->a);
-            corr_potential_kernel<T><<<PGeo<32>::grid(C), 128, 0, st>>>(q, (const T*)model->a, g, U, C, d);
+            if (!gradient_only) corr_potential_kernel<T><<<PGeo<32>::grid(C), 128, 0, st>>>(q, (const T*)model->a, g, U, C, d);
             break;
         case B2H_MODEL_LOGISTIC:
             return logistic_potential_and_grad<T>(ctx, model, q, U, g, C, ws, ws_bytes, 0);
@@ -82,9 +82,9 @@ int potential_and_grad_impl(b2h_ctx* ctx, const b2h_model* model, const T* q, T*
     B2H_LAUNCH_CHECK();
     return 0;
 }
-template int potential_and_grad_impl<float>(b2h_ctx*, const b2h_model*, const float*, float*, float*, i64, void*, i64);
+template int potential_and_grad_impl<float>(b2h_ctx*, const b2h_model*, const float*, float*, float*, i64, void*, i64, bool);
 template int potential_and_grad_impl<double>(b2h_ctx*, const b2h_model*, const double*, double*, double*, i64, void*,
-                                             i64);
+                                             i64, bool);
 
 i64 potential_workspace_bytes_impl(const b2h_model* m, int dtype, i64 C) {
     if (m->kind == B2H_MODEL_LOGISTIC) return logistic_workspace_bytes(m, dtype, C);

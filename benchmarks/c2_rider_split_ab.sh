@@ -1,6 +1,6 @@
 #!/bin/bash
 # c2: split-K slices of the momentum contractions of restarting chains (B2H_RIDER_SPLIT)
-for rs in 5 3 2 1; do
+for rs in 5 3 4; do
   B2H_RIDER_SPLIT=$rs python bench.py --workload c2 --no-ess --no-cpu --no-secondary > gpurun_out/c2_rs.json 2> gpurun_out/c2_rs.err
   python - <<PY
 import json
