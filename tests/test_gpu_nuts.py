@@ -344,6 +344,36 @@ def test_nuts_dense_metric_triangular_flag(ab, monkeypatch):
 
 
 @pytest.mark.parametrize("metric_kind", ["diag", "dense"])
+def test_nuts_gaussian_potential_formed_by_tick_kernel(ab, monkeypatch, metric_kind):
+    """Correlated Gaussian target: the tile tick kernel forms U = 0.5 (q' - mu) . g' in its pass A (engine_split.inl,
+    EngineView::u_center) -- against the oracle, and against the same run with the separate potential kernel
+    (B2H_TICK_POTENTIAL=0).  d = 200: rows longer than one ring piece, i.e. the one-chain layouts that carry it."""
+    from aehmc_b200 import _engine
+    rng = np.random.default_rng(47)
+    C, T, d = 5, 2, 200
+    mu, cov, prec = _corr_case(rng, d)
+    imm = cov if metric_kind == "dense" else np.diag(cov).copy()
+    q0 = mu + rng.standard_normal((C, d))
+    draws = parity.random_draws(rng, C, T, d)
+    ref = parity.oracle_nuts(o_models.CorrelatedGaussian(mu, prec), q0, 0.1, imm, draws, T)
+    model = ab.models.CorrelatedGaussian(mu, prec)
+
+    def run():
+        srng = ab.InjectedDraws(draws["z"], draws["u_dir"], draws["u_biased"], draws["u_uniform"])
+        return _engine.run("nuts", model, imm, srng, ab.nuts.new_state(q0, model), 0.1, n_transitions=T, store_draws=T)
+
+    info1, ex1 = run()
+    monkeypatch.setenv("B2H_TICK_POTENTIAL", "0")
+    info0, ex0 = run()
+    for info, ex in ((info1, ex1), (info0, ex0)):
+        np.testing.assert_array_equal(_np(info.num_doublings), ref["num_doublings"])
+        np.testing.assert_array_equal(_np(ex["n_leapfrog"]), ref["n_leapfrog"])
+        np.testing.assert_allclose(_np(ex["draws"]), ref["draws"], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(_np(info.state.potential_energy), ref["U"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(_np(info1.acceptance_probability), _np(info0.acceptance_probability), rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("metric_kind", ["diag", "dense"])
 def test_hmc_proposal_closure_matches_oracle(ab, metric_kind):
     """hmc.hmc_proposal(integrator, kinetic_energy, L, threshold) -> propose(srng, state, step_size)
     (reference hmc.py:129-206), composed the way hmc.new_kernel.step composes it (hmc.py:110-123)."""
