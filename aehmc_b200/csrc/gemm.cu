@@ -384,15 +384,25 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
     // One tile per CTA (gridDim.x == total_tiles), except for launches whose row count only the device knows (the
     // momentum contractions of restarting chains: the grid would cover all C rows and 9 of 10 CTAs -- each needing a
     // whole SM's shared memory -- would exit at once): a small grid walks the tiles and skips the empty ones.
+    // LOOP: the walk enumerates only the row tiles that hold rows (vt0 / vt1 / vt2 of the three groups, from the
+    // device-side counts), so that the few valid tiles spread evenly over the grid
+    int vt0 = tiles_m0, vt1 = tiles_m1, vt2 = total_tiles / tiles_n - tiles_m0 - tiles_m1;
+    if (LOOP) {
+        if (g0.m_dev) vt0 = min(vt0, (min(g0.M, *g0.m_dev) + BM - 1) / BM);
+        if (g1.m_dev) vt1 = min(vt1, (min(g1.M, *g1.m_dev) + BM - 1) / BM);
+        if (g2.m_dev) vt2 = min(vt2, (min(g2.M, *g2.m_dev) + BM - 1) / BM);
+        total_tiles = (vt0 + vt1 + vt2) * tiles_n;
+        if ((int)blockIdx.x >= total_tiles) return;
+    }
     int tile = blockIdx.x;
     do {
     if (LOOP && tile != (int)blockIdx.x) __syncthreads();         // every warp is done with the previous tile's stages
     int k_chunk = k_chunk_in;
     int tile_m = tile / tiles_n;
     const int tile_n = tile % tiles_n;
-    const int which = tile_m < tiles_m0 ? 0 : (tile_m < tiles_m0 + tiles_m1 ? 1 : 2);
+    const int which = tile_m < vt0 ? 0 : (tile_m < vt0 + vt1 ? 1 : 2);
     const GemmGroup<T>& g = which == 0 ? g0 : (which == 1 ? g1 : g2);
-    tile_m -= which == 0 ? 0 : (which == 1 ? tiles_m0 : tiles_m0 + tiles_m1);
+    tile_m -= which == 0 ? 0 : (which == 1 ? vt0 : vt0 + vt1);
     int M = g.M;
     if (g.m_dev) M = min(M, *g.m_dev);
     const int m0 = tile_m * BM, n0 = tile_n * BN_;
@@ -546,7 +556,10 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
                     for (int j = 0; j < NJ; ++j) Dmma<8>::run(acc[i][j], fa[i], fb[j]);
             }
         };
-        if (sub) ktile(std::true_type{});
+        // device-counted launches: a warp whose 32 rows lie past the row count only copies (the last 128-row tile of a
+        // few hundred restarting chains is mostly empty)
+        if (LOOP && m0 + wm >= M) refill();
+        else if (sub) ktile(std::true_type{});
         else ktile(std::false_type{});
 #else
         refill();
