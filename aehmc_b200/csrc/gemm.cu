@@ -327,8 +327,10 @@ dense_apply_dmma_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGroup<do
 // FP64 main path: the same DMMA warp tiling fed by a 3-stage cp.async (LDGSTS) pipeline -- no register
 // staging, one barrier per k-tile -- and a CTA tile width chosen per problem (BN = 128 / 112 / 96) so
 // that the tile count fills whole waves of 148 SMs (d = 1000: 32 x 9 tiles of 128 x 112 = 288 of 296
-// slots).  A stays row-major [m][k] in shared memory (rows padded to 20 doubles: the 8 rows x 4 k a warp
-// reads per fragment are 32 distinct 8-byte words = 2 wavefronts); B is [k][n] with rows padded by 8.
+// slots).  A stays row-major [m][k] in shared memory, B is [k][n]; row paddings: see kApad / kBpad below.  The two
+// warps of a scheduler refill the freed stage at different points of a k-tile, launches without a vector to subtract
+// take a loop body without the subtraction, launches whose row count lives on the device walk the valid tiles with a
+// small grid (LOOP).
 // Requires 16-byte aligned rows (even K, N, leading dimensions); otherwise the register-staged kernel runs.
 // ---------------------------------------------------------------------------------------------
 constexpr int STAGES = 3;
@@ -339,17 +341,13 @@ constexpr int STAGES = 3;
 #define B2H_GEMM_BK_DEFAULT 32
 #endif
 
-// Fragment loads.  B2H_GEMM_FRAG128 = 1 (default): every lane fetches TWO fragment values per shared-memory load
-// (LDS.128) -- the k-slots tq / tq + 4 of the m16n8k8 shape are bound to the adjacent reduction indices 2 tq / 2 tq + 1
-// (the same binding for A and B, so the product is unchanged up to the order of the partial sums) and the n8 tiles 2 p /
-// 2 p + 1 of a warp take the even / odd columns of a 16-column group -- and the fragments of the next k8 step are in
-// flight while the current one is multiplied.  12 loads per 14 MMAs instead of 22; the paddings make the quarter-warp
-// accesses conflict free (A rows shift by 16 banks, B row pairs by 8).
-#ifndef B2H_GEMM_FRAG128
-#define B2H_GEMM_FRAG128 1
-#endif
-constexpr int kApad = B2H_GEMM_FRAG128 ? 8 : 4;
-constexpr int kBpad = B2H_GEMM_FRAG128 ? 2 : 8;
+// Fragment loads: every lane fetches TWO fragment values per shared-memory load (LDS.128) -- the k-slots tq / tq + 4 of
+// the m16n8k8 shape are bound to the adjacent reduction indices 2 tq / 2 tq + 1 (the same binding for A and B, so the
+// product is unchanged up to the order of the partial sums) and the n8 tiles 2 p / 2 p + 1 of a warp take the even / odd
+// columns of a 16-column group.  12 loads per 14 MMAs instead of the 22 of one value per load; the paddings make the
+// quarter-warp accesses conflict free (A rows shift by 16 banks, B row pairs by 8).
+constexpr int kApad = 8;
+constexpr int kBpad = 2;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -510,7 +508,6 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
             cp_async_commit();
         };
         const int stage = kt % STAGES;
-#if B2H_GEMM_FRAG128
         const T* as = As + stage * A_STAGE + (wm + gq) * ALD_ + 2 * tq;
         const T* bs = Bs + stage * B_STAGE + (2 * tq) * BLD + wn;
         const T* ss = Ss + stage * BK_ + 2 * tq;
@@ -561,32 +558,6 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
         if (LOOP && m0 + wm >= M) refill();
         else if (sub) ktile(std::true_type{});
         else ktile(std::false_type{});
-#else
-        refill();
-        const T* as = As + stage * A_STAGE + (wm + gq) * ALD_;
-        const T* bs = Bs + stage * B_STAGE + wn + gq;
-        const T* ss = Ss + stage * BK_;
-#pragma unroll
-        for (int k0 = 0; k0 < BK_; k0 += 8) {
-            T fa[MI][4], fb[NJ][2];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int kk = k0 + tq + 4 * q;
-                const T sv = sub ? ss[kk] : 0.0;
-#pragma unroll
-                for (int i = 0; i < MI; ++i) {
-                    fa[i][2 * q] = as[(i * 16) * ALD_ + kk] - sv;
-                    fa[i][2 * q + 1] = as[(i * 16 + 8) * ALD_ + kk] - sv;
-                }
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) fb[j][q] = bs[kk * BLD + j * 8];
-            }
-#pragma unroll
-            for (int i = 0; i < MI; ++i)
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) Dmma<8>::run(acc[i][j], fa[i], fb[j]);
-        }
-#endif
     }
     cp_async_wait<0>();
 
@@ -597,7 +568,6 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
             const int gr = m0 + wm + i * 16 + h * 8 + gq;
             if (gr >= M) continue;
             const i64 orow = (i64)((g.out_rows && !split) ? g.out_rows[gr] : gr) * ldo;
-#if B2H_GEMM_FRAG128
             // tiles 2 p / 2 p + 1 hold the even / odd columns of group p: a lane owns 4 consecutive columns of it
 #pragma unroll
             for (int pp = 0; pp < NJ / 2; ++pp) {
@@ -613,13 +583,6 @@ dense_apply_dmma_async_kernel(GemmGroup<double> g0, GemmGroup<double> g1, GemmGr
                 if (gn < N)
                     *reinterpret_cast<double2*>(out + orow + gn) = make_double2(acc[i][NJ - 1][2 * h], acc[i][NJ - 1][2 * h + 1]);
             }
-#else
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const int gn = n0 + wn + j * 8 + tq * 2;
-                if (gn < N) *reinterpret_cast<double2*>(out + orow + gn) = make_double2(acc[i][j][2 * h], acc[i][j][2 * h + 1]);
-            }
-#endif
         }
     } while (LOOP && (tile += gridDim.x) < total_tiles);          // tiles of this CTA
 }
